@@ -1,0 +1,184 @@
+/*
+ * wwfeat.h - C ABI of libwwfeat.so: the B200 (sm_100a) audio feature / augmentation path.
+ *
+ * Drop-in boundary for the hot path of sarpel/wakeword_trainer_home.  The reference has
+ * no FFI of its own: the path is the Python call surface of its (uncommitted) src/data
+ * package.  Each entry point below names the reference interface it stands behind
+ * (paths relative to the reference checkout) so a maintainer can bind it with ctypes
+ * (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - plain C types only; every buffer is a raw pointer + sizes; no torch types.
+ *   - "dev" pointers are CUDA device pointers on the plan's device, owned by the caller
+ *     (PyTorch's allocator); "host" pointers are ordinary host memory read during the call.
+ *   - stream arguments are a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - every function returns WWF_OK (0) or a negative wwf_status; the message for the
+ *     calling thread's last failure is wwf_last_error().  No C++ exception crosses the ABI.
+ *     Asynchronous CUDA faults surface at the caller's next synchronisation.
+ *   - a plan is immutable after wwf_bank_register calls finish: wwf_featurize /
+ *     wwf_augment / wwf_spec_augment are re-entrant across streams and host threads.
+ *   - There is NO CPU implementation behind this ABI: without a CUDA device the library
+ *     returns WWF_ERR_CUDA.
+ */
+#ifndef WWFEAT_H_
+#define WWFEAT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WWF_VERSION 100 /* 0.1.0 */
+
+typedef enum wwf_status {
+  WWF_OK = 0,
+  WWF_ERR_INVALID = -1,     /* bad argument / config outside the supported envelope */
+  WWF_ERR_UNSUPPORTED = -2, /* valid in the reference, not built here */
+  WWF_ERR_CUDA = -3,        /* CUDA runtime error (message has cudaGetErrorString) */
+  WWF_ERR_WORKSPACE = -4,   /* caller's workspace is too small / misaligned */
+  WWF_ERR_NOMEM = -5
+} wwf_status;
+
+enum { WWF_FEAT_LOGMEL = 0, WWF_FEAT_MFCC = 1 };
+enum { WWF_OUT_F32 = 0, WWF_OUT_F16 = 1 };
+enum { WWF_BANK_NOISE = 0, WWF_BANK_RIR = 1 };
+
+/*
+ * Feature configuration = the reference's FeatureExtractor constructor arguments
+ * (src/evaluation/evaluator.py:86-94, src/evaluation/inference.py:94-102) and the
+ * DataConfig fields that feed them (src/config/defaults.py:12-24), plus the
+ * torchaudio defaults the missing module relies on.
+ */
+typedef struct wwf_config {
+  int32_t sample_rate;  /* DataConfig.sample_rate (16000) */
+  int32_t n_fft;        /* 256 | 400 | 512 | 1024 | 2048  (validator.py:129 set + BASELINE's 400) */
+  int32_t hop_length;   /* 0 < hop < n_fft (validator.py:138) */
+  int32_t n_mels;       /* 1..128 */
+  int32_t n_mfcc;       /* 1..n_mels; used when feature_type == WWF_FEAT_MFCC */
+  int32_t feature_type; /* WWF_FEAT_LOGMEL ('mel') | WWF_FEAT_MFCC ('mfcc') (validator.py:145) */
+  int32_t out_dtype;    /* WWF_OUT_F32 | WWF_OUT_F16 */
+  int32_t cmvn;         /* 0 = off (reference behaviour), 1 = per-utterance CMVN epilogue */
+  float top_db;         /* AmplitudeToDB top_db (80); < 0 disables the floor */
+  float f_min;          /* mel f_min (0) */
+  float f_max;          /* mel f_max; <= 0 means sample_rate/2 */
+  float cmvn_eps;       /* (x-mean)/(std+eps) */
+  float mask_value;     /* SpecAugment fill value (0) */
+  int32_t n_freq_masks; /* columns of wwf_aug.fmask_* (SpecAugment n_freq_masks), 0..8 */
+  int32_t n_time_masks; /* columns of wwf_aug.tmask_* (SpecAugment n_time_masks), 0..8 */
+  /* Optional host constants.  NULL = computed by the library (double precision, rounded).
+   * The Python shim passes torch-computed float32 arrays so that the constants are
+   * bit-identical to torchaudio's (their last ulp moves results by ~1e-4 dB). */
+  const float* window;  /* host [n_fft]                       torch.hann_window(n_fft) */
+  const float* mel_fb;  /* host [n_fft/2+1][n_mels] row-major melscale_fbanks(...)      */
+  const float* dct;     /* host [n_mels][n_mfcc] row-major    create_dct(n_mfcc,n_mels,'ortho') */
+} wwf_config;
+
+/*
+ * Per-batch augmentation draws, all explicit (BASELINE.json north_star: "RIR/noise
+ * indices, SNRs and SpecAugment masks passed in explicitly").  Struct-of-arrays of DEVICE
+ * pointers, each nullable (NULL = that augmentation is off for the whole batch).
+ * Reference surface: AudioAugmentation(...)(wave) and SpecAugment(...)(spec),
+ * tests/test_training_pipeline.py:230-262; kwargs src/ui/panel_training.py:309-318.
+ */
+typedef struct wwf_aug {
+  const int32_t* rir_idx;     /* dev [B]  index into the RIR bank, < 0 = no reverb     */
+  const int32_t* noise_idx;   /* dev [B]  index into the noise bank, < 0 = no noise    */
+  const int64_t* noise_off;   /* dev [B]  first sample inside the noise clip (wraps)   */
+  const float* snr_db;        /* dev [B]  target SNR in dB                             */
+  const int32_t* fmask_start; /* dev [B][n_freq_masks]  first masked feature row       */
+  const int32_t* fmask_len;   /* dev [B][n_freq_masks]  rows masked (0 = none)         */
+  const int32_t* tmask_start; /* dev [B][n_time_masks]  first masked frame             */
+  const int32_t* tmask_len;   /* dev [B][n_time_masks]  frames masked (0 = none)       */
+} wwf_aug;
+
+typedef struct wwf_plan wwf_plan; /* opaque */
+
+/* Shape facts of a plan (filled by wwf_plan_info). */
+typedef struct wwf_info {
+  int32_t n_freq;         /* n_fft/2 + 1 */
+  int32_t n_feat;         /* rows of the output: n_mels or n_mfcc */
+  int32_t device;         /* CUDA device ordinal */
+  int32_t sm_count;       /* SMs of that device */
+  int32_t rir_fft_size;   /* real FFT size P of the overlap-save reverb blocks (0 = no RIR bank) */
+  int32_t rir_max_len;    /* longest registered RIR */
+  int32_t n_rir, n_noise; /* registered bank sizes */
+} wwf_info;
+
+/* Library version (WWF_VERSION of the build). */
+int wwf_version(void);
+
+/* Message of the calling thread's most recent failure ("" if none). */
+const char* wwf_last_error(void);
+
+/*
+ * Build the immutable device constants (window, FFT twiddles, sparse mel rows, DCT).
+ * Replaces:  FeatureExtractor.__init__(sample_rate, feature_type, n_mels, n_mfcc, n_fft,
+ *            hop_length, device)   src/evaluation/evaluator.py:86-94
+ */
+int wwf_plan_create(const wwf_config* cfg, int device, wwf_plan** out);
+void wwf_plan_destroy(wwf_plan* plan);
+int wwf_plan_info(const wwf_plan* plan, wwf_info* out);
+
+/* Frames produced for n_samples: n_samples / hop + 1 (src/export/onnx_exporter.py:316-317). */
+int wwf_num_frames(const wwf_plan* plan, int n_samples);
+
+/*
+ * Register a ragged bank of background-noise clips or room impulse responses that
+ * wwf_aug.noise_idx / rir_idx index into.
+ *   data    dev  float32, all clips back to back; BORROWED for noise (must outlive the plan's
+ *                use), consumed during the call for RIRs (their spectra are plan-owned).
+ *   offsets host int64 [count+1], clip i = data[offsets[i] .. offsets[i+1])
+ * Replaces: the noise / RIR file lists AudioAugmentation loads from data/raw/{background,rirs}
+ *           (README.md:57-58, src/ui/panel_training.py:329).  Synchronises `stream`.
+ */
+int wwf_bank_register(wwf_plan* plan, int kind, const float* data, const int64_t* offsets,
+                      int count, void* stream);
+
+/* Scratch bytes wwf_featurize / wwf_augment need for a (B, N) batch (0 if no RIR bank). */
+size_t wwf_workspace_bytes(const wwf_plan* plan, int B, int N);
+
+/*
+ * The hot path: raw clips -> [RIR reverb] -> [noise @ SNR] -> STFT -> mel -> dB/top_db
+ * -> [DCT-II] -> [CMVN] -> [SpecAugment masks] -> features.
+ *   wav         dev float32 [B][N], row stride wav_stride elements (>= N)
+ *   aug         NULL = no augmentation (FeatureExtractor.__call__ only)
+ *   out         dev [B][1][n_feat][T] (float32 or float16 per plan), clip stride out_stride
+ *               elements (>= n_feat*T)
+ *   workspace   dev, >= wwf_workspace_bytes(plan,B,N), 16-byte aligned (may be NULL if 0)
+ * Replaces: WakewordDataset.__getitem__'s  AudioAugmentation(wave) -> FeatureExtractor(wave)
+ *           -> SpecAugment(feat) chain (src/evaluation/evaluator.py:125,204;
+ *           src/evaluation/inference.py:197), batched.
+ */
+int wwf_featurize(wwf_plan* plan, const float* wav, int B, int N, int64_t wav_stride,
+                  const wwf_aug* aug, void* out, int64_t out_stride, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
+/*
+ * Time-domain half only: [RIR reverb] -> [noise @ SNR], (B,N) -> (B,N) float32.
+ * out_wav may alias wav only when aug->rir_idx is NULL.
+ * Replaces: AudioAugmentation.__call__(waveform)  tests/test_training_pipeline.py:239-243.
+ */
+int wwf_augment(wwf_plan* plan, const float* wav, int B, int N, int64_t wav_stride,
+                const wwf_aug* aug, float* out_wav, int64_t out_stride, void* workspace,
+                size_t workspace_bytes, void* stream);
+
+/*
+ * In-place explicit-index SpecAugment on an existing feature tensor [B][F][T]
+ * (float32 or float16 per `dtype`): rows [fstart, fstart+flen) and frames
+ * [tstart, tstart+tlen) := mask_value.  Needs no plan.
+ * Replaces: SpecAugment.__call__(spec)  tests/test_training_pipeline.py:252-262.
+ */
+int wwf_spec_augment(void* spec, int dtype, int B, int F, int T, int64_t clip_stride,
+                     const int32_t* fmask_start, const int32_t* fmask_len, int n_freq_masks,
+                     const int32_t* tmask_start, const int32_t* tmask_len, int n_time_masks,
+                     float mask_value, int device, void* stream);
+
+/* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
+int64_t wwf_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WWFEAT_H_ */

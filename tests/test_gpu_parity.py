@@ -1,0 +1,222 @@
+"""GPU parity tests: the CUDA path (through the C ABI, via the ctypes shim) against the oracle
+and the committed torchaudio golden vectors.  Run on the B200 box: pytest -m gpu."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ABS_DB, assert_features_close, aug_case_inputs, make_inputs, synth_banks
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ww():
+    if not torch.cuda.is_available():
+        pytest.fail("pytest -m gpu needs a CUDA device")
+    import wakeword_trainer_home_b200 as w
+    assert os.path.exists(w.LIB_PATH), "libwwfeat.so must be built in-tree"
+    return w
+
+
+def _golden(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+FEAT_CASES = [("feat_cfg1", 400, 40, 40), ("feat_refdefault", 1024, 128, 40), ("feat_n512", 512, 64, 32)]
+
+
+@pytest.mark.parametrize("name,n_fft,n_mels,n_mfcc", FEAT_CASES)
+def test_features_match_torchaudio_golden(ww, golden_dir, name, n_fft, n_mels, n_mfcc):
+    g = _golden(golden_dir, name)
+    x = make_inputs(int(g["seed"]), int(g["B"]), int(g["N"])).cuda()
+    mel = ww.FeatureExtractor(16000, "mel", n_mels, n_mfcc, n_fft, 160, "cuda")(x).cpu().numpy()
+    mf = ww.FeatureExtractor(16000, "mfcc", n_mels, n_mfcc, n_fft, 160, "cuda")(x).cpu().numpy()
+    assert mel.shape == g["logmel"].shape and mf.shape == g["mfcc"].shape
+    # clip 1 is digital silence: exactly -100 dB everywhere (1e-10 clamp), bit-exact
+    assert (mel[1] == -100.0).all()
+    for c in range(mel.shape[0]):
+        # clip 2 is a full-scale pure tone: its -78 dB side lobes sit at the float32 noise floor of
+        # ANY float32 FFT (torchaudio-f32 vs torchaudio-f64 already differ by up to 6e-4 dB there),
+        # so it is held to 3x the oracle's own float32 error, never less than the stated 1e-3.
+        tol = ABS_DB
+        if c == 2:
+            tol = max(ABS_DB, 3.0 * float(np.abs(g["logmel"][c] - g["logmel64"][c]).max()))
+        assert_features_close(mel[c], g["logmel"][c], f"{name} log-mel clip {c}", abs_tol=tol)
+        assert_features_close(mel[c], g["logmel64"][c], f"{name} log-mel clip {c} vs f64", abs_tol=tol)
+        assert_features_close(mf[c], g["mfcc"][c], f"{name} mfcc clip {c}", abs_tol=tol * (3.0 if c == 2 else 1.0))
+
+
+def test_augment_matches_torchaudio_golden(ww, golden_dir):
+    g = _golden(golden_dir, "aug_cfg2")
+    x, noise, rirs = aug_case_inputs(g)
+    plan = ww.FeaturePlan(16000, "mfcc", 40, 40, 400, 160, "cuda")
+    plan.register_noise(noise)
+    plan.register_rirs(rirs)
+    p = ww.AugParams(rir_idx=torch.from_numpy(g["rir_idx"]), noise_idx=torch.from_numpy(g["noise_idx"]),
+                     noise_off=torch.from_numpy(g["noise_off"]), snr_db=torch.from_numpy(g["snr"]))
+    only_rir = ww.AugParams(rir_idx=p.rir_idx)
+    rev = plan.augment(x.cuda(), only_rir).cpu().numpy()
+    mixed = plan.augment(x.cuda(), p).cpu().numpy()
+    for b in range(x.shape[0]):
+        rms = float(np.sqrt((g["reverb"][b].astype(np.float64) ** 2).mean()))
+        assert np.abs(rev[b] - g["reverb"][b]).max() <= 2e-5 * rms, f"reverb clip {b}"
+        if g["rir_idx"][b] < 0:
+            assert (rev[b] == x[b].numpy()).all(), "dry clip must pass through bit-exactly"
+        rms = float(np.sqrt((g["mixed"][b].astype(np.float64) ** 2).mean()))
+        assert np.abs(mixed[b] - g["mixed"][b]).max() <= 2e-5 * rms, f"mixed clip {b}"
+    feats = plan.featurize(x.cuda(), p).cpu().numpy()
+    assert_features_close(feats, g["mfcc"], "cfg2 MFCC after reverb + noise")
+
+
+def test_specaugment_masks_bit_exact(ww, golden_dir):
+    g = _golden(golden_dir, "mask_ref")
+    torch.manual_seed(int(g["seed"]))
+    spec = torch.randn(4, 1, 64, 50)
+    sa = ww.SpecAugment(15, 35, 2, 2)
+    p = ww.AugParams(fmask_start=torch.from_numpy(g["fstart"]), fmask_len=torch.from_numpy(g["flen"]),
+                     tmask_start=torch.from_numpy(g["tstart"]), tmask_len=torch.from_numpy(g["tlen"]))
+    out = sa(spec.cuda(), p).cpu().numpy()
+    assert np.array_equal(out, g["out"])           # masked -> 0.0, everything else untouched, bit-exact
+    # reference's own assertion (tests/test_training_pipeline.py:259-262): shape preserved, random draw
+    t = torch.randn(1, 64, 50).cuda()
+    assert sa(t).shape == t.shape
+
+
+def test_fused_masks_equal_oracle_mask_of_unmasked_features(ww):
+    from oracle import ta_oracle as tao
+    B, N = 8, 24000
+    x = make_inputs(11, B, N)
+    plan0 = ww.FeaturePlan(16000, "mel", 40, 40, 400, 160, "cuda")
+    plan = ww.FeaturePlan(16000, "mel", 40, 40, 400, 160, "cuda", n_freq_masks=2, n_time_masks=2, mask_value=-7.5)
+    gen = torch.Generator().manual_seed(5)
+    fs, fl = tao.draw_mask_params(gen, B, 40, 15, 2)
+    ts, tl = tao.draw_mask_params(gen, B, 151, 35, 2)
+    base = plan0.featurize(x.cuda()).cpu()
+    got = plan.featurize(x.cuda(), ww.AugParams(fmask_start=fs, fmask_len=fl, tmask_start=ts, tmask_len=tl)).cpu()
+    want = tao.spec_mask(base, fs, fl, ts, tl, -7.5)
+    assert torch.equal(got, want)                  # indices and fill bit-exact; unmasked values identical
+
+
+@pytest.mark.parametrize("n_fft,hop,n_mels,n_mfcc,N,ftype", [
+    (256, 128, 40, 13, 16000, "mfcc"), (256, 100, 32, 20, 12345, "mel"), (400, 160, 40, 40, 24000, "mfcc"),
+    (400, 200, 64, 40, 19999, "mel"), (512, 160, 64, 32, 32000, "mfcc"), (1024, 160, 128, 40, 40000, "mel"),
+    (1024, 256, 80, 40, 16000, "mfcc"), (2048, 512, 128, 40, 24000, "mel"), (2048, 160, 128, 64, 16000, "mfcc"),
+    (400, 160, 40, 40, 201, "mel"), (1024, 160, 128, 40, 513, "mel"),
+])
+def test_feature_configs_vs_oracle(ww, n_fft, hop, n_mels, n_mfcc, N, ftype):
+    from oracle import ta_oracle as tao
+    B = 5
+    x = make_inputs(n_fft + hop + N, B, N)
+    got = ww.FeatureExtractor(16000, ftype, n_mels, n_mfcc, n_fft, hop, "cuda")(x).cpu().numpy()
+    kw = dict(sample_rate=16000, feature_type=ftype, n_mels=n_mels, n_mfcc=n_mfcc, n_fft=n_fft, hop_length=hop)
+    ref32 = tao.featurize(x, **kw).numpy()
+    ref64 = tao.featurize(x, dtype=torch.float64, **kw).numpy()
+    assert got.shape == (B, 1, n_mfcc if ftype == "mfcc" else n_mels, N // hop + 1)
+    for c in range(B):
+        tol = ABS_DB if c != 2 else max(ABS_DB, 3.0 * float(np.abs(ref32[c] - ref64[c]).max()))
+        assert_features_close(got[c], ref64[c], f"clip {c} vs f64 oracle", abs_tol=tol)
+        assert_features_close(got[c], ref32[c], f"clip {c} vs f32 oracle", abs_tol=2 * tol if c == 2 else tol)
+
+
+def test_call_surface_like_reference(ww):
+    """Shapes the reference's callers rely on: evaluator.py:122-128, inference.py:197-200,
+    tests/test_training_pipeline.py:239-243."""
+    fe = ww.FeatureExtractor(sample_rate=16000, feature_type="mel_spectrogram", n_mels=64, n_mfcc=40,
+                             n_fft=1024, hop_length=160, device="cuda")
+    audio = torch.randn(16000)                                    # CPU 1-D like torch.from_numpy(audio).float()
+    f = fe(audio)
+    assert f.shape == (1, 64, 16000 // 160 + 1) and f.is_cuda and f.dtype == torch.float32
+    assert fe(audio.unsqueeze(0)).shape == f.shape
+    assert fe(torch.randn(3, 16000)).shape == (3, 1, 64, 101)
+    assert fe(torch.randn(3, 1, 16000)).shape == (3, 1, 64, 101)
+    aug = ww.AudioAugmentation(sample_rate=16000, device="cuda", time_stretch_range=(0.8, 1.2),
+                               pitch_shift_range=(-2, 2), background_noise_prob=0.5)
+    t = torch.randn(1, 16000).cuda()
+    a = aug(t)
+    assert a.shape == t.shape and torch.isfinite(a).all()
+    with pytest.raises(ww.WwfError):
+        ww.FeatureExtractor(n_fft=300, device="cuda")
+    with pytest.raises(ww.WwfError):
+        fe(torch.randn(100))                                      # N <= n_fft/2: reflect pad impossible
+
+
+def test_audio_augmentation_class_vs_oracle(ww):
+    from oracle import ta_oracle as tao
+    noise, rirs = synth_banks(3, 4, 30000, 3, 4000)
+    B, N = 16, 16000
+    x = 0.1 * torch.randn(B, N, generator=torch.Generator().manual_seed(1))
+    aug = ww.AudioAugmentation(16000, "cuda", background_noise_prob=0.7, noise_snr_range=(0.0, 15.0), rir_prob=0.5,
+                               background_noise=noise, rirs=rirs, seed=9)
+    p = aug.draw(B)
+    got = aug(x.cuda(), p).cpu()
+    want = tao.augment_wave(x, rirs=rirs, rir_idx=p.rir_idx, noise_bank=noise, noise_idx=p.noise_idx,
+                            noise_off=p.noise_off, snr_db=p.snr_db)
+    rms = want.pow(2).mean(dim=1).sqrt()
+    assert ((got - want).abs().amax(dim=1) <= 2e-5 * rms).all()
+    dry = (p.rir_idx < 0) & (p.noise_idx < 0)
+    assert torch.equal(got[dry], x[dry])
+
+
+def test_noise_shorter_than_clip_wraps_and_long_clip_overlap_save(ww):
+    from oracle import ta_oracle as tao
+    B, N = 3, 40000                                      # 2.5 s preset: needs 2 overlap-save blocks
+    gen = torch.Generator().manual_seed(2)
+    x = 0.2 * torch.randn(B, N, generator=gen)
+    noise = [0.05 * torch.randn(7001, generator=gen), 0.05 * torch.randn(50000, generator=gen)]
+    t = torch.arange(8000, dtype=torch.float32)
+    rirs = [torch.randn(8000, generator=gen) * torch.exp(-t / 800.0), torch.randn(300, generator=gen)]
+    plan = ww.FeaturePlan(16000, "mel", 128, 40, 1024, 160, "cuda")
+    plan.register_noise(noise); plan.register_rirs(rirs)
+    p = ww.AugParams(rir_idx=torch.tensor([0, 1, -1]), noise_idx=torch.tensor([0, 1, 0]),
+                     noise_off=torch.tensor([6999, 49999, 3]), snr_db=torch.tensor([10.0, 3.0, 20.0]))
+    got = plan.augment(x.cuda(), p).cpu()
+    want = tao.augment_wave(x, rirs=rirs, rir_idx=p.rir_idx, noise_bank=noise, noise_idx=p.noise_idx,
+                            noise_off=p.noise_off, snr_db=p.snr_db)
+    rms = want.pow(2).mean(dim=1).sqrt()
+    assert ((got - want).abs().amax(dim=1) <= 2e-5 * rms).all()
+    feats = plan.featurize(x.cuda(), p).cpu().numpy()
+    ref = tao.featurize(want.double(), sample_rate=16000, feature_type="mel", n_mels=128, n_fft=1024,
+                        hop_length=160, dtype=torch.float64).numpy()
+    assert_features_close(feats, ref, "2.5 s default-preset features after augmentation")
+
+
+def test_fp16_output_and_cmvn(ww):
+    from oracle import ta_oracle as tao
+    x = make_inputs(21, 6, 32000)
+    kw = dict(sample_rate=16000, feature_type="mel", n_mels=64, n_mfcc=40, n_fft=400, hop_length=160)
+    ref = tao.featurize(x, **kw)
+    h = ww.FeatureExtractor(device="cuda", out_dtype=torch.float16, **kw)(x)
+    assert h.dtype == torch.float16
+    assert torch.equal(h.cpu(), ref.to(torch.float16)) or (h.cpu().float() - ref).abs().max() <= 0.07  # 1 fp16 ulp at |x|<128
+    for ftype in ("mel", "mfcc"):
+        kw["feature_type"] = ftype
+        got = ww.FeatureExtractor(device="cuda", cmvn=True, **kw)(x).cpu()
+        want = tao.featurize(x, use_cmvn=True, dtype=torch.float64, **kw)
+        keep = [0, 2, 3, 4, 5]                            # clip 1 is silence: 0/eps, skip
+        assert (got[keep] - want[keep]).abs().max() <= 2e-3
+
+
+def test_batch_invariance_and_determinism_at_full_size(ww):
+    """BASELINE.json configs[1] size (B=1024, 1.5 s, MFCC-40 + noise + RIR): results must not depend
+    on batch composition or run, and a 2x louder clip shifts un-floored log-mel by 20*log10(2) dB."""
+    B, N = 1024, 24000
+    gen = torch.Generator().manual_seed(0)
+    x = (0.1 * torch.randn(B, N, generator=gen)).cuda()
+    noise, rirs = synth_banks(0, 256, 24000, 64, 8000)
+    plan = ww.FeaturePlan(16000, "mfcc", 40, 40, 400, 160, "cuda")
+    plan.register_noise(noise); plan.register_rirs(rirs)
+    p = ww.AugParams(rir_idx=torch.randint(0, 64, (B,), generator=gen, dtype=torch.int32),
+                     noise_idx=torch.randint(0, 256, (B,), generator=gen, dtype=torch.int32),
+                     noise_off=torch.randint(0, 24000, (B,), generator=gen),
+                     snr_db=5.0 + 15.0 * torch.rand(B, generator=gen))
+    a = plan.featurize(x, p)
+    b = plan.featurize(x, p)
+    assert torch.equal(a, b) and torch.isfinite(a).all()
+    sub = slice(100, 116)
+    ps = ww.AugParams(rir_idx=p.rir_idx[sub], noise_idx=p.noise_idx[sub], noise_off=p.noise_off[sub], snr_db=p.snr_db[sub])
+    assert torch.equal(plan.featurize(x[sub], ps), a[sub])
+    lm = ww.FeaturePlan(16000, "mel", 40, 40, 400, 160, "cuda", top_db=None)
+    d = lm.featurize(2.0 * x[:64]) - lm.featurize(x[:64])
+    assert (d - 20.0 * np.log10(2.0)).abs().max() <= 1e-4

@@ -1,0 +1,15 @@
+"""wakeword_trainer_home_b200 - B200 (sm_100a) audio feature / augmentation path.
+
+Drop-in for the ``src.data`` feature-extraction and augmentation surface of
+sarpel/wakeword_trainer_home, executed by hand-written CUDA kernels behind a C ABI
+(include/wwfeat.h -> lib/libwwfeat.so).  No CPU fallback: constructing any class needs the
+built library and a CUDA device.
+"""
+from ._native import WwfError, LIB_PATH, launch_count  # noqa: F401
+from .pipeline import AugParams, FeaturePlan, draw_mask_params, spec_augment_  # noqa: F401
+from .feature_extraction import FeatureExtractor  # noqa: F401
+from .augmentation import AudioAugmentation, SpecAugment  # noqa: F401
+
+__version__ = "0.1.0"
+__all__ = ["FeatureExtractor", "AudioAugmentation", "SpecAugment", "FeaturePlan", "AugParams",
+           "draw_mask_params", "spec_augment_", "WwfError", "launch_count"]

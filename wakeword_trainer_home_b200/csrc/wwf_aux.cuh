@@ -1,0 +1,76 @@
+// wwf_aux.cuh - the two stand-alone entry points of the reference surface that are not the
+// fused feature kernel: AudioAugmentation.__call__'s noise mix writing a waveform (A1) and
+// SpecAugment.__call__ on an existing feature tensor (A9).  SURVEY.md section 8a.
+#pragma once
+#include "wwf_feat.cuh"
+
+namespace wwf {
+
+struct MixParams {
+  const float* wav; int64_t wav_stride;
+  const float* rev; int64_t rev_stride;     // reverberated clips or nullptr
+  const int32_t* rir_idx; const int32_t* noise_idx; const int64_t* noise_off; const float* snr_db;
+  const float* noise_data; const int64_t* noise_offsets; int n_noise;
+  float* out; int64_t out_stride;
+  int B, N;
+};
+
+// One CTA per clip: y = src + scale * noise, scale from the two clip energies
+// (F.add_noise, TA/functional/functional.py:2374-2382); plain copy when the clip has no noise.
+__global__ void __launch_bounds__(512) mix_kernel(const MixParams p) {
+  __shared__ float red[64];
+  const int b = blockIdx.x;
+  const bool has_rev = p.rev != nullptr && p.rir_idx != nullptr && __ldg(p.rir_idx + b) >= 0;
+  const float* x = has_rev ? p.rev + (size_t)b * p.rev_stride : p.wav + (size_t)b * p.wav_stride;
+  float* y = p.out + (size_t)b * p.out_stride;
+  const float* nz = nullptr;
+  int noff = 0, nlen = 1;
+  float scale = 0.f;
+  if (p.noise_idx != nullptr && p.noise_data != nullptr) {
+    const int ni = __ldg(p.noise_idx + b);
+    if (ni >= 0 && ni < p.n_noise) {
+      const int64_t o0 = __ldg(p.noise_offsets + ni), o1 = __ldg(p.noise_offsets + ni + 1);
+      nlen = (int)(o1 - o0);
+      nz = p.noise_data + o0;
+      int64_t off = p.noise_off ? __ldg(p.noise_off + b) : 0;
+      off %= nlen; if (off < 0) off += nlen;
+      noff = (int)off;
+      float es, en;
+      clip_energies(x, p.N, nz, noff, nlen, es, en, red);
+      scale = snr_scale(es, en, p.snr_db ? __ldg(p.snr_db + b) : 0.f);
+    }
+  }
+  if (nz != nullptr) {
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) y[i] = fmaf(scale, noise_at(nz, noff, nlen, i), x[i]);
+  } else if (x != y) {
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) y[i] = x[i];
+  }
+}
+
+// In-place explicit-index SpecAugment: one CTA per (clip, row-chunk); only masked elements are
+// written (mask_along_axis fill semantics, TA/functional/functional.py:864-870,939-953).
+template <typename T>
+__global__ void __launch_bounds__(256) spec_mask_kernel(T* spec, int B, int F, int Tn, int64_t clip_stride,
+                                                        const int32_t* fs, const int32_t* fl, int nF,
+                                                        const int32_t* ts, const int32_t* tl, int nT, float mask_value) {
+  const int b = blockIdx.y;
+  T* s = spec + (size_t)b * clip_stride;
+  const T mv = to_out<T>(mask_value);
+  for (int f = blockIdx.x; f < F; f += gridDim.x) {
+    bool row = false;
+    for (int i = 0; i < nF; ++i) {
+      const int s0 = fs[(size_t)b * nF + i], l = fl[(size_t)b * nF + i];
+      row |= (f >= s0) && (f < s0 + l);
+    }
+    for (int t = threadIdx.x; t < Tn; t += blockDim.x) {
+      bool mk = row;
+      for (int i = 0; i < nT; ++i) {
+        const int s0 = ts[(size_t)b * nT + i], l = tl[(size_t)b * nT + i];
+        mk |= (t >= s0) && (t < s0 + l);
+      }
+      if (mk) s[(size_t)f * Tn + t] = mv;
+    }
+  }
+}
+
+}  // namespace wwf

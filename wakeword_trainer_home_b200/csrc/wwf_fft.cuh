@@ -1,0 +1,276 @@
+// wwf_fft.cuh - register-level DFT butterflies and the in-place mixed-radix pass used by
+// both FFT users of the path: the STFT (A4, torch.stft semantics) and the RIR overlap-save
+// convolution (A2, torchaudio fftconvolve semantics).  SURVEY.md section 8a.
+//
+// Everything here is __host__ __device__ so tests/emul can run the exact task functions
+// sequentially on the CPU to check index math (no product code path runs on the CPU).
+//
+// Conventions: forward transform uses w_N = exp(-2*pi*i/N).  A length-n FFT is a list of
+// radix passes R_0, R_1, ... with prod R_i = n, executed as in-place decimation in
+// frequency: pass i works on sub-transforms of length L_i = n / (R_0 ... R_{i-1}), combines
+// elements at stride s_i = L_i / R_i and multiplies output r by w_{L_i}^{j r}.  The result
+// is left in digit-reversed order: frequency k = d_0 + R_0 d_1 + R_0 R_1 d_2 + ... sits at
+// position p = d_0 s_0 + d_1 s_1 + ... .  The inverse runs the adjoint passes in reverse
+// order (decimation in time) and therefore consumes exactly that order - a convolution
+// never has to reorder.
+#pragma once
+#include <cuda_runtime.h>
+#include <type_traits>
+
+#define WWF_HD __host__ __device__ __forceinline__
+
+namespace wwf {
+
+// ----------------------------------------------------------------------------------------
+// compile-time helpers
+// ----------------------------------------------------------------------------------------
+template <int I, int N, class F>
+WWF_HD void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
+constexpr double kPi = 3.14159265358979323846264338327950288;
+
+// sin/cos by Taylor series around 0 after folding the argument into [-pi/4, pi/4];
+// evaluated only at compile time (double precision, then rounded to float once).
+constexpr double cx_sin_core(double x) {
+  double x2 = x * x, term = x, sum = x;
+  for (int i = 1; i < 14; ++i) {
+    term *= -x2 / double((2 * i) * (2 * i + 1));
+    sum += term;
+  }
+  return sum;
+}
+constexpr double cx_cos_core(double x) {
+  double x2 = x * x, term = 1.0, sum = 1.0;
+  for (int i = 1; i < 14; ++i) {
+    term *= -x2 / double((2 * i - 1) * (2 * i));
+    sum += term;
+  }
+  return sum;
+}
+// cos(2 pi e / n), sin(2 pi e / n) with exact octant folding on the integer ratio.
+constexpr double cx_cos2pi(long long e, long long n) {
+  e %= n; if (e < 0) e += n;
+  if (2 * e > n) e = n - e;                 // cos is even around pi
+  if (4 * e > n) return -cx_cos2pi(n - 2 * e, 2 * n);  // cos(pi - t) = -cos t, t = 2pi(n-2e)/(2n)
+  if (8 * e > n) return cx_sin_core(2.0 * kPi * double(n - 4 * e) / double(4 * n));  // cos(pi/2 - t) = sin t
+  return cx_cos_core(2.0 * kPi * double(e) / double(n));
+}
+constexpr double cx_sin2pi(long long e, long long n) {
+  // sin(a) = cos(a - pi/2) = cos(2 pi (4e - n) / (4n))
+  return cx_cos2pi(4 * e - n, 4 * n);
+}
+
+// w_N^E = exp(-2 pi i E / N) = (c, -s)
+template <int E, int N>
+struct TwC {
+  static constexpr int e = ((E % N) + N) % N;
+  static constexpr float c = float(cx_cos2pi(e, N));
+  static constexpr float s = float(cx_sin2pi(e, N));
+};
+
+// ----------------------------------------------------------------------------------------
+// complex helpers
+// ----------------------------------------------------------------------------------------
+WWF_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+WWF_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+WWF_HD float2 cmul(float2 a, float2 b) {
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+}
+WWF_HD float2 cmulc(float2 a, float2 b) {  // a * conj(b)
+  return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+}
+WWF_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+template <bool INV>
+WWF_HD float2 mul_mi(float2 a) {  // forward: * (-i); inverse: * (+i)
+  return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+
+// v * w_N^E (forward) or v * conj(w_N^E) (inverse), E and N compile-time.
+template <int E, int N, bool INV>
+WWF_HD float2 twmul(float2 v) {
+  constexpr int e = ((E % N) + N) % N;
+  if constexpr (e == 0) {
+    return v;
+  } else if constexpr (4 * e == N) {
+    return mul_mi<INV>(v);
+  } else if constexpr (2 * e == N) {
+    return make_float2(-v.x, -v.y);
+  } else if constexpr (4 * e == 3 * N) {
+    return mul_mi<!INV>(v);
+  } else if constexpr (8 * e == N) {  // (1 - i)/sqrt2 fwd
+    constexpr float r = 0.70710678118654752440f;
+    return INV ? make_float2((v.x - v.y) * r, (v.x + v.y) * r) : make_float2((v.x + v.y) * r, (v.y - v.x) * r);
+  } else if constexpr (8 * e == 3 * N) {  // (-1 - i)/sqrt2 fwd
+    constexpr float r = 0.70710678118654752440f;
+    return INV ? make_float2((-v.x - v.y) * r, (v.x - v.y) * r) : make_float2((v.y - v.x) * r, (-v.x - v.y) * r);
+  } else if constexpr (8 * e == 5 * N) {  // (-1 + i)/sqrt2 fwd
+    constexpr float r = 0.70710678118654752440f;
+    return INV ? make_float2((v.y - v.x) * r, (-v.x - v.y) * r) : make_float2((-v.x - v.y) * r, (v.x - v.y) * r);
+  } else if constexpr (8 * e == 7 * N) {  // (1 + i)/sqrt2 fwd
+    constexpr float r = 0.70710678118654752440f;
+    return INV ? make_float2((v.x + v.y) * r, (v.y - v.x) * r) : make_float2((v.x - v.y) * r, (v.x + v.y) * r);
+  } else {
+    constexpr float c = TwC<e, N>::c;
+    constexpr float s = TwC<e, N>::s;
+    // forward w = (c, -s): (x + iy)(c - is) = (xc + ys) + i(yc - xs)
+    return INV ? make_float2(fmaf(v.x, c, -v.y * s), fmaf(v.y, c, v.x * s))
+               : make_float2(fmaf(v.x, c, v.y * s), fmaf(v.y, c, -v.x * s));
+  }
+}
+
+// ----------------------------------------------------------------------------------------
+// elementary butterflies on individual registers
+// ----------------------------------------------------------------------------------------
+template <bool INV>
+WWF_HD void dft2(float2& a0, float2& a1) {
+  float2 t = a0;
+  a0 = cadd(t, a1);
+  a1 = csub(t, a1);
+}
+
+template <bool INV>
+WWF_HD void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
+  float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_mi<INV>(csub(a1, a3));
+  a0 = cadd(t0, t2);
+  a2 = csub(t0, t2);
+  a1 = cadd(t1, t3);
+  a3 = csub(t1, t3);
+}
+
+template <bool INV>
+WWF_HD void dft5(float2& a0, float2& a1, float2& a2, float2& a3, float2& a4) {
+  constexpr float c1 = TwC<1, 5>::c, c2 = TwC<2, 5>::c, s1 = TwC<1, 5>::s, s2 = TwC<2, 5>::s;
+  float2 p1 = cadd(a1, a4), m1 = csub(a1, a4), p2 = cadd(a2, a3), m2 = csub(a2, a3);
+  float2 r1 = make_float2(a0.x + fmaf(c1, p1.x, c2 * p2.x), a0.y + fmaf(c1, p1.y, c2 * p2.y));
+  float2 r2 = make_float2(a0.x + fmaf(c2, p1.x, c1 * p2.x), a0.y + fmaf(c2, p1.y, c1 * p2.y));
+  float2 q1 = make_float2(fmaf(s1, m1.x, s2 * m2.x), fmaf(s1, m1.y, s2 * m2.y));
+  float2 q2 = make_float2(fmaf(s2, m1.x, -s1 * m2.x), fmaf(s2, m1.y, -s1 * m2.y));
+  float2 iq1 = mul_mi<INV>(q1), iq2 = mul_mi<INV>(q2);  // forward: -i q
+  a0 = make_float2(a0.x + p1.x + p2.x, a0.y + p1.y + p2.y);
+  a1 = cadd(r1, iq1);
+  a4 = csub(r1, iq1);
+  a2 = cadd(r2, iq2);
+  a3 = csub(r2, iq2);
+}
+
+// elementary R-point DFT on v[0], v[S], v[2S], ...
+template <int R, bool INV, int S>
+WWF_HD void dft_strided(float2* v) {
+  static_assert(R == 2 || R == 4 || R == 5, "elementary radix");
+  if constexpr (R == 2) dft2<INV>(v[0], v[S]);
+  if constexpr (R == 4) dft4<INV>(v[0], v[S], v[2 * S], v[3 * S]);
+  if constexpr (R == 5) dft5<INV>(v[0], v[S], v[2 * S], v[3 * S], v[4 * S]);
+}
+
+// N = A*B point DFT in registers (Cooley-Tukey, natural-order in and out):
+//   X[B r1 + r2] = sum_{q1} w_A^{q1 r1} [ w_N^{q1 r2} sum_{q2} x[q1 + A q2] w_B^{q2 r2} ]
+template <int A, int B, bool INV>
+WWF_HD void dft_composite(float2 (&v)[A * B]) {
+  static_for<0, A>([&](auto Q1) { dft_strided<B, INV, A>(&v[decltype(Q1)::value]); });
+  static_for<1, A>([&](auto Q1) {
+    static_for<1, B>([&](auto R2) {
+      constexpr int q1 = decltype(Q1)::value, r2 = decltype(R2)::value;
+      v[q1 + A * r2] = twmul<q1 * r2, A * B, INV>(v[q1 + A * r2]);
+    });
+  });
+  static_for<0, B>([&](auto R2) { dft_strided<A, INV, 1>(&v[A * decltype(R2)::value]); });
+  float2 t[A * B];
+#pragma unroll
+  for (int i = 0; i < A * B; ++i) t[i] = v[i];
+  static_for<0, A>([&](auto R1) {
+    static_for<0, B>([&](auto R2) {
+      constexpr int r1 = decltype(R1)::value, r2 = decltype(R2)::value;
+      v[B * r1 + r2] = t[r1 + A * r2];
+    });
+  });
+}
+
+template <int R, bool INV>
+WWF_HD void dft(float2 (&v)[R]) {
+  if constexpr (R == 2 || R == 4 || R == 5) dft_strided<R, INV, 1>(&v[0]);
+  else if constexpr (R == 8) dft_composite<2, 4, INV>(v);
+  else if constexpr (R == 16) dft_composite<4, 4, INV>(v);
+  else if constexpr (R == 25) dft_composite<5, 5, INV>(v);
+  else static_assert(R == 2, "unsupported radix");
+}
+
+// ----------------------------------------------------------------------------------------
+// One radix-R butterfly task of an in-place pass over one FFT stored at z (through the
+// index map `Map`, e.g. shared-memory padding).
+//   L  : current sub-transform length, s = L / R the element stride
+//   u  : task id in [0, n/R): sub-transform u / s, column j = u % s
+//   tw : this pass's table, tw[(r-1)*s + j] = w_L^{j r}, r = 1..R-1 (forward values; the
+//        inverse pass multiplies by their conjugates); ignored when s == 1.
+// Forward (DIF): v' [r] = w_L^{j r} * DFT_R(v)[r].   Inverse (DIT): v = IDFT_R(conj(tw) * v').
+// ----------------------------------------------------------------------------------------
+struct IdentityMap {
+  WWF_HD int operator()(int i) const { return i; }
+};
+
+template <int R, bool INV, class Map = IdentityMap, class TwLoad>
+WWF_HD void pass_task(float2* z, int L, int u, TwLoad twload, Map map = Map()) {
+  const int s = L / R;
+  const int blk = u / s;
+  const int j = u - blk * s;
+  const int base = blk * L + j;
+  float2 v[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) v[q] = z[map(base + q * s)];
+  if constexpr (!INV) {
+    dft<R, false>(v);
+    if (s > 1) {
+#pragma unroll
+      for (int r = 1; r < R; ++r) v[r] = cmul(v[r], twload((r - 1) * s + j));
+    }
+  } else {
+    if (s > 1) {
+#pragma unroll
+      for (int r = 1; r < R; ++r) v[r] = cmulc(v[r], twload((r - 1) * s + j));
+    }
+    dft<R, true>(v);
+  }
+#pragma unroll
+  for (int q = 0; q < R; ++q) z[map(base + q * s)] = v[q];
+}
+
+// ----------------------------------------------------------------------------------------
+// Static description of an FFT as a list of radices (up to 4 passes).
+// ----------------------------------------------------------------------------------------
+template <int R0, int R1 = 1, int R2 = 1, int R3 = 1>
+struct Radices {
+  static constexpr int n = R0 * R1 * R2 * R3;
+  static constexpr int npass = 1 + (R1 > 1) + (R2 > 1) + (R3 > 1);
+  static constexpr int R(int i) { return i == 0 ? R0 : i == 1 ? R1 : i == 2 ? R2 : R3; }
+  static constexpr int L(int i) {  // sub-transform length of pass i
+    int l = n;
+    for (int k = 0; k < i; ++k) l /= R(k);
+    return l;
+  }
+  static constexpr int S(int i) { return L(i) / R(i); }
+  // twiddle table size of pass i (entries) and offset of pass i in the concatenated table
+  static constexpr int tw_size(int i) { return S(i) > 1 ? (R(i) - 1) * S(i) : 0; }
+  static constexpr int tw_off(int i) {
+    int o = 0;
+    for (int k = 0; k < i; ++k) o += tw_size(k);
+    return o;
+  }
+  static constexpr int tw_total = tw_off(npass);
+  // position of frequency k after the forward passes
+  static WWF_HD int pos(int k) {
+    int p = 0;
+#pragma unroll
+    for (int i = 0; i < npass; ++i) {
+      const int d = k % R(i);
+      k /= R(i);
+      p += d * S(i);
+    }
+    return p;
+  }
+};
+
+}  // namespace wwf

@@ -1,0 +1,439 @@
+// wwfeat.cu - host side of libwwfeat.so: plan construction (device constants), bank
+// registration, launch logic and the extern "C" ABI declared in include/wwfeat.h.
+// There is deliberately no CPU implementation in this file: every entry point that
+// computes needs a CUDA device and fails with WWF_ERR_CUDA otherwise.
+#include "../../include/wwfeat.h"
+
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#include "wwf_aux.cuh"
+#include "wwf_conv.cuh"
+#include "wwf_feat.cuh"
+#include "wwf_tables.h"
+
+using namespace wwf;
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<int64_t> g_launches{0};
+
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define WWF_CUDA(expr)                                                                          \
+  do {                                                                                          \
+    cudaError_t e__ = (expr);                                                                   \
+    if (e__ != cudaSuccess)                                                                     \
+      return fail(WWF_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) == cudaSuccess && cudaSetDevice(dev) == cudaSuccess) ok = true;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------
+typedef void (*FeatKernel)(const FeatParams);
+
+struct wwf_plan {
+  wwf_config cfg;
+  int device = 0, sm_count = 0, max_smem = 0;
+  int K = 0, n_feat = 0, G = 1;
+  FeatKernel kernel = nullptr;
+  // device constants
+  float* d_window = nullptr;
+  float2* d_tw = nullptr;
+  int* d_mel_lo = nullptr;
+  int* d_mel_ofs = nullptr;
+  float* d_mel_w = nullptr;
+  float* d_dct = nullptr;
+  // noise bank (borrowed data, owned offsets)
+  const float* noise_data = nullptr;
+  int64_t* d_noise_offsets = nullptr;
+  int n_noise = 0;
+  // RIR bank (owned spectra) + conv constants
+  float4* d_spec = nullptr;
+  float2* d_conv_tw = nullptr;
+  float2* d_conv_tw_pair = nullptr;
+  int n_rir = 0, rir_max_len = 0;
+  int feat_warps_override = 0;
+};
+
+template <typename T>
+static int upload(T** dst, const std::vector<T>& src) {
+  *dst = nullptr;
+  if (src.empty()) return WWF_OK;
+  WWF_CUDA(cudaMalloc((void**)dst, src.size() * sizeof(T)));
+  WWF_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  return WWF_OK;
+}
+
+template <int NFFT>
+static void select_kernel(wwf_plan* p, std::vector<float2>& tw) {
+  using Plan = StftPlan<NFFT>;
+  build_stft_twiddles<typename Plan::Rad>(tw);
+  p->G = Plan::G;
+  p->kernel = p->cfg.out_dtype == WWF_OUT_F16 ? (FeatKernel)feat_kernel<NFFT, __half> : (FeatKernel)feat_kernel<NFFT, float>;
+}
+
+extern "C" int wwf_version(void) { return WWF_VERSION; }
+extern "C" const char* wwf_last_error(void) { return g_err; }
+extern "C" int64_t wwf_launch_count(void) { return g_launches.load(); }
+
+extern "C" void wwf_plan_destroy(wwf_plan* p) {
+  if (!p) return;
+  DeviceGuard g(p->device);
+  cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_mel_lo); cudaFree(p->d_mel_ofs);
+  cudaFree(p->d_mel_w); cudaFree(p->d_dct); cudaFree(p->d_noise_offsets); cudaFree(p->d_spec);
+  cudaFree(p->d_conv_tw); cudaFree(p->d_conv_tw_pair);
+  delete p;
+}
+
+extern "C" int wwf_plan_create(const wwf_config* cfg, int device, wwf_plan** out) {
+  if (!cfg || !out) return fail(WWF_ERR_INVALID, "wwf_plan_create: null argument");
+  *out = nullptr;
+  const int n = cfg->n_fft;
+  if (!(n == 256 || n == 400 || n == 512 || n == 1024 || n == 2048))
+    return fail(WWF_ERR_UNSUPPORTED, "n_fft=%d not supported (256, 400, 512, 1024, 2048)", n);
+  if (cfg->hop_length <= 0 || cfg->hop_length >= n) return fail(WWF_ERR_INVALID, "hop_length=%d must be in (0, n_fft)", cfg->hop_length);
+  if (cfg->sample_rate <= 0) return fail(WWF_ERR_INVALID, "sample_rate=%d", cfg->sample_rate);
+  const int K = n / 2 + 1;
+  if (cfg->n_mels < 1 || cfg->n_mels > 128 || cfg->n_mels > K) return fail(WWF_ERR_INVALID, "n_mels=%d must be in [1, min(128, n_fft/2+1)]", cfg->n_mels);
+  if (cfg->feature_type != WWF_FEAT_LOGMEL && cfg->feature_type != WWF_FEAT_MFCC) return fail(WWF_ERR_INVALID, "feature_type=%d", cfg->feature_type);
+  if (cfg->feature_type == WWF_FEAT_MFCC && (cfg->n_mfcc < 1 || cfg->n_mfcc > cfg->n_mels))
+    return fail(WWF_ERR_INVALID, "n_mfcc=%d must be in [1, n_mels=%d]", cfg->n_mfcc, cfg->n_mels);
+  if (cfg->out_dtype != WWF_OUT_F32 && cfg->out_dtype != WWF_OUT_F16) return fail(WWF_ERR_INVALID, "out_dtype=%d", cfg->out_dtype);
+  if (cfg->n_freq_masks < 0 || cfg->n_freq_masks > kMaxMasks || cfg->n_time_masks < 0 || cfg->n_time_masks > kMaxMasks)
+    return fail(WWF_ERR_INVALID, "n_freq_masks/n_time_masks must be in [0, %d]", kMaxMasks);
+
+  int ndev = 0;
+  WWF_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return fail(WWF_ERR_CUDA, "CUDA device %d not present (%d devices)", device, ndev);
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(WWF_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  cudaDeviceProp prop;
+  WWF_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major < 10) return fail(WWF_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+
+  wwf_plan* p = new wwf_plan();
+  p->cfg = *cfg;
+  p->cfg.window = nullptr; p->cfg.mel_fb = nullptr; p->cfg.dct = nullptr;   // host pointers are not retained
+  if (p->cfg.f_max <= 0.f) p->cfg.f_max = (float)(cfg->sample_rate / 2);
+  p->device = device;
+  p->sm_count = prop.multiProcessorCount;
+  p->max_smem = (int)prop.sharedMemPerBlockOptin;
+  p->K = K;
+  p->n_feat = cfg->feature_type == WWF_FEAT_MFCC ? cfg->n_mfcc : cfg->n_mels;
+  if (const char* e = getenv("WWF_FEAT_WARPS")) p->feat_warps_override = atoi(e);
+
+  std::vector<float2> tw;
+  switch (n) {
+    case 256: select_kernel<256>(p, tw); break;
+    case 400: select_kernel<400>(p, tw); break;
+    case 512: select_kernel<512>(p, tw); break;
+    case 1024: select_kernel<1024>(p, tw); break;
+    default: select_kernel<2048>(p, tw); break;
+  }
+
+  std::vector<float> window(n);
+  if (cfg->window) memcpy(window.data(), cfg->window, n * sizeof(float));
+  else for (int i = 0; i < n; ++i) window[i] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * i / n));
+
+  const int M = cfg->n_mels;
+  std::vector<float> fb;
+  if (cfg->mel_fb) fb.assign(cfg->mel_fb, cfg->mel_fb + (size_t)K * M);
+  else fb = mel_fbanks32(K, p->cfg.f_min, p->cfg.f_max, M, cfg->sample_rate);
+  std::vector<int> lo(M), ofs(M + 1);
+  std::vector<float> w;
+  for (int m = 0; m < M; ++m) {
+    int first = -1, last = -1;
+    for (int k = 0; k < K; ++k)
+      if (fb[(size_t)k * M + m] != 0.f) { if (first < 0) first = k; last = k; }
+    ofs[m] = (int)w.size();
+    lo[m] = first < 0 ? 0 : first;
+    if (first >= 0) for (int k = first; k <= last; ++k) w.push_back(fb[(size_t)k * M + m]);
+  }
+  ofs[M] = (int)w.size();
+  if (w.empty()) w.push_back(0.f);
+
+  std::vector<float> dct;
+  if (cfg->feature_type == WWF_FEAT_MFCC) {
+    const int C = cfg->n_mfcc;
+    dct.resize((size_t)M * C);
+    if (cfg->dct) memcpy(dct.data(), cfg->dct, dct.size() * sizeof(float));
+    else
+      for (int m = 0; m < M; ++m)
+        for (int c = 0; c < C; ++c) {
+          double v = cos(M_PI / (double)M * ((double)m + 0.5) * (double)c) * sqrt(2.0 / (double)M);
+          if (c == 0) v *= 1.0 / sqrt(2.0);
+          dct[(size_t)m * C + c] = (float)v;
+        }
+  }
+
+  int rc;
+  if ((rc = upload(&p->d_window, window)) || (rc = upload(&p->d_tw, tw)) || (rc = upload(&p->d_mel_lo, lo)) ||
+      (rc = upload(&p->d_mel_ofs, ofs)) || (rc = upload(&p->d_mel_w, w)) || (rc = upload(&p->d_dct, dct))) {
+    wwf_plan_destroy(p);
+    return rc;
+  }
+  cudaError_t e = cudaFuncSetAttribute((const void*)p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem - 1024);
+  if (e != cudaSuccess) {
+    wwf_plan_destroy(p);
+    return fail(WWF_ERR_CUDA, "cudaFuncSetAttribute(feat_kernel): %s (is libwwfeat.so built for this GPU?)", cudaGetErrorString(e));
+  }
+  *out = p;
+  return WWF_OK;
+}
+
+extern "C" int wwf_plan_info(const wwf_plan* p, wwf_info* out) {
+  if (!p || !out) return fail(WWF_ERR_INVALID, "wwf_plan_info: null argument");
+  out->n_freq = p->K; out->n_feat = p->n_feat; out->device = p->device; out->sm_count = p->sm_count;
+  out->rir_fft_size = p->n_rir > 0 ? kConvP : 0; out->rir_max_len = p->rir_max_len;
+  out->n_rir = p->n_rir; out->n_noise = p->n_noise;
+  return WWF_OK;
+}
+
+extern "C" int wwf_num_frames(const wwf_plan* p, int n_samples) {
+  if (!p || n_samples < 0) return fail(WWF_ERR_INVALID, "wwf_num_frames: bad argument");
+  return n_samples / p->cfg.hop_length + 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// banks
+// ------------------------------------------------------------------------------------------
+static int ensure_conv_constants(wwf_plan* p) {
+  if (p->d_conv_tw) return WWF_OK;
+  std::vector<float2> tw, twp;
+  build_conv_twiddles(tw, twp);
+  int rc;
+  if ((rc = upload(&p->d_conv_tw, tw)) || (rc = upload(&p->d_conv_tw_pair, twp))) return rc;
+  WWF_CUDA(cudaFuncSetAttribute((const void*)conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemBytes));
+  WWF_CUDA(cudaFuncSetAttribute((const void*)rir_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemBytes));
+  return WWF_OK;
+}
+
+extern "C" int wwf_bank_register(wwf_plan* p, int kind, const float* data, const int64_t* offsets, int count, void* stream) {
+  if (!p || !offsets || count < 0 || (count > 0 && !data)) return fail(WWF_ERR_INVALID, "wwf_bank_register: bad argument");
+  DeviceGuard guard(p->device);
+  if (!guard.ok) return fail(WWF_ERR_CUDA, "cudaSetDevice(%d) failed", p->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int i = 0; i < count; ++i)
+    if (offsets[i + 1] <= offsets[i]) return fail(WWF_ERR_INVALID, "bank clip %d is empty or offsets not increasing", i);
+  std::vector<int64_t> ofs(offsets, offsets + count + 1);
+  if (kind == WWF_BANK_NOISE) {
+    for (int i = 0; i < count; ++i)
+      if (offsets[i + 1] - offsets[i] > 0x7fffffffLL) return fail(WWF_ERR_UNSUPPORTED, "noise clip %d longer than 2^31 samples", i);
+    cudaFree(p->d_noise_offsets);
+    p->d_noise_offsets = nullptr;
+    p->noise_data = nullptr;
+    p->n_noise = 0;
+    if (count == 0) return WWF_OK;
+    int rc = upload(&p->d_noise_offsets, ofs);
+    if (rc) return rc;
+    p->noise_data = data;
+    p->n_noise = count;
+    return WWF_OK;
+  }
+  if (kind != WWF_BANK_RIR) return fail(WWF_ERR_INVALID, "unknown bank kind %d", kind);
+  int lmax = 0;
+  for (int i = 0; i < count; ++i) {
+    const int64_t l = offsets[i + 1] - offsets[i];
+    if (l > kConvP / 2) return fail(WWF_ERR_UNSUPPORTED, "RIR %d has %lld taps; at most %d supported", i, (long long)l, kConvP / 2);
+    if (l > lmax) lmax = (int)l;
+  }
+  cudaFree(p->d_spec);
+  p->d_spec = nullptr;
+  p->n_rir = 0;
+  p->rir_max_len = 0;
+  if (count == 0) return WWF_OK;
+  int rc = ensure_conv_constants(p);
+  if (rc) return rc;
+  int64_t* d_ofs = nullptr;
+  if ((rc = upload(&d_ofs, ofs))) return rc;
+  WWF_CUDA(cudaMalloc((void**)&p->d_spec, (size_t)count * (kConvPairTasks + 1) * sizeof(float4)));
+  SpecParams sp{data, d_ofs, count, p->d_spec, p->d_conv_tw, p->d_conv_tw_pair};
+  rir_spectrum_kernel<<<count, kConvThreads, kConvSmemBytes, st>>>(sp);
+  g_launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_ofs);
+  if (e != cudaSuccess) {
+    cudaFree(p->d_spec);
+    p->d_spec = nullptr;
+    return fail(WWF_ERR_CUDA, "rir_spectrum_kernel: %s", cudaGetErrorString(e));
+  }
+  p->n_rir = count;
+  p->rir_max_len = lmax;
+  return WWF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------
+static inline int64_t round_up4(int64_t v) { return (v + 3) & ~(int64_t)3; }
+
+extern "C" size_t wwf_workspace_bytes(const wwf_plan* p, int B, int N) {
+  if (!p || B <= 0 || N <= 0 || p->n_rir == 0) return 0;
+  return (size_t)B * (size_t)round_up4(N) * sizeof(float);
+}
+
+static bool wants_reverb(const wwf_plan* p, const wwf_aug* aug) { return aug && aug->rir_idx && p->n_rir > 0; }
+
+// Overlap-save reverb of the clips that have rir_idx >= 0 into the workspace.
+static int launch_conv(wwf_plan* p, const float* wav, int B, int N, int64_t wav_stride, const wwf_aug* aug,
+                       void* workspace, size_t workspace_bytes, cudaStream_t st, float** rev, int64_t* rev_stride) {
+  *rev = nullptr;
+  *rev_stride = 0;
+  if (!wants_reverb(p, aug)) return WWF_OK;
+  const size_t need = wwf_workspace_bytes(p, B, N);
+  if (!workspace || workspace_bytes < need) return fail(WWF_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
+  if (reinterpret_cast<uintptr_t>(workspace) & 15) return fail(WWF_ERR_WORKSPACE, "workspace must be 16-byte aligned");
+  ConvParams cp{};
+  cp.wav = wav; cp.wav_stride = wav_stride;
+  cp.rev = (float*)workspace; cp.rev_stride = round_up4(N);
+  cp.rir_idx = aug->rir_idx; cp.B = B; cp.N = N; cp.n_rir = p->n_rir;
+  int nb = 1;
+  if ((int64_t)N + p->rir_max_len - 1 <= kConvP) { cp.hist = 0; cp.valid = kConvP; }
+  else {
+    cp.hist = (int)round_up4(p->rir_max_len - 1);
+    cp.valid = kConvP - cp.hist;
+    nb = (N + cp.valid - 1) / cp.valid;
+  }
+  cp.spec = p->d_spec; cp.tw = p->d_conv_tw; cp.tw_pair = p->d_conv_tw_pair;
+  dim3 grid(nb, B);
+  conv_kernel<<<grid, kConvThreads, kConvSmemBytes, st>>>(cp);
+  g_launches++;
+  WWF_CUDA(cudaGetLastError());
+  *rev = cp.rev;
+  *rev_stride = cp.rev_stride;
+  return WWF_OK;
+}
+
+static int check_batch(const wwf_plan* p, const void* wav, int B, int N, int64_t wav_stride, const char* who) {
+  if (!p || !wav) return fail(WWF_ERR_INVALID, "%s: null argument", who);
+  if (B <= 0) return fail(WWF_ERR_INVALID, "%s: B=%d", who, B);
+  if (N <= p->cfg.n_fft / 2) return fail(WWF_ERR_INVALID, "%s: N=%d must exceed n_fft/2=%d (reflect padding)", who, N, p->cfg.n_fft / 2);
+  if (N > (1 << 24)) return fail(WWF_ERR_UNSUPPORTED, "%s: N=%d > 2^24 samples", who, N);
+  if (wav_stride < N) return fail(WWF_ERR_INVALID, "%s: wav_stride=%lld < N=%d", who, (long long)wav_stride, N);
+  return WWF_OK;
+}
+
+extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_t wav_stride, const wwf_aug* aug,
+                             void* out, int64_t out_stride, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_batch(p, wav, B, N, wav_stride, "wwf_featurize");
+  if (rc) return rc;
+  if (!out) return fail(WWF_ERR_INVALID, "wwf_featurize: out is null");
+  const int T = N / p->cfg.hop_length + 1;
+  const int F = p->n_feat, M = p->cfg.n_mels;
+  if (out_stride < (int64_t)F * T) return fail(WWF_ERR_INVALID, "wwf_featurize: out_stride=%lld < n_feat*T=%d", (long long)out_stride, F * T);
+  DeviceGuard guard(p->device);
+  if (!guard.ok) return fail(WWF_ERR_CUDA, "cudaSetDevice(%d) failed", p->device);
+  cudaStream_t st = (cudaStream_t)stream;
+
+  float* rev = nullptr;
+  int64_t rev_stride = 0;
+  if ((rc = launch_conv(p, wav, B, N, wav_stride, aug, workspace, workspace_bytes, st, &rev, &rev_stride))) return rc;
+
+  const bool mfcc = p->cfg.feature_type == WWF_FEAT_MFCC;
+  const int pitch = T | 1;
+  const int tile_floats = (M * pitch + 1) & ~1;
+  const int res_floats = (mfcc && p->cfg.cmvn) ? ((F * pitch + 1) & ~1) : 0;
+  const size_t tile_bytes = ((size_t)tile_floats + res_floats) * sizeof(float);
+  const size_t per_warp = (size_t)p->G * p->cfg.n_fft * sizeof(float2);
+  const size_t budget = (size_t)p->max_smem - 1024 - 512;   // static smem of the kernel is ~0.5 KB
+  if (tile_bytes + per_warp > budget)
+    return fail(WWF_ERR_UNSUPPORTED, "clip too long for the in-shared-memory tile: n_mels*T*4 = %zu bytes (N=%d, T=%d)", tile_bytes, N, T);
+  int nwarps = (int)((budget - tile_bytes) / per_warp);
+  if (nwarps > 16) nwarps = 16;
+  if (p->feat_warps_override > 0 && p->feat_warps_override < nwarps) nwarps = p->feat_warps_override;
+  const size_t smem = tile_bytes + (size_t)nwarps * per_warp;
+
+  FeatParams fp{};
+  fp.wav = wav; fp.wav_stride = wav_stride; fp.rev = rev; fp.rev_stride = rev_stride;
+  fp.B = B; fp.N = N; fp.T = T; fp.hop = p->cfg.hop_length;
+  fp.n_mels = M; fp.n_mfcc = p->cfg.n_mfcc; fp.n_feat = F; fp.is_mfcc = mfcc; fp.out_f16 = p->cfg.out_dtype == WWF_OUT_F16;
+  fp.cmvn = p->cfg.cmvn != 0; fp.top_db = p->cfg.top_db; fp.cmvn_eps = p->cfg.cmvn_eps; fp.mask_value = p->cfg.mask_value;
+  fp.tile_pitch = pitch; fp.tile_floats = tile_floats; fp.res_floats = res_floats;
+  fp.window = p->d_window; fp.tw = p->d_tw; fp.mel_lo = p->d_mel_lo; fp.mel_ofs = p->d_mel_ofs; fp.mel_w = p->d_mel_w; fp.dct = p->d_dct;
+  if (aug) {
+    fp.rir_idx = rev ? aug->rir_idx : nullptr;
+    if (aug->noise_idx && p->n_noise > 0) {
+      fp.noise_idx = aug->noise_idx; fp.noise_off = aug->noise_off; fp.snr_db = aug->snr_db;
+      fp.noise_data = p->noise_data; fp.noise_offsets = p->d_noise_offsets; fp.n_noise = p->n_noise;
+    }
+    if (aug->fmask_start && aug->fmask_len && p->cfg.n_freq_masks > 0) { fp.fs = aug->fmask_start; fp.fl = aug->fmask_len; fp.nF = p->cfg.n_freq_masks; }
+    if (aug->tmask_start && aug->tmask_len && p->cfg.n_time_masks > 0) { fp.ts = aug->tmask_start; fp.tl = aug->tmask_len; fp.nT = p->cfg.n_time_masks; }
+  }
+  fp.out = out; fp.out_stride = out_stride;
+  p->kernel<<<B, nwarps * 32, smem, st>>>(fp);
+  g_launches++;
+  WWF_CUDA(cudaGetLastError());
+  return WWF_OK;
+}
+
+extern "C" int wwf_augment(wwf_plan* p, const float* wav, int B, int N, int64_t wav_stride, const wwf_aug* aug,
+                           float* out_wav, int64_t out_stride, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!p || !wav || !out_wav) return fail(WWF_ERR_INVALID, "wwf_augment: null argument");
+  if (B <= 0 || N <= 0 || wav_stride < N || out_stride < N) return fail(WWF_ERR_INVALID, "wwf_augment: bad shape B=%d N=%d", B, N);
+  DeviceGuard guard(p->device);
+  if (!guard.ok) return fail(WWF_ERR_CUDA, "cudaSetDevice(%d) failed", p->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (wants_reverb(p, aug) && out_wav == wav) return fail(WWF_ERR_INVALID, "wwf_augment: in-place is not allowed with reverb");
+  float* rev = nullptr;
+  int64_t rev_stride = 0;
+  int rc = launch_conv(p, wav, B, N, wav_stride, aug, workspace, workspace_bytes, st, &rev, &rev_stride);
+  if (rc) return rc;
+  MixParams mp{};
+  mp.wav = wav; mp.wav_stride = wav_stride; mp.rev = rev; mp.rev_stride = rev_stride;
+  if (aug) {
+    mp.rir_idx = rev ? aug->rir_idx : nullptr;
+    if (aug->noise_idx && p->n_noise > 0) {
+      mp.noise_idx = aug->noise_idx; mp.noise_off = aug->noise_off; mp.snr_db = aug->snr_db;
+      mp.noise_data = p->noise_data; mp.noise_offsets = p->d_noise_offsets; mp.n_noise = p->n_noise;
+    }
+  }
+  mp.out = out_wav; mp.out_stride = out_stride; mp.B = B; mp.N = N;
+  mix_kernel<<<B, 512, 0, st>>>(mp);
+  g_launches++;
+  WWF_CUDA(cudaGetLastError());
+  return WWF_OK;
+}
+
+extern "C" int wwf_spec_augment(void* spec, int dtype, int B, int F, int T, int64_t clip_stride,
+                                const int32_t* fs, const int32_t* fl, int nF, const int32_t* ts, const int32_t* tl, int nT,
+                                float mask_value, int device, void* stream) {
+  if (!spec || B <= 0 || F <= 0 || T <= 0 || clip_stride < (int64_t)F * T) return fail(WWF_ERR_INVALID, "wwf_spec_augment: bad argument");
+  if (nF < 0 || nT < 0 || (nF > 0 && (!fs || !fl)) || (nT > 0 && (!ts || !tl))) return fail(WWF_ERR_INVALID, "wwf_spec_augment: mask arrays missing");
+  if (dtype != WWF_OUT_F32 && dtype != WWF_OUT_F16) return fail(WWF_ERR_INVALID, "wwf_spec_augment: dtype=%d", dtype);
+  if (nF == 0 && nT == 0) return WWF_OK;
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(WWF_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(F < 64 ? F : 64, B);
+  if (dtype == WWF_OUT_F32) spec_mask_kernel<float><<<grid, 256, 0, st>>>((float*)spec, B, F, T, clip_stride, fs, fl, nF, ts, tl, nT, mask_value);
+  else spec_mask_kernel<__half><<<grid, 256, 0, st>>>((__half*)spec, B, F, T, clip_stride, fs, fl, nF, ts, tl, nT, mask_value);
+  g_launches++;
+  WWF_CUDA(cudaGetLastError());
+  return WWF_OK;
+}

@@ -1,0 +1,277 @@
+"""Batched GPU feature pipeline: the thin PyTorch host layer over libwwfeat's C ABI.
+
+``FeaturePlan`` owns one ``wwf_plan`` (device constants + registered noise / RIR banks) and
+routes ``tensor.data_ptr()`` and the current CUDA stream into ``wwf_featurize`` /
+``wwf_augment``.  PyTorch is used only for device memory and streams.
+
+``AugParams`` is the explicit form of every random draw of the reference's
+``AudioAugmentation`` / ``SpecAugment`` (BASELINE.json north_star: "RIR/noise indices, SNRs
+and SpecAugment masks passed in explicitly"), so the same draws can be handed to the oracle.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, fields
+from typing import Optional, Sequence
+
+import torch
+
+from . import _native as N
+from . import constants as K
+
+
+def _dev_index(device) -> int:
+    d = torch.device(device)
+    if d.type != "cuda":
+        raise N.WwfError(-3, f"device {device!r}: this package runs on CUDA (sm_100a) only; there is no CPU path")
+    return d.index if d.index is not None else torch.cuda.current_device()
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+@dataclass
+class AugParams:
+    """Per-batch augmentation draws (all optional; ``None`` = that augmentation is off).
+
+    rir_idx     int32 [B]      index into the registered RIR bank, < 0 = dry
+    noise_idx   int32 [B]      index into the registered noise bank, < 0 = clean
+    noise_off   int64 [B]      first sample inside the noise clip (wraps around its end)
+    snr_db      float32 [B]    target SNR
+    fmask_start/fmask_len  int32 [B, n_freq_masks]  masked feature rows [start, start+len)
+    tmask_start/tmask_len  int32 [B, n_time_masks]  masked frames       [start, start+len)
+    """
+    rir_idx: Optional[torch.Tensor] = None
+    noise_idx: Optional[torch.Tensor] = None
+    noise_off: Optional[torch.Tensor] = None
+    snr_db: Optional[torch.Tensor] = None
+    fmask_start: Optional[torch.Tensor] = None
+    fmask_len: Optional[torch.Tensor] = None
+    tmask_start: Optional[torch.Tensor] = None
+    tmask_len: Optional[torch.Tensor] = None
+
+    _DTYPES = dict(rir_idx=torch.int32, noise_idx=torch.int32, noise_off=torch.int64, snr_db=torch.float32,
+                   fmask_start=torch.int32, fmask_len=torch.int32, tmask_start=torch.int32, tmask_len=torch.int32)
+
+    def to(self, device, non_blocking: bool = False) -> "AugParams":
+        kw = {}
+        for f in fields(self):
+            v = getattr(self, f.name)
+            if v is not None:
+                v = torch.as_tensor(v).to(device=device, dtype=self._DTYPES[f.name], non_blocking=non_blocking).contiguous()
+            kw[f.name] = v
+        return AugParams(**kw)
+
+    def nbytes(self) -> int:
+        return sum(getattr(self, f.name).numel() * getattr(self, f.name).element_size()
+                   for f in fields(self) if getattr(self, f.name) is not None)
+
+
+def draw_mask_params(gen: Optional[torch.Generator], B: int, size: int, mask_param: int, n_masks: int, p: float = 1.0):
+    """Integer (start, len) pairs from the two uniform draws torchaudio's mask_along_axis_iid makes
+    (value = U*param, min_value = U*(size - value); start = floor(min_value), len = floor(value);
+    torchaudio/functional/functional.py:806-810,864-870)."""
+    if p != 1.0:
+        mask_param = min(mask_param, int(size * p))
+    starts = torch.zeros(B, n_masks, dtype=torch.int32)
+    lens = torch.zeros(B, n_masks, dtype=torch.int32)
+    if mask_param < 1:
+        return starts, lens
+    for i in range(n_masks):
+        value = torch.rand(B, generator=gen) * mask_param
+        min_value = torch.rand(B, generator=gen) * (size - value)
+        starts[:, i] = min_value.long().to(torch.int32)
+        lens[:, i] = value.long().to(torch.int32)
+    return starts, lens
+
+
+def _flatten_bank(clips: Sequence[torch.Tensor], device) -> tuple[torch.Tensor, list[int]]:
+    offs = [0]
+    for c in clips:
+        if c.dim() != 1 or c.numel() == 0:
+            raise ValueError("bank clips must be non-empty 1-D tensors")
+        offs.append(offs[-1] + c.numel())
+    flat = torch.cat([torch.as_tensor(c, dtype=torch.float32).reshape(-1) for c in clips]).to(device).contiguous()
+    return flat, offs
+
+
+class FeaturePlan:
+    """One (device, feature config) plan.  Mirrors the reference's FeatureExtractor arguments
+    (src/evaluation/evaluator.py:86-94) plus the knobs the fused path adds."""
+
+    def __init__(self, sample_rate: int = 16000, feature_type: str = "mel", n_mels: int = 128, n_mfcc: int = 40,
+                 n_fft: int = 1024, hop_length: int = 160, device="cuda", *, out_dtype=torch.float32,
+                 cmvn: bool = False, top_db: Optional[float] = 80.0, f_min: float = 0.0, f_max: Optional[float] = None,
+                 cmvn_eps: float = 1e-5, mask_value: float = 0.0, n_freq_masks: int = 0, n_time_masks: int = 0):
+        if feature_type == "mel_spectrogram":            # legacy alias, evaluator.py:82-83
+            feature_type = "mel"
+        if feature_type not in ("mel", "mfcc"):
+            raise ValueError(f"feature_type must be 'mel' or 'mfcc', got {feature_type!r}")
+        if out_dtype not in (torch.float32, torch.float16):
+            raise ValueError("out_dtype must be torch.float32 or torch.float16")
+        self.lib = N.load()
+        self.device = torch.device("cuda", _dev_index(device))
+        self.sample_rate, self.feature_type = sample_rate, feature_type
+        self.n_mels, self.n_mfcc, self.n_fft, self.hop_length = n_mels, n_mfcc, n_fft, hop_length
+        self.out_dtype = out_dtype
+        self.n_freq_masks, self.n_time_masks = n_freq_masks, n_time_masks
+        f_max = float(sample_rate // 2) if f_max is None else float(f_max)
+
+        # float32 constants bit-identical to torchaudio's (see constants.py)
+        self._handle = C.c_void_p()
+        window = mel = dct = None
+        if n_fft in N.SUPPORTED_N_FFT and 0 < n_mels <= n_fft // 2 + 1:
+            window = K.hann_window(n_fft)
+            mel = K.mel_filterbank(n_fft // 2 + 1, f_min, f_max, n_mels, sample_rate)
+            if feature_type == "mfcc" and 0 < n_mfcc <= n_mels:
+                dct = K.dct_matrix(n_mfcc, n_mels)
+        as_fp = lambda t: None if t is None else C.cast(t.data_ptr(), C.POINTER(C.c_float))
+        cfg = N.Config(sample_rate=sample_rate, n_fft=n_fft, hop_length=hop_length, n_mels=n_mels, n_mfcc=n_mfcc,
+                       feature_type=N.FEAT_MFCC if feature_type == "mfcc" else N.FEAT_LOGMEL,
+                       out_dtype=N.OUT_F16 if out_dtype == torch.float16 else N.OUT_F32, cmvn=int(bool(cmvn)),
+                       top_db=-1.0 if top_db is None else float(top_db), f_min=float(f_min), f_max=f_max,
+                       cmvn_eps=float(cmvn_eps), mask_value=float(mask_value),
+                       n_freq_masks=n_freq_masks, n_time_masks=n_time_masks,
+                       window=as_fp(window), mel_fb=as_fp(mel), dct=as_fp(dct))
+        N.check(self.lib.wwf_plan_create(C.byref(cfg), self.device.index, C.byref(self._handle)))
+        info = N.Info()
+        N.check(self.lib.wwf_plan_info(self._handle, C.byref(info)))
+        self.n_feat, self.n_freq, self.sm_count = info.n_feat, info.n_freq, info.sm_count
+        self._noise = None          # keeps the borrowed noise bank alive
+        self._workspace: dict[int, torch.Tensor] = {}
+        self.n_noise = self.n_rir = 0
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h:
+            self.lib.wwf_plan_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ shape facts
+    def num_frames(self, n_samples: int) -> int:
+        """T = n_samples // hop + 1 (src/export/onnx_exporter.py:316-317)."""
+        return n_samples // self.hop_length + 1
+
+    def info(self) -> N.Info:
+        info = N.Info()
+        N.check(self.lib.wwf_plan_info(self._handle, C.byref(info)))
+        return info
+
+    # ------------------------------------------------------------------ banks
+    def _register(self, kind: int, clips: Sequence[torch.Tensor]):
+        flat, offs = _flatten_bank(clips, self.device)
+        arr = (C.c_int64 * len(offs))(*offs)
+        stream = torch.cuda.current_stream(self.device)
+        N.check(self.lib.wwf_bank_register(self._handle, kind, _ptr(flat), arr, len(clips), C.c_void_p(stream.cuda_stream)))
+        return flat
+
+    def register_noise(self, clips: Sequence[torch.Tensor]):
+        """Background-noise recordings (data/raw/background in the reference, README.md:57)."""
+        self._noise = self._register(N.BANK_NOISE, clips)   # borrowed by the plan -> keep alive
+        self.n_noise = len(clips)
+
+    def register_rirs(self, rirs: Sequence[torch.Tensor]):
+        """Room impulse responses (data/raw/rirs, README.md:58); spectra are computed once here."""
+        self._register(N.BANK_RIR, rirs)                     # consumed during the call
+        self.n_rir = len(rirs)
+
+    # ------------------------------------------------------------------ calls
+    def _aug_struct(self, aug: Optional[AugParams], B: int):
+        if aug is None:
+            return None, None
+        a = aug.to(self.device)
+        for name in ("rir_idx", "noise_idx", "noise_off", "snr_db"):
+            v = getattr(a, name)
+            if v is not None and v.shape != (B,):
+                raise ValueError(f"AugParams.{name} must have shape ({B},), got {tuple(v.shape)}")
+        if a.noise_idx is not None and (a.noise_off is None or a.snr_db is None):
+            raise ValueError("AugParams.noise_idx needs noise_off and snr_db")
+        for s, l, n in (("fmask_start", "fmask_len", self.n_freq_masks), ("tmask_start", "tmask_len", self.n_time_masks)):
+            vs, vl = getattr(a, s), getattr(a, l)
+            if (vs is None) != (vl is None):
+                raise ValueError(f"AugParams.{s} and {l} must be given together")
+            if vs is not None and (vs.shape != (B, n) or vl.shape != (B, n)):
+                raise ValueError(f"AugParams.{s}/{l} must have shape ({B}, {n}) for this plan, got {tuple(vs.shape)}")
+        st = N.Aug(*[_ptr(getattr(a, f[0])) for f in N.Aug._fields_])
+        return st, a            # keep `a` alive until the call returns
+
+    def _ws(self, B: int, n: int, stream_id: int):
+        need = int(self.lib.wwf_workspace_bytes(self._handle, B, n))
+        if need == 0:
+            return None, 0
+        ws = self._workspace.get(stream_id)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._workspace[stream_id] = ws
+        return ws, need
+
+    def _check_wav(self, wav: torch.Tensor) -> torch.Tensor:
+        if wav.dim() != 2:
+            raise ValueError(f"expected a (B, N) batch, got shape {tuple(wav.shape)}")
+        if wav.device != self.device or wav.dtype != torch.float32:
+            wav = wav.to(device=self.device, dtype=torch.float32)
+        if wav.stride(1) != 1:
+            wav = wav.contiguous()
+        return wav
+
+    def featurize(self, wav: torch.Tensor, aug: Optional[AugParams] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """(B, N) float32 clips -> (B, 1, n_feat, T) features, one fused GPU pass
+        (reverb -> noise -> STFT -> mel -> dB -> [DCT] -> [CMVN] -> [masks])."""
+        wav = self._check_wav(wav)
+        B, n = wav.shape
+        T = self.num_frames(n)
+        if out is None:
+            out = torch.empty(B, 1, self.n_feat, T, dtype=self.out_dtype, device=self.device)
+        elif out.shape != (B, 1, self.n_feat, T) or out.dtype != self.out_dtype or out.device != self.device or not out.is_contiguous():
+            raise ValueError("out must be a contiguous (B, 1, n_feat, T) tensor of the plan's dtype on the plan's device")
+        st, keep = self._aug_struct(aug, B)
+        stream = torch.cuda.current_stream(self.device)
+        ws, ws_bytes = self._ws(B, n, stream.cuda_stream)
+        N.check(self.lib.wwf_featurize(self._handle, _ptr(wav), B, n, wav.stride(0), None if st is None else C.byref(st),
+                                       _ptr(out), self.n_feat * T, _ptr(ws), ws_bytes, C.c_void_p(stream.cuda_stream)))
+        return out
+
+    def augment(self, wav: torch.Tensor, aug: Optional[AugParams], out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Time-domain half only: (B, N) -> (B, N) float32 (reverb, then noise @ SNR)."""
+        wav = self._check_wav(wav)
+        B, n = wav.shape
+        if out is None:
+            out = torch.empty(B, n, dtype=torch.float32, device=self.device)
+        st, keep = self._aug_struct(aug, B)
+        stream = torch.cuda.current_stream(self.device)
+        ws, ws_bytes = self._ws(B, n, stream.cuda_stream)
+        N.check(self.lib.wwf_augment(self._handle, _ptr(wav), B, n, wav.stride(0), None if st is None else C.byref(st),
+                                     _ptr(out), out.stride(0), _ptr(ws), ws_bytes, C.c_void_p(stream.cuda_stream)))
+        return out
+
+
+def spec_augment_(spec: torch.Tensor, fmask_start=None, fmask_len=None, tmask_start=None, tmask_len=None,
+                  mask_value: float = 0.0) -> torch.Tensor:
+    """In-place explicit-index SpecAugment of a contiguous CUDA (B, F, T) float32/float16 tensor."""
+    if spec.dim() != 3 or not spec.is_cuda or not spec.is_contiguous() or spec.dtype not in (torch.float32, torch.float16):
+        raise ValueError("spec must be a contiguous CUDA (B, F, T) float32/float16 tensor")
+    lib = N.load()
+    B, F_, T_ = spec.shape
+    dev = spec.device
+
+    def prep(s, l):
+        if s is None:
+            return None, None, 0
+        s = torch.as_tensor(s).to(dev, torch.int32).reshape(B, -1).contiguous()
+        l = torch.as_tensor(l).to(dev, torch.int32).reshape(B, -1).contiguous()
+        return s, l, s.shape[1]
+
+    fs, fl, nf = prep(fmask_start, fmask_len)
+    ts, tl, nt = prep(tmask_start, tmask_len)
+    stream = torch.cuda.current_stream(dev)
+    N.check(lib.wwf_spec_augment(_ptr(spec), N.OUT_F16 if spec.dtype == torch.float16 else N.OUT_F32, B, F_, T_, F_ * T_,
+                                 _ptr(fs), _ptr(fl), nf, _ptr(ts), _ptr(tl), nt, float(mask_value),
+                                 dev.index, C.c_void_p(stream.cuda_stream)))
+    return spec
