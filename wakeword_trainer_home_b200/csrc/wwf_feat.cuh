@@ -2,14 +2,23 @@
 // -> sparse mel -> dB -> per-clip top_db floor -> [DCT-II] -> [CMVN] -> [SpecAugment] -> store.
 // SURVEY.md section 8a rows A1 (mix), A4..A10.
 //
-// One CTA per clip (the top_db floor needs the clip's maximum before any element can be
-// finalised, TA/functional/functional.py:393-402).  Inside the CTA every WARP is autonomous:
-// it takes a group of 2*G consecutive frames, packs them two-per-complex-FFT (frame a ->
-// real part, frame b -> imaginary part), runs the in-place mixed-radix FFT in its private
-// shared-memory scratch with __syncwarp() only, separates the two spectra, applies the
-// sparse mel rows and writes dB values into the CTA's [n_mels][T] shared tile.  The only
-// CTA-wide barriers are around the per-clip energy reduction (noise mix) and the tile
-// maximum.
+// Persistent CTAs, one clip at a time per CTA (the top_db floor needs the clip's maximum
+// before any element can be finalised, TA/functional/functional.py:393-402).  All constant
+// tables (window, twiddles, sparse mel rows, DCT) are copied to shared memory once per CTA.
+// Inside the CTA every WARP is autonomous: it takes a group of 2*G consecutive frames, packs
+// them two-per-complex-FFT (frame a -> real part, frame b -> imaginary part), runs the
+// in-place mixed-radix FFT in its private shared-memory scratch with __syncwarp() only,
+// separates the two spectra, applies the sparse mel rows and writes dB values into the
+// CTA's [n_mels][T] shared tile.  The only CTA-wide barriers are around the per-clip
+// energy reduction (noise mix), the tile maximum and the clip hand-over.
+//
+// Frame loading (HOP32 = hop/32 > 0, i.e. hop a multiple of 32 such as the reference's 160):
+// the 2G frames of a group overlap, so the warp loads their common sample span ONCE, fully
+// coalesced, into registers in lane-cyclic order (sample i of the span lives in lane i%32,
+// register i/32).  Because hop is a multiple of 32, sample j of frame f is in the SAME lane
+// as sample j of frame f+1 (HOP32 registers further), so both halves of every complex FFT
+// input come from the lane's own registers with compile-time indices - no shuffles, no
+// per-element index math, and the noise mix happens once per loaded sample.
 #pragma once
 #include <cuda_fp16.h>
 #include <stdint.h>
@@ -35,7 +44,12 @@ struct FeatParams {
   int n_mels, n_mfcc, n_feat, is_mfcc, out_f16, cmvn;
   float top_db, cmvn_eps, mask_value;
   int tile_pitch;                                // odd row pitch of the shared tile (>= T)
-  int tile_floats, res_floats;                   // even float counts of the two shared tiles
+  // dynamic shared-memory layout, offsets in floats from the start (each a multiple of 4):
+  //   tile [n_mels][pitch] | res [n_feat][pitch] (mfcc && cmvn only) | window [NFFT] | tw float2[tw_total]
+  //   | mel_w | dct [n_mels][c8] | mel_lo int[n_mels] | mel_ofs int[n_mels+1] | rowmask u8[n_feat]
+  //   | colmask u8[T] | z float2 [nwarps][G][NFFT]
+  int off_res, off_window, off_tw, off_melw, off_dct, off_mello, off_melofs, off_rowmask, off_colmask, off_z;
+  int n_melw, c8;                                // mel weight count; n_mfcc rounded up to 8
   // device constants (plan-owned)
   const float* window;                           // [NFFT]
   const float2* tw;                              // concatenated per-pass twiddle tables
@@ -131,203 +145,313 @@ template <> __device__ __forceinline__ float to_out<float>(float v) { return v; 
 template <> __device__ __forceinline__ __half to_out<__half>(float v) { return __float2half_rn(v); }
 
 // ---- the kernel ------------------------------------------------------------------------
-// Dynamic shared memory layout (floats):
-//   tile  [n_mels][pitch]            dB mel values of the clip
-//   res   [n_feat][pitch]            only if (mfcc && cmvn): DCT output awaiting normalisation
-//   zbuf  [nwarps][G][NFFT] float2   per-warp FFT scratch
-template <int NFFT, typename OutT>
+template <int NFFT, int HOP32, typename OutT>
 __global__ void __launch_bounds__(512) feat_kernel(const FeatParams p) {
   using Plan = StftPlan<NFFT>;
   using Rad = typename Plan::Rad;
   constexpr int G = Plan::G;
   constexpr int K = NFFT / 2 + 1;
+  constexpr int NC = (NFFT + 31) / 32;                       // 32-sample columns per frame
+  constexpr bool kNatural = NFFT <= 1024;                    // power spectra re-stored in bin order
+  constexpr int NI = (G * K + 31) / 32;                      // split items per lane
   static_assert(Rad::n == NFFT, "radix plan");
 
   extern __shared__ __align__(16) float smem[];
   __shared__ float red[64];
-  __shared__ int s_mask[4 * kMaxMasks];
 
-  const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const int N = p.N, T = p.T, hop = p.hop, M = p.n_mels, pitch = p.tile_pitch;
+  const int N = p.N, T = p.T, hop = p.hop, M = p.n_mels, pitch = p.tile_pitch, F = p.n_feat;
 
   float* tile = smem;
-  float* res = tile + p.tile_floats;
-  float2* zbuf = reinterpret_cast<float2*>(res + p.res_floats);
-  float2* z = zbuf + (size_t)warp * G * NFFT;
+  float* res = smem + p.off_res;
+  float* s_window = smem + p.off_window;
+  float2* s_tw = reinterpret_cast<float2*>(smem + p.off_tw);
+  float* s_melw = smem + p.off_melw;
+  float* s_dct = smem + p.off_dct;
+  int* s_mello = reinterpret_cast<int*>(smem + p.off_mello);
+  int* s_melofs = reinterpret_cast<int*>(smem + p.off_melofs);
+  unsigned char* s_rowmask = reinterpret_cast<unsigned char*>(smem + p.off_rowmask);
+  unsigned char* s_colmask = reinterpret_cast<unsigned char*>(smem + p.off_colmask);
+  float2* z = reinterpret_cast<float2*>(smem + p.off_z) + (size_t)warp * G * NFFT;
 
-  // ---- per-clip setup ---------------------------------------------------------------
-  const bool has_rev = p.rev != nullptr && p.rir_idx != nullptr && __ldg(p.rir_idx + b) >= 0;
-  const float* x = has_rev ? p.rev + (size_t)b * p.rev_stride : p.wav + (size_t)b * p.wav_stride;
-
-  if (tid < 4 * kMaxMasks) {
-    const int which = tid / kMaxMasks, i = tid % kMaxMasks;   // 0 fs, 1 fl, 2 ts, 3 tl
-    int v = 0;
-    if (which < 2) { if (p.fs && i < p.nF) v = __ldg((which == 0 ? p.fs : p.fl) + (size_t)b * p.nF + i); }
-    else           { if (p.ts && i < p.nT) v = __ldg((which == 2 ? p.ts : p.tl) + (size_t)b * p.nT + i); }
-    s_mask[tid] = v;
-  }
-
-  const float* nz = nullptr;
-  int noff = 0, nlen = 1;
-  float scale = 0.f;
-  if (p.noise_idx != nullptr && p.noise_data != nullptr) {
-    const int ni = __ldg(p.noise_idx + b);
-    if (ni >= 0 && ni < p.n_noise) {
-      const int64_t o0 = __ldg(p.noise_offsets + ni), o1 = __ldg(p.noise_offsets + ni + 1);
-      nlen = (int)(o1 - o0);
-      nz = p.noise_data + o0;
-      int64_t off = p.noise_off ? __ldg(p.noise_off + b) : 0;
-      off %= nlen; if (off < 0) off += nlen;
-      noff = (int)off;
-      float es, en;
-      clip_energies(x, N, nz, noff, nlen, es, en, red);
-      scale = snr_scale(es, en, p.snr_db ? __ldg(p.snr_db + b) : 0.f);
+  // ---- constants -> shared memory, once per (persistent) CTA ---------------------------
+  for (int i = tid; i < NFFT; i += blockDim.x) s_window[i] = __ldg(p.window + i);
+  for (int i = tid; i < Rad::tw_total; i += blockDim.x) s_tw[i] = __ldg(p.tw + i);
+  for (int i = tid; i < p.n_melw; i += blockDim.x) s_melw[i] = __ldg(p.mel_w + i);
+  for (int i = tid; i < M; i += blockDim.x) s_mello[i] = __ldg(p.mel_lo + i);
+  for (int i = tid; i <= M; i += blockDim.x) s_melofs[i] = __ldg(p.mel_ofs + i);
+  if (p.is_mfcc)
+    for (int i = tid; i < M * p.c8; i += blockDim.x) {
+      const int m = i / p.c8, c = i - m * p.c8;
+      s_dct[i] = c < p.n_mfcc ? __ldg(p.dct + (size_t)m * p.n_mfcc + c) : 0.f;
     }
-  }
-  const bool mix = nz != nullptr;
 
-  // ---- frames: STFT -> power -> mel -> dB into the tile (warp-autonomous) ----------------
-  const int ngroups = (T + 2 * G - 1) / (2 * G);
-  for (int grp = warp; grp < ngroups; grp += nwarps) {
-    const int f0 = grp * 2 * G;
-    // 1. load + window: z[g][j] = w[j] * (frame(f0+2g)[j] + i frame(f0+2g+1)[j])
-    for (int idx = lane; idx < G * NFFT; idx += 32) {
-      const int g = idx / NFFT, j = idx - g * NFFT;
-      const int ta = f0 + 2 * g, tb = ta + 1;
-      const float w = __ldg(p.window + j);
-      float re = 0.f, im = 0.f;
-      if (ta < T) {
-        const int i = reflect_index(ta * hop - NFFT / 2 + j, N);
-        re = __ldg(x + i);
-        if (mix) re = fmaf(scale, noise_at(nz, noff, nlen, i), re);
-      }
-      if (tb < T) {
-        const int i = reflect_index(tb * hop - NFFT / 2 + j, N);
-        im = __ldg(x + i);
-        if (mix) im = fmaf(scale, noise_at(nz, noff, nlen, i), im);
-      }
-      z[idx] = make_float2(re * w, im * w);
+  for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
+    // ---- per-clip setup -------------------------------------------------------------
+    const bool has_rev = p.rev != nullptr && p.rir_idx != nullptr && __ldg(p.rir_idx + b) >= 0;
+    const float* x = has_rev ? p.rev + (size_t)b * p.rev_stride : p.wav + (size_t)b * p.wav_stride;
+
+    // SpecAugment flags: one byte per feature row / frame
+    for (int i = tid; i < F + T; i += blockDim.x) {
+      const bool is_row = i < F;
+      const int q = is_row ? i : i - F;
+      const int32_t* st = is_row ? p.fs : p.ts;
+      const int32_t* ln = is_row ? p.fl : p.tl;
+      const int nm = is_row ? p.nF : p.nT;
+      bool mk = false;
+      if (st != nullptr)
+        for (int j = 0; j < nm; ++j) {
+          const int s0 = __ldg(st + (size_t)b * nm + j), l = __ldg(ln + (size_t)b * nm + j);
+          mk |= (q >= s0) && (q < s0 + l);
+        }
+      (is_row ? s_rowmask : s_colmask)[q] = mk ? 1 : 0;
     }
-    __syncwarp();
-    // 2. forward FFT passes (in place, digit-reversed result)
-    static_for<0, Rad::npass>([&](auto I) {
-      constexpr int i = decltype(I)::value;
-      constexpr int R = Rad::R(i), L = Rad::L(i), tasks = NFFT / R;
-      const float2* tw = p.tw + Rad::tw_off(i);
-      for (int u = lane; u < G * tasks; u += 32) {
-        const int g = u / tasks, uu = u - g * tasks;
-        pass_task<R, false>(z + g * NFFT, L, uu, [&](int q) { return __ldg(tw + q); });
+
+    const float* nz = nullptr;
+    int noff = 0, nlen = 1;
+    float scale = 0.f;
+    if (p.noise_idx != nullptr && p.noise_data != nullptr) {
+      const int ni = __ldg(p.noise_idx + b);
+      if (ni >= 0 && ni < p.n_noise) {
+        const int64_t o0 = __ldg(p.noise_offsets + ni), o1 = __ldg(p.noise_offsets + ni + 1);
+        nlen = (int)(o1 - o0);
+        nz = p.noise_data + o0;
+        int64_t off = p.noise_off ? __ldg(p.noise_off + b) : 0;
+        off %= nlen; if (off < 0) off += nlen;
+        noff = (int)off;
+        float es, en;
+        clip_energies(x, N, nz, noff, nlen, es, en, red);
+        scale = snr_scale(es, en, p.snr_db ? __ldg(p.snr_db + b) : 0.f);
+      }
+    }
+    const bool mix = nz != nullptr;
+    __syncthreads();   // constants + mask flags visible
+
+    // ---- frames: STFT -> power -> mel -> dB into the tile (warp-autonomous) --------------
+    const int ngroups = (T + 2 * G - 1) / (2 * G);
+    for (int grp = warp; grp < ngroups; grp += nwarps) {
+      const int f0 = grp * 2 * G;
+      // 1. load + window: z[g][j] = w[j] * (frame(f0+2g)[j] + i frame(f0+2g+1)[j])
+      if constexpr (HOP32 > 0) {
+        constexpr int NR = (2 * G - 1) * HOP32 + NC;         // registers holding the group's sample span
+        float sreg[NR];
+        const int s0 = f0 * hop - NFFT / 2;
+        const bool interior = s0 >= 0 && s0 + 32 * NR <= N;
+        if (interior) {
+          const float* xs = x + s0 + lane;
+#pragma unroll
+          for (int r = 0; r < NR; ++r) sreg[r] = __ldg(xs + 32 * r);
+          if (mix) {
+            int q0 = noff + s0;                              // < 2 nlen
+            if (q0 >= nlen) q0 -= nlen;
+            if (q0 + 32 * NR <= nlen) {
+              const float* ns = nz + q0 + lane;
+#pragma unroll
+              for (int r = 0; r < NR; ++r) sreg[r] = fmaf(scale, __ldg(ns + 32 * r), sreg[r]);
+            } else {
+#pragma unroll
+              for (int r = 0; r < NR; ++r) sreg[r] = fmaf(scale, noise_at(nz, noff, nlen, s0 + 32 * r + lane), sreg[r]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < NR; ++r) {
+            const int i = reflect_index(s0 + 32 * r + lane, N);
+            float v = 0.f;
+            if (i >= 0 && i < N) {                           // beyond the reflected range only in frames >= T
+              v = __ldg(x + i);
+              if (mix) v = fmaf(scale, noise_at(nz, noff, nlen, i), v);
+            }
+            sreg[r] = v;
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+          const int j = 32 * c + lane;
+          if (NFFT % 32 == 0 || j < NFFT) {
+            const float w = s_window[j];
+#pragma unroll
+            for (int g = 0; g < G; ++g) {
+              const bool va = f0 + 2 * g < T, vb = f0 + 2 * g + 1 < T;
+              z[g * NFFT + j] = make_float2(va ? w * sreg[2 * g * HOP32 + c] : 0.f, vb ? w * sreg[(2 * g + 1) * HOP32 + c] : 0.f);
+            }
+          }
+        }
+      } else {
+        for (int idx = lane; idx < G * NFFT; idx += 32) {
+          const int g = idx / NFFT, j = idx - g * NFFT;
+          const int ta = f0 + 2 * g, tb = ta + 1;
+          const float w = s_window[j];
+          float re = 0.f, im = 0.f;
+          if (ta < T) {
+            const int i = reflect_index(ta * hop - NFFT / 2 + j, N);
+            re = __ldg(x + i);
+            if (mix) re = fmaf(scale, noise_at(nz, noff, nlen, i), re);
+          }
+          if (tb < T) {
+            const int i = reflect_index(tb * hop - NFFT / 2 + j, N);
+            im = __ldg(x + i);
+            if (mix) im = fmaf(scale, noise_at(nz, noff, nlen, i), im);
+          }
+          z[idx] = make_float2(re * w, im * w);
+        }
       }
       __syncwarp();
-    });
-    // 3. split the packed pair: A[k] = (Z[k] + conj Z[n-k])/2, B[k] = -i (Z[k] - conj Z[n-k])/2;
-    //    store the two power spectra at Z[k]'s slot (only bin k's lane touches it).
-    for (int idx = lane; idx < G * K; idx += 32) {
-      const int g = idx / K, k = idx - g * K;
-      float2* zz = z + g * NFFT;
-      const int pk = Rad::pos(k), pm = Rad::pos(k == 0 ? 0 : NFFT - k);
-      zz[pk] = pair_split_power(zz[pk], zz[pm]);
-    }
-    __syncwarp();
-    // 4. sparse mel rows + dB
-    for (int idx = lane; idx < G * M; idx += 32) {
-      const int g = idx / M, m = idx - g * M;
-      const float2* zz = z + g * NFFT;
-      const int lo = __ldg(p.mel_lo + m), o0 = __ldg(p.mel_ofs + m), o1 = __ldg(p.mel_ofs + m + 1);
-      float acc_a = 0.f, acc_b = 0.f;
-      for (int o = o0; o < o1; ++o) {
-        const float w = __ldg(p.mel_w + o);
-        const float2 pw = zz[Rad::pos(lo + (o - o0))];
-        acc_a = fmaf(w, pw.x, acc_a);
-        acc_b = fmaf(w, pw.y, acc_b);
+      // 2. forward FFT passes (in place, digit-reversed result)
+      static_for<0, Rad::npass>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        constexpr int R = Rad::R(i), L = Rad::L(i), tasks = NFFT / R;
+        const float2* tw = s_tw + Rad::tw_off(i);
+        for (int u = lane; u < G * tasks; u += 32) {
+          const int g = u / tasks, uu = u - g * tasks;
+          pass_task<R, false>(z + g * NFFT, L, uu, [&](int q) { return tw[q]; });
+        }
+        __syncwarp();
+      });
+      // 3. split the packed pair into two power spectra (|A[k]|^2, |B[k]|^2)
+      if constexpr (kNatural) {
+        // read every (Z[k], Z[n-k]) first, then store the powers in plain bin order
+        float2 pw[NI];
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          const int idx = lane + 32 * i;
+          if (idx < G * K) {
+            const int g = idx / K, k = idx - g * K;
+            const float2* zz = z + g * NFFT;
+            pw[i] = pair_split_power(zz[Rad::pos(k)], zz[Rad::pos(k == 0 ? 0 : NFFT - k)]);
+          }
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          const int idx = lane + 32 * i;
+          if (idx < G * K) {
+            const int g = idx / K, k = idx - g * K;
+            z[g * NFFT + k] = pw[i];
+          }
+        }
+      } else {
+        // in place at Z[k]'s slot (only bin k's lane touches it)
+        for (int idx = lane; idx < G * K; idx += 32) {
+          const int g = idx / K, k = idx - g * K;
+          float2* zz = z + g * NFFT;
+          const int pk = Rad::pos(k), pm = Rad::pos(k == 0 ? 0 : NFFT - k);
+          zz[pk] = pair_split_power(zz[pk], zz[pm]);
+        }
       }
-      const int ta = f0 + 2 * g;
-      if (ta < T) tile[m * pitch + ta] = 10.0f * log10f(fmaxf(acc_a, 1e-10f));
-      if (ta + 1 < T) tile[m * pitch + ta + 1] = 10.0f * log10f(fmaxf(acc_b, 1e-10f));
+      __syncwarp();
+      // 4. sparse mel rows + dB: one lane per filter, all 2G frames of the group at once
+      for (int m = lane; m < M; m += 32) {
+        const int lo = s_mello[m], o0 = s_melofs[m], o1 = s_melofs[m + 1];
+        float2 acc[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) acc[g] = make_float2(0.f, 0.f);
+        for (int o = o0; o < o1; ++o) {
+          const float w = s_melw[o];
+          const int k = lo + (o - o0);
+          const int pk = kNatural ? k : Rad::pos(k);
+#pragma unroll
+          for (int g = 0; g < G; ++g) {
+            const float2 v = z[g * NFFT + pk];
+            acc[g].x = fmaf(w, v.x, acc[g].x);
+            acc[g].y = fmaf(w, v.y, acc[g].y);
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          const int ta = f0 + 2 * g;
+          if (ta < T) tile[m * pitch + ta] = 10.0f * log10f(fmaxf(acc[g].x, 1e-10f));
+          if (ta + 1 < T) tile[m * pitch + ta + 1] = 10.0f * log10f(fmaxf(acc[g].y, 1e-10f));
+        }
+      }
+      __syncwarp();
     }
-    __syncwarp();
-  }
-  __syncthreads();
-
-  // ---- per-clip top_db floor -------------------------------------------------------------
-  float cutoff = -INFINITY;
-  if (p.top_db >= 0.f) {
-    float mx = -INFINITY;
-    for (int m = warp; m < M; m += nwarps)
-      for (int t = lane; t < T; t += 32) mx = fmaxf(mx, tile[m * pitch + t]);
-    mx = warp_max(mx);
-    if (lane == 0) red[warp] = mx;
     __syncthreads();
-    mx = lane < nwarps ? red[lane] : -INFINITY;
-    mx = warp_max(mx);
-    cutoff = mx - p.top_db;
-  }
 
-  OutT* out = reinterpret_cast<OutT*>(p.out) + (size_t)b * p.out_stride;
-  const int F = p.n_feat;
-  auto masked = [&](int f, int t) -> bool {
-    bool mk = false;
-#pragma unroll
-    for (int i = 0; i < kMaxMasks; ++i) {
-      mk |= (i < p.nF) && (f >= s_mask[i]) && (f < s_mask[i] + s_mask[kMaxMasks + i]);
-      mk |= (i < p.nT) && (t >= s_mask[2 * kMaxMasks + i]) && (t < s_mask[2 * kMaxMasks + i] + s_mask[3 * kMaxMasks + i]);
-    }
-    return mk;
-  };
-
-  if (!p.is_mfcc) {
-    if (!p.cmvn) {
+    // ---- per-clip top_db floor -----------------------------------------------------------
+    float cutoff = -INFINITY;
+    if (p.top_db >= 0.f) {
+      float mx = -INFINITY;
       for (int m = warp; m < M; m += nwarps)
+        for (int t = lane; t < T; t += 32) mx = fmaxf(mx, tile[m * pitch + t]);
+      mx = warp_max(mx);
+      if (lane == 0) red[warp] = mx;
+      __syncthreads();
+      mx = lane < nwarps ? red[lane] : -INFINITY;
+      mx = warp_max(mx);
+      cutoff = mx - p.top_db;
+    }
+
+    OutT* out = reinterpret_cast<OutT*>(p.out) + (size_t)b * p.out_stride;
+    const OutT mv = to_out<OutT>(p.mask_value);
+    const float* rsrc = tile;   // rows to normalise in the CMVN epilogue
+    bool done = false;
+
+    if (!p.is_mfcc) {
+      if (!p.cmvn) {
+        for (int m = warp; m < M; m += nwarps) {
+          const bool rm = s_rowmask[m] != 0;
+          for (int t = lane; t < T; t += 32) {
+            const float v = fmaxf(tile[m * pitch + t], cutoff);
+            out[(size_t)m * T + t] = (rm || s_colmask[t]) ? mv : to_out<OutT>(v);
+          }
+        }
+        done = true;
+      } else {
+        for (int m = warp; m < M; m += nwarps)
+          for (int t = lane; t < T; t += 32) tile[m * pitch + t] = fmaxf(tile[m * pitch + t], cutoff);
+      }
+    } else {
+      // DCT-II: out[c][t] = sum_m dct[m][c] * max(tile[m][t], cutoff); 8 coefficients per thread
+      const int C = F, c8 = p.c8, ncg = c8 / 8;
+      for (int idx = tid; idx < ncg * T; idx += blockDim.x) {
+        const int cg = idx / T, t = idx - cg * T, c0 = cg * 8;
+        float acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        const float* d = s_dct + c0;
+#pragma unroll 4
+        for (int m = 0; m < M; ++m) {
+          const float a = fmaxf(tile[m * pitch + t], cutoff);
+          const float4 d0 = *reinterpret_cast<const float4*>(d + m * c8);
+          const float4 d1 = *reinterpret_cast<const float4*>(d + m * c8 + 4);
+          acc[0] = fmaf(a, d0.x, acc[0]); acc[1] = fmaf(a, d0.y, acc[1]);
+          acc[2] = fmaf(a, d0.z, acc[2]); acc[3] = fmaf(a, d0.w, acc[3]);
+          acc[4] = fmaf(a, d1.x, acc[4]); acc[5] = fmaf(a, d1.y, acc[5]);
+          acc[6] = fmaf(a, d1.z, acc[6]); acc[7] = fmaf(a, d1.w, acc[7]);
+        }
+        const bool cm = s_colmask[t] != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int c = c0 + i;
+          if (c < C) {
+            if (p.cmvn) res[c * pitch + t] = acc[i];
+            else out[(size_t)c * T + t] = (cm || s_rowmask[c]) ? mv : to_out<OutT>(acc[i]);
+          }
+        }
+      }
+      rsrc = res;
+      done = !p.cmvn;
+    }
+    if (!done) {
+      // ---- CMVN epilogue: per row (x - mean) / (population std + eps) ------------------
+      __syncthreads();
+      for (int f = warp; f < F; f += nwarps) {
+        float s = 0.f;
+        for (int t = lane; t < T; t += 32) s += rsrc[f * pitch + t];
+        const float mean = warp_sum(s) / (float)T;
+        float q = 0.f;
+        for (int t = lane; t < T; t += 32) { const float dlt = rsrc[f * pitch + t] - mean; q = fmaf(dlt, dlt, q); }
+        const float sd = sqrtf(warp_sum(q) / (float)T);
+        const float inv = 1.0f / (sd + p.cmvn_eps);
+        const bool rm = s_rowmask[f] != 0;
         for (int t = lane; t < T; t += 32) {
-          const float v = fmaxf(tile[m * pitch + t], cutoff);
-          out[(size_t)m * T + t] = to_out<OutT>(masked(m, t) ? p.mask_value : v);
-        }
-      return;
-    }
-    for (int m = warp; m < M; m += nwarps)
-      for (int t = lane; t < T; t += 32) tile[m * pitch + t] = fmaxf(tile[m * pitch + t], cutoff);
-    res = tile;
-  } else {
-    // DCT-II: out[c][t] = sum_m dct[m][c] * max(tile[m][t], cutoff); 8 coefficients per thread
-    const int C = F, ncg = (C + 7) / 8;
-    for (int idx = tid; idx < ncg * T; idx += blockDim.x) {
-      const int cg = idx / T, t = idx - cg * T, c0 = cg * 8;
-      float acc[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-      for (int m = 0; m < M; ++m) {
-        const float a = fmaxf(tile[m * pitch + t], cutoff);
-        const float* d = p.dct + (size_t)m * C + c0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (c0 + i < C) acc[i] = fmaf(a, __ldg(d + i), acc[i]);
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int c = c0 + i;
-        if (c < C) {
-          if (p.cmvn) res[c * pitch + t] = acc[i];
-          else out[(size_t)c * T + t] = to_out<OutT>(masked(c, t) ? p.mask_value : acc[i]);
+          const float v = (rsrc[f * pitch + t] - mean) * inv;
+          out[(size_t)f * T + t] = (rm || s_colmask[t]) ? mv : to_out<OutT>(v);
         }
       }
     }
-    if (!p.cmvn) return;
-  }
-  // ---- CMVN epilogue: per row (x - mean) / (population std + eps) ----------------------
-  __syncthreads();
-  for (int f = warp; f < F; f += nwarps) {
-    float s = 0.f;
-    for (int t = lane; t < T; t += 32) s += res[f * pitch + t];
-    const float mean = warp_sum(s) / (float)T;
-    float q = 0.f;
-    for (int t = lane; t < T; t += 32) { const float d = res[f * pitch + t] - mean; q = fmaf(d, d, q); }
-    const float sd = sqrtf(warp_sum(q) / (float)T);
-    const float inv = 1.0f / (sd + p.cmvn_eps);
-    for (int t = lane; t < T; t += 32) {
-      const float v = (res[f * pitch + t] - mean) * inv;
-      out[(size_t)f * T + t] = to_out<OutT>(masked(f, t) ? p.mask_value : v);
-    }
+    __syncthreads();   // tile / flags are reused by the next clip
   }
 }
 

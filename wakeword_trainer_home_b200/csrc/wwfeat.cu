@@ -59,7 +59,7 @@ typedef void (*FeatKernel)(const FeatParams);
 struct wwf_plan {
   wwf_config cfg;
   int device = 0, sm_count = 0, max_smem = 0;
-  int K = 0, n_feat = 0, G = 1;
+  int K = 0, n_feat = 0, G = 1, tw_total = 0, n_melw = 0;
   FeatKernel kernel = nullptr;
   // device constants
   float* d_window = nullptr;
@@ -89,12 +89,21 @@ static int upload(T** dst, const std::vector<T>& src) {
   return WWF_OK;
 }
 
+// Kernel variant: frames loaded through the register-staged path when hop == 160 (HOP32 = 5,
+// the reference's hop for every preset) and the sample span fits in registers; generic
+// per-element loads otherwise.
 template <int NFFT>
 static void select_kernel(wwf_plan* p, std::vector<float2>& tw) {
   using Plan = StftPlan<NFFT>;
   build_stft_twiddles<typename Plan::Rad>(tw);
   p->G = Plan::G;
-  p->kernel = p->cfg.out_dtype == WWF_OUT_F16 ? (FeatKernel)feat_kernel<NFFT, __half> : (FeatKernel)feat_kernel<NFFT, float>;
+  p->tw_total = Plan::Rad::tw_total;
+  const bool f16 = p->cfg.out_dtype == WWF_OUT_F16;
+  p->kernel = f16 ? (FeatKernel)feat_kernel<NFFT, 0, __half> : (FeatKernel)feat_kernel<NFFT, 0, float>;
+  if constexpr (NFFT <= 1024) {
+    if (p->cfg.hop_length == 160 && !getenv("WWF_FEAT_GENERIC_LOAD"))
+      p->kernel = f16 ? (FeatKernel)feat_kernel<NFFT, 5, __half> : (FeatKernel)feat_kernel<NFFT, 5, float>;
+  }
 }
 
 extern "C" int wwf_version(void) { return WWF_VERSION; }
@@ -175,6 +184,7 @@ extern "C" int wwf_plan_create(const wwf_config* cfg, int device, wwf_plan** out
     if (first >= 0) for (int k = first; k <= last; ++k) w.push_back(fb[(size_t)k * M + m]);
   }
   ofs[M] = (int)w.size();
+  p->n_melw = (int)w.size();
   if (w.empty()) w.push_back(0.f);
 
   std::vector<float> dct;
@@ -357,24 +367,48 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
 
   const bool mfcc = p->cfg.feature_type == WWF_FEAT_MFCC;
   const int pitch = T | 1;
-  const int tile_floats = (M * pitch + 1) & ~1;
-  const int res_floats = (mfcc && p->cfg.cmvn) ? ((F * pitch + 1) & ~1) : 0;
-  const size_t tile_bytes = ((size_t)tile_floats + res_floats) * sizeof(float);
-  const size_t per_warp = (size_t)p->G * p->cfg.n_fft * sizeof(float2);
-  const size_t budget = (size_t)p->max_smem - 1024 - 512;   // static smem of the kernel is ~0.5 KB
-  if (tile_bytes + per_warp > budget)
-    return fail(WWF_ERR_UNSUPPORTED, "clip too long for the in-shared-memory tile: n_mels*T*4 = %zu bytes (N=%d, T=%d)", tile_bytes, N, T);
-  int nwarps = (int)((budget - tile_bytes) / per_warp);
-  if (nwarps > 16) nwarps = 16;
-  if (p->feat_warps_override > 0 && p->feat_warps_override < nwarps) nwarps = p->feat_warps_override;
-  const size_t smem = tile_bytes + (size_t)nwarps * per_warp;
-
+  const int nfft = p->cfg.n_fft;
+  auto al4 = [](int v) { return (v + 3) & ~3; };
   FeatParams fp{};
+  fp.c8 = mfcc ? ((F + 7) & ~7) : 0;
+  fp.n_melw = p->n_melw;
+  int o = al4(M * pitch);
+  fp.off_res = o;      o += (mfcc && p->cfg.cmvn) ? al4(F * pitch) : 0;
+  fp.off_window = o;   o += al4(nfft);
+  fp.off_tw = o;       o += al4(2 * p->tw_total);
+  fp.off_melw = o;     o += al4(p->n_melw);
+  fp.off_dct = o;      o += mfcc ? M * fp.c8 : 0;
+  fp.off_mello = o;    o += al4(M);
+  fp.off_melofs = o;   o += al4(M + 1);
+  fp.off_rowmask = o;  o += al4((F + 3) / 4);
+  fp.off_colmask = o;  o += al4((T + 3) / 4);
+  fp.off_z = o;
+  const size_t fixed_bytes = (size_t)o * sizeof(float);
+  const size_t per_warp = (size_t)p->G * nfft * sizeof(float2);
+  const size_t budget = (size_t)p->max_smem - 1024;   // static smem of the kernel is 256 B
+  if (fixed_bytes + per_warp > budget)
+    return fail(WWF_ERR_UNSUPPORTED, "clip too long for the in-shared-memory tile: %zu bytes of tiles/tables (N=%d, T=%d, n_mels=%d)", fixed_bytes, N, T, M);
+  // CTA shape: the candidate (warps per CTA) that keeps the most warps resident per SM
+  int nwarps = 0, ctas_per_sm = 1, best = -1;
+  const int cands[] = {16, 12, 11, 10, 8, 6, 4, 2, 1};
+  for (int c : cands) {
+    if (p->feat_warps_override > 0 && c != p->feat_warps_override) continue;
+    const size_t sm = fixed_bytes + (size_t)c * per_warp;
+    if (sm > budget) continue;
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)p->kernel, c * 32, sm) != cudaSuccess || nb < 1) continue;
+    if (nb * c > best) { best = nb * c; nwarps = c; ctas_per_sm = nb; }
+  }
+  if (nwarps == 0) return fail(WWF_ERR_CUDA, "feat_kernel does not fit on this device (%zu + %zu bytes of shared memory)", fixed_bytes, per_warp);
+  const size_t smem = fixed_bytes + (size_t)nwarps * per_warp;
+  int grid = p->sm_count * ctas_per_sm;
+  if (grid > B) grid = B;
+
   fp.wav = wav; fp.wav_stride = wav_stride; fp.rev = rev; fp.rev_stride = rev_stride;
   fp.B = B; fp.N = N; fp.T = T; fp.hop = p->cfg.hop_length;
   fp.n_mels = M; fp.n_mfcc = p->cfg.n_mfcc; fp.n_feat = F; fp.is_mfcc = mfcc; fp.out_f16 = p->cfg.out_dtype == WWF_OUT_F16;
   fp.cmvn = p->cfg.cmvn != 0; fp.top_db = p->cfg.top_db; fp.cmvn_eps = p->cfg.cmvn_eps; fp.mask_value = p->cfg.mask_value;
-  fp.tile_pitch = pitch; fp.tile_floats = tile_floats; fp.res_floats = res_floats;
+  fp.tile_pitch = pitch;
   fp.window = p->d_window; fp.tw = p->d_tw; fp.mel_lo = p->d_mel_lo; fp.mel_ofs = p->d_mel_ofs; fp.mel_w = p->d_mel_w; fp.dct = p->d_dct;
   if (aug) {
     fp.rir_idx = rev ? aug->rir_idx : nullptr;
@@ -386,7 +420,7 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
     if (aug->tmask_start && aug->tmask_len && p->cfg.n_time_masks > 0) { fp.ts = aug->tmask_start; fp.tl = aug->tmask_len; fp.nT = p->cfg.n_time_masks; }
   }
   fp.out = out; fp.out_stride = out_stride;
-  p->kernel<<<B, nwarps * 32, smem, st>>>(fp);
+  p->kernel<<<grid, nwarps * 32, smem, st>>>(fp);
   g_launches++;
   WWF_CUDA(cudaGetLastError());
   return WWF_OK;
