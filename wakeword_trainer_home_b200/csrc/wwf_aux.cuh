@@ -10,7 +10,8 @@ struct MixParams {
   const float* wav; int64_t wav_stride;
   const float* rev; int64_t rev_stride;     // reverberated clips or nullptr
   const int32_t* rir_idx; const int32_t* noise_idx; const int64_t* noise_off; const float* snr_db;
-  const float* noise_data; const int64_t* noise_offsets; int n_noise;
+  NoiseBankDev noise;
+  const float* es_part; int es_nb;
   float* out; int64_t out_stride;
   int B, N;
 };
@@ -23,27 +24,28 @@ __global__ void __launch_bounds__(512) mix_kernel(const MixParams p) {
   const bool has_rev = p.rev != nullptr && p.rir_idx != nullptr && __ldg(p.rir_idx + b) >= 0;
   const float* x = has_rev ? p.rev + (size_t)b * p.rev_stride : p.wav + (size_t)b * p.wav_stride;
   float* y = p.out + (size_t)b * p.out_stride;
-  const float* nz = nullptr;
-  int noff = 0, nlen = 1;
-  float scale = 0.f;
-  if (p.noise_idx != nullptr && p.noise_data != nullptr) {
-    const int ni = __ldg(p.noise_idx + b);
-    if (ni >= 0 && ni < p.n_noise) {
-      const int64_t o0 = __ldg(p.noise_offsets + ni), o1 = __ldg(p.noise_offsets + ni + 1);
-      nlen = (int)(o1 - o0);
-      nz = p.noise_data + o0;
-      int64_t off = p.noise_off ? __ldg(p.noise_off + b) : 0;
-      off %= nlen; if (off < 0) off += nlen;
-      noff = (int)off;
-      float es, en;
-      clip_energies(x, p.N, nz, noff, nlen, es, en, red);
-      scale = snr_scale(es, en, p.snr_db ? __ldg(p.snr_db + b) : 0.f);
-    }
-  }
+  const ClipNoise cn = resolve_noise(p.noise, p.noise_idx, p.noise_off, b);
+  const float* nz = cn.nz;
+  const int noff = cn.off, nlen = cn.len;
+  const float scale = clip_mix_scale(cn, x, p.N, has_rev, p.es_part, p.es_nb, b, p.snr_db, red);
   if (nz != nullptr) {
     for (int i = threadIdx.x; i < p.N; i += blockDim.x) y[i] = fmaf(scale, noise_at(nz, noff, nlen, i), x[i]);
   } else if (x != y) {
     for (int i = threadIdx.x; i < p.N; i += blockDim.x) y[i] = x[i];
+  }
+}
+
+// Registration helper: sums[j] = sum of squares of block j (kNoiseBlk samples, last one partial)
+// of one noise clip, in double.  One warp per block.
+__global__ void __launch_bounds__(256) noise_block_sums_kernel(const float* __restrict__ data, int64_t len, double* __restrict__ sums) {
+  const int64_t nblk = (len + kNoiseBlk - 1) / kNoiseBlk;
+  const int lane = threadIdx.x & 31;
+  for (int64_t j = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < nblk; j += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+    double e = 0.0;
+    for (int64_t q = j * kNoiseBlk + lane; q < (j + 1) * kNoiseBlk && q < len; q += 32) { const double v = (double)data[q]; e += v * v; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    if (lane == 0) sums[j] = e;
   }
 }
 

@@ -46,6 +46,7 @@ WWF_HD int pair_task_k(int v) {
 struct ConvParams {
   const float* wav; int64_t wav_stride;      // [B][N]
   float* rev; int64_t rev_stride;            // [B][N] output (workspace)
+  float* es_part; int es_nb;                 // [B][es_nb] energy of this block's output samples (for the SNR mix)
   const int32_t* rir_idx;                    // [B]
   int B, N, n_rir;
   int hist;                                  // H0: history samples per block (0 = single block)
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams 
   // store the valid outputs: block sample i in [hist, P) -> clip sample blk*valid + i - hist
   float* y = p.rev + (size_t)b * p.rev_stride;
   const bool st_ok = ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+  float e0 = 0.f, e1 = 0.f;
   for (int q = threadIdx.x; q < kConvP / 4; q += kConvThreads) {
     const int i = 4 * q;
     if (i < p.hist) continue;
@@ -169,12 +171,27 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams 
     const float2 a = zc[pad(2 * q)], c = zc[pad(2 * q + 1)];
     if (n + 3 < p.N && st_ok) {
       *reinterpret_cast<float4*>(y + n) = make_float4(a.x, a.y, c.x, c.y);
+      e0 = fmaf(a.x, a.x, fmaf(a.y, a.y, e0));
+      e1 = fmaf(c.x, c.x, fmaf(c.y, c.y, e1));
     } else {
-      y[n] = a.x;
-      if (n + 1 < p.N) y[n + 1] = a.y;
-      if (n + 2 < p.N) y[n + 2] = c.x;
-      if (n + 3 < p.N) y[n + 3] = c.y;
+      y[n] = a.x; e0 = fmaf(a.x, a.x, e0);
+      if (n + 1 < p.N) { y[n + 1] = a.y; e0 = fmaf(a.y, a.y, e0); }
+      if (n + 2 < p.N) { y[n + 2] = c.x; e1 = fmaf(c.x, c.x, e1); }
+      if (n + 3 < p.N) { y[n + 3] = c.y; e1 = fmaf(c.y, c.y, e1); }
     }
+  }
+  // energy of this block's output samples, for the SNR mix that follows (fixed reduction order)
+  __shared__ float red[kConvThreads / 32];
+  float e = e0 + e1;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    e = threadIdx.x < kConvThreads / 32 ? red[threadIdx.x] : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+    if (threadIdx.x == 0 && p.es_part != nullptr) p.es_part[(size_t)b * p.es_nb + blk] = e;
   }
 }
 

@@ -28,12 +28,34 @@ namespace wwf {
 
 constexpr int kMaxMasks = 8;
 
+// Per-n_fft plan: radix list, G = complex FFTs (frame pairs) per warp iteration, and the launch
+// bounds (max threads per CTA, min CTAs per SM) the kernel is compiled for.
 template <int NFFT> struct StftPlan;
-template <> struct StftPlan<256>  { using Rad = Radices<16, 16>;    static constexpr int G = 2; };
-template <> struct StftPlan<400>  { using Rad = Radices<16, 25>;    static constexpr int G = 2; };
-template <> struct StftPlan<512>  { using Rad = Radices<16, 8, 4>;  static constexpr int G = 1; };
-template <> struct StftPlan<1024> { using Rad = Radices<16, 16, 4>; static constexpr int G = 1; };
-template <> struct StftPlan<2048> { using Rad = Radices<16, 16, 8>; static constexpr int G = 1; };
+template <> struct StftPlan<256>  { using Rad = Radices<16, 16>;    static constexpr int G = 2, kThreads = 320, kMinCtas = 2; };
+template <> struct StftPlan<400>  { using Rad = Radices<16, 25>;    static constexpr int G = 2, kThreads = 320, kMinCtas = 2; };
+template <> struct StftPlan<512>  { using Rad = Radices<16, 8, 4>;  static constexpr int G = 1, kThreads = 512, kMinCtas = 1; };
+template <> struct StftPlan<1024> { using Rad = Radices<16, 16, 4>; static constexpr int G = 1, kThreads = 512, kMinCtas = 1; };
+template <> struct StftPlan<2048> { using Rad = Radices<16, 16, 8>; static constexpr int G = 1, kThreads = 512, kMinCtas = 1; };
+
+constexpr int kNoiseBlk = 128;   // granularity of the noise bank's squared-sample prefix sums
+
+// Registered background-noise bank (device view).  sq_prefix holds, per clip, the running sum
+// (double) of squared samples at every kNoiseBlk boundary: P[j] = sum_{q < j*128} n[q]^2, with a
+// final entry for the whole clip, so the energy of ANY segment costs two table reads plus at
+// most 2*127 edge samples instead of a pass over the segment.
+struct NoiseBankDev {
+  const float* data;              // all clips back to back (borrowed from the caller)
+  const int64_t* offsets;         // [count+1] sample offsets
+  const double* sq_prefix;        // concatenated per-clip prefix tables
+  const int64_t* prefix_offsets;  // [count] start of clip i's table
+  int count;
+};
+
+struct ClipNoise {
+  const float* nz;     // nullptr = this clip has no noise
+  const double* P;
+  int len, off;
+};
 
 struct FeatParams {
   // inputs
@@ -59,7 +81,8 @@ struct FeatParams {
   const float* dct;                              // [n_mels][n_mfcc]
   // augmentation draws (device, nullable)
   const int32_t* rir_idx; const int32_t* noise_idx; const int64_t* noise_off; const float* snr_db;
-  const float* noise_data; const int64_t* noise_offsets; int n_noise;
+  NoiseBankDev noise;
+  const float* es_part; int es_nb;               // per-clip energy partials written by conv_kernel [B][es_nb]
   const int32_t* fs; const int32_t* fl; const int32_t* ts; const int32_t* tl; int nF, nT;
   // output
   void* out; int64_t out_stride;
@@ -107,37 +130,94 @@ __device__ __forceinline__ float snr_scale(float es, float en, float snr_db) {
   return exp10f((snr0 - snr_db) / 20.0f);
 }
 
-// Block-wide sum of two values; result broadcast to all threads. red: >= 2*32 floats of smem.
-__device__ __forceinline__ void block_sum2(float& a, float& b, float* red) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-  a = warp_sum(a);
-  b = warp_sum(b);
-  __syncthreads();
-  if (lane == 0) { red[warp] = a; red[32 + warp] = b; }
-  __syncthreads();
-  float x = lane < nw ? red[lane] : 0.f, y = lane < nw ? red[32 + lane] : 0.f;
-  a = warp_sum(x);
-  b = warp_sum(y);
+// Noise clip, wrapped start offset and prefix table of batch item b (nz == nullptr: no noise).
+__device__ __forceinline__ ClipNoise resolve_noise(const NoiseBankDev& bank, const int32_t* noise_idx,
+                                                   const int64_t* noise_off, int b) {
+  ClipNoise c{nullptr, nullptr, 1, 0};
+  if (noise_idx == nullptr || bank.data == nullptr) return c;
+  const int ni = __ldg(noise_idx + b);
+  if (ni < 0 || ni >= bank.count) return c;
+  const int64_t o0 = __ldg(bank.offsets + ni), o1 = __ldg(bank.offsets + ni + 1);
+  c.len = (int)(o1 - o0);
+  c.nz = bank.data + o0;
+  c.P = bank.sq_prefix + __ldg(bank.prefix_offsets + ni);
+  int64_t off = noise_off ? __ldg(noise_off + b) : 0;
+  off %= c.len;
+  if (off < 0) off += c.len;
+  c.off = (int)off;
+  return c;
 }
 
-// Energies of the clip and of its noise segment (two independent accumulators per thread).
-__device__ __forceinline__ void clip_energies(const float* x, int N, const float* nz, int noff, int nlen,
-                                              float& es, float& en, float* red) {
-  float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
-  int i = threadIdx.x;
-  for (; i + (int)blockDim.x < N; i += 2 * blockDim.x) {
-    const float x0 = __ldg(x + i), x1 = __ldg(x + i + blockDim.x);
-    const float n0 = noise_at(nz, noff, nlen, i), n1 = noise_at(nz, noff, nlen, i + blockDim.x);
-    a0 = fmaf(x0, x0, a0); a1 = fmaf(x1, x1, a1);
-    b0 = fmaf(n0, n0, b0); b1 = fmaf(n1, n1, b1);
+// sum of nz[q]^2 over [a, b), 0 <= a <= b <= len: prefix table for whole 128-blocks, direct sum
+// of the (< 128-sample) edges.  Executed by a full warp; every lane returns the result.
+__device__ __forceinline__ double warp_seg_energy(const ClipNoise& c, int a, int b) {
+  const int lane = threadIdx.x & 31;
+  const int lo = (a + kNoiseBlk - 1) / kNoiseBlk, hi = b / kNoiseBlk;
+  float e = 0.f;
+  double mid = 0.0;
+  if (lo <= hi) {
+    mid = c.P[hi] - c.P[lo];
+    for (int q = a + lane; q < lo * kNoiseBlk; q += 32) { const float v = __ldg(c.nz + q); e = fmaf(v, v, e); }
+    for (int q = hi * kNoiseBlk + lane; q < b; q += 32) { const float v = __ldg(c.nz + q); e = fmaf(v, v, e); }
+  } else {
+    for (int q = a + lane; q < b; q += 32) { const float v = __ldg(c.nz + q); e = fmaf(v, v, e); }
   }
-  if (i < N) {
-    const float x0 = __ldg(x + i), n0 = noise_at(nz, noff, nlen, i);
-    a0 = fmaf(x0, x0, a0); b0 = fmaf(n0, n0, b0);
+  return mid + (double)warp_sum(e);
+}
+
+// Energy of the N-sample noise segment nz[(off + i) mod len], i < N.
+__device__ __forceinline__ float warp_noise_energy(const ClipNoise& c, int N) {
+  const int first = min(N, c.len - c.off);
+  double e = warp_seg_energy(c, c.off, c.off + first);
+  int rem = N - first;
+  if (rem > 0) {
+    const int loops = rem / c.len;
+    rem -= loops * c.len;
+    if (loops > 0) e += (double)loops * c.P[(c.len + kNoiseBlk - 1) / kNoiseBlk];
+    if (rem > 0) e += warp_seg_energy(c, 0, rem);
   }
-  es = a0 + a1;
-  en = b0 + b1;
-  block_sum2(es, en, red);
+  return (float)e;
+}
+
+// Block-wide sum of x[i]^2, i < N (8 independent loads in flight per thread); result in all
+// threads.  red: >= 32 floats of shared memory.  Contains __syncthreads().
+__device__ __forceinline__ float block_energy(const float* __restrict__ x, int N, float* red) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  float acc[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) acc[u] = 0.f;
+  int i = tid;
+  for (; i + 7 * nt < N; i += 8 * nt) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = __ldg(x + i + u * nt);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = fmaf(v[u], v[u], acc[u]);
+  }
+  for (; i < N; i += nt) { const float v = __ldg(x + i); acc[0] = fmaf(v, v, acc[0]); }
+  float s = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
+  const int lane = tid & 31, warp = tid >> 5, nw = (nt + 31) >> 5;
+  s = warp_sum(s);
+  __syncthreads();
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  s = lane < nw ? red[lane] : 0.f;
+  return warp_sum(s);
+}
+
+// Mix scale of batch item b (0 if it has no noise): energies of the (possibly reverberated)
+// clip and of its noise segment -> F.add_noise's scale.  CTA-uniform control flow.
+__device__ __forceinline__ float clip_mix_scale(const ClipNoise& cn, const float* x, int N, bool has_rev,
+                                                const float* es_part, int es_nb, int b, const float* snr_db, float* red) {
+  if (cn.nz == nullptr) return 0.f;
+  float es = 0.f;
+  if (has_rev && es_part != nullptr) {
+    for (int i = 0; i < es_nb; ++i) es += __ldg(es_part + (size_t)b * es_nb + i);   // fixed order: deterministic
+  } else {
+    es = block_energy(x, N, red);
+  }
+  const float en = warp_noise_energy(cn, N);
+  return snr_scale(es, en, snr_db ? __ldg(snr_db + b) : 0.f);
 }
 
 template <typename OutT> __device__ __forceinline__ OutT to_out(float v);
@@ -146,7 +226,7 @@ template <> __device__ __forceinline__ __half to_out<__half>(float v) { return _
 
 // ---- the kernel ------------------------------------------------------------------------
 template <int NFFT, int HOP32, typename OutT>
-__global__ void __launch_bounds__(512) feat_kernel(const FeatParams p) {
+__global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMinCtas) feat_kernel(const FeatParams p) {
   using Plan = StftPlan<NFFT>;
   using Rad = typename Plan::Rad;
   constexpr int G = Plan::G;
@@ -207,23 +287,10 @@ __global__ void __launch_bounds__(512) feat_kernel(const FeatParams p) {
       (is_row ? s_rowmask : s_colmask)[q] = mk ? 1 : 0;
     }
 
-    const float* nz = nullptr;
-    int noff = 0, nlen = 1;
-    float scale = 0.f;
-    if (p.noise_idx != nullptr && p.noise_data != nullptr) {
-      const int ni = __ldg(p.noise_idx + b);
-      if (ni >= 0 && ni < p.n_noise) {
-        const int64_t o0 = __ldg(p.noise_offsets + ni), o1 = __ldg(p.noise_offsets + ni + 1);
-        nlen = (int)(o1 - o0);
-        nz = p.noise_data + o0;
-        int64_t off = p.noise_off ? __ldg(p.noise_off + b) : 0;
-        off %= nlen; if (off < 0) off += nlen;
-        noff = (int)off;
-        float es, en;
-        clip_energies(x, N, nz, noff, nlen, es, en, red);
-        scale = snr_scale(es, en, p.snr_db ? __ldg(p.snr_db + b) : 0.f);
-      }
-    }
+    const ClipNoise cn = resolve_noise(p.noise, p.noise_idx, p.noise_off, b);
+    const float* nz = cn.nz;
+    const int noff = cn.off, nlen = cn.len;
+    const float scale = clip_mix_scale(cn, x, N, has_rev, p.es_part, p.es_nb, b, p.snr_db, red);
     const bool mix = nz != nullptr;
     __syncthreads();   // constants + mask flags visible
 

@@ -59,7 +59,7 @@ typedef void (*FeatKernel)(const FeatParams);
 struct wwf_plan {
   wwf_config cfg;
   int device = 0, sm_count = 0, max_smem = 0;
-  int K = 0, n_feat = 0, G = 1, tw_total = 0, n_melw = 0;
+  int K = 0, n_feat = 0, G = 1, tw_total = 0, n_melw = 0, max_warps = 16;
   FeatKernel kernel = nullptr;
   // device constants
   float* d_window = nullptr;
@@ -71,7 +71,10 @@ struct wwf_plan {
   // noise bank (borrowed data, owned offsets)
   const float* noise_data = nullptr;
   int64_t* d_noise_offsets = nullptr;
+  double* d_noise_prefix = nullptr;
+  int64_t* d_noise_prefix_offsets = nullptr;
   int n_noise = 0;
+  NoiseBankDev noise_dev() const { return NoiseBankDev{noise_data, d_noise_offsets, d_noise_prefix, d_noise_prefix_offsets, n_noise}; }
   // RIR bank (owned spectra) + conv constants
   float4* d_spec = nullptr;
   float2* d_conv_tw = nullptr;
@@ -97,6 +100,7 @@ static void select_kernel(wwf_plan* p, std::vector<float2>& tw) {
   using Plan = StftPlan<NFFT>;
   build_stft_twiddles<typename Plan::Rad>(tw);
   p->G = Plan::G;
+  p->max_warps = Plan::kThreads / 32;
   p->tw_total = Plan::Rad::tw_total;
   const bool f16 = p->cfg.out_dtype == WWF_OUT_F16;
   p->kernel = f16 ? (FeatKernel)feat_kernel<NFFT, 0, __half> : (FeatKernel)feat_kernel<NFFT, 0, float>;
@@ -115,6 +119,7 @@ extern "C" void wwf_plan_destroy(wwf_plan* p) {
   DeviceGuard g(p->device);
   cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_mel_lo); cudaFree(p->d_mel_ofs);
   cudaFree(p->d_mel_w); cudaFree(p->d_dct); cudaFree(p->d_noise_offsets); cudaFree(p->d_spec);
+  cudaFree(p->d_noise_prefix); cudaFree(p->d_noise_prefix_offsets);
   cudaFree(p->d_conv_tw); cudaFree(p->d_conv_tw_pair);
   delete p;
 }
@@ -254,12 +259,39 @@ extern "C" int wwf_bank_register(wwf_plan* p, int kind, const float* data, const
   if (kind == WWF_BANK_NOISE) {
     for (int i = 0; i < count; ++i)
       if (offsets[i + 1] - offsets[i] > 0x7fffffffLL) return fail(WWF_ERR_UNSUPPORTED, "noise clip %d longer than 2^31 samples", i);
-    cudaFree(p->d_noise_offsets);
-    p->d_noise_offsets = nullptr;
+    cudaFree(p->d_noise_offsets); cudaFree(p->d_noise_prefix); cudaFree(p->d_noise_prefix_offsets);
+    p->d_noise_offsets = nullptr; p->d_noise_prefix = nullptr; p->d_noise_prefix_offsets = nullptr;
     p->noise_data = nullptr;
     p->n_noise = 0;
     if (count == 0) return WWF_OK;
+    // squared-sample prefix sums at every kNoiseBlk boundary (double): block sums on the GPU,
+    // running sum on the host (one-time cost; lets the kernels get any segment's energy in O(1))
+    std::vector<int64_t> pofs(count + 1, 0);
+    for (int i = 0; i < count; ++i) pofs[i + 1] = pofs[i] + (offsets[i + 1] - offsets[i] + kNoiseBlk - 1) / kNoiseBlk + 1;
+    double* d_sums = nullptr;
+    WWF_CUDA(cudaMalloc((void**)&d_sums, (size_t)pofs[count] * sizeof(double)));
+    for (int i = 0; i < count; ++i) {
+      const int64_t len = offsets[i + 1] - offsets[i];
+      const int64_t nblk = (len + kNoiseBlk - 1) / kNoiseBlk;
+      int grid = (int)((nblk + 7) / 8);
+      if (grid > 4096) grid = 4096;
+      noise_block_sums_kernel<<<grid, 256, 0, st>>>(data + offsets[i], len, d_sums + pofs[i] + 1);
+      g_launches++;
+    }
+    std::vector<double> pre((size_t)pofs[count]);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(pre.data(), d_sums, pre.size() * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_sums);
+    if (e != cudaSuccess) return fail(WWF_ERR_CUDA, "noise_block_sums_kernel: %s", cudaGetErrorString(e));
+    for (int i = 0; i < count; ++i) {
+      pre[pofs[i]] = 0.0;
+      for (int64_t j = pofs[i] + 1; j < pofs[i + 1]; ++j) pre[j] += pre[j - 1];
+    }
+    pofs.pop_back();
     int rc = upload(&p->d_noise_offsets, ofs);
+    if (!rc) rc = upload(&p->d_noise_prefix, pre);
+    if (!rc) rc = upload(&p->d_noise_prefix_offsets, pofs);
     if (rc) return rc;
     p->noise_data = data;
     p->n_noise = count;
@@ -303,18 +335,34 @@ extern "C" int wwf_bank_register(wwf_plan* p, int kind, const float* data, const
 // ------------------------------------------------------------------------------------------
 static inline int64_t round_up4(int64_t v) { return (v + 3) & ~(int64_t)3; }
 
+// overlap-save geometry for N-sample clips: history, valid outputs per block, block count
+static void conv_geometry(const wwf_plan* p, int N, int* hist, int* valid, int* nb) {
+  if ((int64_t)N + p->rir_max_len - 1 <= kConvP) { *hist = 0; *valid = kConvP; *nb = 1; }
+  else {
+    *hist = (int)round_up4(p->rir_max_len - 1);
+    *valid = kConvP - *hist;
+    *nb = (N + *valid - 1) / *valid;
+  }
+}
+
+// workspace = reverberated clips [B][roundup4(N)] + their per-block energies [B][nb]
 extern "C" size_t wwf_workspace_bytes(const wwf_plan* p, int B, int N) {
   if (!p || B <= 0 || N <= 0 || p->n_rir == 0) return 0;
-  return (size_t)B * (size_t)round_up4(N) * sizeof(float);
+  int hist, valid, nb;
+  conv_geometry(p, N, &hist, &valid, &nb);
+  return ((size_t)B * (size_t)round_up4(N) + (size_t)round_up4((int64_t)B * nb)) * sizeof(float);
 }
 
 static bool wants_reverb(const wwf_plan* p, const wwf_aug* aug) { return aug && aug->rir_idx && p->n_rir > 0; }
 
 // Overlap-save reverb of the clips that have rir_idx >= 0 into the workspace.
 static int launch_conv(wwf_plan* p, const float* wav, int B, int N, int64_t wav_stride, const wwf_aug* aug,
-                       void* workspace, size_t workspace_bytes, cudaStream_t st, float** rev, int64_t* rev_stride) {
+                       void* workspace, size_t workspace_bytes, cudaStream_t st, float** rev, int64_t* rev_stride,
+                       const float** es_part, int* es_nb) {
   *rev = nullptr;
   *rev_stride = 0;
+  *es_part = nullptr;
+  *es_nb = 0;
   if (!wants_reverb(p, aug)) return WWF_OK;
   const size_t need = wwf_workspace_bytes(p, B, N);
   if (!workspace || workspace_bytes < need) return fail(WWF_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
@@ -324,12 +372,9 @@ static int launch_conv(wwf_plan* p, const float* wav, int B, int N, int64_t wav_
   cp.rev = (float*)workspace; cp.rev_stride = round_up4(N);
   cp.rir_idx = aug->rir_idx; cp.B = B; cp.N = N; cp.n_rir = p->n_rir;
   int nb = 1;
-  if ((int64_t)N + p->rir_max_len - 1 <= kConvP) { cp.hist = 0; cp.valid = kConvP; }
-  else {
-    cp.hist = (int)round_up4(p->rir_max_len - 1);
-    cp.valid = kConvP - cp.hist;
-    nb = (N + cp.valid - 1) / cp.valid;
-  }
+  conv_geometry(p, N, &cp.hist, &cp.valid, &nb);
+  cp.es_part = cp.rev + (size_t)B * cp.rev_stride;
+  cp.es_nb = nb;
   cp.spec = p->d_spec; cp.tw = p->d_conv_tw; cp.tw_pair = p->d_conv_tw_pair;
   dim3 grid(nb, B);
   conv_kernel<<<grid, kConvThreads, kConvSmemBytes, st>>>(cp);
@@ -337,6 +382,8 @@ static int launch_conv(wwf_plan* p, const float* wav, int B, int N, int64_t wav_
   WWF_CUDA(cudaGetLastError());
   *rev = cp.rev;
   *rev_stride = cp.rev_stride;
+  *es_part = cp.es_part;
+  *es_nb = nb;
   return WWF_OK;
 }
 
@@ -363,7 +410,9 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
 
   float* rev = nullptr;
   int64_t rev_stride = 0;
-  if ((rc = launch_conv(p, wav, B, N, wav_stride, aug, workspace, workspace_bytes, st, &rev, &rev_stride))) return rc;
+  const float* es_part = nullptr;
+  int es_nb = 0;
+  if ((rc = launch_conv(p, wav, B, N, wav_stride, aug, workspace, workspace_bytes, st, &rev, &rev_stride, &es_part, &es_nb))) return rc;
 
   const bool mfcc = p->cfg.feature_type == WWF_FEAT_MFCC;
   const int pitch = T | 1;
@@ -392,7 +441,7 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
   int nwarps = 0, ctas_per_sm = 1, best = -1;
   const int cands[] = {16, 12, 11, 10, 8, 6, 4, 2, 1};
   for (int c : cands) {
-    if (p->feat_warps_override > 0 && c != p->feat_warps_override) continue;
+    if (c > p->max_warps || (p->feat_warps_override > 0 && c != p->feat_warps_override)) continue;
     const size_t sm = fixed_bytes + (size_t)c * per_warp;
     if (sm > budget) continue;
     int nb = 0;
@@ -414,11 +463,12 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
     fp.rir_idx = rev ? aug->rir_idx : nullptr;
     if (aug->noise_idx && p->n_noise > 0) {
       fp.noise_idx = aug->noise_idx; fp.noise_off = aug->noise_off; fp.snr_db = aug->snr_db;
-      fp.noise_data = p->noise_data; fp.noise_offsets = p->d_noise_offsets; fp.n_noise = p->n_noise;
+      fp.noise = p->noise_dev();
     }
     if (aug->fmask_start && aug->fmask_len && p->cfg.n_freq_masks > 0) { fp.fs = aug->fmask_start; fp.fl = aug->fmask_len; fp.nF = p->cfg.n_freq_masks; }
     if (aug->tmask_start && aug->tmask_len && p->cfg.n_time_masks > 0) { fp.ts = aug->tmask_start; fp.tl = aug->tmask_len; fp.nT = p->cfg.n_time_masks; }
   }
+  fp.es_part = es_part; fp.es_nb = es_nb;
   fp.out = out; fp.out_stride = out_stride;
   p->kernel<<<grid, nwarps * 32, smem, st>>>(fp);
   g_launches++;
@@ -436,7 +486,9 @@ extern "C" int wwf_augment(wwf_plan* p, const float* wav, int B, int N, int64_t 
   if (wants_reverb(p, aug) && out_wav == wav) return fail(WWF_ERR_INVALID, "wwf_augment: in-place is not allowed with reverb");
   float* rev = nullptr;
   int64_t rev_stride = 0;
-  int rc = launch_conv(p, wav, B, N, wav_stride, aug, workspace, workspace_bytes, st, &rev, &rev_stride);
+  const float* es_part = nullptr;
+  int es_nb = 0;
+  int rc = launch_conv(p, wav, B, N, wav_stride, aug, workspace, workspace_bytes, st, &rev, &rev_stride, &es_part, &es_nb);
   if (rc) return rc;
   MixParams mp{};
   mp.wav = wav; mp.wav_stride = wav_stride; mp.rev = rev; mp.rev_stride = rev_stride;
@@ -444,9 +496,10 @@ extern "C" int wwf_augment(wwf_plan* p, const float* wav, int B, int N, int64_t 
     mp.rir_idx = rev ? aug->rir_idx : nullptr;
     if (aug->noise_idx && p->n_noise > 0) {
       mp.noise_idx = aug->noise_idx; mp.noise_off = aug->noise_off; mp.snr_db = aug->snr_db;
-      mp.noise_data = p->noise_data; mp.noise_offsets = p->d_noise_offsets; mp.n_noise = p->n_noise;
+      mp.noise = p->noise_dev();
     }
   }
+  mp.es_part = es_part; mp.es_nb = es_nb;
   mp.out = out_wav; mp.out_stride = out_stride; mp.B = B; mp.N = N;
   mix_kernel<<<B, 512, 0, st>>>(mp);
   g_launches++;
