@@ -29,7 +29,6 @@ struct PadMap {
   WWF_HD int operator()(int i) const { return i + (i >> 4); }
 };
 constexpr int kConvSmemElems = kConvM + (kConvM >> 4);
-constexpr size_t kConvSmemBytes = (size_t)kConvSmemElems * sizeof(float2);
 
 // Pair-pass task v in [0, M/2] -> frequency k (k <= M/2) and its partner M-k.  Tasks are ordered
 // so that the 16 lanes of a half-warp touch 16 distinct 8-byte banks both at pos(k) and at
@@ -62,13 +61,20 @@ constexpr int kConvTw0 = 0;
 constexpr int kConvTw1 = kConvTw0 + ConvRad::S(0);
 constexpr int kConvTw2 = kConvTw1 + 15 * ConvRad::S(1);
 constexpr int kConvTwTotal = kConvTw2 + 15 * ConvRad::S(2);
+// dynamic shared memory: padded data array followed by a copy of the pass twiddle tables
+constexpr size_t kConvSmemBytes = (size_t)(kConvSmemElems + kConvTwTotal) * sizeof(float2);
+
+// copy the pass tables into shared memory (once per persistent CTA)
+__device__ __forceinline__ void conv_load_tables(float2* s_tw, const float2* __restrict__ tw) {
+  for (int i = threadIdx.x; i < kConvTwTotal; i += kConvThreads) s_tw[i] = __ldg(tw + i);
+}
 
 template <bool INV>
-__device__ __forceinline__ void conv_fft_passes(float2* z, const float2* __restrict__ tw) {
+__device__ __forceinline__ void conv_fft_passes(float2* z, const float2* tw) {   // tw: shared-memory copy
   const int tid = threadIdx.x;
   auto pass4 = [&]() {
     for (int u = tid; u < kConvM / 4; u += kConvThreads) {
-      const float2 w1 = __ldg(tw + kConvTw0 + u);
+      const float2 w1 = tw[kConvTw0 + u];
       const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
       pass_task<4, INV, PadMap>(z, ConvRad::L(0), u, [&](int q) {
         const int r = q / ConvRad::S(0);     // q = (r-1)*s + j
@@ -78,7 +84,7 @@ __device__ __forceinline__ void conv_fft_passes(float2* z, const float2* __restr
   };
   auto pass16 = [&](int L, const float2* t) {
     for (int u = tid; u < kConvM / 16; u += kConvThreads)
-      pass_task<16, INV, PadMap>(z, L, u, [&](int q) { return __ldg(t + q); });
+      pass_task<16, INV, PadMap>(z, L, u, [&](int q) { return t[q]; });
   };
   if constexpr (!INV) {
     pass4();                             __syncthreads();
@@ -131,67 +137,86 @@ WWF_HD void pair_inverse(float2 Yk, float2 Ym, float2 w, float2& Zk, float2& Zm)
   Zm = make_float2(Ue.x + Uo.y, Uo.x - Ue.y);    // conj(Ue) + i conj(Uo)
 }
 
-__global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams p) {
-  extern __shared__ __align__(16) float2 zc[];
-  const int b = blockIdx.y, blk = blockIdx.x;
-  const int r = __ldg(p.rir_idx + b);
-  if (r < 0 || r >= p.n_rir) return;
-  const float* x = p.wav + (size_t)b * p.wav_stride;
-  const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-  const int start = blk * p.valid - p.hist;
-  conv_load_block(zc, x, p.N, start, vec_ok);
-  __syncthreads();
-  conv_fft_passes<false>(zc, p.tw);
-
+// The (k, M-k) pass of one block: 16 pair tasks per thread, global operands (pair twiddle, RIR
+// spectrum) fetched four tasks ahead of their use.
+__device__ __forceinline__ void conv_pair_pass(float2* zc, const float4* __restrict__ spec, const float2* __restrict__ tw_pair) {
   PadMap pad;
-  const float4* spec = p.spec + (size_t)r * (kConvPairTasks + 1);
-  for (int v = threadIdx.x; v <= kConvPairTasks; v += kConvThreads) {
+  auto one = [&](int v, float2 w, float4 h) {
     const int k = pair_task_k(v);
     const int pk = pad(ConvRad::pos(k)), pm = pad(ConvRad::pos((kConvM - k) & (kConvM - 1)));
-    const float2 w = __ldg(p.tw_pair + v);
-    const float4 h = __ldg(spec + v);
     float2 R2k, R2m, Zk, Zm;
     pair_forward(zc[pk], zc[pm], w, R2k, R2m);
     pair_inverse(cmul(R2k, make_float2(h.x, h.y)), cmul(R2m, make_float2(h.z, h.w)), w, Zk, Zm);
     zc[pm] = Zm;
     zc[pk] = Zk;   // k == 0 and k == M/2 are self-paired: Zk == Zm there
-  }
-  __syncthreads();
-  conv_fft_passes<true>(zc, p.tw);
-
-  // store the valid outputs: block sample i in [hist, P) -> clip sample blk*valid + i - hist
-  float* y = p.rev + (size_t)b * p.rev_stride;
-  const bool st_ok = ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
-  float e0 = 0.f, e1 = 0.f;
-  for (int q = threadIdx.x; q < kConvP / 4; q += kConvThreads) {
-    const int i = 4 * q;
-    if (i < p.hist) continue;
-    const int n = blk * p.valid + i - p.hist;
-    if (n >= p.N) continue;
-    const float2 a = zc[pad(2 * q)], c = zc[pad(2 * q + 1)];
-    if (n + 3 < p.N && st_ok) {
-      *reinterpret_cast<float4*>(y + n) = make_float4(a.x, a.y, c.x, c.y);
-      e0 = fmaf(a.x, a.x, fmaf(a.y, a.y, e0));
-      e1 = fmaf(c.x, c.x, fmaf(c.y, c.y, e1));
-    } else {
-      y[n] = a.x; e0 = fmaf(a.x, a.x, e0);
-      if (n + 1 < p.N) { y[n + 1] = a.y; e0 = fmaf(a.y, a.y, e0); }
-      if (n + 2 < p.N) { y[n + 2] = c.x; e1 = fmaf(c.x, c.x, e1); }
-      if (n + 3 < p.N) { y[n + 3] = c.y; e1 = fmaf(c.y, c.y, e1); }
-    }
-  }
-  // energy of this block's output samples, for the SNR mix that follows (fixed reduction order)
-  __shared__ float red[kConvThreads / 32];
-  float e = e0 + e1;
+  };
+  static_assert(kConvPairTasks % (4 * kConvThreads) == 0, "pair pass unroll");
+  for (int v0 = threadIdx.x; v0 < kConvPairTasks; v0 += 4 * kConvThreads) {
+    float2 w[4];
+    float4 h[4];
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    e = threadIdx.x < kConvThreads / 32 ? red[threadIdx.x] : 0.f;
+    for (int u = 0; u < 4; ++u) { w[u] = __ldg(tw_pair + v0 + u * kConvThreads); h[u] = __ldg(spec + v0 + u * kConvThreads); }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) one(v0 + u * kConvThreads, w[u], h[u]);
+  }
+  if (threadIdx.x == 0) one(kConvPairTasks, __ldg(tw_pair + kConvPairTasks), __ldg(spec + kConvPairTasks));
+}
+
+// Persistent: grid = min(#SMs, work items); work item = (clip b, overlap-save block blk).
+__global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams p) {
+  extern __shared__ __align__(16) float2 zc[];
+  __shared__ float red[kConvThreads / 32];
+  float2* s_tw = zc + kConvSmemElems;
+  conv_load_tables(s_tw, p.tw);
+  PadMap pad;
+  const int nblk = p.es_nb;
+  for (int item = blockIdx.x; item < p.B * nblk; item += gridDim.x) {
+    const int b = item / nblk, blk = item - b * nblk;
+    const int r = __ldg(p.rir_idx + b);
+    if (r < 0 || r >= p.n_rir) continue;                     // dry clip (CTA-uniform)
+    const float* x = p.wav + (size_t)b * p.wav_stride;
+    const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    __syncthreads();                                          // previous item's stores / table copy done
+    conv_load_block(zc, x, p.N, blk * p.valid - p.hist, vec_ok);
+    __syncthreads();
+    conv_fft_passes<false>(zc, s_tw);
+    conv_pair_pass(zc, p.spec + (size_t)r * (kConvPairTasks + 1), p.tw_pair);
+    __syncthreads();
+    conv_fft_passes<true>(zc, s_tw);
+
+    // store the valid outputs: block sample i in [hist, P) -> clip sample blk*valid + i - hist
+    float* y = p.rev + (size_t)b * p.rev_stride;
+    const bool st_ok = ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    float e0 = 0.f, e1 = 0.f;
+    for (int q = threadIdx.x; q < kConvP / 4; q += kConvThreads) {
+      const int i = 4 * q;
+      if (i < p.hist) continue;
+      const int n = blk * p.valid + i - p.hist;
+      if (n >= p.N) continue;
+      const float2 a = zc[pad(2 * q)], c = zc[pad(2 * q + 1)];
+      if (n + 3 < p.N && st_ok) {
+        *reinterpret_cast<float4*>(y + n) = make_float4(a.x, a.y, c.x, c.y);
+        e0 = fmaf(a.x, a.x, fmaf(a.y, a.y, e0));
+        e1 = fmaf(c.x, c.x, fmaf(c.y, c.y, e1));
+      } else {
+        y[n] = a.x; e0 = fmaf(a.x, a.x, e0);
+        if (n + 1 < p.N) { y[n + 1] = a.y; e0 = fmaf(a.y, a.y, e0); }
+        if (n + 2 < p.N) { y[n + 2] = c.x; e1 = fmaf(c.x, c.x, e1); }
+        if (n + 3 < p.N) { y[n + 3] = c.y; e1 = fmaf(c.y, c.y, e1); }
+      }
+    }
+    // energy of this block's output samples, for the SNR mix that follows (fixed reduction order)
+    float e = e0 + e1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-    if (threadIdx.x == 0 && p.es_part != nullptr) p.es_part[(size_t)b * p.es_nb + blk] = e;
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      e = threadIdx.x < kConvThreads / 32 ? red[threadIdx.x] : 0.f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+      if (threadIdx.x == 0 && p.es_part != nullptr) p.es_part[(size_t)b * nblk + blk] = e;
+    }
   }
 }
 
@@ -209,9 +234,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) rir_spectrum_kernel(const Spe
   const int r = blockIdx.x;
   const int64_t o0 = p.offsets[r], o1 = p.offsets[r + 1];
   const float* h = p.data + o0;
+  float2* s_tw = zc + kConvSmemElems;
+  conv_load_tables(s_tw, p.tw);
   conv_load_block(zc, h, (int)(o1 - o0), 0, false);
   __syncthreads();
-  conv_fft_passes<false>(zc, p.tw);
+  conv_fft_passes<false>(zc, s_tw);
   PadMap pad;
   const float sc = 1.0f / (8.0f * (float)kConvM);
   float4* spec = p.spec + (size_t)r * (kConvPairTasks + 1);

@@ -124,6 +124,12 @@ __device__ __forceinline__ float noise_at(const float* nz, int noff, int nlen, i
   return __ldg(nz + q);
 }
 
+// 10*log10(max(x, 1e-10)) = (10/log2(10)) * log2(.) through MUFU.LG2 (lg2.approx: max abs error
+// 2^-22.6 on log2 => < 5e-7 dB; the argument is >= 1e-10, never denormal).
+__device__ __forceinline__ float power_to_db(float x) {
+  return x > 1e-10f ? 3.01029995663981195f * __log2f(x) : -100.0f;   // the clamp value is exact, like the oracle's
+}
+
 // scale of F.add_noise (TA/functional/functional.py:2376-2378), float32 like the oracle
 __device__ __forceinline__ float snr_scale(float es, float en, float snr_db) {
   const float snr0 = 10.0f * (log10f(es) - log10f(en));
@@ -296,6 +302,7 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
 
     // ---- frames: STFT -> power -> mel -> dB into the tile (warp-autonomous) --------------
     const int ngroups = (T + 2 * G - 1) / (2 * G);
+    float vmax = -INFINITY;                                  // running maximum of the dB values this lane wrote
     for (int grp = warp; grp < ngroups; grp += nwarps) {
       const int f0 = grp * 2 * G;
       // 1. load + window: z[g][j] = w[j] * (frame(f0+2g)[j] + i frame(f0+2g+1)[j])
@@ -427,26 +434,20 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           const int ta = f0 + 2 * g;
-          if (ta < T) tile[m * pitch + ta] = 10.0f * log10f(fmaxf(acc[g].x, 1e-10f));
-          if (ta + 1 < T) tile[m * pitch + ta + 1] = 10.0f * log10f(fmaxf(acc[g].y, 1e-10f));
+          if (ta < T) { const float d = power_to_db(acc[g].x); tile[m * pitch + ta] = d; vmax = fmaxf(vmax, d); }
+          if (ta + 1 < T) { const float d = power_to_db(acc[g].y); tile[m * pitch + ta + 1] = d; vmax = fmaxf(vmax, d); }
         }
       }
       __syncwarp();
     }
+    // ---- per-clip top_db floor: max over the tile, gathered while it was written ------------
+    vmax = warp_max(vmax);
+    if (lane == 0) red[warp] = vmax;
     __syncthreads();
-
-    // ---- per-clip top_db floor -----------------------------------------------------------
     float cutoff = -INFINITY;
     if (p.top_db >= 0.f) {
-      float mx = -INFINITY;
-      for (int m = warp; m < M; m += nwarps)
-        for (int t = lane; t < T; t += 32) mx = fmaxf(mx, tile[m * pitch + t]);
-      mx = warp_max(mx);
-      if (lane == 0) red[warp] = mx;
-      __syncthreads();
-      mx = lane < nwarps ? red[lane] : -INFINITY;
-      mx = warp_max(mx);
-      cutoff = mx - p.top_db;
+      float mx = lane < nwarps ? red[lane] : -INFINITY;
+      cutoff = warp_max(mx) - p.top_db;
     }
 
     OutT* out = reinterpret_cast<OutT*>(p.out) + (size_t)b * p.out_stride;

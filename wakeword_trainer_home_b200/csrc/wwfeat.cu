@@ -376,7 +376,7 @@ static int launch_conv(wwf_plan* p, const float* wav, int B, int N, int64_t wav_
   cp.es_part = cp.rev + (size_t)B * cp.rev_stride;
   cp.es_nb = nb;
   cp.spec = p->d_spec; cp.tw = p->d_conv_tw; cp.tw_pair = p->d_conv_tw_pair;
-  dim3 grid(nb, B);
+  int grid = nb * B < p->sm_count ? nb * B : p->sm_count;
   conv_kernel<<<grid, kConvThreads, kConvSmemBytes, st>>>(cp);
   g_launches++;
   WWF_CUDA(cudaGetLastError());
