@@ -126,10 +126,12 @@ def log_mel(x, sample_rate, n_fft, hop_length, n_mels, top_db=80.0, f_min=0.0, f
     return amplitude_to_db(mel, top_db)
 
 
-def mfcc(x, sample_rate, n_fft, hop_length, n_mels, n_mfcc, top_db=80.0, dtype=np.float64, **kw):
-    """MFCC(log_mels=False, norm='ortho'): DCT-II of the dB mel, TA/transforms/_transforms.py:672-719."""
+def mfcc(x, sample_rate, n_fft, hop_length, n_mels, n_mfcc, top_db=80.0, dtype=np.float64, dct=None, **kw):
+    """MFCC(log_mels=False, norm='ortho'): DCT-II of the dB mel, TA/transforms/_transforms.py:672-719.
+    ``dct`` may inject torchaudio's float32 matrix: its cos() of arguments up to ~120 rad is only
+    good to ~1.3e-6, which times |dB| ~ 100 over n_mels terms is visible at the 1e-3 level."""
     mel_db = log_mel(x, sample_rate, n_fft, hop_length, n_mels, top_db, dtype=dtype, **kw)
-    dct = create_dct(n_mfcc, n_mels, dtype)
+    dct = create_dct(n_mfcc, n_mels, dtype) if dct is None else np.asarray(dct).astype(dtype)
     return np.einsum("bmt,mc->bct", mel_db, dct).astype(dtype)
 
 
@@ -214,12 +216,13 @@ def spec_mask(feat: np.ndarray, fstart=None, flen=None, tstart=None, tlen=None, 
 
 
 def features(x, *, sample_rate=16000, feature_type="mel", n_mels=128, n_mfcc=40, n_fft=1024,
-             hop_length=160, top_db=80.0, use_cmvn=False, cmvn_eps=1e-5, dtype=np.float64, fb=None, window=None):
+             hop_length=160, top_db=80.0, use_cmvn=False, cmvn_eps=1e-5, dtype=np.float64, fb=None, window=None,
+             dct=None):
     """FeatureExtractor.__call__ arithmetic on a batch: (B, N) -> (B, 1, F, T)."""
     if feature_type in ("mel", "mel_spectrogram"):
         f = log_mel(x, sample_rate, n_fft, hop_length, n_mels, top_db, dtype=dtype, fb=fb, window=window)
     elif feature_type == "mfcc":
-        f = mfcc(x, sample_rate, n_fft, hop_length, n_mels, n_mfcc, top_db, dtype=dtype, fb=fb, window=window)
+        f = mfcc(x, sample_rate, n_fft, hop_length, n_mels, n_mfcc, top_db, dtype=dtype, dct=dct, fb=fb, window=window)
     else:
         raise ValueError(f"unknown feature_type {feature_type!r}")
     if use_cmvn:

@@ -1,0 +1,31 @@
+"""Clip-index sharding of a global batch across ranks (one process per GPU).
+
+The feature path has no exchange step: every clip is independent (per-clip top_db maximum,
+per-clip energies, per-clip masks), so ranks just take disjoint index ranges - the same
+partition torch's DistributedSampler would give a DDP trainer - and no collective is issued.
+"""
+from __future__ import annotations
+
+import os
+from typing import Tuple
+
+
+def rank_world() -> Tuple[int, int, int]:
+    """(rank, local_rank, world_size) from the torchrun environment (1-process defaults)."""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
+            int(os.environ.get("WORLD_SIZE", "1")))
+
+
+def shard_range(n_items: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous [start, stop) of `n_items` owned by `rank`; sizes differ by at most one."""
+    if not (0 <= rank < world):
+        raise ValueError(f"rank {rank} outside world of {world}")
+    base, extra = divmod(n_items, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_seed(seed: int, rank: int, step: int = 0) -> int:
+    """Distinct, reproducible RNG seed per (run seed, rank, step) for the augmentation draws;
+    saving (seed, step) is all a resumed run needs to redraw the same augmentations."""
+    return (seed * 1_000_003 + rank * 7919 + step * 104_729) % (2 ** 63 - 1)
