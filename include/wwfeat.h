@@ -175,6 +175,15 @@ int wwf_spec_augment(void* spec, int dtype, int B, int F, int T, int64_t clip_st
                      const int32_t* tmask_start, const int32_t* tmask_len, int n_time_masks,
                      float mask_value, int device, void* stream);
 
+/*
+ * Measurement hook (bench.py's roofline): when enabled, wwf_featurize brackets each of its
+ * kernels with CUDA events on the launching stream.  wwf_profile_read waits for them, returns
+ * the AVERAGE duration (ms) of the reverb kernel and of the feature kernel per call since the
+ * last read plus the number of calls, and resets the counters.  Off by default.
+ */
+int wwf_profile_enable(wwf_plan* plan, int enable);
+int wwf_profile_read(wwf_plan* plan, double* conv_ms, double* feat_ms, int* n_calls);
+
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 int64_t wwf_launch_count(void);
 

@@ -9,7 +9,10 @@ from ._native import WwfError, LIB_PATH, launch_count  # noqa: F401
 from .pipeline import AugParams, FeaturePlan, draw_mask_params, spec_augment_  # noqa: F401
 from .feature_extraction import FeatureExtractor  # noqa: F401
 from .augmentation import AudioAugmentation, SpecAugment  # noqa: F401
+from .loader import GpuBatchLoader, StreamedFeaturizer  # noqa: F401
+from .sharding import shard_range, shard_seed  # noqa: F401
 
 __version__ = "0.1.0"
 __all__ = ["FeatureExtractor", "AudioAugmentation", "SpecAugment", "FeaturePlan", "AugParams",
-           "draw_mask_params", "spec_augment_", "WwfError", "launch_count"]
+           "draw_mask_params", "spec_augment_", "WwfError", "launch_count", "GpuBatchLoader", "StreamedFeaturizer",
+           "shard_range", "shard_seed"]

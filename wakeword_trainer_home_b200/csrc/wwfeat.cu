@@ -81,6 +81,9 @@ struct wwf_plan {
   float2* d_conv_tw_pair = nullptr;
   int n_rir = 0, rir_max_len = 0;
   int feat_warps_override = 0;
+  // optional per-kernel timing (wwf_profile_enable)
+  bool prof = false;
+  std::vector<cudaEvent_t> prof_events;   // triples: before conv, between, after feat
 };
 
 template <typename T>
@@ -120,6 +123,7 @@ extern "C" void wwf_plan_destroy(wwf_plan* p) {
   cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_mel_lo); cudaFree(p->d_mel_ofs);
   cudaFree(p->d_mel_w); cudaFree(p->d_dct); cudaFree(p->d_noise_offsets); cudaFree(p->d_spec);
   cudaFree(p->d_noise_prefix); cudaFree(p->d_noise_prefix_offsets);
+  for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
   cudaFree(p->d_conv_tw); cudaFree(p->d_conv_tw_pair);
   delete p;
 }
@@ -218,6 +222,32 @@ extern "C" int wwf_plan_create(const wwf_config* cfg, int device, wwf_plan** out
     return fail(WWF_ERR_CUDA, "cudaFuncSetAttribute(feat_kernel): %s (is libwwfeat.so built for this GPU?)", cudaGetErrorString(e));
   }
   *out = p;
+  return WWF_OK;
+}
+
+extern "C" int wwf_profile_enable(wwf_plan* p, int enable) {
+  if (!p) return fail(WWF_ERR_INVALID, "wwf_profile_enable: null plan");
+  p->prof = enable != 0;
+  return WWF_OK;
+}
+
+extern "C" int wwf_profile_read(wwf_plan* p, double* conv_ms, double* feat_ms, int* n_calls) {
+  if (!p || !conv_ms || !feat_ms || !n_calls) return fail(WWF_ERR_INVALID, "wwf_profile_read: null argument");
+  DeviceGuard guard(p->device);
+  const int n = (int)(p->prof_events.size() / 3);
+  double c = 0.0, f = 0.0;
+  cudaError_t err = cudaSuccess;
+  for (int i = 0; i < n && err == cudaSuccess; ++i) {
+    float a = 0.f, b = 0.f;
+    err = cudaEventSynchronize(p->prof_events[3 * i + 2]);
+    if (err == cudaSuccess) err = cudaEventElapsedTime(&a, p->prof_events[3 * i], p->prof_events[3 * i + 1]);
+    if (err == cudaSuccess) err = cudaEventElapsedTime(&b, p->prof_events[3 * i + 1], p->prof_events[3 * i + 2]);
+    c += a; f += b;
+  }
+  for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
+  p->prof_events.clear();
+  if (err != cudaSuccess) return fail(WWF_ERR_CUDA, "wwf_profile_read: %s", cudaGetErrorString(err));
+  *conv_ms = n ? c / n : 0.0; *feat_ms = n ? f / n : 0.0; *n_calls = n;
   return WWF_OK;
 }
 
@@ -408,11 +438,17 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
   if (!guard.ok) return fail(WWF_ERR_CUDA, "cudaSetDevice(%d) failed", p->device);
   cudaStream_t st = (cudaStream_t)stream;
 
+  cudaEvent_t pe[3] = {nullptr, nullptr, nullptr};
+  if (p->prof) {
+    for (auto& e : pe) WWF_CUDA(cudaEventCreate(&e));
+    WWF_CUDA(cudaEventRecord(pe[0], st));
+  }
   float* rev = nullptr;
   int64_t rev_stride = 0;
   const float* es_part = nullptr;
   int es_nb = 0;
   if ((rc = launch_conv(p, wav, B, N, wav_stride, aug, workspace, workspace_bytes, st, &rev, &rev_stride, &es_part, &es_nb))) return rc;
+  if (p->prof) WWF_CUDA(cudaEventRecord(pe[1], st));
 
   const bool mfcc = p->cfg.feature_type == WWF_FEAT_MFCC;
   const int pitch = T | 1;
@@ -473,6 +509,10 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
   p->kernel<<<grid, nwarps * 32, smem, st>>>(fp);
   g_launches++;
   WWF_CUDA(cudaGetLastError());
+  if (p->prof) {
+    WWF_CUDA(cudaEventRecord(pe[2], st));
+    p->prof_events.insert(p->prof_events.end(), pe, pe + 3);
+  }
   return WWF_OK;
 }
 

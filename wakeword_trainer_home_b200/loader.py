@@ -1,0 +1,139 @@
+"""Host-fed streaming front end of the feature path and the batched loader that replaces the
+reference's ``WakewordDataset`` + ``DataLoader`` pair.
+
+``StreamedFeaturizer`` keeps the GPU busy when clips live in HOST memory: a copy stream uploads
+batch i+1 (pinned clips + augmentation draws) while the compute stream featurizes batch i and a
+third stream downloads the features of batch i-1.  It is plain use of the public
+``FeaturePlan.featurize`` call on torch streams - the end-to-end path bench.py times.
+
+``GpuBatchLoader`` iterates ``(inputs, targets)`` exactly like the object the reference's
+``Trainer.train_epoch`` consumes (src/training/trainer.py:147-157): one fused GPU pass per batch
+instead of 16 DataLoader workers calling torchaudio per sample (src/ui/panel_training.py:342-349).
+It shards clip indices across ranks (no collective) and redraws augmentations from
+``shard_seed(seed, rank, step)`` so a resumed run reproduces them.
+"""
+from __future__ import annotations
+
+from typing import Callable, Iterable, Iterator, Optional, Tuple
+
+import torch
+
+from .pipeline import AugParams, FeaturePlan, draw_mask_params
+from .sharding import shard_range, shard_seed
+
+
+class StreamedFeaturizer:
+    """Double-buffered host -> device -> host featurization through ``FeaturePlan.featurize``."""
+
+    def __init__(self, plan: FeaturePlan, batch: int, n_samples: int, depth: int = 2, copy_back: bool = True):
+        self.plan, self.depth, self.copy_back = plan, depth, copy_back
+        dev = plan.device
+        T = plan.num_frames(n_samples)
+        self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
+        self.d_wav = [torch.empty(batch, n_samples, dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.d_out = [torch.empty(batch, 1, plan.n_feat, T, dtype=plan.out_dtype, device=dev) for _ in range(depth)]
+        self.h_out = [torch.empty(batch, 1, plan.n_feat, T, dtype=plan.out_dtype).pin_memory() for _ in range(depth)] if copy_back else None
+        self.ev_in = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_run = [torch.cuda.Event() for _ in range(depth)]
+        self.ev_out = [torch.cuda.Event() for _ in range(depth)]
+        self.n = 0
+
+    def submit(self, host_wav: torch.Tensor, host_aug: Optional[AugParams]) -> int:
+        """Queue one batch (pinned host clips + host draws).  Returns its slot; the features are
+        in ``d_out[slot]`` after ``ev_run[slot]`` and in ``h_out[slot]`` after ``ev_out[slot]``."""
+        k = self.n % self.depth
+        self.n += 1
+        with torch.cuda.stream(self.s_in):
+            self.s_in.wait_event(self.ev_run[k])          # previous use of this input slot has been consumed
+            self.d_wav[k].copy_(host_wav, non_blocking=True)
+            aug = None if host_aug is None else host_aug.to(self.plan.device, non_blocking=True)
+            self.ev_in[k].record(self.s_in)
+        with torch.cuda.stream(self.s_run):
+            self.s_run.wait_event(self.ev_in[k])
+            self.s_run.wait_event(self.ev_out[k])         # previous features of this slot have left
+            self.plan.featurize(self.d_wav[k], aug, out=self.d_out[k])
+            if aug is not None:                           # keep the draw tensors alive until the kernel ran
+                for f in ("rir_idx", "noise_idx", "noise_off", "snr_db", "fmask_start", "fmask_len", "tmask_start", "tmask_len"):
+                    v = getattr(aug, f)
+                    if v is not None:
+                        v.record_stream(self.s_run)
+            self.ev_run[k].record(self.s_run)
+        if self.copy_back:
+            with torch.cuda.stream(self.s_out):
+                self.s_out.wait_event(self.ev_run[k])
+                self.h_out[k].copy_(self.d_out[k], non_blocking=True)
+                self.ev_out[k].record(self.s_out)
+        return k
+
+    def wait(self, slot: int) -> torch.Tensor:
+        (self.ev_out if self.copy_back else self.ev_run)[slot].synchronize()
+        return self.h_out[slot] if self.copy_back else self.d_out[slot]
+
+    def synchronize(self):
+        for s in (self.s_in, self.s_run, self.s_out):
+            s.synchronize()
+
+
+class GpuBatchLoader:
+    """``for inputs, targets in loader`` over an in-memory clip set, features computed on the GPU.
+
+    clips    (n, N) float32, pinned host or device-resident
+    labels   (n,) integer targets
+    augment  optional ``AudioAugmentation``-like object with ``draw(B) -> AugParams``
+    spec_augment optional ``SpecAugment``-like object with ``draw(B, F, T) -> AugParams``;
+             its ``n_freq_masks / n_time_masks`` must match the plan's
+    """
+
+    def __init__(self, clips: torch.Tensor, labels: torch.Tensor, plan: FeaturePlan, batch_size: int,
+                 augment=None, spec_augment=None, shuffle: bool = True, seed: int = 0, rank: int = 0,
+                 world_size: int = 1, drop_last: bool = False):
+        if clips.dim() != 2 or labels.shape[0] != clips.shape[0]:
+            raise ValueError("clips must be (n, N) and labels (n,)")
+        self.clips, self.labels, self.plan = clips, labels, plan
+        self.batch_size, self.shuffle, self.seed = batch_size, shuffle, seed
+        self.rank, self.world, self.drop_last = rank, world_size, drop_last
+        self.augment, self.spec_augment = augment, spec_augment
+        self.epoch = 0
+        self.step = 0
+
+    def set_epoch(self, epoch: int):
+        self.epoch = epoch
+
+    def _indices(self) -> torch.Tensor:
+        n = self.clips.shape[0]
+        if self.shuffle:
+            g = torch.Generator().manual_seed(self.seed + self.epoch)     # same permutation on every rank
+            perm = torch.randperm(n, generator=g)
+        else:
+            perm = torch.arange(n)
+        a, b = shard_range(n, self.rank, self.world)
+        return perm[a:b]
+
+    def __len__(self) -> int:
+        a, b = shard_range(self.clips.shape[0], self.rank, self.world)
+        n = b - a
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+        idx = self._indices()
+        dev = self.plan.device
+        on_dev = self.clips.is_cuda
+        for i in range(len(self)):
+            sel = idx[i * self.batch_size:(i + 1) * self.batch_size]
+            B = sel.numel()
+            wav = self.clips.index_select(0, sel.to(self.clips.device))
+            if not on_dev:
+                wav = wav.pin_memory().to(dev, non_blocking=True)
+            g = torch.Generator().manual_seed(shard_seed(self.seed, self.rank, self.step))
+            aug = None
+            if self.augment is not None:
+                self.augment.gen = g
+                aug = self.augment.draw(B)
+            if self.spec_augment is not None:
+                self.spec_augment.gen = g
+                m = self.spec_augment.draw(B, self.plan.n_feat, self.plan.num_frames(wav.shape[1]))
+                aug = aug or AugParams()
+                aug.fmask_start, aug.fmask_len, aug.tmask_start, aug.tmask_len = m.fmask_start, m.fmask_len, m.tmask_start, m.tmask_len
+            self.step += 1
+            feats = self.plan.featurize(wav, aug)
+            yield feats, self.labels.index_select(0, sel.to(self.labels.device)).to(dev, non_blocking=True)

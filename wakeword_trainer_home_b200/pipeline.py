@@ -164,6 +164,16 @@ class FeaturePlan:
         N.check(self.lib.wwf_plan_info(self._handle, C.byref(info)))
         return info
 
+    # ------------------------------------------------------------------ measurement hook
+    def profile(self, enable: bool = True):
+        N.check(self.lib.wwf_profile_enable(self._handle, int(enable)))
+
+    def profile_read(self):
+        """(avg reverb-kernel ms, avg feature-kernel ms, calls) since the last read."""
+        c, f, n = C.c_double(), C.c_double(), C.c_int()
+        N.check(self.lib.wwf_profile_read(self._handle, C.byref(c), C.byref(f), C.byref(n)))
+        return c.value, f.value, n.value
+
     # ------------------------------------------------------------------ banks
     def _register(self, kind: int, clips: Sequence[torch.Tensor]):
         flat, offs = _flatten_bank(clips, self.device)
