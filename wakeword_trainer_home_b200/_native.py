@@ -11,7 +11,7 @@ import ctypes as C
 import os
 
 LIB_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "lib")
-LIB_PATH = os.path.join(LIB_DIR, "libwwfeat.so")
+LIB_PATH = os.environ.get("WWF_LIB", os.path.join(LIB_DIR, "libwwfeat.so"))   # WWF_LIB: A/B-test another build
 
 WWF_OK = 0
 FEAT_LOGMEL, FEAT_MFCC = 0, 1

@@ -156,7 +156,7 @@ __device__ __forceinline__ ClipNoise resolve_noise(const NoiseBankDev& bank, con
 
 // sum of nz[q]^2 over [a, b), 0 <= a <= b <= len: prefix table for whole 128-blocks, direct sum
 // of the (< 128-sample) edges.  Executed by a full warp; every lane returns the result.
-__device__ __forceinline__ double warp_seg_energy(const ClipNoise& c, int a, int b) {
+__device__ __noinline__ double warp_seg_energy(const ClipNoise& c, int a, int b) {
   const int lane = threadIdx.x & 31;
   const int lo = (a + kNoiseBlk - 1) / kNoiseBlk, hi = b / kNoiseBlk;
   float e = 0.f;
@@ -187,7 +187,7 @@ __device__ __forceinline__ float warp_noise_energy(const ClipNoise& c, int N) {
 
 // Block-wide sum of x[i]^2, i < N (8 independent loads in flight per thread); result in all
 // threads.  red: >= 32 floats of shared memory.  Contains __syncthreads().
-__device__ __forceinline__ float block_energy(const float* __restrict__ x, int N, float* red) {
+__device__ __noinline__ float block_energy(const float* __restrict__ x, int N, float* red) {
   const int tid = threadIdx.x, nt = blockDim.x;
   float acc[8];
 #pragma unroll
@@ -306,52 +306,50 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
     for (int grp = warp; grp < ngroups; grp += nwarps) {
       const int f0 = grp * 2 * G;
       // 1. load + window: z[g][j] = w[j] * (frame(f0+2g)[j] + i frame(f0+2g+1)[j])
+      bool staged = false;
       if constexpr (HOP32 > 0) {
         constexpr int NR = (2 * G - 1) * HOP32 + NC;         // registers holding the group's sample span
-        float sreg[NR];
         const int s0 = f0 * hop - NFFT / 2;
-        const bool interior = s0 >= 0 && s0 + 32 * NR <= N;
-        if (interior) {
+        int q0 = 0;                                          // first noise sample of the span (mix only)
+        if (mix && s0 >= 0) { q0 = noff + s0; if (q0 >= nlen) q0 %= nlen; }
+        // fast path: the whole span is inside the clip (no reflection); the noise segment may wrap
+        // around the end of its clip once (needs a noise clip at least as long as the span)
+        if (s0 >= 0 && s0 + 32 * NR <= N && f0 + 2 * G <= T && (!mix || (q0 >= 0 && nlen >= 32 * NR))) {
+          staged = true;
+          float sreg[NR];
           const float* xs = x + s0 + lane;
 #pragma unroll
           for (int r = 0; r < NR; ++r) sreg[r] = __ldg(xs + 32 * r);
           if (mix) {
-            int q0 = noff + s0;                              // < 2 nlen
-            if (q0 >= nlen) q0 -= nlen;
             if (q0 + 32 * NR <= nlen) {
               const float* ns = nz + q0 + lane;
 #pragma unroll
               for (int r = 0; r < NR; ++r) sreg[r] = fmaf(scale, __ldg(ns + 32 * r), sreg[r]);
             } else {
 #pragma unroll
-              for (int r = 0; r < NR; ++r) sreg[r] = fmaf(scale, noise_at(nz, noff, nlen, s0 + 32 * r + lane), sreg[r]);
+              for (int r = 0; r < NR; ++r) {
+                int q = q0 + 32 * r + lane;
+                q -= q >= nlen ? nlen : 0;
+                sreg[r] = fmaf(scale, __ldg(nz + q), sreg[r]);
+              }
             }
           }
-        } else {
 #pragma unroll
-          for (int r = 0; r < NR; ++r) {
-            const int i = reflect_index(s0 + 32 * r + lane, N);
-            float v = 0.f;
-            if (i >= 0 && i < N) {                           // beyond the reflected range only in frames >= T
-              v = __ldg(x + i);
-              if (mix) v = fmaf(scale, noise_at(nz, noff, nlen, i), v);
-            }
-            sreg[r] = v;
-          }
-        }
+          for (int c = 0; c < NC; ++c) {
+            const int j = 32 * c + lane;
+            if (NFFT % 32 == 0 || j < NFFT) {
+              const float w = s_window[j];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) {
-          const int j = 32 * c + lane;
-          if (NFFT % 32 == 0 || j < NFFT) {
-            const float w = s_window[j];
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-              const bool va = f0 + 2 * g < T, vb = f0 + 2 * g + 1 < T;
-              z[g * NFFT + j] = make_float2(va ? w * sreg[2 * g * HOP32 + c] : 0.f, vb ? w * sreg[(2 * g + 1) * HOP32 + c] : 0.f);
+              for (int g = 0; g < G; ++g)
+                z[g * NFFT + j] = make_float2(w * sreg[2 * g * HOP32 + c], w * sreg[(2 * g + 1) * HOP32 + c]);
             }
           }
         }
-      } else {
+      }
+      if (!staged) {
+        // boundary groups (reflect padding, frames >= T, wrapping noise) and hops that are not a
+        // multiple of 32: plain per-element gather, deliberately not unrolled (cold code)
+#pragma unroll 1
         for (int idx = lane; idx < G * NFFT; idx += 32) {
           const int g = idx / NFFT, j = idx - g * NFFT;
           const int ta = f0 + 2 * g, tb = ta + 1;
@@ -376,6 +374,7 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
         constexpr int i = decltype(I)::value;
         constexpr int R = Rad::R(i), L = Rad::L(i), tasks = NFFT / R;
         const float2* tw = s_tw + Rad::tw_off(i);
+#pragma unroll 1   // one copy of each radix butterfly: the hot loop has to stay inside the instruction cache
         for (int u = lane; u < G * tasks; u += 32) {
           const int g = u / tasks, uu = u - g * tasks;
           pass_task<R, false>(z + g * NFFT, L, uu, [&](int q) { return tw[q]; });
