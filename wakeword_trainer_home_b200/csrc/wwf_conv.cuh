@@ -100,21 +100,30 @@ __device__ __forceinline__ void conv_fft_passes(float2* z, const float2* tw) {  
 }
 
 // Load one block of P reals (clip samples [start, start+P), zero outside [0, N)) as M complex.
+// All 16 float4 loads of a thread are issued before the first shared-memory store, so the
+// HBM latency is paid once per block instead of once per load.
 __device__ __forceinline__ void conv_load_block(float2* z, const float* __restrict__ x, int N, int start, bool vec_ok) {
   PadMap pad;
-  for (int q = threadIdx.x; q < kConvP / 4; q += kConvThreads) {
-    const int n = start + 4 * q;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  constexpr int kPer = kConvP / 4 / kConvThreads;     // float4 per thread
+  float4 v[kPer];
+#pragma unroll
+  for (int u = 0; u < kPer; ++u) {
+    const int n = start + 4 * (threadIdx.x + u * kConvThreads);
+    v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (n >= 0 && n + 3 < N && vec_ok) {
-      v = __ldg(reinterpret_cast<const float4*>(x + n));
-    } else {
-      if (n >= 0 && n < N) v.x = __ldg(x + n);
-      if (n + 1 >= 0 && n + 1 < N) v.y = __ldg(x + n + 1);
-      if (n + 2 >= 0 && n + 2 < N) v.z = __ldg(x + n + 2);
-      if (n + 3 >= 0 && n + 3 < N) v.w = __ldg(x + n + 3);
+      v[u] = __ldg(reinterpret_cast<const float4*>(x + n));
+    } else if (n + 3 >= 0 && n < N) {
+      if (n >= 0) v[u].x = __ldg(x + n);
+      if (n + 1 >= 0 && n + 1 < N) v[u].y = __ldg(x + n + 1);
+      if (n + 2 >= 0 && n + 2 < N) v[u].z = __ldg(x + n + 2);
+      if (n + 3 < N) v[u].w = __ldg(x + n + 3);
     }
-    z[pad(2 * q)] = make_float2(v.x, v.y);
-    z[pad(2 * q + 1)] = make_float2(v.z, v.w);
+  }
+#pragma unroll
+  for (int u = 0; u < kPer; ++u) {
+    const int q = threadIdx.x + u * kConvThreads;
+    z[pad(2 * q)] = make_float2(v[u].x, v[u].y);
+    z[pad(2 * q + 1)] = make_float2(v[u].z, v[u].w);
   }
 }
 

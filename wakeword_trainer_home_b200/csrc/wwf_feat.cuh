@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
 
   extern __shared__ __align__(16) float smem[];
   __shared__ float red[64];
+  __shared__ int s_next_group;                                // dynamic frame-group queue of the current clip
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
   const int N = p.N, T = p.T, hop = p.hop, M = p.n_mels, pitch = p.tile_pitch, F = p.n_feat;
@@ -298,12 +299,19 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
     const int noff = cn.off, nlen = cn.len;
     const float scale = clip_mix_scale(cn, x, N, has_rev, p.es_part, p.es_nb, b, p.snr_db, red);
     const bool mix = nz != nullptr;
-    __syncthreads();   // constants + mask flags visible
+    if (tid == 0) s_next_group = 0;
+    __syncthreads();   // constants + mask flags + group queue visible
 
     // ---- frames: STFT -> power -> mel -> dB into the tile (warp-autonomous) --------------
     const int ngroups = (T + 2 * G - 1) / (2 * G);
     float vmax = -INFINITY;                                  // running maximum of the dB values this lane wrote
-    for (int grp = warp; grp < ngroups; grp += nwarps) {
+    // Groups are handed out dynamically: the warp schedulers do not serve the warps of a CTA
+    // evenly, and a static split makes everyone wait at the barrier for the slowest warp.
+    for (;;) {
+      int grp = 0;
+      if (lane == 0) grp = atomicAdd(&s_next_group, 1);
+      grp = __shfl_sync(0xffffffffu, grp, 0);
+      if (grp >= ngroups) break;
       const int f0 = grp * 2 * G;
       // 1. load + window: z[g][j] = w[j] * (frame(f0+2g)[j] + i frame(f0+2g+1)[j])
       bool staged = false;

@@ -482,7 +482,10 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
     if (sm > budget) continue;
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)p->kernel, c * 32, sm) != cudaSuccess || nb < 1) continue;
-    if (nb * c > best) { best = nb * c; nwarps = c; ctas_per_sm = nb; }
+    // resident warps, plus a bonus for a third CTA: the per-clip CTA-wide phases (max, DCT, store)
+    // of one CTA then overlap with the frame phases of two others (measured: 3x6 warps beats 2x10)
+    const int score = nb * c + (nb >= 3 ? 3 : 0);
+    if (score > best) { best = score; nwarps = c; ctas_per_sm = nb; }
   }
   if (nwarps == 0) return fail(WWF_ERR_CUDA, "feat_kernel does not fit on this device (%zu + %zu bytes of shared memory)", fixed_bytes, per_warp);
   const size_t smem = fixed_bytes + (size_t)nwarps * per_warp;
