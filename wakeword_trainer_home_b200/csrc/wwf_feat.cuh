@@ -109,9 +109,10 @@ WWF_HD int reflect_index(int i, int N) {
 // Two real frames a, b were transformed as one complex signal a + i b.  Given Z[k] and Z[n-k]
 // return (|A[k]|^2, |B[k]|^2) with A[k] = (Z[k] + conj Z[n-k])/2, B[k] = -i (Z[k] - conj Z[n-k])/2.
 WWF_HD float2 pair_split_power(float2 a, float2 c) {
-  const float sx = a.x + c.x, sy = a.y - c.y;   // Z[k] + conj(Z[n-k])
-  const float dx = a.x - c.x, dy = a.y + c.y;   // Z[k] - conj(Z[n-k])
-  return make_float2(0.25f * fmaf(sx, sx, sy * sy), 0.25f * fmaf(dx, dx, dy * dy));
+  const float2 cc = cconj(c);
+  const float2 s = cadd(a, cc);                 // Z[k] + conj(Z[n-k])
+  const float2 d = csub(a, cc);                 // Z[k] - conj(Z[n-k])
+  return make_float2(0.25f * fmaf(s.x, s.x, s.y * s.y), 0.25f * fmaf(d.x, d.x, d.y * d.y));
 }
 
 // noise sample for clip position i: bank[(off + i) mod len]
@@ -433,9 +434,7 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
           const int pk = kNatural ? k : Rad::pos(k);
 #pragma unroll
           for (int g = 0; g < G; ++g) {
-            const float2 v = z[g * NFFT + pk];
-            acc[g].x = fmaf(w, v.x, acc[g].x);
-            acc[g].y = fmaf(w, v.y, acc[g].y);
+            acc[g] = cfma_s(z[g * NFFT + pk], w, acc[g]);
           }
         }
 #pragma unroll
@@ -481,20 +480,21 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
       const int C = F, c8 = p.c8, ncg = c8 / 8;
       for (int idx = tid; idx < ncg * T; idx += blockDim.x) {
         const int cg = idx / T, t = idx - cg * T, c0 = cg * 8;
-        float acc[8];
+        float2 acc2[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (int i = 0; i < 4; ++i) acc2[i] = make_float2(0.f, 0.f);
         const float* d = s_dct + c0;
 #pragma unroll 4
         for (int m = 0; m < M; ++m) {
           const float a = fmaxf(tile[m * pitch + t], cutoff);
           const float4 d0 = *reinterpret_cast<const float4*>(d + m * c8);
           const float4 d1 = *reinterpret_cast<const float4*>(d + m * c8 + 4);
-          acc[0] = fmaf(a, d0.x, acc[0]); acc[1] = fmaf(a, d0.y, acc[1]);
-          acc[2] = fmaf(a, d0.z, acc[2]); acc[3] = fmaf(a, d0.w, acc[3]);
-          acc[4] = fmaf(a, d1.x, acc[4]); acc[5] = fmaf(a, d1.y, acc[5]);
-          acc[6] = fmaf(a, d1.z, acc[6]); acc[7] = fmaf(a, d1.w, acc[7]);
+          acc2[0] = cfma_s(make_float2(d0.x, d0.y), a, acc2[0]);   // FFMA2: two coefficients per instruction
+          acc2[1] = cfma_s(make_float2(d0.z, d0.w), a, acc2[1]);
+          acc2[2] = cfma_s(make_float2(d1.x, d1.y), a, acc2[2]);
+          acc2[3] = cfma_s(make_float2(d1.z, d1.w), a, acc2[3]);
         }
+        const float acc[8] = {acc2[0].x, acc2[0].y, acc2[1].x, acc2[1].y, acc2[2].x, acc2[2].y, acc2[3].x, acc2[3].y};
         const bool cm = s_colmask[t] != 0;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {

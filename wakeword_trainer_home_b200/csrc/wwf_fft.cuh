@@ -75,25 +75,85 @@ struct TwC {
 
 // ----------------------------------------------------------------------------------------
 // complex helpers
+//
+// On sm_100a every complex operation is issued as Blackwell's packed fp32x2 instructions
+// (FADD2 / FMUL2 / FFMA2): one instruction works on the (re, im) register pair, a scalar operand
+// is broadcast (.F32), and the operand swizzles .LO_HI / .NP give "swap halves" and "negate one
+// half" for free - so a complex add, a multiply by +-i folded into an add, and a full complex
+// multiply cost 1, 1 and 2 instructions instead of 2, 2 and 4.  Both kernels are
+// instruction-issue bound with mostly complex arithmetic, which makes this the main lever.
+// The host versions (tests/emul) perform the same roundings in the same order: results are
+// bit-identical.
 // ----------------------------------------------------------------------------------------
-WWF_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-WWF_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-WWF_HD float2 cmul(float2 a, float2 b) {
-  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+#define WWF_PACKED_F32X2 1
+#endif
+
+WWF_HD float2 cadd(float2 a, float2 b) {
+#ifdef WWF_PACKED_F32X2
+  return __fadd2_rn(a, b);
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
 }
-WWF_HD float2 cmulc(float2 a, float2 b) {  // a * conj(b)
+WWF_HD float2 csub(float2 a, float2 b) {
+#ifdef WWF_PACKED_F32X2
+  return __fadd2_rn(a, make_float2(-b.x, -b.y));
+#else
+  return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
+// a * s + c with real scalar s
+WWF_HD float2 cfma_s(float2 a, float s, float2 c) {
+#ifdef WWF_PACKED_F32X2
+  return __ffma2_rn(a, make_float2(s, s), c);
+#else
+  return make_float2(fmaf(a.x, s, c.x), fmaf(a.y, s, c.y));
+#endif
+}
+WWF_HD float2 cmul_s(float2 a, float s) {
+#ifdef WWF_PACKED_F32X2
+  return __fmul2_rn(a, make_float2(s, s));
+#else
+  return make_float2(a.x * s, a.y * s);
+#endif
+}
+WWF_HD float2 cmul(float2 a, float2 b) {   // (a.x b.x - a.y b.y, a.x b.y + a.y b.x)
+#ifdef WWF_PACKED_F32X2
+  return __ffma2_rn(b, make_float2(a.x, a.x), __fmul2_rn(make_float2(b.y, b.x), make_float2(-a.y, a.y)));
+#else
+  return make_float2(fmaf(a.x, b.x, -a.y * b.y), fmaf(a.x, b.y, a.y * b.x));
+#endif
+}
+WWF_HD float2 cmulc(float2 a, float2 b) {  // a * conj(b) = (a.x b.x + a.y b.y, a.y b.x - a.x b.y)
+#ifdef WWF_PACKED_F32X2
+  return __ffma2_rn(a, make_float2(b.x, b.x), __fmul2_rn(make_float2(a.y, a.x), make_float2(b.y, -b.y)));
+#else
   return make_float2(fmaf(a.x, b.x, a.y * b.y), fmaf(a.y, b.x, -a.x * b.y));
+#endif
 }
 WWF_HD float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
 template <bool INV>
-WWF_HD float2 mul_mi(float2 a) {  // forward: * (-i); inverse: * (+i)
+WWF_HD float2 mul_mi(float2 a) {  // forward: * (-i); inverse: * (+i)   (folds into the consumer's swizzle)
   return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+// (v.x c + v.y s, v.y c - v.x s) = v * (c - i s);  SGN = -1 gives v * (c + i s)
+template <bool CONJ>
+WWF_HD float2 cmul_cs(float2 v, float c, float s) {
+#ifdef WWF_PACKED_F32X2
+  return CONJ ? __ffma2_rn(v, make_float2(c, c), __fmul2_rn(make_float2(v.y, v.x), make_float2(-s, s)))
+              : __ffma2_rn(v, make_float2(c, c), __fmul2_rn(make_float2(v.y, v.x), make_float2(s, -s)));
+#else
+  return CONJ ? make_float2(fmaf(v.x, c, -v.y * s), fmaf(v.y, c, v.x * s))
+              : make_float2(fmaf(v.x, c, v.y * s), fmaf(v.y, c, -v.x * s));
+#endif
 }
 
 // v * w_N^E (forward) or v * conj(w_N^E) (inverse), E and N compile-time.
 template <int E, int N, bool INV>
 WWF_HD float2 twmul(float2 v) {
   constexpr int e = ((E % N) + N) % N;
+  constexpr float r = 0.70710678118654752440f;
   if constexpr (e == 0) {
     return v;
   } else if constexpr (4 * e == N) {
@@ -102,24 +162,16 @@ WWF_HD float2 twmul(float2 v) {
     return make_float2(-v.x, -v.y);
   } else if constexpr (4 * e == 3 * N) {
     return mul_mi<!INV>(v);
-  } else if constexpr (8 * e == N) {  // (1 - i)/sqrt2 fwd
-    constexpr float r = 0.70710678118654752440f;
-    return INV ? make_float2((v.x - v.y) * r, (v.x + v.y) * r) : make_float2((v.x + v.y) * r, (v.y - v.x) * r);
-  } else if constexpr (8 * e == 3 * N) {  // (-1 - i)/sqrt2 fwd
-    constexpr float r = 0.70710678118654752440f;
-    return INV ? make_float2((-v.x - v.y) * r, (v.x - v.y) * r) : make_float2((v.y - v.x) * r, (-v.x - v.y) * r);
-  } else if constexpr (8 * e == 5 * N) {  // (-1 + i)/sqrt2 fwd
-    constexpr float r = 0.70710678118654752440f;
-    return INV ? make_float2((v.y - v.x) * r, (-v.x - v.y) * r) : make_float2((-v.x - v.y) * r, (v.x - v.y) * r);
-  } else if constexpr (8 * e == 7 * N) {  // (1 + i)/sqrt2 fwd
-    constexpr float r = 0.70710678118654752440f;
-    return INV ? make_float2((v.x + v.y) * r, (v.y - v.x) * r) : make_float2((v.x - v.y) * r, (v.x + v.y) * r);
+  } else if constexpr (8 * e == N) {      // fwd (1 - i)/sqrt2: ((x + y) r, (y - x) r)
+    return cmul_s(cadd(v, mul_mi<INV>(v)), r);
+  } else if constexpr (8 * e == 3 * N) {  // fwd (-1 - i)/sqrt2: ((y - x) r, (-x - y) r)
+    return cmul_s(csub(mul_mi<INV>(v), v), r);
+  } else if constexpr (8 * e == 5 * N) {  // fwd (-1 + i)/sqrt2: ((-x - y) r, (x - y) r)
+    return cmul_s(cadd(v, mul_mi<INV>(v)), -r);
+  } else if constexpr (8 * e == 7 * N) {  // fwd (1 + i)/sqrt2: ((x - y) r, (x + y) r)
+    return cmul_s(csub(v, mul_mi<INV>(v)), r);
   } else {
-    constexpr float c = TwC<e, N>::c;
-    constexpr float s = TwC<e, N>::s;
-    // forward w = (c, -s): (x + iy)(c - is) = (xc + ys) + i(yc - xs)
-    return INV ? make_float2(fmaf(v.x, c, -v.y * s), fmaf(v.y, c, v.x * s))
-               : make_float2(fmaf(v.x, c, v.y * s), fmaf(v.y, c, -v.x * s));
+    return cmul_cs<INV>(v, TwC<e, N>::c, TwC<e, N>::s);   // forward w = (c, -s)
   }
 }
 
@@ -145,13 +197,13 @@ WWF_HD void dft4(float2& a0, float2& a1, float2& a2, float2& a3) {
 template <bool INV>
 WWF_HD void dft5(float2& a0, float2& a1, float2& a2, float2& a3, float2& a4) {
   constexpr float c1 = TwC<1, 5>::c, c2 = TwC<2, 5>::c, s1 = TwC<1, 5>::s, s2 = TwC<2, 5>::s;
-  float2 p1 = cadd(a1, a4), m1 = csub(a1, a4), p2 = cadd(a2, a3), m2 = csub(a2, a3);
-  float2 r1 = make_float2(a0.x + fmaf(c1, p1.x, c2 * p2.x), a0.y + fmaf(c1, p1.y, c2 * p2.y));
-  float2 r2 = make_float2(a0.x + fmaf(c2, p1.x, c1 * p2.x), a0.y + fmaf(c2, p1.y, c1 * p2.y));
-  float2 q1 = make_float2(fmaf(s1, m1.x, s2 * m2.x), fmaf(s1, m1.y, s2 * m2.y));
-  float2 q2 = make_float2(fmaf(s2, m1.x, -s1 * m2.x), fmaf(s2, m1.y, -s1 * m2.y));
-  float2 iq1 = mul_mi<INV>(q1), iq2 = mul_mi<INV>(q2);  // forward: -i q
-  a0 = make_float2(a0.x + p1.x + p2.x, a0.y + p1.y + p2.y);
+  const float2 p1 = cadd(a1, a4), m1 = csub(a1, a4), p2 = cadd(a2, a3), m2 = csub(a2, a3);
+  const float2 r1 = cadd(a0, cfma_s(p1, c1, cmul_s(p2, c2)));
+  const float2 r2 = cadd(a0, cfma_s(p1, c2, cmul_s(p2, c1)));
+  const float2 q1 = cfma_s(m1, s1, cmul_s(m2, s2));
+  const float2 q2 = cfma_s(m1, s2, cmul_s(m2, -s1));
+  const float2 iq1 = mul_mi<INV>(q1), iq2 = mul_mi<INV>(q2);  // forward: -i q
+  a0 = cadd(cadd(a0, p1), p2);
   a1 = cadd(r1, iq1);
   a4 = csub(r1, iq1);
   a2 = cadd(r2, iq2);
