@@ -220,3 +220,79 @@ def test_batch_invariance_and_determinism_at_full_size(ww):
     lm = ww.FeaturePlan(16000, "mel", 40, 40, 400, 160, "cuda", top_db=None)
     d = lm.featurize(2.0 * x[:64]) - lm.featurize(x[:64])
     assert (d - 20.0 * np.log10(2.0)).abs().max() <= 1e-4
+
+
+def _draw_preset(gen, B, N, n_noise, n_rir, noise_len, p_noise, p_rir, p_mask, F, T):
+    """Default/Edge-preset style draws (src/config/defaults.py:82-91): per-clip apply flags gate each op."""
+    from oracle import ta_oracle as tao
+    on_r = torch.rand(B, generator=gen) < p_rir
+    on_n = torch.rand(B, generator=gen) < p_noise
+    rir_idx = torch.where(on_r, torch.randint(0, n_rir, (B,), generator=gen, dtype=torch.int32), torch.tensor(-1, dtype=torch.int32))
+    noise_idx = torch.where(on_n, torch.randint(0, n_noise, (B,), generator=gen, dtype=torch.int32), torch.tensor(-1, dtype=torch.int32))
+    noise_off = torch.randint(0, noise_len, (B,), generator=gen)
+    snr = 5.0 + 15.0 * torch.rand(B, generator=gen)
+    fs, fl = tao.draw_mask_params(gen, B, F, 15, 2)
+    ts, tl = tao.draw_mask_params(gen, B, T, 35, 2)
+    on_f = (torch.rand(B, generator=gen) < p_mask).to(torch.int32).unsqueeze(1)
+    on_t = (torch.rand(B, generator=gen) < p_mask).to(torch.int32).unsqueeze(1)
+    return dict(rir_idx=rir_idx, noise_idx=noise_idx, noise_off=noise_off, snr_db=snr,
+                fmask_start=fs, fmask_len=fl * on_f, tmask_start=ts, tmask_len=tl * on_t)
+
+
+@pytest.mark.parametrize("N", [24000, 40000])
+def test_baseline_config3_default_preset_pipeline(ww, N):
+    """BASELINE.json configs[2] feature side: Default preset (n_fft 1024, 128 mels, hop 160), noise p=.5,
+    RIR p=.25, masks p=.5, at 1.5 s and the preset's own 2.5 s."""
+    from oracle import ta_oracle as tao
+    B, F, T = 48, 128, N // 160 + 1
+    gen = torch.Generator().manual_seed(N)
+    x = 0.1 * torch.randn(B, N, generator=gen)
+    noise, rirs = synth_banks(5, 8, 48000, 6, 8000)
+    d = _draw_preset(gen, B, N, 8, 6, 48000, 0.5, 0.25, 0.5, F, T)
+    plan = ww.FeaturePlan(16000, "mel", 128, 40, 1024, 160, "cuda", n_freq_masks=2, n_time_masks=2)
+    plan.register_noise(noise); plan.register_rirs(rirs)
+    got = plan.featurize(x.cuda(), ww.AugParams(**d)).cpu()
+    ref = tao.pipeline(x.double(), rirs=rirs, rir_idx=d["rir_idx"], noise_bank=noise, noise_idx=d["noise_idx"],
+                       noise_off=d["noise_off"], snr_db=d["snr_db"], fstart=d["fmask_start"], flen=d["fmask_len"],
+                       tstart=d["tmask_start"], tlen=d["tmask_len"], dtype=torch.float64, sample_rate=16000,
+                       feature_type="mel", n_mels=128, n_fft=1024, hop_length=160)
+    assert got.shape == (B, 1, F, T)
+    assert torch.equal(got == 0.0, ref == 0.0)                 # masked cells identical (fill value 0.0)
+    assert_features_close(got.numpy(), ref.numpy(), f"default preset, N={N}")
+
+
+def test_baseline_config4_edge_fp16(ww):
+    """BASELINE.json configs[3]: 2 s clips, 64 mels, FP16 features, Edge-preset augmentation probabilities."""
+    from oracle import ta_oracle as tao
+    B, N, F = 64, 32000, 64
+    T = N // 160 + 1
+    gen = torch.Generator().manual_seed(44)
+    x = 0.1 * torch.randn(B, N, generator=gen)
+    noise, rirs = synth_banks(6, 8, 40000, 6, 6000)
+    d = _draw_preset(gen, B, N, 8, 6, 40000, 0.5, 0.3, 0.0, F, T)
+    d = {k: v for k, v in d.items() if "mask" not in k}
+    plan = ww.FeaturePlan(16000, "mel", 64, 40, 400, 160, "cuda", out_dtype=torch.float16)
+    plan.register_noise(noise); plan.register_rirs(rirs)
+    got = plan.featurize(x.cuda(), ww.AugParams(**d)).cpu()
+    ref = tao.pipeline(x, rirs=rirs, rir_idx=d["rir_idx"], noise_bank=noise, noise_idx=d["noise_idx"],
+                       noise_off=d["noise_off"], snr_db=d["snr_db"], sample_rate=16000, feature_type="mel",
+                       n_mels=64, n_fft=400, hop_length=160)
+    assert got.dtype == torch.float16 and got.shape == (B, 1, F, T)
+    # float16 has 11 significant bits: |x| < 64 dB -> half an ulp is 2^-6 = 0.0156 dB on top of the 1e-3 path error
+    assert (got.float() - ref).abs().max() <= 0.0157 + 1e-3
+
+
+def test_baseline_config5_large_sweep_shape(ww):
+    """BASELINE.json configs[4]: 2 s clips through the cfg1 front end at a large batch (8192):
+    oracle check on a strided sample, bit-exact agreement between batch sizes."""
+    from oracle import ta_oracle as tao
+    B, N = 8192, 32000
+    gen = torch.Generator().manual_seed(55)
+    x = (0.1 * torch.randn(B, N, generator=gen)).cuda()
+    fe = ww.FeatureExtractor(16000, "mel", 40, 40, 400, 160, "cuda")
+    got = fe(x)
+    assert got.shape == (B, 1, 40, 201)
+    pick = torch.arange(0, B, 257)
+    ref = tao.featurize(x[pick].cpu(), sample_rate=16000, feature_type="mel", n_mels=40, n_fft=400, hop_length=160)
+    assert_features_close(got[pick].cpu().numpy(), ref.numpy(), "cfg5 sample")
+    assert torch.equal(fe(x[:256]), got[:256]) and torch.equal(fe(x[4096:4096 + 300]), got[4096:4096 + 300])

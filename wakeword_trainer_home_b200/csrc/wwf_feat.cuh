@@ -425,18 +425,30 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
       // 4. sparse mel rows + dB: one lane per filter, all 2G frames of the group at once
       for (int m = lane; m < M; m += 32) {
         const int lo = s_mello[m], o0 = s_melofs[m], o1 = s_melofs[m + 1];
-        float2 acc[G];
+        // two independent accumulator chains per frame pair (even / odd taps) hide the LDS + FFMA2 latency
+        float2 acc[G], acc1[G];
 #pragma unroll
-        for (int g = 0; g < G; ++g) acc[g] = make_float2(0.f, 0.f);
-        for (int o = o0; o < o1; ++o) {
-          const float w = s_melw[o];
+        for (int g = 0; g < G; ++g) { acc[g] = make_float2(0.f, 0.f); acc1[g] = make_float2(0.f, 0.f); }
+        int o = o0;
+        for (; o + 1 < o1; o += 2) {
+          const float w0 = s_melw[o], w1 = s_melw[o + 1];
           const int k = lo + (o - o0);
-          const int pk = kNatural ? k : Rad::pos(k);
+          const int p0 = kNatural ? k : Rad::pos(k), p1 = kNatural ? k + 1 : Rad::pos(k + 1);
 #pragma unroll
           for (int g = 0; g < G; ++g) {
-            acc[g] = cfma_s(z[g * NFFT + pk], w, acc[g]);
+            acc[g] = cfma_s(z[g * NFFT + p0], w0, acc[g]);
+            acc1[g] = cfma_s(z[g * NFFT + p1], w1, acc1[g]);
           }
         }
+        if (o < o1) {
+          const float w0 = s_melw[o];
+          const int k = lo + (o - o0);
+          const int p0 = kNatural ? k : Rad::pos(k);
+#pragma unroll
+          for (int g = 0; g < G; ++g) acc[g] = cfma_s(z[g * NFFT + p0], w0, acc[g]);
+        }
+#pragma unroll
+        for (int g = 0; g < G; ++g) acc[g] = cadd(acc[g], acc1[g]);
 #pragma unroll
         for (int g = 0; g < G; ++g) {
           const int ta = f0 + 2 * g;
