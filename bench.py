@@ -63,6 +63,15 @@ def synth_banks():
     return noise, rirs
 
 
+def ncu_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/r01_traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return int(json.load(f)[kernel])
+    except Exception:
+        return None
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -278,7 +287,8 @@ def main():
     dom_bytes = (BYTES_CONV if dom == "conv_kernel" else BYTES_FEAT) * B
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": ncu_traffic(dom), "algorithmic_bytes": dom_bytes,
+                "peak_source": peak_src,
                 "kernel_ms": {"conv_kernel": conv_ms, "feat_kernel": feat_ms},
                 "step_achieved": BYTES_STEP * B / (ms_step * 1e-3) / 1e9,
                 "step_frac": BYTES_STEP * B / (ms_step * 1e-3) / 1e9 / peak,
