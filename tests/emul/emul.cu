@@ -52,20 +52,18 @@ static void cfft(const float* in, float* out) {
   for (int k = 0; k < NFFT; ++k) { out[2 * k] = z[Rad::pos(k)].x; out[2 * k + 1] = z[Rad::pos(k)].y; }
 }
 
+// the two shared-memory radix-32 passes of the conv FFT, one task after the other
 template <bool INV>
 static void conv_passes(float2* z, const float2* tw) {
-  auto pass4 = [&]() {
-    for (int u = 0; u < kConvM / 4; ++u) {
-      const float2 w1 = tw[kConvTw0 + u];
-      const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
-      pass_task<4, INV, PadMap>(z, ConvRad::L(0), u, [&](int q) { const int r = q / ConvRad::S(0); return r == 0 ? w1 : (r == 1 ? w2 : w3); });
-    }
-  };
-  auto pass16 = [&](int L, const float2* t) {
-    for (int u = 0; u < kConvM / 16; ++u) pass_task<16, INV, PadMap>(z, L, u, [&](int q) { return t[q]; });
-  };
-  if (!INV) { pass4(); pass16(ConvRad::L(1), tw + kConvTw1); pass16(ConvRad::L(2), tw + kConvTw2); pass16(ConvRad::L(3), tw); }
-  else { pass16(ConvRad::L(3), tw); pass16(ConvRad::L(2), tw + kConvTw2); pass16(ConvRad::L(1), tw + kConvTw1); pass4(); }
+  const float2* t0 = tw + kConvTw0;
+  const float2* t1 = tw + kConvTw1;
+  if (!INV) {
+    for (int u = 0; u < kConvM / 32; ++u) pass32_derived<false, PadMap>(z, ConvRad::L(0), u, [&](int q) { return t0[q]; });
+    for (int u = 0; u < kConvM / 32; ++u) pass_task<32, false, PadMap>(z, ConvRad::L(1), u, [&](int q) { return t1[q]; });
+  } else {
+    for (int u = 0; u < kConvM / 32; ++u) pass_task<32, true, PadMap>(z, ConvRad::L(1), u, [&](int q) { return t1[q]; });
+    for (int u = 0; u < kConvM / 32; ++u) pass32_derived<true, PadMap>(z, ConvRad::L(0), u, [&](int q) { return t0[q]; });
+  }
 }
 
 static void load_block(float2* z, const float* x, int N, int start) {
@@ -74,6 +72,11 @@ static void load_block(float2* z, const float* x, int N, int start) {
     const int n0 = start + 2 * m, n1 = n0 + 1;
     z[pad(m)] = make_float2((n0 >= 0 && n0 < N) ? x[n0] : 0.f, (n1 >= 0 && n1 < N) ? x[n1] : 0.f);
   }
+}
+
+static float2 w_exact_host(int k) {
+  const double a = -2.0 * M_PI * (double)k / (double)kConvP;
+  return make_float2((float)cos(a), (float)sin(a));
 }
 
 extern "C" {
@@ -100,28 +103,35 @@ int emul_cfft(int nfft, const float* in, float* out) {
   return -1;
 }
 
-// every pair task must cover each k in [0, M/2] exactly once
+// the 511 run pairs + 2 self-paired runs must cover every run exactly once
 int emul_pair_task_coverage(void) {
-  std::vector<int> seen(kConvM / 2 + 1, 0);
-  for (int v = 0; v <= kConvPairTasks; ++v) {
-    const int k = pair_task_k(v);
-    if (k < 0 || k > kConvM / 2) return -1;
-    seen[k]++;
+  std::vector<float2> tw, ftw;
+  std::vector<uint16_t> fl;
+  build_conv_tables(tw, fl, ftw);
+  std::vector<int> seen(kRuns, 0);
+  for (int t = 0; t < kFusedTasks; ++t) {
+    const int l = fl[t];
+    if (l <= 0 || l >= kRuns || l == kRuns / 2) return -1;
+    seen[run_of(l)]++;
+    seen[run_of(kRuns - l)]++;
   }
-  for (int k = 0; k <= kConvM / 2; ++k) if (seen[k] != 1) return -2 - k;
+  seen[run_of(0)]++;
+  seen[run_of(kRuns / 2)]++;
+  for (int a = 0; a < kRuns; ++a) if (seen[a] != 1) return -2 - a;
   return 0;
 }
 
-// worst half-warp bank multiplicity (8-byte banks, 16 of them) of the pair pass at pos(k) / pos(M-k)
+// worst half-warp bank multiplicity (8-byte banks, 16 of them) of the fused tasks' run accesses
 int emul_pair_bank_conflicts(void) {
-  PadMap pad;
+  std::vector<float2> tw, ftw;
+  std::vector<uint16_t> fl;
+  build_conv_tables(tw, fl, ftw);
   int worst = 1;
-  for (int v0 = 0; v0 < kConvPairTasks; v0 += 16) {
+  for (int t0 = 0; t0 < kFusedTasks; t0 += 16) {
     int ca[16] = {0}, cb[16] = {0};
-    for (int l = 0; l < 16; ++l) {
-      const int k = pair_task_k(v0 + l);
-      ca[pad(ConvRad::pos(k)) & 15]++;
-      cb[pad(ConvRad::pos((kConvM - k) & (kConvM - 1))) & 15]++;
+    for (int i = 0; i < 16 && t0 + i < kFusedTasks; ++i) {
+      ca[(17 * run_of(fl[t0 + i])) & 15]++;
+      cb[(17 * run_of(kRuns - fl[t0 + i])) & 15]++;
     }
     for (int i = 0; i < 16; ++i) { if (ca[i] > worst) worst = ca[i]; if (cb[i] > worst) worst = cb[i]; }
   }
@@ -131,39 +141,37 @@ int emul_pair_bank_conflicts(void) {
 // y[0..N) = (x * h)[0..N) through the kernel's overlap-save block logic.
 int emul_rir_conv(const float* x, int N, const float* h, int L, int lmax, float* y) {
   if (L > kConvP / 2 || lmax < L) return -1;
-  std::vector<float2> tw, twp;
-  build_conv_twiddles(tw, twp);
+  std::vector<float2> tw, ftw;
+  std::vector<uint16_t> fl;
+  build_conv_tables(tw, fl, ftw);
   std::vector<float2> z(kConvSmemElems);
-  std::vector<float4> spec(kConvPairTasks + 1);
+  std::vector<float4> spec(kSpecPerRir);
   PadMap pad;
   // spectrum (rir_spectrum_kernel)
   load_block(z.data(), h, L, 0);
   conv_passes<false>(z.data(), tw.data());
+  for (int u = 0; u < kRuns; ++u) pass_task<16, false, PadMap>(z.data(), ConvRad::L(2), u, [&](int) { return make_float2(1.f, 0.f); });
   const float sc = 1.0f / (8.0f * (float)kConvM);
-  for (int v = 0; v <= kConvPairTasks; ++v) {
-    const int k = pair_task_k(v);
-    const int pk = pad(ConvRad::pos(k)), pm = pad(ConvRad::pos((kConvM - k) & (kConvM - 1)));
+  auto entry = [&](int k) {
     float2 R2k, R2m;
-    pair_forward(z[pk], z[pm], twp[v], R2k, R2m);
+    pair_forward(z[pad(ConvRad::pos(k))], z[pad(ConvRad::pos((kConvM - k) & (kConvM - 1)))], w_exact_host(k), R2k, R2m);
     if (k == 0) { R2k.y = 0.f; R2m.y = 0.f; }
-    spec[v] = make_float4(R2k.x * sc, R2k.y * sc, R2m.x * sc, R2m.y * sc);
-  }
+    return make_float4(R2k.x * sc, R2k.y * sc, R2m.x * sc, R2m.y * sc);
+  };
+  for (int rr = 0; rr < 16; ++rr)
+    for (int t = 0; t < kFusedTasks; ++t) spec[rr * 512 + t] = entry((int)fl[t] + 1024 * rr);
+  for (int i = 0; i < 17; ++i) spec[kSpecSpecial + i] = entry(i < 9 ? 1024 * i : 512 + 1024 * (i - 9));
   // blocks (conv_kernel)
   int hist = 0, valid = kConvP, nb = 1;
   if ((int64_t)N + lmax - 1 > kConvP) { hist = (lmax - 1 + 3) & ~3; valid = kConvP - hist; nb = (N + valid - 1) / valid; }
   for (int blk = 0; blk < nb; ++blk) {
     load_block(z.data(), x, N, blk * valid - hist);
     conv_passes<false>(z.data(), tw.data());
-    for (int v = 0; v <= kConvPairTasks; ++v) {
-      const int k = pair_task_k(v);
-      const int pk = pad(ConvRad::pos(k)), pm = pad(ConvRad::pos((kConvM - k) & (kConvM - 1)));
-      const float4 hh = spec[v];
-      float2 R2k, R2m, Zk, Zm;
-      pair_forward(z[pk], z[pm], twp[v], R2k, R2m);
-      pair_inverse(cmul(R2k, make_float2(hh.x, hh.y)), cmul(R2m, make_float2(hh.z, hh.w)), twp[v], Zk, Zm);
-      z[pm] = Zm;
-      z[pk] = Zk;
+    for (int t = 0; t < kFusedTasks; ++t) {
+      const float4* sp = spec.data() + t;
+      fused_pair_task(z.data(), (int)fl[t], ftw[t], [&](int r) { return sp[r * 512]; });
     }
+    fused_special_task(z.data(), [&](int i) { return spec[kSpecSpecial + i]; });
     conv_passes<true>(z.data(), tw.data());
     for (int m = 0; m < kConvM; ++m) {
       for (int c = 0; c < 2; ++c) {

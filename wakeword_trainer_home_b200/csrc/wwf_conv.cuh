@@ -2,16 +2,24 @@
 // oracle: torchaudio F.fftconvolve(x, h, "full")[..., :N], TA/functional/functional.py:2255-2258).
 //
 // One CTA convolves one block of P = 2M = 32768 real samples of one clip entirely in shared
-// memory:  the P reals are read as M complex numbers z[m] = x[2m] + i x[2m+1] (free: it is
-// the same memory), transformed by an M-point in-place DIF FFT (radices 4,16,16,16, result
-// digit-reversed), turned into the P-point real spectrum and multiplied by the RIR's
-// pre-scaled spectrum pair-by-pair (k, M-k), folded back, and inverse-transformed by the
-// adjoint DIT passes, which consume the digit-reversed order - no reordering pass exists.
+// memory.  The P reals are read as M = 16384 complex numbers z[m] = x[2m] + i x[2m+1] (free: it
+// is the same memory) and transformed by an in-place DIF FFT with radices 32, 32, 16 whose
+// output is digit-reversed: frequency k = d0 + 32 d1 + 1024 d2 sits at p = 512 d0 + 16 d1 + d2.
+// Only the two radix-32 passes go through shared memory.  The last forward pass (radix 16 on 16
+// contiguous elements = one "run"), the real-spectrum unpacking, the multiplication by the
+// RIR spectrum, the re-packing and the first inverse pass are FUSED in registers: the partner
+// of frequency k = l + 1024 d2 is M - k = (1024 - l) + 1024 (15 - d2), i.e. run(l) pairs with
+// run(1024 - l) element d2 <-> 15 - d2, so one thread owns both runs (32 complex values), and
+// the inverse consumes the digit-reversed order - no reordering or separate pair pass exists.
+// Shared-memory traffic per block: load + 2 radix-32 passes + fused + 2 radix-32 passes + store
+// = 6 round trips (was 10 with radices 4,16,16,16 and a separate pair pass).
+//
 // A clip with N + Lmax - 1 <= P is a single block (plain zero-padded linear convolution);
 // longer clips use overlap-save blocks with H0 = roundup4(Lmax-1) samples of history.
 //
-// Shared-memory index map pad(i) = i + (i >> 4) makes every pass bank-conflict free for
-// 8-byte elements ("K_conv shared-memory layout").
+// Index map pad(i) = i + (i >> 4) keeps every access pattern conflict-free for 8-byte elements:
+// the radix-32 passes touch 16 consecutive elements per half-warp, and the fused tasks are
+// ordered (host table) so that the 16 lanes of a half-warp own runs with distinct (run mod 16).
 #pragma once
 #include <stdint.h>
 #include "wwf_fft.cuh"
@@ -22,80 +30,204 @@ constexpr int kConvLogM = 14;
 constexpr int kConvM = 1 << kConvLogM;       // complex FFT length
 constexpr int kConvP = 2 * kConvM;           // real block length
 constexpr int kConvThreads = 512;
-constexpr int kConvPairTasks = kConvM / 2;   // k in [0, M/2) enumerated by pair_task_index; k = M/2 is extra
-using ConvRad = Radices<4, 16, 16, 16>;
+using ConvRad = Radices<32, 32, 16>;
+constexpr int kRunLen = 16;                  // last radix: 16 contiguous positions = one run
+constexpr int kRuns = kConvM / kRunLen;      // 1024 runs, run(l) for l = k mod 1024
+constexpr int kFusedTasks = kRuns / 2 - 1;   // 511 run pairs {l, 1024-l}; l = 0 and l = 512 are self-paired
 
 struct PadMap {
   WWF_HD int operator()(int i) const { return i + (i >> 4); }
 };
 constexpr int kConvSmemElems = kConvM + (kConvM >> 4);
 
-// Pair-pass task v in [0, M/2] -> frequency k (k <= M/2) and its partner M-k.  Tasks are ordered
-// so that the 16 lanes of a half-warp touch 16 distinct 8-byte banks both at pos(k) and at
-// pos(M-k): lanes vary the top digit d3 (consecutive positions) over 0..7 for two 16-runs
-// that are 8 runs apart.
-WWF_HD int pair_task_k(int v) {
-  if (v >= kConvPairTasks) return kConvM / 2;
-  const int d3 = v & 7;                                   // top digit of k, 0..7  (k < M/2)
-  const int a = (v >> 7) * 16 + ((v >> 3) & 1) * 8 + ((v >> 4) & 7);  // run index = pos >> 4
-  const int d0 = a >> 8, d1 = (a >> 4) & 15, d2 = a & 15; // pos = d0*4096 + d1*256 + d2*16 + d3
-  return d0 + 4 * d1 + 64 * d2 + 1024 * d3;
-}
+// Twiddle tables (float2), one copy in shared memory per persistent CTA:
+//   pass 0 (radix 32, s = 512): powers w^{j}, w^{2j}, w^{4j}, w^{8j}, w^{16j}  [5][512]; the other 26
+//       of the 31 output twiddles w^{jr} are products of at most three of them (formed in registers)
+//   pass 1 (radix 32, s = 16): full table [(r-1)*16 + j] = w_512^{jr}
+constexpr int kConvTw0 = 0;
+constexpr int kConvTw1 = kConvTw0 + 5 * ConvRad::S(0);
+constexpr int kConvTwTotal = kConvTw1 + 31 * ConvRad::S(1);
+constexpr size_t kConvSmemBytes = (size_t)(kConvSmemElems + kConvTwTotal) * sizeof(float2);
+
+// Per-RIR spectrum layout consumed by the fused task (float4 = (H''[k], H''[M-k]), H'' = rfft(h,P)/(4M)):
+//   general  [r*512 + t]      k = l(t) + 1024 r,  t < 511 (task order), r < 16
+//   special  [16*512 + i]     i < 9: k = 1024 i;  i >= 9: k = 512 + 1024 (i - 9)
+constexpr int kSpecSpecial = 16 * 512;
+constexpr int kSpecPerRir = kSpecSpecial + 17;
 
 struct ConvParams {
   const float* wav; int64_t wav_stride;      // [B][N]
   float* rev; int64_t rev_stride;            // [B][N] output (workspace)
-  float* es_part; int es_nb;                 // [B][es_nb] energy of this block's output samples (for the SNR mix)
+  float* es_part; int es_nb;                 // [B][es_nb] energy of each block's output samples (for the SNR mix)
   const int32_t* rir_idx;                    // [B]
   int B, N, n_rir;
   int hist;                                  // H0: history samples per block (0 = single block)
   int valid;                                 // V = P - H0 output samples per block
-  const float4* spec;                        // [n_rir][M/2+1]: (H''[k], H''[M-k]) in pair-task order
-  const float2* tw;                          // pass tables of ConvRad (radix-4 pass: only r = 1)
-  const float2* tw_pair;                     // [M/2+1] w_P^k in pair-task order
+  const float4* spec;                        // [n_rir][kSpecPerRir]
+  const float2* tw;                          // pass tables (kConvTwTotal)
+  const uint16_t* fused_l;                   // [511] l of fused task t (bank-conflict-free order)
+  const float2* fused_tw;                    // [511] w_P^{l(t)}
 };
 
-// twiddle table layout for the conv FFT: pass 0 (radix 4, s = 4096) stores only w^j (r = 1);
-// w^{2j}, w^{3j} are formed by multiplication.  Passes 1, 2 store the full (R-1)*s tables.
-constexpr int kConvTw0 = 0;
-constexpr int kConvTw1 = kConvTw0 + ConvRad::S(0);
-constexpr int kConvTw2 = kConvTw1 + 15 * ConvRad::S(1);
-constexpr int kConvTwTotal = kConvTw2 + 15 * ConvRad::S(2);
-// dynamic shared memory: padded data array followed by a copy of the pass twiddle tables
-constexpr size_t kConvSmemBytes = (size_t)(kConvSmemElems + kConvTwTotal) * sizeof(float2);
+// ------------------------------------------------------------------------------------------
+// radix-32 pass with derived twiddles (pass 0).  tw5[b*s + j] = w_L^{j 2^b}, b = 0..4.
+// ------------------------------------------------------------------------------------------
+template <bool INV, class Map, class TwLoad>
+WWF_HD void pass32_derived(float2* z, int L, int u, TwLoad tw5, Map map = Map()) {
+  constexpr int R = 32;
+  const int s = L / R;
+  const int blk = u / s, j = u - blk * s;
+  const int base = blk * L + j;
+  float2 v[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) v[q] = z[map(base + q * s)];
+  const float2 w1 = tw5(j), w2 = tw5(s + j), w4 = tw5(2 * s + j), w8 = tw5(3 * s + j), w16 = tw5(4 * s + j);
+  const float2 w24 = cmul(w16, w8);
+  auto apply = [&](float2 x, float2 w) { return INV ? cmulc(x, w) : cmul(x, w); };
+  if constexpr (!INV) dft<R, false>(v);
+  // r = 8 r1 + r2: w^{jr} = low(r2) * high(r1), low in {1, w1, .., w7}, high in {1, w8, w16, w24}
+  static_for<0, 8>([&](auto R2) {
+    constexpr int r2 = decltype(R2)::value;
+    float2 lo = make_float2(1.f, 0.f);
+    if constexpr (r2 == 1) lo = w1;
+    if constexpr (r2 == 2) lo = w2;
+    if constexpr (r2 == 3) lo = cmul(w2, w1);
+    if constexpr (r2 == 4) lo = w4;
+    if constexpr (r2 == 5) lo = cmul(w4, w1);
+    if constexpr (r2 == 6) lo = cmul(w4, w2);
+    if constexpr (r2 == 7) lo = cmul(cmul(w4, w2), w1);
+    if constexpr (r2 > 0) v[r2] = apply(v[r2], lo);
+    v[8 + r2] = apply(v[8 + r2], r2 == 0 ? w8 : cmul(lo, w8));
+    v[16 + r2] = apply(v[16 + r2], r2 == 0 ? w16 : cmul(lo, w16));
+    v[24 + r2] = apply(v[24 + r2], r2 == 0 ? w24 : cmul(lo, w24));
+  });
+  if constexpr (INV) dft<R, true>(v);
+#pragma unroll
+  for (int q = 0; q < R; ++q) z[map(base + q * s)] = v[q];
+}
 
+// ------------------------------------------------------------------------------------------
+// real-spectrum pair algebra
+// ------------------------------------------------------------------------------------------
+// One (k, M-k) pair.  A = Z[k], Bm = Z[M-k], w = w_P^k.
+// Forward half:  R2k = 2 R[k],  R2m = 2 R[M-k]  (R = P-point spectrum of the real block).
+WWF_HD void pair_forward(float2 A, float2 Bm, float2 w, float2& R2k, float2& R2m) {
+  const float2 Bc = cconj(Bm);
+  const float2 Se = cadd(A, Bc);                 // 2 Xe[k]
+  const float2 So = mul_mi<false>(csub(A, Bc));  // 2 Xo[k] = -i (A - conj B)
+  const float2 Tt = cmul(w, So);
+  R2k = cadd(Se, Tt);
+  R2m = cconj(csub(Se, Tt));
+}
+// Inverse half: from Yk, Ym (spectrum of the result at k and M-k) to Zy[k], Zy[M-k].
+WWF_HD void pair_inverse(float2 Yk, float2 Ym, float2 w, float2& Zk, float2& Zm) {
+  const float2 Yc = cconj(Ym);
+  const float2 Ue = cadd(Yk, Yc);
+  const float2 Uo = cmulc(csub(Yk, Yc), w);      // conj(w^k) (Yk - conj Ym)
+  Zk = make_float2(Ue.x - Uo.y, Ue.y + Uo.x);    // Ue + i Uo
+  Zm = make_float2(Ue.x + Uo.y, Uo.x - Ue.y);    // conj(Ue) + i conj(Uo)
+}
+// Both halves with the RIR spectrum in between: (Z[k], Z[M-k]) -> (Zy[k], Zy[M-k]).
+WWF_HD void pair_convolve(float2& zk, float2& zm, float2 w, float4 h) {
+  float2 R2k, R2m;
+  pair_forward(zk, zm, w, R2k, R2m);
+  pair_inverse(cmul(R2k, make_float2(h.x, h.y)), cmul(R2m, make_float2(h.z, h.w)), w, zk, zm);
+}
+
+WWF_HD int run_of(int l) { return ConvRad::pos(l) >> 4; }   // run holding frequencies l + 1024 d2
+
+// General fused task: runs of l and 1024 - l (l not in {0, 512}).  wl = w_P^l;
+// spec(r) = (H''[k], H''[M-k]) for k = l + 1024 r.
+template <class SpecLoad>
+WWF_HD void fused_pair_task(float2* z, int l, float2 wl, SpecLoad spec) {
+  const int a = run_of(l), ap = run_of(kRuns - l);
+  float2* zu = z + 17 * a;    // pad(16 a + q) = 17 a + q
+  float2* zv = z + 17 * ap;
+  float2 u[16], v[16];
+#pragma unroll
+  for (int q = 0; q < 16; ++q) { u[q] = zu[q]; v[q] = zv[q]; }
+  dft<16, false>(u);          // last forward pass (s = 1: no twiddles) -> u[r] = Z[l + 1024 r]
+  dft<16, false>(v);          //                                        -> v[r] = Z[1024 - l + 1024 r]
+  static_for<0, 16>([&](auto Rr) {
+    constexpr int r = decltype(Rr)::value;
+    const float2 w = cmul_cs<false>(wl, TwC<r, 32>::c, TwC<r, 32>::s);   // w_P^{l + 1024 r} = w_P^l w_32^r
+    pair_convolve(u[r], v[15 - r], r == 0 ? wl : w, spec(r));
+  });
+  dft<16, true>(u);           // first inverse pass
+  dft<16, true>(v);
+#pragma unroll
+  for (int q = 0; q < 16; ++q) { zu[q] = u[q]; zv[q] = v[q]; }
+}
+
+// The two self-paired runs.  spec(i): i < 9 -> k = 1024 i; i >= 9 -> k = 512 + 1024 (i - 9).
+template <class SpecLoad>
+WWF_HD void fused_special_task(float2* z, SpecLoad spec) {
+  {  // l = 0: k = 1024 r pairs with 1024 (16 - r); r = 0 carries DC and Nyquist, r = 8 is its own partner
+    float2* zu = z + 17 * run_of(0);
+    float2 u[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) u[q] = zu[q];
+    dft<16, false>(u);
+    {
+      float2 a = u[0], b = u[0];
+      pair_convolve(a, b, make_float2(1.f, 0.f), spec(0));
+      u[0] = a;
+    }
+    static_for<1, 8>([&](auto Rr) {
+      constexpr int r = decltype(Rr)::value;
+      pair_convolve(u[r], u[16 - r], make_float2(TwC<r, 32>::c, -TwC<r, 32>::s), spec(r));
+    });
+    {
+      float2 a = u[8], b = u[8];
+      pair_convolve(a, b, make_float2(0.f, -1.f), spec(8));   // w_32^8 = -i
+      u[8] = a;
+    }
+    dft<16, true>(u);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) zu[q] = u[q];
+  }
+  {  // l = 512: k = 512 + 1024 r pairs with 512 + 1024 (15 - r); w_P^k = w_64^{1 + 2r}
+    float2* zu = z + 17 * run_of(kRuns / 2);
+    float2 u[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) u[q] = zu[q];
+    dft<16, false>(u);
+    static_for<0, 8>([&](auto Rr) {
+      constexpr int r = decltype(Rr)::value;
+      pair_convolve(u[r], u[15 - r], make_float2(TwC<1 + 2 * r, 64>::c, -TwC<1 + 2 * r, 64>::s), spec(9 + r));
+    });
+    dft<16, true>(u);
+#pragma unroll
+    for (int q = 0; q < 16; ++q) zu[q] = u[q];
+  }
+}
+
+#if defined(__CUDACC__)
+// ------------------------------------------------------------------------------------------
+// device side
+// ------------------------------------------------------------------------------------------
 // copy the pass tables into shared memory (once per persistent CTA)
 __device__ __forceinline__ void conv_load_tables(float2* s_tw, const float2* __restrict__ tw) {
   for (int i = threadIdx.x; i < kConvTwTotal; i += kConvThreads) s_tw[i] = __ldg(tw + i);
 }
 
+// the shared-memory passes: forward = radix-32 (L = M), radix-32 (L = 512); inverse = the reverse
 template <bool INV>
-__device__ __forceinline__ void conv_fft_passes(float2* z, const float2* tw) {   // tw: shared-memory copy
-  const int tid = threadIdx.x;
-  auto pass4 = [&]() {
-    for (int u = tid; u < kConvM / 4; u += kConvThreads) {
-      const float2 w1 = tw[kConvTw0 + u];
-      const float2 w2 = cmul(w1, w1), w3 = cmul(w2, w1);
-      pass_task<4, INV, PadMap>(z, ConvRad::L(0), u, [&](int q) {
-        const int r = q / ConvRad::S(0);     // q = (r-1)*s + j
-        return r == 0 ? w1 : (r == 1 ? w2 : w3);
-      });
-    }
-  };
-  auto pass16 = [&](int L, const float2* t) {
-    for (int u = tid; u < kConvM / 16; u += kConvThreads)
-      pass_task<16, INV, PadMap>(z, L, u, [&](int q) { return t[q]; });
-  };
+__device__ __forceinline__ void conv_smem_passes(float2* z, const float2* tw) {   // tw: shared-memory copy
+  static_assert(kConvM / 32 == kConvThreads, "one radix-32 task per thread");
+  const int u = threadIdx.x;
+  const float2* t0 = tw + kConvTw0;
+  const float2* t1 = tw + kConvTw1;
   if constexpr (!INV) {
-    pass4();                             __syncthreads();
-    pass16(ConvRad::L(1), tw + kConvTw1); __syncthreads();
-    pass16(ConvRad::L(2), tw + kConvTw2); __syncthreads();
-    pass16(ConvRad::L(3), tw);            __syncthreads();   // s == 1: table unused
+    pass32_derived<false, PadMap>(z, ConvRad::L(0), u, [&](int q) { return t0[q]; });
+    __syncthreads();
+    pass_task<32, false, PadMap>(z, ConvRad::L(1), u, [&](int q) { return t1[q]; });
+    __syncthreads();
   } else {
-    pass16(ConvRad::L(3), tw);            __syncthreads();
-    pass16(ConvRad::L(2), tw + kConvTw2); __syncthreads();
-    pass16(ConvRad::L(1), tw + kConvTw1); __syncthreads();
-    pass4();                             __syncthreads();
+    pass_task<32, true, PadMap>(z, ConvRad::L(1), u, [&](int q) { return t1[q]; });
+    __syncthreads();
+    pass32_derived<true, PadMap>(z, ConvRad::L(0), u, [&](int q) { return t0[q]; });
+    __syncthreads();
   }
 }
 
@@ -127,48 +259,17 @@ __device__ __forceinline__ void conv_load_block(float2* z, const float* __restri
   }
 }
 
-// One (k, M-k) pair of the real-spectrum step.  A = Z[k], Bm = Z[M-k], w = w_P^k.
-// Returns the forward half:  R2k = 2 R[k],  R2m = 2 R[M-k]  (R = P-point real spectrum).
-WWF_HD void pair_forward(float2 A, float2 Bm, float2 w, float2& R2k, float2& R2m) {
-  const float2 Bc = cconj(Bm);
-  const float2 Se = cadd(A, Bc);                 // 2 Xe[k]
-  const float2 So = mul_mi<false>(csub(A, Bc));  // 2 Xo[k] = -i (A - conj B)
-  const float2 Tt = cmul(w, So);
-  R2k = cadd(Se, Tt);
-  R2m = cconj(csub(Se, Tt));
-}
-// Inverse half: from Yk, Ym (spectrum of the result at k and M-k) to Zy[k], Zy[M-k].
-WWF_HD void pair_inverse(float2 Yk, float2 Ym, float2 w, float2& Zk, float2& Zm) {
-  const float2 Yc = cconj(Ym);
-  const float2 Ue = cadd(Yk, Yc);
-  const float2 Uo = cmulc(csub(Yk, Yc), w);      // conj(w^k) (Yk - conj Ym)
-  Zk = make_float2(Ue.x - Uo.y, Ue.y + Uo.x);    // Ue + i Uo
-  Zm = make_float2(Ue.x + Uo.y, Uo.x - Ue.y);    // conj(Ue) + i conj(Uo)
-}
-
-// The (k, M-k) pass of one block: 16 pair tasks per thread, global operands (pair twiddle, RIR
-// spectrum) fetched four tasks ahead of their use.
-__device__ __forceinline__ void conv_pair_pass(float2* zc, const float4* __restrict__ spec, const float2* __restrict__ tw_pair) {
-  PadMap pad;
-  auto one = [&](int v, float2 w, float4 h) {
-    const int k = pair_task_k(v);
-    const int pk = pad(ConvRad::pos(k)), pm = pad(ConvRad::pos((kConvM - k) & (kConvM - 1)));
-    float2 R2k, R2m, Zk, Zm;
-    pair_forward(zc[pk], zc[pm], w, R2k, R2m);
-    pair_inverse(cmul(R2k, make_float2(h.x, h.y)), cmul(R2m, make_float2(h.z, h.w)), w, Zk, Zm);
-    zc[pm] = Zm;
-    zc[pk] = Zk;   // k == 0 and k == M/2 are self-paired: Zk == Zm there
-  };
-  static_assert(kConvPairTasks % (4 * kConvThreads) == 0, "pair pass unroll");
-  for (int v0 = threadIdx.x; v0 < kConvPairTasks; v0 += 4 * kConvThreads) {
-    float2 w[4];
-    float4 h[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) { w[u] = __ldg(tw_pair + v0 + u * kConvThreads); h[u] = __ldg(spec + v0 + u * kConvThreads); }
-#pragma unroll
-    for (int u = 0; u < 4; ++u) one(v0 + u * kConvThreads, w[u], h[u]);
+// fused middle of one block: thread t < 511 owns run pair l(t); thread 511 the two self-paired runs
+__device__ __forceinline__ void conv_fused_middle(float2* zc, const float4* __restrict__ spec,
+                                                  const uint16_t* __restrict__ fused_l, const float2* __restrict__ fused_tw) {
+  const int t = threadIdx.x;
+  if (t < kFusedTasks) {
+    const float4* sp = spec + t;
+    fused_pair_task(zc, (int)__ldg(fused_l + t), __ldg(fused_tw + t), [&](int r) { return __ldg(sp + r * 512); });
+  } else {
+    const float4* sp = spec + kSpecSpecial;
+    fused_special_task(zc, [&](int i) { return __ldg(sp + i); });
   }
-  if (threadIdx.x == 0) one(kConvPairTasks, __ldg(tw_pair + kConvPairTasks), __ldg(spec + kConvPairTasks));
 }
 
 // Persistent: grid = min(#SMs, work items); work item = (clip b, overlap-save block blk).
@@ -188,10 +289,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams 
     __syncthreads();                                          // previous item's stores / table copy done
     conv_load_block(zc, x, p.N, blk * p.valid - p.hist, vec_ok);
     __syncthreads();
-    conv_fft_passes<false>(zc, s_tw);
-    conv_pair_pass(zc, p.spec + (size_t)r * (kConvPairTasks + 1), p.tw_pair);
+    conv_smem_passes<false>(zc, s_tw);
+    conv_fused_middle(zc, p.spec + (size_t)r * kSpecPerRir, p.fused_l, p.fused_tw);
     __syncthreads();
-    conv_fft_passes<true>(zc, s_tw);
+    conv_smem_passes<true>(zc, s_tw);
 
     // store the valid outputs: block sample i in [hist, P) -> clip sample blk*valid + i - hist
     float* y = p.rev + (size_t)b * p.rev_stride;
@@ -229,36 +330,49 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams 
   }
 }
 
-// Spectrum of one zero-padded RIR in the layout conv_kernel consumes:
-// spec[v] = (R[k], R[M-k]) / (4M)  with k = pair_task_k(v), R = rfft(h, P).
-// (R2 = 2R, so the stored value is R2 / (8M); the 1/(4M) folds the two 1/2 of the even/odd
-// split and the 1/M of the unnormalised inverse.)
+// Spectrum of one zero-padded RIR in the layout the fused task consumes (registration time).
+// Forward FFT including the last radix-16 pass in shared memory, then every (k, M-k) pair.
 struct SpecParams {
   const float* data; const int64_t* offsets; int n_rir;
-  float4* spec; const float2* tw; const float2* tw_pair;
+  float4* spec; const float2* tw; const uint16_t* fused_l;
 };
+
+__device__ __forceinline__ float2 w_exact(int k) {   // w_P^k, double-precision sincospi
+  double s, c;
+  sincospi(-2.0 * (double)k / (double)kConvP, &s, &c);
+  return make_float2((float)c, (float)s);
+}
 
 __global__ void __launch_bounds__(kConvThreads, 1) rir_spectrum_kernel(const SpecParams p) {
   extern __shared__ __align__(16) float2 zc[];
-  const int r = blockIdx.x;
-  const int64_t o0 = p.offsets[r], o1 = p.offsets[r + 1];
-  const float* h = p.data + o0;
   float2* s_tw = zc + kConvSmemElems;
   conv_load_tables(s_tw, p.tw);
-  conv_load_block(zc, h, (int)(o1 - o0), 0, false);
+  const int r = blockIdx.x;
+  const int64_t o0 = p.offsets[r], o1 = p.offsets[r + 1];
+  conv_load_block(zc, p.data + o0, (int)(o1 - o0), 0, false);
   __syncthreads();
-  conv_fft_passes<false>(zc, s_tw);
+  conv_smem_passes<false>(zc, s_tw);
+  for (int u = threadIdx.x; u < kRuns; u += kConvThreads)
+    pass_task<16, false, PadMap>(zc, ConvRad::L(2), u, [&](int) { return make_float2(1.f, 0.f); });
+  __syncthreads();
   PadMap pad;
-  const float sc = 1.0f / (8.0f * (float)kConvM);
-  float4* spec = p.spec + (size_t)r * (kConvPairTasks + 1);
-  for (int v = threadIdx.x; v <= kConvPairTasks; v += kConvThreads) {
-    const int k = pair_task_k(v);
-    const int pk = pad(ConvRad::pos(k)), pm = pad(ConvRad::pos((kConvM - k) & (kConvM - 1)));
+  const float sc = 1.0f / (8.0f * (float)kConvM);   // R2 = 2R, H'' = R / (4M)
+  float4* spec = p.spec + (size_t)r * kSpecPerRir;
+  auto entry = [&](int k) {
     float2 R2k, R2m;
-    pair_forward(zc[pk], zc[pm], __ldg(p.tw_pair + v), R2k, R2m);
-    if (k == 0) { R2k.y = 0.f; R2m.y = 0.f; }   // DC and Nyquist of a real signal are real
-    spec[v] = make_float4(R2k.x * sc, R2k.y * sc, R2m.x * sc, R2m.y * sc);
+    pair_forward(zc[pad(ConvRad::pos(k))], zc[pad(ConvRad::pos((kConvM - k) & (kConvM - 1)))], w_exact(k), R2k, R2m);
+    if (k == 0) { R2k.y = 0.f; R2m.y = 0.f; }     // DC and Nyquist of a real signal are real
+    return make_float4(R2k.x * sc, R2k.y * sc, R2m.x * sc, R2m.y * sc);
+  };
+  for (int i = threadIdx.x; i < 16 * kFusedTasks; i += kConvThreads) {
+    const int rr = i / kFusedTasks, t = i - rr * kFusedTasks;
+    spec[rr * 512 + t] = entry((int)p.fused_l[t] + 1024 * rr);
+  }
+  if (threadIdx.x < 17) {
+    const int i = threadIdx.x;
+    spec[kSpecSpecial + i] = entry(i < 9 ? 1024 * i : 512 + 1024 * (i - 9));
   }
 }
+#endif  // __CUDACC__
 
 }  // namespace wwf

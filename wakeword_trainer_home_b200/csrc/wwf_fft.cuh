@@ -210,44 +210,53 @@ WWF_HD void dft5(float2& a0, float2& a1, float2& a2, float2& a3, float2& a4) {
   a3 = csub(r2, iq2);
 }
 
-// elementary R-point DFT on v[0], v[S], v[2S], ...
-template <int R, bool INV, int S>
-WWF_HD void dft_strided(float2* v) {
-  static_assert(R == 2 || R == 4 || R == 5, "elementary radix");
-  if constexpr (R == 2) dft2<INV>(v[0], v[S]);
-  if constexpr (R == 4) dft4<INV>(v[0], v[S], v[2 * S], v[3 * S]);
-  if constexpr (R == 5) dft5<INV>(v[0], v[S], v[2 * S], v[3 * S], v[4 * S]);
-}
+template <int R, bool INV>
+WWF_HD void dft(float2 (&v)[R]);
 
 // N = A*B point DFT in registers (Cooley-Tukey, natural-order in and out):
 //   X[B r1 + r2] = sum_{q1} w_A^{q1 r1} [ w_N^{q1 r2} sum_{q2} x[q1 + A q2] w_B^{q2 r2} ]
+// Sub-transforms gather/scatter through small register arrays (free after unrolling), so A and B
+// may themselves be composite.
 template <int A, int B, bool INV>
 WWF_HD void dft_composite(float2 (&v)[A * B]) {
-  static_for<0, A>([&](auto Q1) { dft_strided<B, INV, A>(&v[decltype(Q1)::value]); });
+  static_for<0, A>([&](auto Q1) {
+    constexpr int q1 = decltype(Q1)::value;
+    float2 t[B];
+#pragma unroll
+    for (int q2 = 0; q2 < B; ++q2) t[q2] = v[q1 + A * q2];
+    dft<B, INV>(t);
+#pragma unroll
+    for (int q2 = 0; q2 < B; ++q2) v[q1 + A * q2] = t[q2];
+  });
   static_for<1, A>([&](auto Q1) {
     static_for<1, B>([&](auto R2) {
       constexpr int q1 = decltype(Q1)::value, r2 = decltype(R2)::value;
       v[q1 + A * r2] = twmul<q1 * r2, A * B, INV>(v[q1 + A * r2]);
     });
   });
-  static_for<0, B>([&](auto R2) { dft_strided<A, INV, 1>(&v[A * decltype(R2)::value]); });
-  float2 t[A * B];
+  float2 o[A * B];
+  static_for<0, B>([&](auto R2) {
+    constexpr int r2 = decltype(R2)::value;
+    float2 t[A];
 #pragma unroll
-  for (int i = 0; i < A * B; ++i) t[i] = v[i];
-  static_for<0, A>([&](auto R1) {
-    static_for<0, B>([&](auto R2) {
-      constexpr int r1 = decltype(R1)::value, r2 = decltype(R2)::value;
-      v[B * r1 + r2] = t[r1 + A * r2];
-    });
+    for (int q1 = 0; q1 < A; ++q1) t[q1] = v[q1 + A * r2];
+    dft<A, INV>(t);
+#pragma unroll
+    for (int r1 = 0; r1 < A; ++r1) o[B * r1 + r2] = t[r1];
   });
+#pragma unroll
+  for (int i = 0; i < A * B; ++i) v[i] = o[i];
 }
 
 template <int R, bool INV>
 WWF_HD void dft(float2 (&v)[R]) {
-  if constexpr (R == 2 || R == 4 || R == 5) dft_strided<R, INV, 1>(&v[0]);
+  if constexpr (R == 2) dft2<INV>(v[0], v[1]);
+  else if constexpr (R == 4) dft4<INV>(v[0], v[1], v[2], v[3]);
+  else if constexpr (R == 5) dft5<INV>(v[0], v[1], v[2], v[3], v[4]);
   else if constexpr (R == 8) dft_composite<2, 4, INV>(v);
   else if constexpr (R == 16) dft_composite<4, 4, INV>(v);
   else if constexpr (R == 25) dft_composite<5, 5, INV>(v);
+  else if constexpr (R == 32) dft_composite<4, 8, INV>(v);
   else static_assert(R == 2, "unsupported radix");
 }
 

@@ -2,6 +2,7 @@
 // mel filterbank).  Shared by wwfeat.cu (plan creation) and tests/emul (CPU index-math checks).
 #pragma once
 #include <cmath>
+#include <cstdint>
 #include <vector>
 #include "wwf_conv.cuh"
 #include "wwf_fft.cuh"
@@ -23,19 +24,27 @@ inline void build_stft_twiddles(std::vector<float2>& tw) {
 }
 
 
-inline void build_conv_twiddles(std::vector<float2>& tw, std::vector<float2>& twp) {
-  tw.assign(kConvTwTotal, make_float2(1.f, 0.f));
-  twp.assign(kConvPairTasks + 1, make_float2(1.f, 0.f));
+// Tables of the overlap-save FFT (wwf_conv.cuh): pass twiddles, fused-task order and w_P^l.
+inline void build_conv_tables(std::vector<float2>& tw, std::vector<uint16_t>& fused_l, std::vector<float2>& fused_tw) {
   auto W = [](long long e, long long n) {
     const double a = -2.0 * M_PI * (double)(e % n) / (double)n;
     return make_float2((float)cos(a), (float)sin(a));
   };
-  for (int j = 0; j < ConvRad::S(0); ++j) tw[kConvTw0 + j] = W(j, ConvRad::L(0));
-  for (int r = 1; r < 16; ++r) {
-    for (int j = 0; j < ConvRad::S(1); ++j) tw[kConvTw1 + (r - 1) * ConvRad::S(1) + j] = W((long long)j * r, ConvRad::L(1));
-    for (int j = 0; j < ConvRad::S(2); ++j) tw[kConvTw2 + (r - 1) * ConvRad::S(2) + j] = W((long long)j * r, ConvRad::L(2));
+  tw.assign(kConvTwTotal, make_float2(1.f, 0.f));
+  const int s0 = ConvRad::S(0), s1 = ConvRad::S(1);
+  for (int b = 0; b < 5; ++b)
+    for (int j = 0; j < s0; ++j) tw[kConvTw0 + b * s0 + j] = W((long long)j << b, ConvRad::L(0));
+  for (int r = 1; r < 32; ++r)
+    for (int j = 0; j < s1; ++j) tw[kConvTw1 + (r - 1) * s1 + j] = W((long long)j * r, ConvRad::L(1));
+  // task t owns runs l and 1024 - l, l = d0 + 32 d1 with d1 = (t+1) & 15, d0 = (t+1) >> 4: the 16 lanes of
+  // a half-warp get 16 distinct (run mod 16) = d1 for both runs -> conflict-free 8-byte accesses
+  fused_l.resize(kFusedTasks);
+  fused_tw.resize(kFusedTasks);
+  for (int t = 0; t < kFusedTasks; ++t) {
+    const int tt = t + 1, l = (tt >> 4) + 32 * (tt & 15);
+    fused_l[t] = (uint16_t)l;
+    fused_tw[t] = W(l, kConvP);
   }
-  for (int v = 0; v <= kConvPairTasks; ++v) twp[v] = W(pair_task_k(v), kConvP);
 }
 
 // torch.linspace(start, end, steps) in float32 (forward from start / backward from end)

@@ -78,7 +78,8 @@ struct wwf_plan {
   // RIR bank (owned spectra) + conv constants
   float4* d_spec = nullptr;
   float2* d_conv_tw = nullptr;
-  float2* d_conv_tw_pair = nullptr;
+  uint16_t* d_fused_l = nullptr;
+  float2* d_fused_tw = nullptr;
   int n_rir = 0, rir_max_len = 0;
   int feat_warps_override = 0;
   // optional per-kernel timing (wwf_profile_enable)
@@ -124,7 +125,7 @@ extern "C" void wwf_plan_destroy(wwf_plan* p) {
   cudaFree(p->d_mel_w); cudaFree(p->d_dct); cudaFree(p->d_noise_offsets); cudaFree(p->d_spec);
   cudaFree(p->d_noise_prefix); cudaFree(p->d_noise_prefix_offsets);
   for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
-  cudaFree(p->d_conv_tw); cudaFree(p->d_conv_tw_pair);
+  cudaFree(p->d_conv_tw); cudaFree(p->d_fused_l); cudaFree(p->d_fused_tw);
   delete p;
 }
 
@@ -269,10 +270,11 @@ extern "C" int wwf_num_frames(const wwf_plan* p, int n_samples) {
 // ------------------------------------------------------------------------------------------
 static int ensure_conv_constants(wwf_plan* p) {
   if (p->d_conv_tw) return WWF_OK;
-  std::vector<float2> tw, twp;
-  build_conv_twiddles(tw, twp);
+  std::vector<float2> tw, ftw;
+  std::vector<uint16_t> fl;
+  build_conv_tables(tw, fl, ftw);
   int rc;
-  if ((rc = upload(&p->d_conv_tw, tw)) || (rc = upload(&p->d_conv_tw_pair, twp))) return rc;
+  if ((rc = upload(&p->d_conv_tw, tw)) || (rc = upload(&p->d_fused_l, fl)) || (rc = upload(&p->d_fused_tw, ftw))) return rc;
   WWF_CUDA(cudaFuncSetAttribute((const void*)conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemBytes));
   WWF_CUDA(cudaFuncSetAttribute((const void*)rir_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemBytes));
   return WWF_OK;
@@ -343,8 +345,8 @@ extern "C" int wwf_bank_register(wwf_plan* p, int kind, const float* data, const
   if (rc) return rc;
   int64_t* d_ofs = nullptr;
   if ((rc = upload(&d_ofs, ofs))) return rc;
-  WWF_CUDA(cudaMalloc((void**)&p->d_spec, (size_t)count * (kConvPairTasks + 1) * sizeof(float4)));
-  SpecParams sp{data, d_ofs, count, p->d_spec, p->d_conv_tw, p->d_conv_tw_pair};
+  WWF_CUDA(cudaMalloc((void**)&p->d_spec, (size_t)count * kSpecPerRir * sizeof(float4)));
+  SpecParams sp{data, d_ofs, count, p->d_spec, p->d_conv_tw, p->d_fused_l};
   rir_spectrum_kernel<<<count, kConvThreads, kConvSmemBytes, st>>>(sp);
   g_launches++;
   cudaError_t e = cudaGetLastError();
@@ -405,7 +407,7 @@ static int launch_conv(wwf_plan* p, const float* wav, int B, int N, int64_t wav_
   conv_geometry(p, N, &cp.hist, &cp.valid, &nb);
   cp.es_part = cp.rev + (size_t)B * cp.rev_stride;
   cp.es_nb = nb;
-  cp.spec = p->d_spec; cp.tw = p->d_conv_tw; cp.tw_pair = p->d_conv_tw_pair;
+  cp.spec = p->d_spec; cp.tw = p->d_conv_tw; cp.fused_l = p->d_fused_l; cp.fused_tw = p->d_fused_tw;
   int grid = nb * B < p->sm_count ? nb * B : p->sm_count;
   conv_kernel<<<grid, kConvThreads, kConvSmemBytes, st>>>(cp);
   g_launches++;
