@@ -292,6 +292,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams 
     conv_smem_passes<false>(zc, s_tw);
     conv_fused_middle(zc, p.spec + (size_t)r * kSpecPerRir, p.fused_l, p.fused_tw);
     __syncthreads();
+    {  // pull the next work item's samples into L2 while this block's inverse passes run (no registers held)
+      const int nitem = item + gridDim.x;
+      if (nitem < p.B * nblk) {
+        const int nb_ = nitem / nblk, nblk_ = nitem - nb_ * nblk;
+        const float* nx = p.wav + (size_t)nb_ * p.wav_stride;
+        const int nstart = nblk_ * p.valid - p.hist;
+        for (int q = threadIdx.x * 32; q < kConvP; q += kConvThreads * 32) {   // one 128-byte line per request
+          const int n = nstart + q;
+          if (n >= 0 && n < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(nx + n));
+        }
+      }
+    }
     conv_smem_passes<true>(zc, s_tw);
 
     // store the valid outputs: block sample i in [hist, P) -> clip sample blk*valid + i - hist
