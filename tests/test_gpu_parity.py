@@ -296,3 +296,82 @@ def test_baseline_config5_large_sweep_shape(ww):
     ref = tao.featurize(x[pick].cpu(), sample_rate=16000, feature_type="mel", n_mels=40, n_fft=400, hop_length=160)
     assert_features_close(got[pick].cpu().numpy(), ref.numpy(), "cfg5 sample")
     assert torch.equal(fe(x[:256]), got[:256]) and torch.equal(fe(x[4096:4096 + 300]), got[4096:4096 + 300])
+
+
+def test_strided_input_streams_and_inplace_augment(ww):
+    """Row-strided clip batches, a non-default stream, caller-provided output and in-place noise mix."""
+    from oracle import ta_oracle as tao
+    gen = torch.Generator().manual_seed(77)
+    big = (0.1 * torch.randn(12, 20000, generator=gen)).cuda()
+    view = big[:, 1000:17000]                                   # row stride 20000, N = 16000, 16-byte aligned start
+    odd = big[:, 1001:17001]                                    # 4-byte aligned only
+    plan = ww.FeaturePlan(16000, "mel", 40, 40, 400, 160, "cuda")
+    ref = tao.featurize(view.cpu(), sample_rate=16000, feature_type="mel", n_mels=40, n_fft=400, hop_length=160)
+    out = torch.empty(12, 1, 40, 101, device="cuda")
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        got = plan.featurize(view, out=out)
+    s.synchronize()
+    assert got.data_ptr() == out.data_ptr()
+    assert_features_close(got.cpu().numpy(), ref.numpy(), "strided rows")
+    ref2 = tao.featurize(odd.cpu(), sample_rate=16000, feature_type="mel", n_mels=40, n_fft=400, hop_length=160)
+    assert_features_close(plan.featurize(odd).cpu().numpy(), ref2.numpy(), "unaligned rows")
+    # reverb from unaligned, strided rows + in-place noise-only augmentation
+    noise, rirs = synth_banks(8, 4, 20000, 3, 5000)
+    plan.register_noise(noise); plan.register_rirs(rirs)
+    p = ww.AugParams(rir_idx=torch.arange(12) % 3, noise_idx=torch.arange(12) % 4, noise_off=torch.arange(12) * 997,
+                     snr_db=torch.full((12,), 10.0))
+    want = tao.augment_wave(odd.cpu(), rirs=rirs, rir_idx=p.rir_idx, noise_bank=noise, noise_idx=p.noise_idx,
+                            noise_off=p.noise_off, snr_db=p.snr_db)
+    got = plan.augment(odd, p).cpu()
+    rms = want.pow(2).mean(dim=1).sqrt()
+    assert ((got - want).abs().amax(dim=1) <= 2e-5 * rms).all()
+    only_noise = ww.AugParams(noise_idx=p.noise_idx, noise_off=p.noise_off, snr_db=p.snr_db)
+    buf = view.contiguous()
+    want2 = tao.augment_wave(buf.cpu(), noise_bank=noise, noise_idx=p.noise_idx, noise_off=p.noise_off, snr_db=p.snr_db)
+    plan.augment(buf, only_noise, out=buf)                       # in place is allowed without reverb
+    assert ((buf.cpu() - want2).abs().amax(dim=1) <= 2e-5 * want2.pow(2).mean(dim=1).sqrt()).all()
+    with pytest.raises(ww.WwfError):
+        plan.augment(buf, p, out=buf)                            # ... and refused with reverb
+
+
+def test_streamed_featurizer_and_batch_loader(ww):
+    """Host-fed triple-stream pipeline and the DataLoader replacement feed a small CNN train step."""
+    gen = torch.Generator().manual_seed(5)
+    n, N, B = 200, 16000, 64
+    clips = 0.1 * torch.randn(n, N, generator=gen)
+    labels = torch.randint(0, 2, (n,), generator=gen)
+    noise, rirs = synth_banks(9, 4, 24000, 3, 4000)
+    plan = ww.FeaturePlan(16000, "mel", 64, 40, 400, 160, "cuda", n_freq_masks=2, n_time_masks=2)
+    aug = ww.AudioAugmentation(16000, "cuda", background_noise_prob=0.5, rir_prob=0.25, background_noise=noise,
+                               rirs=rirs, plan=plan, seed=1)
+    sa = ww.SpecAugment(15, 35, 2, 2)
+    # streamed: results equal the plain call, whatever the slot
+    sf = ww.StreamedFeaturizer(plan, B, N, depth=2, copy_back=True)
+    draws = [aug.draw(B) for _ in range(5)]
+    batches = [clips[i * 20:i * 20 + B].contiguous().pin_memory() for i in range(5)]
+    outs = []
+    for w_, d in zip(batches, draws):
+        k = sf.submit(w_, d)
+        outs.append(sf.wait(k).clone())
+    for w_, d, o in zip(batches, draws, outs):
+        assert torch.equal(o, plan.featurize(w_.cuda(), d).cpu())
+    # loader: shards tile the set, shapes are what the reference's models take, a train step runs
+    seen = 0
+    for rank in range(2):
+        ld = ww.GpuBatchLoader(clips.pin_memory(), labels, plan, B, augment=aug, spec_augment=sa, shuffle=True, seed=3,
+                               rank=rank, world_size=2)
+        assert len(ld) == 2
+        for x, y in ld:
+            assert x.shape[1:] == (1, 64, 101) and x.is_cuda and y.shape[0] == x.shape[0] and torch.isfinite(x).all()
+            seen += x.shape[0]
+    assert seen == n
+    net = torch.nn.Sequential(torch.nn.Conv2d(1, 8, 3, padding=1), torch.nn.ReLU(), torch.nn.AdaptiveAvgPool2d(1),
+                              torch.nn.Flatten(), torch.nn.Linear(8, 2)).cuda()
+    opt = torch.optim.SGD(net.parameters(), lr=0.01)
+    ld = ww.GpuBatchLoader(clips.cuda(), labels, plan, B, augment=aug, spec_augment=sa, seed=3)
+    for x, y in ld:                                               # trainer.py:147-193 in miniature
+        loss = torch.nn.functional.cross_entropy(net(x), y)
+        opt.zero_grad(); loss.backward(); opt.step()
+    assert torch.isfinite(loss)

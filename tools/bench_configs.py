@@ -52,3 +52,6 @@ run("cfg4 edge n400 M64 fp16 2s B=1024", 1024, 32000, "mel", 64, 40, 400, 0.5, 0
 run("cfg5 sweep n400 M40 2s B=256", 256, 32000, "mel", 40, 40, 400, 0, 0, False)
 run("cfg5 sweep n400 M40 2s B=8192", 8192, 32000, "mel", 40, 40, 400, 0, 0, False)
 run("ref-default mfcc n1024 M128 C40 2.5s B=1024", 1024, 40000, "mfcc", 128, 40, 1024, 0, 0, False)
+run("isolate: mfcc40 n400 no aug B=1024", 1024, 24000, "mfcc", 40, 40, 400, 0, 0, False)
+run("isolate: log-mel40 n400 + noise B=1024", 1024, 24000, "mel", 40, 40, 400, 1.0, 0, False)
+run("isolate: mfcc40 n400 + noise B=1024", 1024, 24000, "mfcc", 40, 40, 400, 1.0, 0, False)
