@@ -41,6 +41,7 @@ T_FRAMES = N_SAMPLES // HOP + 1
 BYTES_STEP = 4 * (N_SAMPLES + N_SAMPLES + RIR_LEN) + 4 * N_MFCC * T_FRAMES          # 248 160
 BYTES_CONV = 4 * (N_SAMPLES + RIR_LEN + N_SAMPLES)                                  # x, h in; y out
 BYTES_FEAT = 4 * (N_SAMPLES + N_SAMPLES) + 4 * N_MFCC * T_FRAMES                    # y, noise in; features out
+METRIC = "featurized clips/sec (1.5s@16kHz, aug+log-mel+DCT: configs[1] MFCC-40 + noise@SNR + RIR)"
 WORKLOAD = ("configs[1]: MFCC-40 (n_fft 400, hop 160, 40 mels) + noise@SNR U[5,20] dB + RIR reverb "
             "(8000 taps), batch 1024 x 1.5 s @ 16 kHz per GPU")
 
@@ -150,7 +151,7 @@ def run_reference(args, rank: int):
         return
     n_clips = 256 if args.steps <= 60 else (128 if args.steps <= 150 else 64)   # keep the whole run to a few minutes
     cps, sec, cores = cpu_reference(n_clips, reps=args.steps, warm=max(1, min(args.warmup, 3)))
-    line = {"impl": "reference", "metric": "featurized clips/sec (aug + MFCC)", "value": cps, "unit": "clips/s",
+    line = {"impl": "reference", "metric": METRIC, "value": cps, "unit": "clips/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "sample_per_step": f"{n_clips} clips of the workload, one batched "
@@ -302,7 +303,7 @@ def main():
                          "(torchaudio CPU, batched)"}
 
     if rank == 0:
-        line = {"metric": "featurized clips/sec (aug + MFCC)", "value": value, "unit": "clips/s", "n_gpus": world,
+        line = {"metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world, "n_samples": N_SAMPLES,
