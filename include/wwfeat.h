@@ -176,6 +176,14 @@ int wwf_spec_augment(void* spec, int dtype, int B, int F, int T, int64_t clip_st
                      float mask_value, int device, void* stream);
 
 /*
+ * Non-finite guard: wwf_featurize raises a plan-owned device flag when any feature it computed is
+ * NaN/Inf (e.g. an all-zero noise clip makes F.add_noise's scale infinite, exactly like the oracle).
+ * This call waits for `stream`, returns the flag (0/1) and clears it.
+ * Serves: the reference trainer's "skip non-finite batch" rule, src/training/trainer.py:177-179.
+ */
+int wwf_check_finite(wwf_plan* plan, void* stream, int* nonfinite);
+
+/*
  * Measurement hook (bench.py's roofline): when enabled, wwf_featurize brackets each of its
  * kernels with CUDA events on the launching stream.  wwf_profile_read waits for them, returns
  * the AVERAGE duration (ms) of the reverb kernel and of the feature kernel per call since the

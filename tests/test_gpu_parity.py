@@ -375,3 +375,23 @@ def test_streamed_featurizer_and_batch_loader(ww):
         loss = torch.nn.functional.cross_entropy(net(x), y)
         opt.zero_grad(); loss.backward(); opt.step()
     assert torch.isfinite(loss)
+
+
+def test_nonfinite_guard(ww):
+    """An all-zero noise clip makes F.add_noise's scale infinite (inf * 0 = NaN) in the oracle and here;
+    the plan's flag reports it without scanning the features."""
+    from oracle import ta_oracle as tao
+    x = 0.1 * torch.randn(4, 16000, generator=torch.Generator().manual_seed(1))
+    noise = [torch.zeros(16000), 0.05 * torch.randn(16000, generator=torch.Generator().manual_seed(2))]
+    plan = ww.FeaturePlan(16000, "mel", 40, 40, 400, 160, "cuda")
+    plan.register_noise(noise)
+    ok = ww.AugParams(noise_idx=torch.tensor([1, 1, -1, 1]), noise_off=torch.zeros(4, dtype=torch.int64), snr_db=torch.full((4,), 10.0))
+    f = plan.featurize(x.cuda(), ok)
+    assert plan.check_finite() and torch.isfinite(f).all()
+    bad = ww.AugParams(noise_idx=torch.tensor([1, 0, -1, 1]), noise_off=torch.zeros(4, dtype=torch.int64), snr_db=torch.full((4,), 10.0))
+    f = plan.featurize(x.cuda(), bad)
+    ref = tao.pipeline(x, noise_bank=noise, noise_idx=bad.noise_idx, noise_off=bad.noise_off, snr_db=bad.snr_db,
+                       sample_rate=16000, feature_type="mel", n_mels=40, n_fft=400, hop_length=160)
+    assert not plan.check_finite()
+    assert torch.equal(torch.isfinite(f).cpu(), torch.isfinite(ref))        # same clip is poisoned, the others are fine
+    assert plan.check_finite()                                               # flag was cleared by the read

@@ -76,6 +76,7 @@ SYMBOLS = {
     "wwf_spec_augment": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                    C.c_float, C.c_int, C.c_void_p]),
+    "wwf_check_finite": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "wwf_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "wwf_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "wwf_launch_count": (C.c_int64, []),

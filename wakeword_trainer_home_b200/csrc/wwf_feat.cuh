@@ -86,6 +86,7 @@ struct FeatParams {
   const int32_t* fs; const int32_t* fl; const int32_t* ts; const int32_t* tl; int nF, nT;
   // output
   void* out; int64_t out_stride;
+  int* nonfinite_flag;                           // plan-owned device int, set to 1 if any feature is NaN/Inf
 };
 
 // ---- small device utilities --------------------------------------------------------------
@@ -128,7 +129,8 @@ __device__ __forceinline__ float noise_at(const float* nz, int noff, int nlen, i
 // 10*log10(max(x, 1e-10)) = (10/log2(10)) * log2(.) through MUFU.LG2 (lg2.approx: max abs error
 // 2^-22.6 on log2 => < 5e-7 dB; the argument is >= 1e-10, never denormal).
 __device__ __forceinline__ float power_to_db(float x) {
-  return x > 1e-10f ? 3.01029995663981195f * __log2f(x) : -100.0f;   // the clamp value is exact, like the oracle's
+  // the clamp value is exact like the oracle's; NaN takes the log branch and stays NaN (torch.clamp keeps NaN)
+  return x <= 1e-10f ? -100.0f : 3.01029995663981195f * __log2f(x);
 }
 
 // scale of F.add_noise (TA/functional/functional.py:2376-2378), float32 like the oracle
@@ -470,6 +472,7 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
 
     OutT* out = reinterpret_cast<OutT*>(p.out) + (size_t)b * p.out_stride;
     const OutT mv = to_out<OutT>(p.mask_value);
+    bool bad = false;                                        // any non-finite feature of this clip (pre-mask)
     const float* rsrc = tile;   // rows to normalise in the CMVN epilogue
     bool done = false;
 
@@ -479,6 +482,7 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
           const bool rm = s_rowmask[m] != 0;
           for (int t = lane; t < T; t += 32) {
             const float v = fmaxf(tile[m * pitch + t], cutoff);
+            bad |= !isfinite(v);
             out[(size_t)m * T + t] = (rm || s_colmask[t]) ? mv : to_out<OutT>(v);
           }
         }
@@ -512,6 +516,7 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
         for (int i = 0; i < 8; ++i) {
           const int c = c0 + i;
           if (c < C) {
+            bad |= !isfinite(acc[i]);
             if (p.cmvn) res[c * pitch + t] = acc[i];
             else out[(size_t)c * T + t] = (cm || s_rowmask[c]) ? mv : to_out<OutT>(acc[i]);
           }
@@ -534,10 +539,14 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
         const bool rm = s_rowmask[f] != 0;
         for (int t = lane; t < T; t += 32) {
           const float v = (rsrc[f * pitch + t] - mean) * inv;
+          bad |= !isfinite(v);
           out[(size_t)f * T + t] = (rm || s_colmask[t]) ? mv : to_out<OutT>(v);
         }
       }
     }
+    // the reference's trainer skips batches with non-finite values (src/training/trainer.py:177-179):
+    // give the caller a cheap way to know without scanning the features
+    if (__any_sync(0xffffffffu, bad) && lane == 0 && p.nonfinite_flag != nullptr) atomicOr(p.nonfinite_flag, 1);
     __syncthreads();   // tile / flags are reused by the next clip
   }
 }

@@ -66,6 +66,7 @@ struct wwf_plan {
   float2* d_tw = nullptr;
   int* d_mel_lo = nullptr;
   int* d_mel_ofs = nullptr;
+  int* d_nonfinite = nullptr;
   float* d_mel_w = nullptr;
   float* d_dct = nullptr;
   // noise bank (borrowed data, owned offsets)
@@ -122,7 +123,7 @@ extern "C" void wwf_plan_destroy(wwf_plan* p) {
   if (!p) return;
   DeviceGuard g(p->device);
   cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_mel_lo); cudaFree(p->d_mel_ofs);
-  cudaFree(p->d_mel_w); cudaFree(p->d_dct); cudaFree(p->d_noise_offsets); cudaFree(p->d_spec);
+  cudaFree(p->d_mel_w); cudaFree(p->d_dct); cudaFree(p->d_nonfinite); cudaFree(p->d_noise_offsets); cudaFree(p->d_spec);
   cudaFree(p->d_noise_prefix); cudaFree(p->d_noise_prefix_offsets);
   for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
   cudaFree(p->d_conv_tw); cudaFree(p->d_fused_l); cudaFree(p->d_fused_tw);
@@ -217,12 +218,28 @@ extern "C" int wwf_plan_create(const wwf_config* cfg, int device, wwf_plan** out
     wwf_plan_destroy(p);
     return rc;
   }
+  if (cudaMalloc((void**)&p->d_nonfinite, sizeof(int)) != cudaSuccess || cudaMemset(p->d_nonfinite, 0, sizeof(int)) != cudaSuccess) {
+    wwf_plan_destroy(p);
+    return fail(WWF_ERR_NOMEM, "cudaMalloc(nonfinite flag) failed");
+  }
   cudaError_t e = cudaFuncSetAttribute((const void*)p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem - 1024);
   if (e != cudaSuccess) {
     wwf_plan_destroy(p);
     return fail(WWF_ERR_CUDA, "cudaFuncSetAttribute(feat_kernel): %s (is libwwfeat.so built for this GPU?)", cudaGetErrorString(e));
   }
   *out = p;
+  return WWF_OK;
+}
+
+extern "C" int wwf_check_finite(wwf_plan* p, void* stream, int* nonfinite) {
+  if (!p || !nonfinite) return fail(WWF_ERR_INVALID, "wwf_check_finite: null argument");
+  DeviceGuard guard(p->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int v = 0;
+  WWF_CUDA(cudaMemcpyAsync(&v, p->d_nonfinite, sizeof(int), cudaMemcpyDeviceToHost, st));
+  WWF_CUDA(cudaMemsetAsync(p->d_nonfinite, 0, sizeof(int), st));
+  WWF_CUDA(cudaStreamSynchronize(st));
+  *nonfinite = v;
   return WWF_OK;
 }
 
@@ -511,6 +528,7 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
   }
   fp.es_part = es_part; fp.es_nb = es_nb;
   fp.out = out; fp.out_stride = out_stride;
+  fp.nonfinite_flag = p->d_nonfinite;
   p->kernel<<<grid, nwarps * 32, smem, st>>>(fp);
   g_launches++;
   WWF_CUDA(cudaGetLastError());

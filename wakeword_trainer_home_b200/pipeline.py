@@ -164,6 +164,14 @@ class FeaturePlan:
         N.check(self.lib.wwf_plan_info(self._handle, C.byref(info)))
         return info
 
+    def check_finite(self) -> bool:
+        """True if every feature computed since the last call was finite (synchronises the current
+        stream).  Mirrors the reference trainer's non-finite batch skip, src/training/trainer.py:177-179."""
+        flag = C.c_int()
+        stream = torch.cuda.current_stream(self.device)
+        N.check(self.lib.wwf_check_finite(self._handle, C.c_void_p(stream.cuda_stream), C.byref(flag)))
+        return flag.value == 0
+
     # ------------------------------------------------------------------ measurement hook
     def profile(self, enable: bool = True):
         N.check(self.lib.wwf_profile_enable(self._handle, int(enable)))
