@@ -502,8 +502,10 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)p->kernel, c * 32, sm) != cudaSuccess || nb < 1) continue;
     // resident warps, plus a bonus for a third CTA: the per-clip CTA-wide phases (max, DCT, store)
-    // of one CTA then overlap with the frame phases of two others (measured: 3x6 warps beats 2x10)
-    const int score = nb * c + (nb >= 3 ? 3 : 0);
+    // of one CTA then overlap with the frame phases of two others (measured: 3x6 warps beats 2x10).
+    // A small batch cannot fill several CTAs per SM: count only the CTAs it will actually place.
+    const int nb_eff = std::min(nb, (B + p->sm_count - 1) / p->sm_count);
+    const int score = nb_eff * c + (nb_eff >= 3 ? 3 : 0);
     if (score > best) { best = score; nwarps = c; ctas_per_sm = nb; }
   }
   if (nwarps == 0) return fail(WWF_ERR_CUDA, "feat_kernel does not fit on this device (%zu + %zu bytes of shared memory)", fixed_bytes, per_warp);
