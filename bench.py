@@ -189,6 +189,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the feature path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    from wakeword_trainer_home_b200.sharding import bind_to_gpu_numa
+    numa_bound = bind_to_gpu_numa(local_rank) if world > 1 else False   # NUMA-local pinned buffers per rank
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -311,7 +313,8 @@ def main():
                            "parallelism": f"clip-sharded x{world}, no collective",
                            "l2": f"ring of {RING} distinct input batches ({RING * B * N_SAMPLES * 4 / 1e6:.0f} MB) > 126 MB L2"},
                 "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps},
+                        "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
+                        "numa_bound": numa_bound},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -29,3 +29,17 @@ def shard_seed(seed: int, rank: int, step: int = 0) -> int:
     """Distinct, reproducible RNG seed per (run seed, rank, step) for the augmentation draws;
     saving (seed, step) is all a resumed run needs to redraw the same augmentations."""
     return (seed * 1_000_003 + rank * 7919 + step * 104_729) % (2 ** 63 - 1)
+
+
+def bind_to_gpu_numa(local_rank: int) -> bool:
+    """Pin the calling process to the CPU cores nearest to GPU `local_rank` (NVML's ideal affinity), so
+    the pinned host buffers it allocates afterwards are NUMA-local to that GPU's PCIe root.  Matters
+    only for the host-fed path when several ranks upload at once.  Returns False if NVML refuses
+    (containers with a restricted cpuset)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local_rank))
+        return True
+    except Exception:
+        return False
