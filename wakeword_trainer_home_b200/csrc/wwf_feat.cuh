@@ -492,33 +492,48 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
           for (int t = lane; t < T; t += 32) tile[m * pitch + t] = fmaxf(tile[m * pitch + t], cutoff);
       }
     } else {
-      // DCT-II: out[c][t] = sum_m dct[m][c] * max(tile[m][t], cutoff); 8 coefficients per thread
-      const int C = F, c8 = p.c8, ncg = c8 / 8;
-      for (int idx = tid; idx < ncg * T; idx += blockDim.x) {
-        const int cg = idx / T, t = idx - cg * T, c0 = cg * 8;
-        float2 acc2[4];
+      // DCT-II: out[c][t] = sum_m dct[m][c] * max(tile[m][t], cutoff).  One task = 8 coefficients x 4
+      // frames (frames tb, tb+TB, tb+2TB, tb+3TB so that a warp reads consecutive tile columns): each
+      // 16-byte broadcast load of DCT coefficients feeds eight FFMA2.
+      const int C = F, c8 = p.c8, ncg = c8 / 8, TB = (T + 3) / 4;
+      for (int idx = tid; idx < ncg * TB; idx += blockDim.x) {
+        const int cg = idx / TB, tb = idx - cg * TB, c0 = cg * 8;
+        float2 acc2[4][4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc2[i] = make_float2(0.f, 0.f);
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc2[i][j] = make_float2(0.f, 0.f);
         const float* d = s_dct + c0;
-#pragma unroll 4
+#pragma unroll 2
         for (int m = 0; m < M; ++m) {
-          const float a = fmaxf(tile[m * pitch + t], cutoff);
           const float4 d0 = *reinterpret_cast<const float4*>(d + m * c8);
           const float4 d1 = *reinterpret_cast<const float4*>(d + m * c8 + 4);
-          acc2[0] = cfma_s(make_float2(d0.x, d0.y), a, acc2[0]);   // FFMA2: two coefficients per instruction
-          acc2[1] = cfma_s(make_float2(d0.z, d0.w), a, acc2[1]);
-          acc2[2] = cfma_s(make_float2(d1.x, d1.y), a, acc2[2]);
-          acc2[3] = cfma_s(make_float2(d1.z, d1.w), a, acc2[3]);
-        }
-        const float acc[8] = {acc2[0].x, acc2[0].y, acc2[1].x, acc2[1].y, acc2[2].x, acc2[2].y, acc2[3].x, acc2[3].y};
-        const bool cm = s_colmask[t] != 0;
+          const float* row = tile + m * pitch + tb;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int c = c0 + i;
-          if (c < C) {
-            bad |= !isfinite(acc[i]);
-            if (p.cmvn) res[c * pitch + t] = acc[i];
-            else out[(size_t)c * T + t] = (cm || s_rowmask[c]) ? mv : to_out<OutT>(acc[i]);
+          for (int i = 0; i < 4; ++i) {
+            // frames beyond T read a neighbouring (finite) tile entry and are never stored
+            const float a = fmaxf(row[tb + i * TB < T ? i * TB : 0], cutoff);
+            acc2[i][0] = cfma_s(make_float2(d0.x, d0.y), a, acc2[i][0]);   // FFMA2: two coefficients per instruction
+            acc2[i][1] = cfma_s(make_float2(d0.z, d0.w), a, acc2[i][1]);
+            acc2[i][2] = cfma_s(make_float2(d1.x, d1.y), a, acc2[i][2]);
+            acc2[i][3] = cfma_s(make_float2(d1.z, d1.w), a, acc2[i][3]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int t = tb + i * TB;
+          if (t < T) {
+            const bool cm = s_colmask[t] != 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const int c = c0 + j;
+              const float v = (j & 1) ? acc2[i][j >> 1].y : acc2[i][j >> 1].x;
+              if (c < C) {
+                bad |= !isfinite(v);
+                if (p.cmvn) res[c * pitch + t] = v;
+                else out[(size_t)c * T + t] = (cm || s_rowmask[c]) ? mv : to_out<OutT>(v);
+              }
+            }
           }
         }
       }
