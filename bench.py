@@ -146,6 +146,23 @@ def cpu_reference(n_clips: int, reps: int, warm: int):
     return n_clips * len(ts) / sum(ts), sum(ts) / len(ts), torch.get_num_threads()
 
 
+def cpu_per_clip_loop(n_clips: int = 24):
+    """The reference's real usage pattern (one call chain per clip, src/evaluation/evaluator.py:202-205,
+    Dataset.__getitem__): clips/s of the oracle called clip by clip."""
+    from oracle import ta_oracle as tao
+    noise, rirs = synth_banks()
+    wav, d = synth(8, n_clips)
+    kw = dict(sample_rate=SR, feature_type="mfcc", n_mels=N_MELS, n_mfcc=N_MFCC, n_fft=N_FFT, hop_length=HOP)
+    def one(i):
+        tao.pipeline(wav[i:i + 1], rirs=rirs, rir_idx=d["rir_idx"][i:i + 1], noise_bank=noise, noise_idx=d["noise_idx"][i:i + 1],
+                     noise_off=d["noise_off"][i:i + 1], snr_db=d["snr_db"][i:i + 1], **kw)
+    one(0)
+    t0 = time.perf_counter()
+    for i in range(n_clips):
+        one(i)
+    return n_clips / (time.perf_counter() - t0)
+
+
 def run_reference(args, rank: int):
     if rank != 0:
         return
@@ -302,7 +319,9 @@ def main():
         cps, sec, cores = cpu_reference(256, reps=8, warm=1)
         cpu = {"value": cps, "unit": "clips/s", "cores": cores, "kind": "port",
                "sample": f"256 clips x 8 reps of the same workload ({sec * 1e3:.0f} ms each), oracle/ta_oracle.py "
-                         "(torchaudio CPU, batched)"}
+                         "(torchaudio CPU, batched = the CPU's best case)",
+               "per_clip_loop_value": cpu_per_clip_loop(), "per_clip_loop_sample": "24 clips, one call chain per clip "
+               "(the reference's __getitem__ pattern)"}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world,
