@@ -165,6 +165,15 @@ int wwf_augment(wwf_plan* plan, const float* wav, int B, int N, int64_t wav_stri
                 size_t workspace_bytes, void* stream);
 
 /*
+ * Per-clip peak normalisation y = x / max|x| (all-zero clips pass through), float32 [B][N] -> [B][N];
+ * out may alias wav.  Needs no plan.
+ * Replaces: the chunk normalisation in front of the feature extractor,
+ *           src/evaluation/inference.py:189-191 (DataConfig.normalize_audio, src/config/defaults.py:24).
+ */
+int wwf_peak_normalize(const float* wav, int B, int N, int64_t wav_stride, float* out, int64_t out_stride,
+                       int device, void* stream);
+
+/*
  * In-place explicit-index SpecAugment on an existing feature tensor [B][F][T]
  * (float32 or float16 per `dtype`): rows [fstart, fstart+flen) and frames
  * [tstart, tstart+tlen) := mask_value.  Needs no plan.

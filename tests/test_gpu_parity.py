@@ -395,3 +395,21 @@ def test_nonfinite_guard(ww):
     assert not plan.check_finite()
     assert torch.equal(torch.isfinite(f).cpu(), torch.isfinite(ref))        # same clip is poisoned, the others are fine
     assert plan.check_finite()                                               # flag was cleared by the read
+
+
+def test_peak_normalize_bit_exact(ww):
+    """inference.py:189-191: chunk / max|chunk| unless the chunk is all zero - float32 division, bit-exact."""
+    gen = torch.Generator().manual_seed(12)
+    x = torch.randn(6, 16001, generator=gen) * torch.tensor([1.0, 1e-3, 30.0, 0.0, 0.5, 7.0]).unsqueeze(1)
+    x[4, 100] = -3.25                                            # the peak is a negative sample
+    want = x.numpy().copy()
+    for b in range(6):
+        m = np.max(np.abs(want[b]))
+        if m > 0:
+            want[b] = want[b] / m
+    got = ww.peak_normalize(x.cuda())
+    assert np.array_equal(got.cpu().numpy(), want)
+    y = x.cuda()
+    ww.peak_normalize(y, out=y)                                  # in place
+    assert np.array_equal(y.cpu().numpy(), want)
+    assert np.array_equal(ww.peak_normalize(x[2].cuda()).cpu().numpy(), want[2])   # 1-D chunk like _process_chunk

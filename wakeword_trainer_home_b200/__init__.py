@@ -6,7 +6,7 @@ sarpel/wakeword_trainer_home, executed by hand-written CUDA kernels behind a C A
 built library and a CUDA device.
 """
 from ._native import WwfError, LIB_PATH, launch_count  # noqa: F401
-from .pipeline import AugParams, FeaturePlan, draw_mask_params, spec_augment_  # noqa: F401
+from .pipeline import AugParams, FeaturePlan, draw_mask_params, peak_normalize, spec_augment_  # noqa: F401
 from .feature_extraction import FeatureExtractor  # noqa: F401
 from .augmentation import AudioAugmentation, SpecAugment  # noqa: F401
 from .loader import GpuBatchLoader, StreamedFeaturizer  # noqa: F401
@@ -14,5 +14,5 @@ from .sharding import shard_range, shard_seed  # noqa: F401
 
 __version__ = "0.1.0"
 __all__ = ["FeatureExtractor", "AudioAugmentation", "SpecAugment", "FeaturePlan", "AugParams",
-           "draw_mask_params", "spec_augment_", "WwfError", "launch_count", "GpuBatchLoader", "StreamedFeaturizer",
+           "draw_mask_params", "spec_augment_", "peak_normalize", "WwfError", "launch_count", "GpuBatchLoader", "StreamedFeaturizer",
            "shard_range", "shard_seed"]

@@ -73,6 +73,7 @@ SYMBOLS = {
                                 C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "wwf_augment": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.POINTER(Aug),
                               C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "wwf_peak_normalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "wwf_spec_augment": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                    C.c_float, C.c_int, C.c_void_p]),

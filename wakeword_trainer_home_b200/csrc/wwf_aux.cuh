@@ -35,6 +35,28 @@ __global__ void __launch_bounds__(512) mix_kernel(const MixParams p) {
   }
 }
 
+// Peak normalisation of each clip, y = x / max|x| (unchanged if the clip is all zero): what the reference
+// does to a chunk right before FeatureExtractor (src/evaluation/inference.py:189-191).  IEEE division,
+// so results are bit-identical to numpy's float32 arithmetic.  One CTA per clip; in place allowed.
+__global__ void __launch_bounds__(512) peak_normalize_kernel(const float* __restrict__ wav, int64_t wav_stride, float* out,
+                                                             int64_t out_stride, int N) {
+  __shared__ float red[32];
+  const float* x = wav + (size_t)blockIdx.x * wav_stride;
+  float* y = out + (size_t)blockIdx.x * out_stride;
+  float m = 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) m = fmaxf(m, fabsf(x[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  m = (threadIdx.x & 31) < (blockDim.x >> 5) ? red[threadIdx.x & 31] : 0.f;
+  m = warp_max(m);
+  if (m > 0.f) {
+    for (int i = threadIdx.x; i < N; i += blockDim.x) y[i] = x[i] / m;
+  } else if (x != y) {
+    for (int i = threadIdx.x; i < N; i += blockDim.x) y[i] = x[i];
+  }
+}
+
 // Registration helper: sums[j] = sum of squares of block j (kNoiseBlk samples, last one partial)
 // of one noise clip, in double.  One warp per block.
 __global__ void __launch_bounds__(256) noise_block_sums_kernel(const float* __restrict__ data, int64_t len, double* __restrict__ sums) {

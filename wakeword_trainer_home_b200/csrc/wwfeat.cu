@@ -572,6 +572,17 @@ extern "C" int wwf_augment(wwf_plan* p, const float* wav, int B, int N, int64_t 
   return WWF_OK;
 }
 
+extern "C" int wwf_peak_normalize(const float* wav, int B, int N, int64_t wav_stride, float* out, int64_t out_stride,
+                                  int device, void* stream) {
+  if (!wav || !out || B <= 0 || N <= 0 || wav_stride < N || out_stride < N) return fail(WWF_ERR_INVALID, "wwf_peak_normalize: bad argument");
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(WWF_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  peak_normalize_kernel<<<B, 512, 0, (cudaStream_t)stream>>>(wav, wav_stride, out, out_stride, N);
+  g_launches++;
+  WWF_CUDA(cudaGetLastError());
+  return WWF_OK;
+}
+
 extern "C" int wwf_spec_augment(void* spec, int dtype, int B, int F, int T, int64_t clip_stride,
                                 const int32_t* fs, const int32_t* fl, int nF, const int32_t* ts, const int32_t* tl, int nT,
                                 float mask_value, int device, void* stream) {

@@ -270,6 +270,22 @@ class FeaturePlan:
         return out
 
 
+def peak_normalize(wav: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Per-clip ``x / max|x|`` of a CUDA float32 (N,) or (B, N) tensor (all-zero clips unchanged) -
+    the normalisation the reference applies to a chunk before FeatureExtractor
+    (src/evaluation/inference.py:189-191).  ``out=wav`` normalises in place."""
+    if not wav.is_cuda or wav.dtype != torch.float32 or wav.dim() not in (1, 2):
+        raise ValueError("wav must be a CUDA float32 (N,) or (B, N) tensor")
+    w2 = wav.reshape(-1, wav.shape[-1])
+    if w2.stride(1) != 1:
+        w2 = w2.contiguous()
+    o2 = torch.empty_like(w2) if out is None else out.reshape(-1, wav.shape[-1])
+    stream = torch.cuda.current_stream(wav.device)
+    N.check(N.load().wwf_peak_normalize(_ptr(w2), w2.shape[0], w2.shape[1], w2.stride(0), _ptr(o2), o2.stride(0),
+                                        wav.device.index, C.c_void_p(stream.cuda_stream)))
+    return o2.reshape(wav.shape)
+
+
 def spec_augment_(spec: torch.Tensor, fmask_start=None, fmask_len=None, tmask_start=None, tmask_len=None,
                   mask_value: float = 0.0) -> torch.Tensor:
     """In-place explicit-index SpecAugment of a contiguous CUDA (B, F, T) float32/float16 tensor."""
