@@ -35,9 +35,6 @@ constexpr int kRunLen = 16;                  // last radix: 16 contiguous positi
 constexpr int kRuns = kConvM / kRunLen;      // 1024 runs, run(l) for l = k mod 1024
 constexpr int kFusedTasks = kRuns / 2 - 1;   // 511 run pairs {l, 1024-l}; l = 0 and l = 512 are self-paired
 
-struct PadMap {
-  WWF_HD int operator()(int i) const { return i + (i >> 4); }
-};
 constexpr int kConvSmemElems = kConvM + (kConvM >> 4);
 
 // Twiddle tables (float2), one copy in shared memory per persistent CTA:

@@ -28,14 +28,20 @@ namespace wwf {
 
 constexpr int kMaxMasks = 8;
 
-// Per-n_fft plan: radix list, G = complex FFTs (frame pairs) per warp iteration, and the launch
-// bounds (max threads per CTA, min CTAs per SM) the kernel is compiled for.
+// Per-n_fft plan: radix list, G = complex FFTs (frame pairs) per warp iteration, the launch bounds
+// (max threads per CTA, min CTAs per SM) the kernel is compiled for, and the index map of the warp's
+// FFT scratch: the power-of-two sizes need one pad element per 16 (their later passes would
+// otherwise be 4- to 16-way bank conflicted); 400 = 16 x 25 has an odd stride and needs none.
 template <int NFFT> struct StftPlan;
-template <> struct StftPlan<256>  { using Rad = Radices<16, 16>;    static constexpr int G = 2, kThreads = 320, kMinCtas = 2; };
-template <> struct StftPlan<400>  { using Rad = Radices<16, 25>;    static constexpr int G = 2, kThreads = 320, kMinCtas = 2; };
-template <> struct StftPlan<512>  { using Rad = Radices<16, 8, 4>;  static constexpr int G = 1, kThreads = 512, kMinCtas = 1; };
-template <> struct StftPlan<1024> { using Rad = Radices<16, 16, 4>; static constexpr int G = 1, kThreads = 512, kMinCtas = 1; };
-template <> struct StftPlan<2048> { using Rad = Radices<16, 16, 8>; static constexpr int G = 1, kThreads = 512, kMinCtas = 1; };
+template <> struct StftPlan<256>  { using Rad = Radices<16, 16>;    using Map = PadMap;      static constexpr int G = 2, kThreads = 320, kMinCtas = 2; };
+template <> struct StftPlan<400>  { using Rad = Radices<16, 25>;    using Map = IdentityMap; static constexpr int G = 2, kThreads = 320, kMinCtas = 2; };
+template <> struct StftPlan<512>  { using Rad = Radices<16, 8, 4>;  using Map = PadMap;      static constexpr int G = 1, kThreads = 512, kMinCtas = 1; };
+template <> struct StftPlan<1024> { using Rad = Radices<16, 16, 4>; using Map = PadMap;      static constexpr int G = 1, kThreads = 512, kMinCtas = 1; };
+template <> struct StftPlan<2048> { using Rad = Radices<16, 16, 8>; using Map = PadMap;      static constexpr int G = 1, kThreads = 512, kMinCtas = 1; };
+// complex elements of one FFT's scratch buffer (mapped length, rounded up to an even count)
+template <int NFFT> constexpr int stft_zlen() {
+  return (typename StftPlan<NFFT>::Map()(NFFT - 1) + 2) & ~1;
+}
 
 constexpr int kNoiseBlk = 128;   // granularity of the noise bank's squared-sample prefix sums
 
@@ -242,6 +248,9 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
   constexpr int K = NFFT / 2 + 1;
   constexpr int NC = (NFFT + 31) / 32;                       // 32-sample columns per frame
   constexpr bool kNatural = NFFT <= 1024;                    // power spectra re-stored in bin order
+  using Map = typename Plan::Map;
+  constexpr int ZL = stft_zlen<NFFT>();                      // scratch elements per FFT (with padding)
+  const Map zmap;
   constexpr int NI = (G * K + 31) / 32;                      // split items per lane
   static_assert(Rad::n == NFFT, "radix plan");
 
@@ -262,7 +271,7 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
   int* s_melofs = reinterpret_cast<int*>(smem + p.off_melofs);
   unsigned char* s_rowmask = reinterpret_cast<unsigned char*>(smem + p.off_rowmask);
   unsigned char* s_colmask = reinterpret_cast<unsigned char*>(smem + p.off_colmask);
-  float2* z = reinterpret_cast<float2*>(smem + p.off_z) + (size_t)warp * G * NFFT;
+  float2* z = reinterpret_cast<float2*>(smem + p.off_z) + (size_t)warp * G * ZL;
 
   // ---- constants -> shared memory, once per (persistent) CTA ---------------------------
   for (int i = tid; i < NFFT; i += blockDim.x) s_window[i] = __ldg(p.window + i);
@@ -352,7 +361,7 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
               const float w = s_window[j];
 #pragma unroll
               for (int g = 0; g < G; ++g)
-                z[g * NFFT + j] = make_float2(w * sreg[2 * g * HOP32 + c], w * sreg[(2 * g + 1) * HOP32 + c]);
+                z[g * ZL + zmap(j)] = make_float2(w * sreg[2 * g * HOP32 + c], w * sreg[(2 * g + 1) * HOP32 + c]);
             }
           }
         }
@@ -376,7 +385,7 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
             im = __ldg(x + i);
             if (mix) im = fmaf(scale, noise_at(nz, noff, nlen, i), im);
           }
-          z[idx] = make_float2(re * w, im * w);
+          z[g * ZL + zmap(j)] = make_float2(re * w, im * w);
         }
       }
       __syncwarp();
@@ -388,7 +397,7 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
 #pragma unroll 1   // one copy of each radix butterfly: the hot loop has to stay inside the instruction cache
         for (int u = lane; u < G * tasks; u += 32) {
           const int g = u / tasks, uu = u - g * tasks;
-          pass_task<R, false>(z + g * NFFT, L, uu, [&](int q) { return tw[q]; });
+          pass_task<R, false, Map>(z + g * ZL, L, uu, [&](int q) { return tw[q]; });
         }
         __syncwarp();
       });
@@ -401,8 +410,8 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
           const int idx = lane + 32 * i;
           if (idx < G * K) {
             const int g = idx / K, k = idx - g * K;
-            const float2* zz = z + g * NFFT;
-            pw[i] = pair_split_power(zz[Rad::pos(k)], zz[Rad::pos(k == 0 ? 0 : NFFT - k)]);
+            const float2* zz = z + g * ZL;
+            pw[i] = pair_split_power(zz[zmap(Rad::pos(k))], zz[zmap(Rad::pos(k == 0 ? 0 : NFFT - k))]);
           }
         }
         __syncwarp();
@@ -411,15 +420,15 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
           const int idx = lane + 32 * i;
           if (idx < G * K) {
             const int g = idx / K, k = idx - g * K;
-            z[g * NFFT + k] = pw[i];
+            z[g * ZL + zmap(k)] = pw[i];
           }
         }
       } else {
         // in place at Z[k]'s slot (only bin k's lane touches it)
         for (int idx = lane; idx < G * K; idx += 32) {
           const int g = idx / K, k = idx - g * K;
-          float2* zz = z + g * NFFT;
-          const int pk = Rad::pos(k), pm = Rad::pos(k == 0 ? 0 : NFFT - k);
+          float2* zz = z + g * ZL;
+          const int pk = zmap(Rad::pos(k)), pm = zmap(Rad::pos(k == 0 ? 0 : NFFT - k));
           zz[pk] = pair_split_power(zz[pk], zz[pm]);
         }
       }
@@ -435,19 +444,19 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
         for (; o + 1 < o1; o += 2) {
           const float w0 = s_melw[o], w1 = s_melw[o + 1];
           const int k = lo + (o - o0);
-          const int p0 = kNatural ? k : Rad::pos(k), p1 = kNatural ? k + 1 : Rad::pos(k + 1);
+          const int p0 = zmap(kNatural ? k : Rad::pos(k)), p1 = zmap(kNatural ? k + 1 : Rad::pos(k + 1));
 #pragma unroll
           for (int g = 0; g < G; ++g) {
-            acc[g] = cfma_s(z[g * NFFT + p0], w0, acc[g]);
-            acc1[g] = cfma_s(z[g * NFFT + p1], w1, acc1[g]);
+            acc[g] = cfma_s(z[g * ZL + p0], w0, acc[g]);
+            acc1[g] = cfma_s(z[g * ZL + p1], w1, acc1[g]);
           }
         }
         if (o < o1) {
           const float w0 = s_melw[o];
           const int k = lo + (o - o0);
-          const int p0 = kNatural ? k : Rad::pos(k);
+          const int p0 = zmap(kNatural ? k : Rad::pos(k));
 #pragma unroll
-          for (int g = 0; g < G; ++g) acc[g] = cfma_s(z[g * NFFT + p0], w0, acc[g]);
+          for (int g = 0; g < G; ++g) acc[g] = cfma_s(z[g * ZL + p0], w0, acc[g]);
         }
 #pragma unroll
         for (int g = 0; g < G; ++g) acc[g] = cadd(acc[g], acc1[g]);

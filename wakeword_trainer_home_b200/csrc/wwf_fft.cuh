@@ -270,7 +270,12 @@ WWF_HD void dft(float2 (&v)[R]) {
 // Forward (DIF): v' [r] = w_L^{j r} * DFT_R(v)[r].   Inverse (DIT): v = IDFT_R(conj(tw) * v').
 // ----------------------------------------------------------------------------------------
 struct IdentityMap {
-  WWF_HD int operator()(int i) const { return i; }
+  WWF_HD constexpr int operator()(int i) const { return i; }
+};
+// One padding element after every 16: makes the power-of-two strides of radix-2^k passes hit 16
+// distinct 8-byte banks per half-warp (stride 16 -> 17, 64 -> 68, 4 -> 4 + carry, ...).
+struct PadMap {
+  WWF_HD constexpr int operator()(int i) const { return i + (i >> 4); }
 };
 
 template <int R, bool INV, class Map = IdentityMap, class TwLoad>

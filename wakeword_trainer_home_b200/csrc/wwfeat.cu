@@ -59,7 +59,7 @@ typedef void (*FeatKernel)(const FeatParams);
 struct wwf_plan {
   wwf_config cfg;
   int device = 0, sm_count = 0, max_smem = 0;
-  int K = 0, n_feat = 0, G = 1, tw_total = 0, n_melw = 0, max_warps = 16;
+  int K = 0, n_feat = 0, G = 1, zlen = 0, tw_total = 0, n_melw = 0, max_warps = 16;
   FeatKernel kernel = nullptr;
   // device constants
   float* d_window = nullptr;
@@ -105,6 +105,7 @@ static void select_kernel(wwf_plan* p, std::vector<float2>& tw) {
   using Plan = StftPlan<NFFT>;
   build_stft_twiddles<typename Plan::Rad>(tw);
   p->G = Plan::G;
+  p->zlen = stft_zlen<NFFT>();
   p->max_warps = Plan::kThreads / 32;
   p->tw_total = Plan::Rad::tw_total;
   const bool f16 = p->cfg.out_dtype == WWF_OUT_F16;
@@ -488,7 +489,7 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
   fp.off_colmask = o;  o += al4((T + 3) / 4);
   fp.off_z = o;
   const size_t fixed_bytes = (size_t)o * sizeof(float);
-  const size_t per_warp = (size_t)p->G * nfft * sizeof(float2);
+  const size_t per_warp = (size_t)p->G * p->zlen * sizeof(float2);
   const size_t budget = (size_t)p->max_smem - 1024;   // static smem of the kernel is 256 B
   if (fixed_bytes + per_warp > budget)
     return fail(WWF_ERR_UNSUPPORTED, "clip too long for the in-shared-memory tile: %zu bytes of tiles/tables (N=%d, T=%d, n_mels=%d)", fixed_bytes, N, T, M);
