@@ -33,11 +33,11 @@ constexpr int kMaxMasks = 8;
 // FFT scratch: the power-of-two sizes need one pad element per 16 (their later passes would
 // otherwise be 4- to 16-way bank conflicted); 400 = 16 x 25 has an odd stride and needs none.
 template <int NFFT> struct StftPlan;
-template <> struct StftPlan<256>  { using Rad = Radices<16, 16>;    using Map = PadMap;      static constexpr int G = 2, kThreads = 320, kMinCtas = 2; };
+template <> struct StftPlan<256>  { using Rad = Radices<16, 16>;    using Map = PadMap2;     static constexpr int G = 2, kThreads = 320, kMinCtas = 2; };
 template <> struct StftPlan<400>  { using Rad = Radices<16, 25>;    using Map = IdentityMap; static constexpr int G = 2, kThreads = 320, kMinCtas = 2; };
-template <> struct StftPlan<512>  { using Rad = Radices<16, 8, 4>;  using Map = PadMap;      static constexpr int G = 1, kThreads = 512, kMinCtas = 1; };
-template <> struct StftPlan<1024> { using Rad = Radices<16, 16, 4>; using Map = PadMap;      static constexpr int G = 1, kThreads = 512, kMinCtas = 1; };
-template <> struct StftPlan<2048> { using Rad = Radices<16, 16, 8>; using Map = PadMap;      static constexpr int G = 1, kThreads = 512, kMinCtas = 1; };
+template <> struct StftPlan<512>  { using Rad = Radices<16, 8, 4>;  using Map = PadMap2;     static constexpr int G = 1, kThreads = 512, kMinCtas = 1; };
+template <> struct StftPlan<1024> { using Rad = Radices<16, 16, 4>; using Map = PadMap2;     static constexpr int G = 1, kThreads = 512, kMinCtas = 1; };
+template <> struct StftPlan<2048> { using Rad = Radices<16, 16, 8>; using Map = PadMap2;     static constexpr int G = 1, kThreads = 512, kMinCtas = 1; };
 // complex elements of one FFT's scratch buffer (mapped length, rounded up to an even count)
 template <int NFFT> constexpr int stft_zlen() {
   return (typename StftPlan<NFFT>::Map()(NFFT - 1) + 2) & ~1;

@@ -277,6 +277,12 @@ struct IdentityMap {
 struct PadMap {
   WWF_HD constexpr int operator()(int i) const { return i + (i >> 4); }
 };
+// Two-level padding: additionally one element per 256.  Keeps the radix passes conflict-free and
+// also spreads the digit-reversed gather of the spectrum split (consecutive k -> positions
+// 64 apart for 1024 = 16.16.4, 128 apart for 2048, 32 apart for 512) over 16 distinct banks.
+struct PadMap2 {
+  WWF_HD constexpr int operator()(int i) const { return i + (i >> 4) + (i >> 8); }
+};
 
 template <int R, bool INV, class Map = IdentityMap, class TwLoad>
 WWF_HD void pass_task(float2* z, int L, int u, TwLoad twload, Map map = Map()) {
