@@ -413,3 +413,23 @@ def test_peak_normalize_bit_exact(ww):
     ww.peak_normalize(y, out=y)                                  # in place
     assert np.array_equal(y.cpu().numpy(), want)
     assert np.array_equal(ww.peak_normalize(x[2].cuda()).cpu().numpy(), want[2])   # 1-D chunk like _process_chunk
+
+
+def test_integration_md_ctypes_stub_works(ww):
+    """The minimal ctypes binding printed in INTEGRATION.md (Option B) is executable as written and
+    agrees with the oracle - it lets the library build its own constants (window/mel/DCT = NULL)."""
+    import re
+    from oracle import ta_oracle as tao
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    code = re.search(r"```python\n(# src/data/_wwfeat\.py.*?)```", md, flags=re.S).group(1)
+    code = code.replace('C.CDLL("libwwfeat.so")', f'C.CDLL({ww.LIB_PATH!r})')
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    fe = ns["FeatureExtractor"](16000, "mfcc", 40, 13, 400, 160, "cuda:0")
+    x = make_inputs(3, 4, 16000)
+    for c in (0, 3):
+        got = fe(x[c]).cpu()
+        assert got.shape == (1, 13, 101)
+        ref = tao.featurize(x[c:c + 1], sample_rate=16000, feature_type="mfcc", n_mels=40, n_mfcc=13, n_fft=400, hop_length=160)[0]
+        assert_features_close(got.numpy(), ref.numpy(), f"INTEGRATION.md stub clip {c}")
