@@ -247,7 +247,8 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
   constexpr int G = Plan::G;
   constexpr int K = NFFT / 2 + 1;
   constexpr int NC = (NFFT + 31) / 32;                       // 32-sample columns per frame
-  constexpr bool kNatural = NFFT <= 1024;                    // power spectra re-stored in bin order
+  constexpr bool kNatural = true;                            // power spectra re-stored in bin order (false: left
+                                                             // at their digit-reversed slots, mel reads through pos())
   using Map = typename Plan::Map;
   constexpr int ZL = stft_zlen<NFFT>();                      // scratch elements per FFT (with padding)
   const Map zmap;
@@ -336,32 +337,40 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
         // around the end of its clip once (needs a noise clip at least as long as the span)
         if (s0 >= 0 && s0 + 32 * NR <= N && f0 + 2 * G <= T && (!mix || (q0 >= 0 && nlen >= 32 * NR))) {
           staged = true;
-          float sreg[NR];
-          const float* xs = x + s0 + lane;
+          // the span is staged in chunks of CH 32-sample columns so that at most (2G-1)*HOP32 + 32
+          // registers are live (n_fft 2048 = 64 columns needs two chunks; everything else one)
+          constexpr int CH = NC < 32 ? NC : 32, NCHUNK = (NC + CH - 1) / CH, NRC = (2 * G - 1) * HOP32 + CH;
+          static_assert(NC % CH == 0, "column chunks");
 #pragma unroll
-          for (int r = 0; r < NR; ++r) sreg[r] = __ldg(xs + 32 * r);
-          if (mix) {
-            if (q0 + 32 * NR <= nlen) {
-              const float* ns = nz + q0 + lane;
+          for (int ch = 0; ch < NCHUNK; ++ch) {
+            const int r0 = ch * CH;
+            float sreg[NRC];
+            const float* xs = x + s0 + 32 * r0 + lane;
 #pragma unroll
-              for (int r = 0; r < NR; ++r) sreg[r] = fmaf(scale, __ldg(ns + 32 * r), sreg[r]);
-            } else {
+            for (int r = 0; r < NRC; ++r) sreg[r] = __ldg(xs + 32 * r);
+            if (mix) {
+              if (q0 + 32 * NR <= nlen) {
+                const float* ns = nz + q0 + 32 * r0 + lane;
 #pragma unroll
-              for (int r = 0; r < NR; ++r) {
-                int q = q0 + 32 * r + lane;
-                q -= q >= nlen ? nlen : 0;
-                sreg[r] = fmaf(scale, __ldg(nz + q), sreg[r]);
+                for (int r = 0; r < NRC; ++r) sreg[r] = fmaf(scale, __ldg(ns + 32 * r), sreg[r]);
+              } else {
+#pragma unroll
+                for (int r = 0; r < NRC; ++r) {
+                  int q = q0 + 32 * (r0 + r) + lane;
+                  q -= q >= nlen ? nlen : 0;
+                  sreg[r] = fmaf(scale, __ldg(nz + q), sreg[r]);
+                }
               }
             }
-          }
 #pragma unroll
-          for (int c = 0; c < NC; ++c) {
-            const int j = 32 * c + lane;
-            if (NFFT % 32 == 0 || j < NFFT) {
-              const float w = s_window[j];
+            for (int c = 0; c < CH; ++c) {
+              const int j = 32 * (r0 + c) + lane;
+              if (NFFT % 32 == 0 || j < NFFT) {
+                const float w = s_window[j];
 #pragma unroll
-              for (int g = 0; g < G; ++g)
-                z[g * ZL + zmap(j)] = make_float2(w * sreg[2 * g * HOP32 + c], w * sreg[(2 * g + 1) * HOP32 + c]);
+                for (int g = 0; g < G; ++g)
+                  z[g * ZL + zmap(j)] = make_float2(w * sreg[2 * g * HOP32 + c], w * sreg[(2 * g + 1) * HOP32 + c]);
+              }
             }
           }
         }

@@ -98,7 +98,7 @@ static int upload(T** dst, const std::vector<T>& src) {
 }
 
 // Kernel variant: frames loaded through the register-staged path when hop is 128, 160 (the
-// reference's hop for every preset) or 256 and the sample span fits in registers; generic
+// reference's hop for every preset), 256 or 512 and the sample span fits in registers; generic
 // per-element loads otherwise.
 template <int NFFT>
 static void select_kernel(wwf_plan* p, std::vector<float2>& tw) {
@@ -110,13 +110,14 @@ static void select_kernel(wwf_plan* p, std::vector<float2>& tw) {
   p->tw_total = Plan::Rad::tw_total;
   const bool f16 = p->cfg.out_dtype == WWF_OUT_F16;
   p->kernel = f16 ? (FeatKernel)feat_kernel<NFFT, 0, __half> : (FeatKernel)feat_kernel<NFFT, 0, float>;
-  if constexpr (NFFT <= 1024) {
+  {
     // register-staged frame loads for hops that are a multiple of 32 and instantiated: 128, 160, 256
     if (!getenv("WWF_FEAT_GENERIC_LOAD")) {
       switch (p->cfg.hop_length) {
         case 128: p->kernel = f16 ? (FeatKernel)feat_kernel<NFFT, 4, __half> : (FeatKernel)feat_kernel<NFFT, 4, float>; break;
         case 160: p->kernel = f16 ? (FeatKernel)feat_kernel<NFFT, 5, __half> : (FeatKernel)feat_kernel<NFFT, 5, float>; break;
         case 256: if constexpr (NFFT > 256) p->kernel = f16 ? (FeatKernel)feat_kernel<NFFT, 8, __half> : (FeatKernel)feat_kernel<NFFT, 8, float>; break;
+        case 512: if constexpr (NFFT >= 1024) p->kernel = f16 ? (FeatKernel)feat_kernel<NFFT, 16, __half> : (FeatKernel)feat_kernel<NFFT, 16, float>; break;
         default: break;
       }
     }
