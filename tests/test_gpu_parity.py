@@ -433,3 +433,45 @@ def test_integration_md_ctypes_stub_works(ww):
         assert got.shape == (1, 13, 101)
         ref = tao.featurize(x[c:c + 1], sample_rate=16000, feature_type="mfcc", n_mels=40, n_mfcc=13, n_fft=400, hop_length=160)[0]
         assert_features_close(got.numpy(), ref.numpy(), f"INTEGRATION.md stub clip {c}")
+
+
+def test_size_independent_properties_at_full_size(ww):
+    """BASELINE.json configs[1] size (B = 1024): properties that need no oracle.
+    reverb is linear; the mixed-in noise lands at the requested SNR; masking twice = masking once;
+    CMVN rows have zero mean and unit (population) variance."""
+    B, N = 1024, 24000
+    gen = torch.Generator().manual_seed(9)
+    x = (0.1 * torch.randn(B, N, generator=gen)).cuda()
+    y = (0.05 * torch.randn(B, N, generator=gen)).cuda()
+    noise, rirs = synth_banks(0, 256, 24000, 64, 8000)
+    plan = ww.FeaturePlan(16000, "mfcc", 40, 40, 400, 160, "cuda", cmvn=True, n_freq_masks=2, n_time_masks=2)
+    plan.register_noise(noise); plan.register_rirs(rirs)
+    rir_idx = torch.randint(0, 64, (B,), generator=gen, dtype=torch.int32)
+    rev = ww.AugParams(rir_idx=rir_idx)
+    # linearity of the overlap-save convolution: conv(2x + y) = 2 conv(x) + conv(y)
+    lhs = plan.augment(2.0 * x + y, rev)
+    rhs = 2.0 * plan.augment(x, rev) + plan.augment(y, rev)
+    rms = lhs.pow(2).mean(dim=1, keepdim=True).sqrt()
+    assert ((lhs - rhs).abs() <= 1e-5 * rms).all()
+    # SNR of the mix: y = s + a n  =>  10 log10(|s|^2 / |a n|^2) = snr
+    snr = 5.0 + 15.0 * torch.rand(B, generator=gen)
+    p = ww.AugParams(rir_idx=rir_idx, noise_idx=torch.randint(0, 256, (B,), generator=gen, dtype=torch.int32),
+                     noise_off=torch.randint(0, 24000, (B,), generator=gen), snr_db=snr)
+    s = plan.augment(x, rev).double()
+    an = plan.augment(x, p).double() - s
+    got_snr = 10.0 * torch.log10(s.pow(2).sum(1) / an.pow(2).sum(1))
+    assert (got_snr.cpu() - snr.double()).abs().max() <= 2e-3     # float32 cancellation in (mix - signal)
+    # masks are idempotent and only touch the masked cells; CMVN statistics
+    fs, fl = ww.draw_mask_params(gen, B, 40, 15, 2)
+    ts, tl = ww.draw_mask_params(gen, B, 151, 35, 2)
+    pm = ww.AugParams(rir_idx=p.rir_idx, noise_idx=p.noise_idx, noise_off=p.noise_off, snr_db=p.snr_db,
+                      fmask_start=fs, fmask_len=fl, tmask_start=ts, tmask_len=tl)
+    plain = plan.featurize(x, p)
+    masked = plan.featurize(x, pm)
+    again = ww.spec_augment_(masked.clone().view(B, 40, 151), fs, fl, ts, tl, 0.0).view_as(masked)
+    assert torch.equal(again, masked)
+    keep = masked != 0.0
+    assert torch.equal(masked[keep], plain[keep])
+    assert plain.mean(dim=-1).abs().max() <= 1e-3
+    assert (plain.var(dim=-1, unbiased=False) - 1.0).abs().max() <= 1e-3
+    assert plan.check_finite()
