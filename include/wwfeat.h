@@ -44,6 +44,7 @@ typedef enum wwf_status {
 enum { WWF_FEAT_LOGMEL = 0, WWF_FEAT_MFCC = 1 };
 enum { WWF_OUT_F32 = 0, WWF_OUT_F16 = 1 };
 enum { WWF_BANK_NOISE = 0, WWF_BANK_RIR = 1 };
+enum { WWF_BANK_F32 = 0, WWF_BANK_I16 = 1 }; /* element type of a device-resident clip bank */
 
 /*
  * Feature configuration = the reference's FeatureExtractor constructor arguments
@@ -163,6 +164,36 @@ int wwf_featurize(wwf_plan* plan, const float* wav, int B, int N, int64_t wav_st
 int wwf_augment(wwf_plan* plan, const float* wav, int B, int N, int64_t wav_stride,
                 const wwf_aug* aug, float* out_wav, int64_t out_stride, void* workspace,
                 size_t workspace_bytes, void* stream);
+
+/*
+ * Device-resident loader, part 1: assemble a batch from a clip bank that lives in HBM.
+ *   bank  dev [n_clips][N] float32, or int16 PCM (converted as x / 32768, exact), row stride bank_stride
+ *   idx   dev int64 [B] clip numbers;  out dev float32 [B][N], row stride out_stride
+ * Replaces: WakewordDataset.__getitem__'s per-sample load for datasets held in memory
+ *           (src/ui/panel_training.py:323-349: load_dataset_splits + DataLoader(num_workers=16)).
+ */
+int wwf_gather_clips(const void* bank, int dtype, int64_t n_clips, int N, int64_t bank_stride, const int64_t* idx,
+                     int B, float* out, int64_t out_stride, int device, void* stream);
+
+/*
+ * Device-resident loader, part 2: make the augmentation draws of one batch ON the GPU.
+ * Counter-based Philox4x32-10; sample i of the call is sample number first_index + i of the run and
+ * its draws are a pure function of (seed, first_index + i) - the host can recompute them bit-exactly
+ * (tests/helpers.py:philox_draws), so they remain "explicit" for the oracle.  Fills the arrays of
+ * `out` (the same wwf_aug the plan's wwf_featurize then consumes; pointers are written through).
+ *   apply probabilities and ranges = AugmentationConfig (src/config/defaults.py:73-95);
+ *   mask arithmetic = torchaudio mask_along_axis; n_freq_masks / n_time_masks, n_feat come from the plan.
+ * Replaces: the random.* / torch.rand calls inside AudioAugmentation.__call__ and SpecAugment.__call__.
+ */
+typedef struct wwf_draw_config {
+  uint64_t seed;
+  double rir_prob, noise_prob;             /* AugmentationConfig.rir_prob, background_noise_prob */
+  double freq_mask_prob, time_mask_prob;   /* gate all freq / all time masks of a clip */
+  float snr_lo, snr_hi;                    /* noise_snr_min / noise_snr_max, dB */
+  int32_t freq_mask_param, time_mask_param;
+} wwf_draw_config;
+int wwf_draw_aug(wwf_plan* plan, const wwf_draw_config* cfg, uint64_t first_index, int B, int T,
+                 const wwf_aug* out, void* stream);
 
 /*
  * Per-clip peak normalisation y = x / max|x| (all-zero clips pass through), float32 [B][N] -> [B][N];

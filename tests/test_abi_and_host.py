@@ -170,3 +170,18 @@ def test_two_rank_sharding_over_gloo(tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert r.stdout.count("ok") == 2
+
+
+def test_philox_mirror_known_answers():
+    """The numpy mirror of the on-GPU sampler is the published Philox4x32-10: Random123's known-answer
+    vectors (kat_vectors: philox4x32 10 rounds)."""
+    from helpers import philox4x32_10
+    z = np.zeros(1, np.uint32)
+    out = philox4x32_10(z, z, z, z, 0, 0)
+    assert [int(v[0]) for v in out] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f = np.full(1, 0xffffffff, np.uint32)
+    out = philox4x32_10(f, f, f, f, 0xffffffff, 0xffffffff)
+    assert [int(v[0]) for v in out] == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    out = philox4x32_10(np.array([0x243f6a88], np.uint32), np.array([0x85a308d3], np.uint32), np.array([0x13198a2e], np.uint32),
+                        np.array([0x03707344], np.uint32), 0xa4093822, 0x299f31d0)
+    assert [int(v[0]) for v in out] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]

@@ -475,3 +475,68 @@ def test_size_independent_properties_at_full_size(ww):
     assert plain.mean(dim=-1).abs().max() <= 1e-3
     assert (plain.var(dim=-1, unbiased=False) - 1.0).abs().max() <= 1e-3
     assert plan.check_finite()
+
+
+def test_device_draws_bit_exact_vs_host_mirror(ww):
+    """wwf_draw_aug (Philox4x32-10 on the GPU) against the numpy mirror: every index, offset, SNR and mask
+    pair identical - so draws made on the device stay explicit for the oracle."""
+    from helpers import philox_draws
+    gen = torch.Generator().manual_seed(3)
+    noise = [0.05 * torch.randn(n, generator=gen) for n in (24000, 7001, 50000, 16001, 33333)]
+    t = torch.arange(2000, dtype=torch.float32)
+    rirs = [torch.randn(2000, generator=gen) * torch.exp(-t / 400.0) for _ in range(7)]
+    for (nF, nT, F, N, seed, first, kw) in ((2, 2, 40, 24000, 1234567890123, 0, {}),
+                                             (3, 1, 128, 40000, 7, 2 ** 33 + 5, dict(rir_prob=1.0, noise_prob=0.0, freq_mask_prob=1.0)),
+                                             (0, 4, 64, 16000, 2 ** 63 + 11, 999, dict(time_mask_prob=0.9, snr_range=(-5.0, 30.0), time_mask_param=50))):
+        plan = ww.FeaturePlan(16000, "mel", F, 40, 1024 if F > 64 else 400, 160, "cuda", n_freq_masks=nF, n_time_masks=nT)
+        plan.register_noise(noise); plan.register_rirs(rirs)
+        B, T = 4099, N // 160 + 1
+        cfg = ww.DrawConfig(seed=seed, **kw)
+        got = plan.draw_aug(cfg, first, B, N)
+        want = philox_draws(seed, first, B, len(rirs), [len(n) for n in noise], F, T, nF, nT, **kw)
+        for name in ("rir_idx", "noise_idx", "noise_off", "snr_db", "fmask_start", "fmask_len", "tmask_start", "tmask_len"):
+            g = getattr(got, name)
+            if g is None:
+                assert want[name].size == 0
+                continue
+            assert np.array_equal(g.cpu().numpy(), want[name]), name
+        if nF:
+            assert (got.fmask_start >= 0).all() and (got.fmask_start + got.fmask_len <= F).all()
+        if nT:
+            assert (got.tmask_start + got.tmask_len <= T).all()
+        on = (got.rir_idx >= 0).float().mean().item()
+        assert abs(on - kw.get("rir_prob", 0.25)) < 0.03           # the gates follow the requested probabilities
+
+
+def test_device_resident_loader_end_to_end(ww):
+    """Clip bank in HBM (int16 PCM and float32), gather + on-GPU draws + fused features; the oracle is fed
+    the host-recomputed draws."""
+    from helpers import philox_draws
+    from oracle import ta_oracle as tao
+    gen = torch.Generator().manual_seed(17)
+    n, N, B = 150, 16000, 64
+    pcm = torch.randint(-20000, 20000, (n, N), generator=gen, dtype=torch.int16)
+    labels = torch.randint(0, 2, (n,), generator=gen)
+    idx = torch.randperm(n, generator=gen)[:B]
+    got = ww.gather_clips(pcm.cuda(), idx)
+    assert torch.equal(got.cpu(), pcm[idx].float() / 32768.0)      # int16 -> float conversion is exact
+    f32 = pcm.float() / 32768.0
+    assert torch.equal(ww.gather_clips(f32.cuda(), idx).cpu(), f32[idx])
+    noise, rirs = synth_banks(21, 4, 20000, 3, 3000)
+    plan = ww.FeaturePlan(16000, "mfcc", 40, 40, 400, 160, "cuda", n_freq_masks=2, n_time_masks=2)
+    plan.register_noise(noise); plan.register_rirs(rirs)
+    cfg = ww.DrawConfig(seed=99, rir_prob=0.5, noise_prob=0.7)
+    ld = ww.DeviceBatchLoader(pcm.cuda(), labels, plan, B, draw=cfg, shuffle=True, seed=5)
+    perm = torch.randperm(n, generator=torch.Generator().manual_seed(5))
+    first = 0
+    for i, (x, y) in enumerate(ld):
+        sel = perm[i * B:(i + 1) * B]
+        d = philox_draws(99, first, sel.numel(), 3, [20000] * 4, 40, 101, 2, 2, rir_prob=0.5, noise_prob=0.7)
+        ref = tao.pipeline(f32[sel], rirs=rirs, rir_idx=d["rir_idx"], noise_bank=noise, noise_idx=d["noise_idx"],
+                           noise_off=d["noise_off"], snr_db=torch.from_numpy(d["snr_db"]), fstart=d["fmask_start"], flen=d["fmask_len"],
+                           tstart=d["tmask_start"], tlen=d["tmask_len"], sample_rate=16000, feature_type="mfcc",
+                           n_mels=40, n_mfcc=40, n_fft=400, hop_length=160)
+        assert torch.equal(y.cpu(), labels[sel])
+        assert_features_close(x.cpu().numpy(), ref.numpy(), f"device loader batch {i}")
+        first += sel.numel()
+    assert first == n and ld.samples_drawn == n

@@ -6,13 +6,14 @@ sarpel/wakeword_trainer_home, executed by hand-written CUDA kernels behind a C A
 built library and a CUDA device.
 """
 from ._native import WwfError, LIB_PATH, launch_count  # noqa: F401
-from .pipeline import AugParams, FeaturePlan, draw_mask_params, peak_normalize, spec_augment_  # noqa: F401
+from .pipeline import (AugParams, DrawConfig, FeaturePlan, draw_mask_params, gather_clips,  # noqa: F401
+                       peak_normalize, spec_augment_)
 from .feature_extraction import FeatureExtractor  # noqa: F401
 from .augmentation import AudioAugmentation, SpecAugment  # noqa: F401
-from .loader import GpuBatchLoader, StreamedFeaturizer  # noqa: F401
+from .loader import DeviceBatchLoader, GpuBatchLoader, StreamedFeaturizer  # noqa: F401
 from .sharding import shard_range, shard_seed  # noqa: F401
 
 __version__ = "0.1.0"
 __all__ = ["FeatureExtractor", "AudioAugmentation", "SpecAugment", "FeaturePlan", "AugParams",
-           "draw_mask_params", "spec_augment_", "peak_normalize", "WwfError", "launch_count", "GpuBatchLoader", "StreamedFeaturizer",
+           "draw_mask_params", "spec_augment_", "peak_normalize", "WwfError", "launch_count", "GpuBatchLoader", "DeviceBatchLoader", "StreamedFeaturizer", "DrawConfig", "gather_clips",
            "shard_range", "shard_seed"]

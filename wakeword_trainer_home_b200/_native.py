@@ -17,6 +17,7 @@ WWF_OK = 0
 FEAT_LOGMEL, FEAT_MFCC = 0, 1
 OUT_F32, OUT_F16 = 0, 1
 BANK_NOISE, BANK_RIR = 0, 1
+BANK_F32, BANK_I16 = 0, 1
 MAX_MASKS = 8
 SUPPORTED_N_FFT = (256, 400, 512, 1024, 2048)
 
@@ -52,6 +53,13 @@ class Aug(C.Structure):
     ]
 
 
+class DrawConfig(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("rir_prob", C.c_double), ("noise_prob", C.c_double),
+                ("freq_mask_prob", C.c_double), ("time_mask_prob", C.c_double),
+                ("snr_lo", C.c_float), ("snr_hi", C.c_float),
+                ("freq_mask_param", C.c_int32), ("time_mask_param", C.c_int32)]
+
+
 class Info(C.Structure):
     _fields_ = [
         ("n_freq", C.c_int32), ("n_feat", C.c_int32), ("device", C.c_int32), ("sm_count", C.c_int32),
@@ -73,6 +81,9 @@ SYMBOLS = {
                                 C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "wwf_augment": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.POINTER(Aug),
                               C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "wwf_gather_clips": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_void_p,
+                                   C.c_int64, C.c_int, C.c_void_p]),
+    "wwf_draw_aug": (C.c_int, [C.c_void_p, C.POINTER(DrawConfig), C.c_uint64, C.c_int, C.c_int, C.POINTER(Aug), C.c_void_p]),
     "wwf_peak_normalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "wwf_spec_augment": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,

@@ -15,6 +15,7 @@
 #include "wwf_aux.cuh"
 #include "wwf_conv.cuh"
 #include "wwf_feat.cuh"
+#include "wwf_loader.cuh"
 #include "wwf_tables.h"
 
 using namespace wwf;
@@ -576,6 +577,44 @@ extern "C" int wwf_augment(wwf_plan* p, const float* wav, int B, int N, int64_t 
   mp.es_part = es_part; mp.es_nb = es_nb;
   mp.out = out_wav; mp.out_stride = out_stride; mp.B = B; mp.N = N;
   mix_kernel<<<B, 512, 0, st>>>(mp);
+  g_launches++;
+  WWF_CUDA(cudaGetLastError());
+  return WWF_OK;
+}
+
+extern "C" int wwf_gather_clips(const void* bank, int dtype, int64_t n_clips, int N, int64_t bank_stride, const int64_t* idx,
+                                int B, float* out, int64_t out_stride, int device, void* stream) {
+  if (!bank || !idx || !out || B <= 0 || N <= 0 || n_clips <= 0 || bank_stride < N || out_stride < N)
+    return fail(WWF_ERR_INVALID, "wwf_gather_clips: bad argument");
+  if (dtype != WWF_BANK_F32 && dtype != WWF_BANK_I16) return fail(WWF_ERR_INVALID, "wwf_gather_clips: dtype=%d", dtype);
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail(WWF_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == WWF_BANK_F32) gather_clips_kernel<float><<<B, 256, 0, st>>>((const float*)bank, n_clips, N, bank_stride, idx, out, out_stride);
+  else gather_clips_kernel<int16_t><<<B, 256, 0, st>>>((const int16_t*)bank, n_clips, N, bank_stride, idx, out, out_stride);
+  g_launches++;
+  WWF_CUDA(cudaGetLastError());
+  return WWF_OK;
+}
+
+extern "C" int wwf_draw_aug(wwf_plan* p, const wwf_draw_config* dc, uint64_t first_index, int B, int T, const wwf_aug* out, void* stream) {
+  if (!p || !dc || !out || B <= 0 || T <= 0) return fail(WWF_ERR_INVALID, "wwf_draw_aug: bad argument");
+  auto thr = [](double prob) { return prob <= 0.0 ? (uint64_t)0 : prob >= 1.0 ? (uint64_t)1 << 32 : (uint64_t)floor(prob * 4294967296.0); };
+  if (p->cfg.n_freq_masks > 0 && (!out->fmask_start || !out->fmask_len)) return fail(WWF_ERR_INVALID, "wwf_draw_aug: fmask arrays missing");
+  if (p->cfg.n_time_masks > 0 && (!out->tmask_start || !out->tmask_len)) return fail(WWF_ERR_INVALID, "wwf_draw_aug: tmask arrays missing");
+  if (p->n_noise > 0 && out->noise_idx && !out->noise_off) return fail(WWF_ERR_INVALID, "wwf_draw_aug: noise_off missing");
+  DeviceGuard guard(p->device);
+  if (!guard.ok) return fail(WWF_ERR_CUDA, "cudaSetDevice(%d) failed", p->device);
+  DrawParams dp{};
+  dp.seed = dc->seed; dp.first_index = first_index;
+  dp.thr_rir = thr(dc->rir_prob); dp.thr_noise = thr(dc->noise_prob); dp.thr_fmask = thr(dc->freq_mask_prob); dp.thr_tmask = thr(dc->time_mask_prob);
+  dp.snr_lo = dc->snr_lo; dp.snr_hi = dc->snr_hi;
+  dp.B = B; dp.n_rir = p->n_rir; dp.n_noise = p->n_noise; dp.F = p->n_feat; dp.T = T;
+  dp.fparam = dc->freq_mask_param; dp.tparam = dc->time_mask_param; dp.nF = p->cfg.n_freq_masks; dp.nT = p->cfg.n_time_masks;
+  dp.noise_offsets = p->d_noise_offsets;
+  dp.rir_idx = (int32_t*)out->rir_idx; dp.noise_idx = (int32_t*)out->noise_idx; dp.noise_off = (int64_t*)out->noise_off; dp.snr_db = (float*)out->snr_db;
+  dp.fs = (int32_t*)out->fmask_start; dp.fl = (int32_t*)out->fmask_len; dp.ts = (int32_t*)out->tmask_start; dp.tl = (int32_t*)out->tmask_len;
+  draw_aug_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dp);
   g_launches++;
   WWF_CUDA(cudaGetLastError());
   return WWF_OK;

@@ -18,7 +18,7 @@ from typing import Callable, Iterable, Iterator, Optional, Tuple
 
 import torch
 
-from .pipeline import AugParams, FeaturePlan, draw_mask_params
+from .pipeline import AugParams, DrawConfig, FeaturePlan, draw_mask_params, gather_clips
 from .sharding import shard_range, shard_seed
 
 
@@ -137,3 +137,53 @@ class GpuBatchLoader:
             self.step += 1
             feats = self.plan.featurize(wav, aug)
             yield feats, self.labels.index_select(0, sel.to(self.labels.device)).to(dev, non_blocking=True)
+
+
+class DeviceBatchLoader:
+    """Fully device-resident variant of ``GpuBatchLoader``: the clip bank (float32 or int16 PCM) lives in
+    HBM, batches are assembled by ``wwf_gather_clips`` and the augmentation draws are made on the GPU by
+    ``wwf_draw_aug`` (counter = number of the sample in the run, so a resumed run that restores
+    ``samples_drawn`` reproduces them).  A training step issues no host->device copy at all.
+    Yields ``(inputs, targets)`` like the DataLoader ``Trainer.train_epoch`` iterates
+    (src/training/trainer.py:147-157)."""
+
+    def __init__(self, bank: torch.Tensor, labels: torch.Tensor, plan: FeaturePlan, batch_size: int,
+                 draw: Optional[DrawConfig] = None, shuffle: bool = True, seed: int = 0, rank: int = 0,
+                 world_size: int = 1, drop_last: bool = False):
+        if not bank.is_cuda or bank.dim() != 2 or labels.shape[0] != bank.shape[0]:
+            raise ValueError("bank must be a CUDA (n, N) tensor and labels (n,)")
+        self.bank, self.plan, self.batch_size = bank, plan, batch_size
+        self.labels = labels.to(bank.device)
+        self.draw, self.shuffle, self.seed = draw, shuffle, seed
+        self.rank, self.world, self.drop_last = rank, world_size, drop_last
+        self.epoch = 0
+        self.samples_drawn = 0          # checkpoint this (with seed) to resume with identical augmentations
+
+    def set_epoch(self, epoch: int):
+        self.epoch = epoch
+
+    def __len__(self) -> int:
+        a, b = shard_range(self.bank.shape[0], self.rank, self.world)
+        n = b - a
+        return n // self.batch_size if self.drop_last else (n + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self) -> Iterator[Tuple[torch.Tensor, torch.Tensor]]:
+        n = self.bank.shape[0]
+        if self.shuffle:
+            g = torch.Generator().manual_seed(self.seed + self.epoch)     # same permutation on every rank
+            perm = torch.randperm(n, generator=g)
+        else:
+            perm = torch.arange(n)
+        a, b = shard_range(n, self.rank, self.world)
+        idx = perm[a:b].to(self.bank.device)                              # one small upload per epoch
+        # ranks draw from disjoint counter ranges: sample numbers are offset by rank * 2^40
+        base = (self.rank << 40) + self.samples_drawn
+        for i in range(len(self)):
+            sel = idx[i * self.batch_size:(i + 1) * self.batch_size]
+            wav = gather_clips(self.bank, sel)
+            aug = None
+            if self.draw is not None:
+                aug = self.plan.draw_aug(self.draw, base, sel.numel(), wav.shape[1])
+            base += sel.numel()
+            self.samples_drawn += sel.numel()
+            yield self.plan.featurize(wav, aug), self.labels.index_select(0, sel)

@@ -68,6 +68,19 @@ class AugParams:
                    for f in fields(self) if getattr(self, f.name) is not None)
 
 
+@dataclass
+class DrawConfig:
+    """Distribution of the on-GPU augmentation draws (AugmentationConfig, src/config/defaults.py:73-95)."""
+    seed: int = 0
+    rir_prob: float = 0.25
+    noise_prob: float = 0.5
+    freq_mask_prob: float = 0.5
+    time_mask_prob: float = 0.5
+    snr_range: tuple = (5.0, 20.0)
+    freq_mask_param: int = 15
+    time_mask_param: int = 35
+
+
 def draw_mask_params(gen: Optional[torch.Generator], B: int, size: int, mask_param: int, n_masks: int, p: float = 1.0):
     """Integer (start, len) pairs from the two uniform draws torchaudio's mask_along_axis_iid makes
     (value = U*param, min_value = U*(size - value); start = floor(min_value), len = floor(value);
@@ -163,6 +176,31 @@ class FeaturePlan:
         info = N.Info()
         N.check(self.lib.wwf_plan_info(self._handle, C.byref(info)))
         return info
+
+    def draw_aug(self, cfg: DrawConfig, first_index: int, B: int, n_samples: int) -> AugParams:
+        """Augmentation draws for B clips made on the GPU (Philox4x32-10, counter = sample number
+        first_index + i, key = cfg.seed): no host RNG, no H2D copy.  Returns device-resident AugParams
+        ready for ``featurize``; tests/helpers.py:philox_draws recomputes them bit-exactly on the host."""
+        dev = self.device
+        a = AugParams(rir_idx=torch.empty(B, dtype=torch.int32, device=dev),
+                      noise_idx=torch.empty(B, dtype=torch.int32, device=dev),
+                      noise_off=torch.empty(B, dtype=torch.int64, device=dev),
+                      snr_db=torch.empty(B, dtype=torch.float32, device=dev))
+        if self.n_freq_masks:
+            a.fmask_start = torch.empty(B, self.n_freq_masks, dtype=torch.int32, device=dev)
+            a.fmask_len = torch.empty(B, self.n_freq_masks, dtype=torch.int32, device=dev)
+        if self.n_time_masks:
+            a.tmask_start = torch.empty(B, self.n_time_masks, dtype=torch.int32, device=dev)
+            a.tmask_len = torch.empty(B, self.n_time_masks, dtype=torch.int32, device=dev)
+        dc = N.DrawConfig(seed=int(cfg.seed) & (2 ** 64 - 1), rir_prob=cfg.rir_prob, noise_prob=cfg.noise_prob,
+                          freq_mask_prob=cfg.freq_mask_prob, time_mask_prob=cfg.time_mask_prob,
+                          snr_lo=float(cfg.snr_range[0]), snr_hi=float(cfg.snr_range[1]),
+                          freq_mask_param=int(cfg.freq_mask_param), time_mask_param=int(cfg.time_mask_param))
+        st = N.Aug(*[_ptr(getattr(a, f[0])) for f in N.Aug._fields_])
+        stream = torch.cuda.current_stream(dev)
+        N.check(self.lib.wwf_draw_aug(self._handle, C.byref(dc), C.c_uint64(int(first_index)), B, self.num_frames(n_samples),
+                                      C.byref(st), C.c_void_p(stream.cuda_stream)))
+        return a
 
     def check_finite(self) -> bool:
         """True if every feature computed since the last call was finite (synchronises the current
@@ -268,6 +306,22 @@ class FeaturePlan:
         N.check(self.lib.wwf_augment(self._handle, _ptr(wav), B, n, wav.stride(0), None if st is None else C.byref(st),
                                      _ptr(out), out.stride(0), _ptr(ws), ws_bytes, C.c_void_p(stream.cuda_stream)))
         return out
+
+
+def gather_clips(bank: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[b] = bank[idx[b]] as float32 from a device-resident clip bank (n, N): float32, or int16 PCM
+    (converted as x / 32768).  The batch-assembly step of the device-resident loader."""
+    if not bank.is_cuda or bank.dim() != 2 or bank.stride(1) != 1 or bank.dtype not in (torch.float32, torch.int16):
+        raise ValueError("bank must be a CUDA (n, N) float32 or int16 tensor with contiguous rows")
+    idx = idx.to(device=bank.device, dtype=torch.int64).contiguous()
+    B, n = idx.numel(), bank.shape[1]
+    if out is None:
+        out = torch.empty(B, n, dtype=torch.float32, device=bank.device)
+    stream = torch.cuda.current_stream(bank.device)
+    N.check(N.load().wwf_gather_clips(_ptr(bank), N.BANK_I16 if bank.dtype == torch.int16 else N.BANK_F32, bank.shape[0], n,
+                                      bank.stride(0), _ptr(idx), B, _ptr(out), out.stride(0), bank.device.index,
+                                      C.c_void_p(stream.cuda_stream)))
+    return out
 
 
 def peak_normalize(wav: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
