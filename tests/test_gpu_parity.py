@@ -540,3 +540,61 @@ def test_device_resident_loader_end_to_end(ww):
         assert_features_close(x.cpu().numpy(), ref.numpy(), f"device loader batch {i}")
         first += sel.numel()
     assert first == n and ld.samples_drawn == n
+
+
+def test_random_configurations_vs_oracle(ww):
+    """Deterministic fuzz over the supported envelope: n_fft x hop x mels x clip length x augmentation x
+    masks x CMVN x fp16, each compared with the float64 oracle on the same explicit draws."""
+    from oracle import ta_oracle as tao
+    rng = np.random.default_rng(20261018)
+    gen = torch.Generator().manual_seed(20261018)
+    skipped = 0
+    for case in range(28):
+        n_fft = int(rng.choice([256, 400, 512, 1024, 2048]))
+        hop = int(rng.choice([h for h in (80, 100, 128, 160, 160, 160, 200, 256, 512) if h < n_fft]))
+        M = int(rng.choice([m for m in (20, 40, 64, 80, 128) if m <= n_fft // 4]))
+        ftype = str(rng.choice(["mel", "mfcc"]))
+        C = int(rng.integers(1, min(M, 40) + 1))
+        N = int(rng.integers(n_fft // 2 + 1, 3 * n_fft)) if case % 7 == 0 else int(rng.integers(4000, 50000))
+        B = int(rng.integers(1, 6))
+        use_aug, use_masks, use_cmvn, f16 = (bool(rng.integers(0, 2)) for _ in range(4))
+        F, T = (C if ftype == "mfcc" else M), N // hop + 1
+        if 4 * M * (T | 1) + (4 * F * (T | 1) if (use_cmvn and ftype == "mfcc") else 0) > 150_000:
+            use_cmvn = False                                   # keep the shared-memory tile inside the envelope
+        x = 0.1 * torch.randn(B, N, generator=gen)
+        plan = ww.FeaturePlan(16000, ftype, M, C, n_fft, hop, "cuda", cmvn=use_cmvn,
+                              out_dtype=torch.float16 if f16 else torch.float32,
+                              n_freq_masks=2 if use_masks else 0, n_time_masks=1 if use_masks else 0, mask_value=-3.0)
+        kw, ap = {}, ww.AugParams()
+        if use_aug:
+            noise = [0.05 * torch.randn(int(rng.integers(500, 60000)), generator=gen) for _ in range(3)]
+            rirs = [torch.randn(int(rng.integers(1, 9000)), generator=gen) * 0.3 for _ in range(3)]
+            plan.register_noise(noise); plan.register_rirs(rirs)
+            ap.rir_idx = torch.from_numpy(rng.integers(-1, 3, B).astype(np.int32))
+            ap.noise_idx = torch.from_numpy(rng.integers(-1, 3, B).astype(np.int32))
+            ap.noise_off = torch.from_numpy(rng.integers(0, 500, B).astype(np.int64))
+            ap.snr_db = torch.from_numpy(rng.uniform(0, 25, B).astype(np.float32))
+            kw.update(rirs=rirs, rir_idx=ap.rir_idx, noise_bank=noise, noise_idx=ap.noise_idx, noise_off=ap.noise_off, snr_db=ap.snr_db)
+        if use_masks:
+            ap.fmask_start, ap.fmask_len = ww.draw_mask_params(gen, B, F, min(15, F), 2)
+            ap.tmask_start, ap.tmask_len = ww.draw_mask_params(gen, B, T, min(35, T), 1)
+            kw.update(fstart=ap.fmask_start, flen=ap.fmask_len, tstart=ap.tmask_start, tlen=ap.tmask_len, mask_value=-3.0)
+        what = f"case {case}: n_fft={n_fft} hop={hop} M={M} {ftype} C={C} N={N} B={B} aug={use_aug} masks={use_masks} cmvn={use_cmvn} f16={f16}"
+        try:
+            got = plan.featurize(x.cuda(), ap).float().cpu().numpy()
+        except ww.WwfError as e:                               # outside the envelope: must be the documented, loud refusal
+            assert e.code == -2 and "shared-memory tile" in str(e), what + f" -> {e}"
+            assert 4 * M * (T | 1) > 60_000, what              # ... and only for genuinely large tiles
+            skipped += 1
+            continue
+        ref = tao.pipeline(x.double(), dtype=torch.float64, sample_rate=16000, feature_type=ftype, n_mels=M, n_mfcc=C,
+                           n_fft=n_fft, hop_length=hop, use_cmvn=use_cmvn, **kw).numpy()
+        assert got.shape == (B, 1, F, T), what
+        if f16:
+            assert np.abs(got - ref).max() <= np.abs(ref).max() * 2.0 ** -10 + 2e-3, what   # one fp16 ulp of the largest value
+        elif use_cmvn:
+            assert np.abs(got - ref).max() <= 2e-3, what       # z-scores: the 1e-3 dB error divided by a std of a few dB
+        else:
+            assert_features_close(got, ref, what)
+        assert plan.check_finite(), what
+    assert skipped <= 6
