@@ -165,7 +165,7 @@ __device__ __forceinline__ ClipNoise resolve_noise(const NoiseBankDev& bank, con
 
 // sum of nz[q]^2 over [a, b), 0 <= a <= b <= len: prefix table for whole 128-blocks, direct sum
 // of the (< 128-sample) edges.  Executed by a full warp; every lane returns the result.
-__device__ __noinline__ double warp_seg_energy(const ClipNoise& c, int a, int b) {
+static __device__ __noinline__ double warp_seg_energy(const ClipNoise& c, int a, int b) {
   const int lane = threadIdx.x & 31;
   const int lo = (a + kNoiseBlk - 1) / kNoiseBlk, hi = b / kNoiseBlk;
   float e = 0.f;
@@ -196,7 +196,7 @@ __device__ __forceinline__ float warp_noise_energy(const ClipNoise& c, int N) {
 
 // Block-wide sum of x[i]^2, i < N (8 independent loads in flight per thread); result in all
 // threads.  red: >= 32 floats of shared memory.  Contains __syncthreads().
-__device__ __noinline__ float block_energy(const float* __restrict__ x, int N, float* red) {
+static __device__ __noinline__ float block_energy(const float* __restrict__ x, int N, float* red) {
   const int tid = threadIdx.x, nt = blockDim.x;
   float acc[8];
 #pragma unroll

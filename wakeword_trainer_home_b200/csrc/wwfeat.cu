@@ -20,6 +20,19 @@
 
 using namespace wwf;
 
+// feat_kernel is instantiated in wwf_feat_inst.cu, one translation unit per n_fft (parallel build)
+namespace wwf {
+#define WWF_EXT(N, H)                                                                  \
+  extern template __global__ void feat_kernel<N, H, float>(const FeatParams);          \
+  extern template __global__ void feat_kernel<N, H, __half>(const FeatParams);
+WWF_EXT(256, 0) WWF_EXT(256, 4) WWF_EXT(256, 5)
+WWF_EXT(400, 0) WWF_EXT(400, 4) WWF_EXT(400, 5) WWF_EXT(400, 8)
+WWF_EXT(512, 0) WWF_EXT(512, 4) WWF_EXT(512, 5) WWF_EXT(512, 8)
+WWF_EXT(1024, 0) WWF_EXT(1024, 4) WWF_EXT(1024, 5) WWF_EXT(1024, 8) WWF_EXT(1024, 16)
+WWF_EXT(2048, 0) WWF_EXT(2048, 4) WWF_EXT(2048, 5) WWF_EXT(2048, 8) WWF_EXT(2048, 16)
+#undef WWF_EXT
+}  // namespace wwf
+
 // ------------------------------------------------------------------------------------------
 // errors
 // ------------------------------------------------------------------------------------------
