@@ -598,3 +598,15 @@ def test_random_configurations_vs_oracle(ww):
             assert_features_close(got, ref, what)
         assert plan.check_finite(), what
     assert skipped <= 6
+
+
+def test_streamed_featurizer_pcm16_equals_float_path(ww):
+    """int16 PCM host batches (converted on the device) give bit-identical features to uploading x/32768."""
+    gen = torch.Generator().manual_seed(8)
+    B, N = 32, 16000
+    pcm = torch.randint(-30000, 30000, (B, N), generator=gen, dtype=torch.int16)
+    plan = ww.FeaturePlan(16000, "mel", 40, 40, 400, 160, "cuda")
+    sf = ww.StreamedFeaturizer(plan, B, N, depth=2, copy_back=True, pcm16=True)
+    k = sf.submit(pcm.pin_memory(), None)
+    got = sf.wait(k).clone()
+    assert torch.equal(got, plan.featurize((pcm.float() / 32768.0).cuda()).cpu())

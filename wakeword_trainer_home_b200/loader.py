@@ -25,12 +25,17 @@ from .sharding import shard_range, shard_seed
 class StreamedFeaturizer:
     """Double-buffered host -> device -> host featurization through ``FeaturePlan.featurize``."""
 
-    def __init__(self, plan: FeaturePlan, batch: int, n_samples: int, depth: int = 2, copy_back: bool = True):
-        self.plan, self.depth, self.copy_back = plan, depth, copy_back
+    def __init__(self, plan: FeaturePlan, batch: int, n_samples: int, depth: int = 2, copy_back: bool = True,
+                 pcm16: bool = False):
+        """pcm16=True: host batches are int16 PCM (the native format of WAV files); they cross PCIe at half
+        the bytes and are converted on the device (x / 32768, exact) by ``wwf_gather_clips``."""
+        self.plan, self.depth, self.copy_back, self.pcm16 = plan, depth, copy_back, pcm16
         dev = plan.device
         T = plan.num_frames(n_samples)
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream(dev) for _ in range(3))
         self.d_wav = [torch.empty(batch, n_samples, dtype=torch.float32, device=dev) for _ in range(depth)]
+        self.d_pcm = [torch.empty(batch, n_samples, dtype=torch.int16, device=dev) for _ in range(depth)] if pcm16 else None
+        self._rows = torch.arange(batch, dtype=torch.int64, device=dev)
         self.d_out = [torch.empty(batch, 1, plan.n_feat, T, dtype=plan.out_dtype, device=dev) for _ in range(depth)]
         self.h_out = [torch.empty(batch, 1, plan.n_feat, T, dtype=plan.out_dtype).pin_memory() for _ in range(depth)] if copy_back else None
         self.ev_in = [torch.cuda.Event() for _ in range(depth)]
@@ -45,12 +50,14 @@ class StreamedFeaturizer:
         self.n += 1
         with torch.cuda.stream(self.s_in):
             self.s_in.wait_event(self.ev_run[k])          # previous use of this input slot has been consumed
-            self.d_wav[k].copy_(host_wav, non_blocking=True)
+            (self.d_pcm if self.pcm16 else self.d_wav)[k].copy_(host_wav, non_blocking=True)
             aug = None if host_aug is None else host_aug.to(self.plan.device, non_blocking=True)
             self.ev_in[k].record(self.s_in)
         with torch.cuda.stream(self.s_run):
             self.s_run.wait_event(self.ev_in[k])
             self.s_run.wait_event(self.ev_out[k])         # previous features of this slot have left
+            if self.pcm16:
+                gather_clips(self.d_pcm[k], self._rows, out=self.d_wav[k])
             self.plan.featurize(self.d_wav[k], aug, out=self.d_out[k])
             if aug is not None:                           # keep the draw tensors alive until the kernel ran
                 for f in ("rir_idx", "noise_idx", "noise_off", "snr_db", "fmask_start", "fmask_len", "tmask_start", "tmask_len"):
