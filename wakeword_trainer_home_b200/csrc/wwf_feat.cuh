@@ -69,7 +69,7 @@ struct FeatParams {
   const float* rev;        int64_t rev_stride;   // reverberated clips (workspace) or nullptr
   int B, N, T, hop;
   // configuration
-  int n_mels, n_mfcc, n_feat, is_mfcc, out_f16, cmvn;
+  int n_mels, n_mfcc, n_feat, is_mfcc, cmvn;
   float top_db, cmvn_eps, mask_value;
   int tile_pitch;                                // odd row pitch of the shared tile (>= T)
   // dynamic shared-memory layout, offsets in floats from the start (each a multiple of 4):

@@ -538,7 +538,7 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
 
   fp.wav = wav; fp.wav_stride = wav_stride; fp.rev = rev; fp.rev_stride = rev_stride;
   fp.B = B; fp.N = N; fp.T = T; fp.hop = p->cfg.hop_length;
-  fp.n_mels = M; fp.n_mfcc = p->cfg.n_mfcc; fp.n_feat = F; fp.is_mfcc = mfcc; fp.out_f16 = p->cfg.out_dtype == WWF_OUT_F16;
+  fp.n_mels = M; fp.n_mfcc = p->cfg.n_mfcc; fp.n_feat = F; fp.is_mfcc = mfcc;
   fp.cmvn = p->cfg.cmvn != 0; fp.top_db = p->cfg.top_db; fp.cmvn_eps = p->cfg.cmvn_eps; fp.mask_value = p->cfg.mask_value;
   fp.tile_pitch = pitch;
   fp.window = p->d_window; fp.tw = p->d_tw; fp.mel_lo = p->d_mel_lo; fp.mel_ofs = p->d_mel_ofs; fp.mel_w = p->d_mel_w; fp.dct = p->d_dct;

@@ -14,11 +14,11 @@ It shards clip indices across ranks (no collective) and redraws augmentations fr
 """
 from __future__ import annotations
 
-from typing import Callable, Iterable, Iterator, Optional, Tuple
+from typing import Iterator, Optional, Tuple
 
 import torch
 
-from .pipeline import AugParams, DrawConfig, FeaturePlan, draw_mask_params, gather_clips
+from .pipeline import AugParams, DrawConfig, FeaturePlan, gather_clips
 from .sharding import shard_range, shard_seed
 
 
