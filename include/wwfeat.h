@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define WWF_VERSION 100 /* 0.1.0 */
+#define WWF_VERSION 110 /* 0.1.1: time-stretch / pitch-shift / resample */
 
 typedef enum wwf_status {
   WWF_OK = 0,
@@ -92,6 +92,11 @@ typedef struct wwf_aug {
   const int32_t* fmask_len;   /* dev [B][n_freq_masks]  rows masked (0 = none)         */
   const int32_t* tmask_start; /* dev [B][n_time_masks]  first masked frame             */
   const int32_t* tmask_len;   /* dev [B][n_time_masks]  frames masked (0 = none)       */
+  /* Draws of the two waveform-shape augmentations.  wwf_featurize / wwf_augment do NOT read them: the
+   * caller runs wwf_time_stretch / wwf_pitch_shift on the batch first (the Python shim does).  They are
+   * part of this struct so that wwf_draw_aug can fill every draw of a sample in one launch. */
+  const double* stretch_rate; /* dev [B]  speed factor (> 1 = faster), exactly 1.0 = untouched */
+  const int32_t* pitch_steps; /* dev [B]  semitones, 0 = untouched                            */
 } wwf_aug;
 
 typedef struct wwf_plan wwf_plan; /* opaque */
@@ -191,9 +196,55 @@ typedef struct wwf_draw_config {
   double freq_mask_prob, time_mask_prob;   /* gate all freq / all time masks of a clip */
   float snr_lo, snr_hi;                    /* noise_snr_min / noise_snr_max, dB */
   int32_t freq_mask_param, time_mask_param;
+  double stretch_prob, stretch_lo, stretch_hi; /* rate ~ U[time_stretch_min, time_stretch_max) with this probability */
+  double pitch_prob;                           /* semitones ~ randint[pitch_shift_min, pitch_shift_max] (inclusive) */
+  int32_t pitch_lo, pitch_hi;
 } wwf_draw_config;
 int wwf_draw_aug(wwf_plan* plan, const wwf_draw_config* cfg, uint64_t first_index, int B, int T,
                  const wwf_aug* out, void* stream);
+
+/*
+ * Time-stretch (pitch-preserving speed change), shape kept: out[b] = the clip played rates[b] times faster,
+ * cropped / zero-padded back to N samples; rates[b] == 1.0 copies the clip.  Arithmetic: torchaudio's
+ * STFT(512, hop 128) -> F.phase_vocoder(rate) -> iSTFT(length = round(N / rate)), i.e. F.pitch_shift's own
+ * stretch stage (TA/functional/functional.py:1644-1693, 732-800) with the rate given directly.
+ *   rates     dev float64 [B];   rate_lo  host lower bound of every rates[b] (sizes the workspace; >= 0.1)
+ *   workspace dev, >= wwf_stretch_workspace_bytes(B, N, rate_lo), 16-byte aligned;  out may alias wav
+ * Replaces: the time-stretch branch of AudioAugmentation.__call__ (kwarg time_stretch_range,
+ *           tests/test_training_pipeline.py:233; AugmentationConfig.time_stretch_min/max, src/config/defaults.py:76-77).
+ */
+size_t wwf_stretch_workspace_bytes(int B, int N, double rate_lo);
+int wwf_time_stretch(wwf_plan* plan, const float* wav, int B, int N, int64_t wav_stride, const double* rates,
+                     double rate_lo, float* out, int64_t out_stride, void* workspace, size_t workspace_bytes,
+                     void* stream);
+
+/*
+ * Pitch shift by an integer number of semitones per clip, shape kept: torchaudio F.pitch_shift
+ * (TA/functional/functional.py:1596-1641) = stretch by 2^(-n/12), resample int(sr / rate) -> sr with the
+ * windowed-sinc kernel, crop / zero-pad to N.  n_steps[b] == 0 copies the clip.  sr = the plan's sample_rate.
+ *   n_steps   dev int32 [B], every value inside [step_lo, step_hi] (host bounds, within [-12, 12])
+ *   workspace dev, >= wwf_pitch_workspace_bytes(B, N, step_lo, step_hi), 16-byte aligned;  out may alias wav
+ * The first call for a new semitone value builds that ratio's coefficient table (synchronises `stream`).
+ * Replaces: the pitch-shift branch of AudioAugmentation.__call__ (kwarg pitch_shift_range, integer semitones:
+ *           tests/test_training_pipeline.py:234, src/config/validator.py:289-294, src/config/defaults.py:78-79).
+ */
+size_t wwf_pitch_workspace_bytes(int B, int N, int step_lo, int step_hi);
+int wwf_pitch_shift(wwf_plan* plan, const float* wav, int B, int N, int64_t wav_stride, const int32_t* n_steps,
+                    int step_lo, int step_hi, float* out, int64_t out_stride, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/*
+ * Sample-rate conversion of a batch, torchaudio F.resample defaults (sinc_interp_hann, lowpass_filter_width 6,
+ * rolloff 0.99; TA/functional/functional.py:1305-1497): in [B][n_in] at orig_freq -> out [B][n_out] at new_freq.
+ * wwf_resample_length(n_in, orig, new) = ceil(new * n_in / orig) is the length torchaudio returns; a smaller
+ * n_out crops, a larger one is zero-padded.  The first call for a new ratio builds its coefficient table
+ * (synchronises `stream`).  in and out must not overlap.
+ * Replaces: the resampling step of AudioProcessor in front of the path (8-48 kHz files -> 16 kHz;
+ *           src/evaluation/evaluator.py:76-79,119, src/ui/panel_docs.py:134-138).
+ */
+int wwf_resample_length(int n_in, int orig_freq, int new_freq);
+int wwf_resample(wwf_plan* plan, const float* in, int B, int n_in, int64_t in_stride, int orig_freq, int new_freq,
+                 float* out, int n_out, int64_t out_stride, void* stream);
 
 /*
  * Per-clip peak normalisation y = x / max|x| (all-zero clips pass through), float32 [B][N] -> [B][N];

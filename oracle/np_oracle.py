@@ -18,6 +18,8 @@ __all__ = [
     "hann_periodic", "stft_power", "mel_fbanks", "create_dct", "amplitude_to_db",
     "log_mel", "mfcc", "cmvn", "rir_reverb", "gather_noise", "add_noise",
     "spec_mask", "num_frames", "features", "pipeline",
+    "stft_complex", "phase_vocoder", "istft", "stretch_core", "time_stretch", "sinc_resample_kernel",
+    "resample", "pitch_shift",
 ]
 
 
@@ -191,6 +193,158 @@ def add_noise(x: np.ndarray, noise: np.ndarray, snr_db: np.ndarray, active=None)
     if active is not None:
         y = np.where(np.asarray(active)[:, None], y, x)
     return y.astype(x.dtype)
+
+
+# --------------------------------------------------------------------------------------
+# A3: time-stretch / pitch-shift / resample
+# --------------------------------------------------------------------------------------
+PV_NFFT, PV_HOP = 512, 128       # F.pitch_shift defaults, TA/functional/functional.py:1596-1604
+
+
+def stft_complex(x: np.ndarray, n_fft: int, hop_length: int, dtype=np.float64, window=None) -> np.ndarray:
+    """torch.stft(center=True, reflect, periodic Hann, onesided, return_complex): (B, N) -> (B, K, T) complex."""
+    x = np.asarray(x, dtype=dtype)
+    pad = n_fft // 2
+    xp = np.pad(x, ((0, 0), (pad, pad)), mode="reflect")
+    T = num_frames(x.shape[1], hop_length)
+    idx = (np.arange(T) * hop_length)[:, None] + np.arange(n_fft)[None, :]
+    w = hann_periodic(n_fft, dtype) if window is None else np.asarray(window).astype(dtype)
+    spec = np.fft.rfft((xp[:, idx] * w[None, None, :]).astype(np.float64), axis=-1)
+    if dtype == np.float32:
+        spec = spec.astype(np.complex64)
+    return np.transpose(spec, (0, 2, 1))
+
+
+def phase_vocoder(spec: np.ndarray, rate: float, hop_length: int, dtype=np.float64) -> np.ndarray:
+    """F.phase_vocoder (TA/functional/functional.py:732-800): (B, K, T) -> (B, K, ceil(T / rate)).
+
+    time_steps = arange(0, T, rate); frames idx = floor(time_steps) and idx + 1 (two zero frames appended);
+    per bin the unwrapped phase increment angle1 - angle0 is accumulated (cumsum) starting from the phase of
+    frame 0; magnitudes are interpolated linearly with alpha = time_steps mod 1."""
+    if rate == 1.0:
+        return spec
+    B, K, T = spec.shape
+    rdt = np.float32 if dtype == np.float32 else np.float64
+    n_out = int(math.ceil(T / rate))
+    ts = (np.arange(n_out, dtype=np.float64) * rate).astype(rdt)
+    alphas = (ts % rdt(1.0)).astype(rdt)
+    pa = _linspace32(0.0, math.pi * hop_length, K).astype(rdt)[None, :, None]   # float32 constants, see stretch_core
+    sp = np.concatenate([spec, np.zeros((B, K, 2), spec.dtype)], axis=-1)
+    i0 = ts.astype(np.int64)
+    i1 = (ts + rdt(1.0)).astype(rdt).astype(np.int64)
+    s0, s1 = sp[..., i0], sp[..., i1]
+    a0, a1 = np.angle(s0).astype(rdt), np.angle(s1).astype(rdt)
+    n0, n1 = np.abs(s0).astype(rdt), np.abs(s1).astype(rdt)
+    two_pi = rdt(2.0 * math.pi)
+    ph = (a1 - a0 - pa).astype(rdt)
+    ph = (ph - two_pi * np.round(ph / two_pi)).astype(rdt)
+    ph = (ph + pa).astype(rdt)
+    ph = np.concatenate([np.angle(spec[..., :1]).astype(rdt), ph[..., :-1]], axis=-1)
+    acc = np.cumsum(ph, axis=-1, dtype=rdt)
+    mag = (alphas * n1 + (rdt(1.0) - alphas) * n0).astype(rdt)
+    out = mag * np.cos(acc) + 1j * (mag * np.sin(acc))
+    return out.astype(np.complex64 if dtype == np.float32 else np.complex128)
+
+
+def istft(spec: np.ndarray, n_fft: int, hop_length: int, length: int, dtype=np.float64, window=None) -> np.ndarray:
+    """torch.istft(center=True, window=periodic Hann, length=length): irfft per frame, * window, overlap-add,
+    divide by the overlap-added squared window, drop n_fft/2 leading samples.  (B, K, T) -> (B, length)."""
+    B, K, T = spec.shape
+    w = (hann_periodic(n_fft, dtype) if window is None else np.asarray(window).astype(dtype)).astype(np.float64)
+    frames = np.fft.irfft(np.transpose(spec, (0, 2, 1)).astype(np.complex128), n=n_fft, axis=-1)   # (B, T, n_fft)
+    if dtype == np.float32:
+        frames = frames.astype(np.float32).astype(np.float64)
+    frames = frames * w
+    total = n_fft + hop_length * (T - 1)
+    y = np.zeros((B, total))
+    env = np.zeros(total)
+    for t in range(T):
+        y[:, t * hop_length:t * hop_length + n_fft] += frames[:, t]
+        env[t * hop_length:t * hop_length + n_fft] += w * w
+    start = n_fft // 2
+    if start + length > total:
+        raise ValueError("istft: requested length exceeds the overlap-added signal")
+    return (y[:, start:start + length] / env[start:start + length]).astype(dtype)
+
+
+def stretch_core(x: np.ndarray, rate: float, dtype=np.float64) -> np.ndarray:
+    """torchaudio's _stretch_waveform (TA/functional/functional.py:1644-1693) with the rate explicit:
+    (B, N) -> (B, round(N / rate))."""
+    N = x.shape[1]
+    w32 = hann_periodic(PV_NFFT, np.float32)     # _stretch_waveform builds window / phase_advance in float32 always
+    spec = stft_complex(x, PV_NFFT, PV_HOP, dtype, window=w32)
+    return istft(phase_vocoder(spec, rate, PV_HOP, dtype), PV_NFFT, PV_HOP, int(round(N / rate)), dtype, window=w32)
+
+
+def _fix_len(y: np.ndarray, N: int) -> np.ndarray:
+    """_fix_waveform_shape, TA/functional/functional.py:1696-1718."""
+    return y[:, :N] if y.shape[1] >= N else np.pad(y, ((0, 0), (0, N - y.shape[1])))
+
+
+def time_stretch(x: np.ndarray, rates, dtype=np.float64) -> np.ndarray:
+    """Per clip stretch_core(rate) cropped / zero-padded back to N; rate == 1.0 = untouched.
+    Reference surface: time_stretch_range, tests/test_training_pipeline.py:233."""
+    out = np.asarray(x, dtype=dtype).copy()
+    for b, r in enumerate([float(v) for v in rates]):
+        if r != 1.0:
+            out[b] = _fix_len(stretch_core(out[b:b + 1], r, dtype), x.shape[1])[0]
+    return out
+
+
+def sinc_resample_kernel(orig_freq: int, new_freq: int, dtype=np.float64, lowpass_filter_width: int = 6,
+                         rolloff: float = 0.99):
+    """_get_sinc_resample_kernel, 'sinc_interp_hann' (TA/functional/functional.py:1305-1402), frequencies
+    already divided by their gcd.  Returns (kernel [new_freq][2*width + orig_freq], width).
+    float32 follows torchaudio's float32 operation order (it builds the kernel in the waveform's dtype)."""
+    f = np.float32 if dtype == np.float32 else np.float64
+    base_freq = min(orig_freq, new_freq) * rolloff
+    width = int(math.ceil(lowpass_filter_width * orig_freq / base_freq))
+    idx = (np.arange(-width, width + orig_freq).astype(f) / f(orig_freq)).astype(f)[None, :]
+    t = ((np.arange(0, -new_freq, -1).astype(f) / f(new_freq)).astype(f)[:, None] + idx).astype(f)
+    t = (t * f(base_freq)).astype(f)
+    t = np.clip(t, f(-lowpass_filter_width), f(lowpass_filter_width))
+    window = np.cos(((t * f(math.pi)).astype(f) / f(lowpass_filter_width)).astype(f) / f(2)).astype(f) ** 2
+    t = (t * f(math.pi)).astype(f)
+    scale = f(base_freq / orig_freq)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        k = np.where(t == 0, f(1.0), (np.sin(t).astype(f) / t).astype(f))
+    return (k * (window * scale).astype(f)).astype(f), width
+
+
+def resample(x: np.ndarray, orig_freq: int, new_freq: int, dtype=np.float64) -> np.ndarray:
+    """F.resample (TA/functional/functional.py:1405-1497): zero-pad (width, width + orig), correlate with the
+    polyphase kernel at stride orig, interleave the new_freq phases, keep ceil(new * N / orig) samples."""
+    x = np.asarray(x, dtype=dtype)
+    if orig_freq == new_freq:
+        return x
+    g = math.gcd(int(orig_freq), int(new_freq))
+    o, n = int(orig_freq) // g, int(new_freq) // g
+    kern, width = sinc_resample_kernel(o, n, dtype)
+    B, N = x.shape
+    xp = np.pad(x, ((0, 0), (width, width + o))).astype(np.float64)
+    nblk = (xp.shape[1] - kern.shape[1]) // o + 1
+    target = int(np.ceil(np.float32(n * N / o)))             # torch.as_tensor(python float) is float32
+    out = np.zeros((B, nblk * n))
+    # only the taps with |t| < lowpass_filter_width matter; use the dense rows for clarity, phase by phase
+    k64 = kern.astype(np.float64)
+    for m in range(nblk):
+        seg = xp[:, m * o:m * o + kern.shape[1]]
+        out[:, m * n:(m + 1) * n] = seg @ k64.T
+    return out[:, :target].astype(dtype)
+
+
+def pitch_shift(x: np.ndarray, n_steps, sample_rate: int = 16000, dtype=np.float64) -> np.ndarray:
+    """F.pitch_shift per clip (TA/functional/functional.py:1596-1641): stretch by rate = 2^(-n/12), resample
+    int(sample_rate / rate) -> sample_rate, crop / zero-pad to N.  0 semitones = untouched."""
+    out = np.asarray(x, dtype=dtype).copy()
+    N = x.shape[1]
+    for b, n in enumerate([int(v) for v in n_steps]):
+        if n == 0:
+            continue
+        rate = 2.0 ** (-float(n) / 12)
+        y = stretch_core(out[b:b + 1], rate, dtype)
+        out[b] = _fix_len(resample(y, int(sample_rate / rate), sample_rate, dtype), N)[0]
+    return out
 
 
 def spec_mask(feat: np.ndarray, fstart=None, flen=None, tstart=None, tlen=None, mask_value=0.0) -> np.ndarray:

@@ -108,11 +108,76 @@ def add_noise(wave, noise, snr_db, active=None) -> torch.Tensor:
     return y
 
 
+# --------------------------------------------------------------------------------------
+# A3: time-stretch / pitch-shift / resample
+# --------------------------------------------------------------------------------------
+PV_NFFT, PV_HOP = 512, 128      # F.pitch_shift defaults: n_fft=512, hop = n_fft // 4 (TA/functional/functional.py:1596-1604)
+
+
+@torch.no_grad()
+def stretch_core(wave: torch.Tensor, rate: float) -> torch.Tensor:
+    """STFT -> F.phase_vocoder(rate) -> iSTFT(length=round(N / rate)): torchaudio's own
+    ``_stretch_waveform`` (TA/functional/functional.py:1644-1693) with the rate given directly
+    instead of through n_steps.  (B, N) -> (B, round(N / rate)), arithmetic in wave.dtype."""
+    import math
+    N = wave.shape[-1]
+    # like _stretch_waveform, the window and phase_advance constants are built in float32 whatever wave.dtype is
+    window = torch.hann_window(PV_NFFT).to(wave.dtype)
+    spec = torch.stft(wave, PV_NFFT, PV_HOP, PV_NFFT, window, center=True, pad_mode="reflect",
+                      normalized=False, onesided=True, return_complex=True)
+    pa = torch.linspace(0, math.pi * PV_HOP, spec.shape[-2]).to(wave.dtype)[..., None]
+    st = AF.phase_vocoder(spec, rate, pa)
+    return torch.istft(st, PV_NFFT, PV_HOP, PV_NFFT, window, length=int(round(N / rate)))
+
+
+def _fix_len(y: torch.Tensor, N: int) -> torch.Tensor:
+    """_fix_waveform_shape (TA/functional/functional.py:1696-1718): crop or zero-pad to N."""
+    return y[..., :N] if y.shape[-1] >= N else torch.nn.functional.pad(y, [0, N - y.shape[-1]])
+
+
+@torch.no_grad()
+def time_stretch(wave: torch.Tensor, rates) -> torch.Tensor:
+    """Pitch-preserving speed change by rates[b] (> 1 = faster), shape kept: (B, N) -> (B, N).
+    rate == 1.0 leaves the clip untouched.  Reference surface: ``time_stretch_range`` kwarg,
+    tests/test_training_pipeline.py:233; AugmentationConfig.time_stretch_min/max, src/config/defaults.py:76-77."""
+    out = wave.clone()
+    for b, r in enumerate([float(v) for v in rates]):
+        if r != 1.0:
+            out[b] = _fix_len(stretch_core(wave[b:b + 1], r), wave.shape[-1])[0]
+    return out
+
+
+@torch.no_grad()
+def pitch_shift(wave: torch.Tensor, n_steps, sample_rate: int = 16000) -> torch.Tensor:
+    """F.pitch_shift(wave[b], sample_rate, n_steps[b]) per clip (TA/functional/functional.py:1596-1641);
+    0 semitones leaves the clip untouched.  Reference surface: ``pitch_shift_range`` kwarg (integer
+    semitones, src/config/validator.py:289-294), tests/test_training_pipeline.py:234."""
+    out = wave.clone()
+    steps = torch.as_tensor(n_steps)
+    for n in steps.unique().tolist():
+        if n == 0:
+            continue
+        sel = (steps == n).nonzero().flatten()
+        out[sel] = AF.pitch_shift(wave[sel], sample_rate, int(n))
+    return out
+
+
+@torch.no_grad()
+def resample(wave: torch.Tensor, orig_freq: int, new_freq: int) -> torch.Tensor:
+    """F.resample, sinc_interp_hann, lowpass_filter_width 6, rolloff 0.99 (TA/functional/functional.py:1435-1497)."""
+    return AF.resample(wave, orig_freq, new_freq)
+
+
 @torch.no_grad()
 def augment_wave(wave, *, rirs=None, rir_idx=None, noise_bank=None, noise_idx=None,
-                 noise_off=None, snr_db=None) -> torch.Tensor:
-    """Time-domain half of the path: RIR reverb, then noise @ SNR.  (B, N) -> (B, N)."""
+                 noise_off=None, snr_db=None, stretch_rate=None, pitch_steps=None, sample_rate=16000) -> torch.Tensor:
+    """Time-domain half of the path: [time-stretch] -> [pitch-shift] -> RIR reverb -> noise @ SNR.
+    (B, N) -> (B, N)."""
     x = wave
+    if stretch_rate is not None:
+        x = time_stretch(x, stretch_rate)
+    if pitch_steps is not None:
+        x = pitch_shift(x, pitch_steps, sample_rate)
     if rirs is not None and rir_idx is not None:
         x = rir_reverb(x, rirs, rir_idx)
     if noise_bank is not None and noise_idx is not None:
@@ -146,10 +211,12 @@ def spec_mask(feat, fstart=None, flen=None, tstart=None, tlen=None, mask_value=0
 @torch.no_grad()
 def pipeline(wave, *, rirs=None, rir_idx=None, noise_bank=None, noise_idx=None, noise_off=None,
              snr_db=None, fstart=None, flen=None, tstart=None, tlen=None, mask_value=0.0,
-             dtype=torch.float32, **feat_kw) -> torch.Tensor:
-    """RIR -> noise -> features -> SpecAugment with every draw explicit."""
+             stretch_rate=None, pitch_steps=None, dtype=torch.float32, **feat_kw) -> torch.Tensor:
+    """[stretch -> pitch ->] RIR -> noise -> features -> SpecAugment with every draw explicit."""
     x = augment_wave(wave.to(dtype), rirs=rirs, rir_idx=rir_idx, noise_bank=noise_bank,
-                     noise_idx=noise_idx, noise_off=noise_off, snr_db=snr_db)
+                     noise_idx=noise_idx, noise_off=noise_off, snr_db=snr_db,
+                     stretch_rate=stretch_rate, pitch_steps=pitch_steps,
+                     sample_rate=feat_kw.get("sample_rate", 16000))
     f = featurize(x, dtype=dtype, **feat_kw)
     if fstart is not None or tstart is not None:
         f = spec_mask(f, fstart, flen, tstart, tlen, mask_value)

@@ -10,6 +10,7 @@
 #include <vector>
 #include "../../wakeword_trainer_home_b200/csrc/wwf_feat.cuh"
 #include "../../wakeword_trainer_home_b200/csrc/wwf_conv.cuh"
+#include "../../wakeword_trainer_home_b200/csrc/wwf_pv.cuh"
 #include "../../wakeword_trainer_home_b200/csrc/wwf_tables.h"
 
 using namespace wwf;
@@ -190,6 +191,43 @@ int emul_reflect_index(int i, int N) { return reflect_index(i, N); }
 int emul_mel_fbanks(int n_freqs, float f_min, float f_max, int n_mels, int sr, float* out) {
   std::vector<float> fb = mel_fbanks32(n_freqs, f_min, f_max, n_mels, sr);
   memcpy(out, fb.data(), fb.size() * sizeof(float));
+  return 0;
+}
+
+
+// The 512-point analysis / synthesis pair of the phase-vocoder kernels (pv_stft_kernel, pv_istft_kernel):
+// two real frames -> packed forward FFT in the padded scratch -> two onesided spectra (spa, spb: 257
+// interleaved complex) -> Hermitian pack -> inverse passes in reverse order -> the two frames back.
+int emul_pv_roundtrip(const float* fa, const float* fb, float* spa, float* spb, float* ya, float* yb) {
+  std::vector<float2> tw;
+  build_stft_twiddles<PvRad>(tw);
+  std::vector<float2> z(kPvZL);
+  const PvMap zmap;
+  for (int j = 0; j < kPvN; ++j) z[zmap(j)] = make_float2(fa[j], fb[j]);
+  static_for<0, PvRad::npass>([&](auto I) {
+    constexpr int i = decltype(I)::value;
+    constexpr int R = PvRad::R(i), L = PvRad::L(i);
+    const float2* t = tw.data() + PvRad::tw_off(i);
+    for (int u = 0; u < kPvN / R; ++u) pass_task<R, false, PvMap>(z.data(), L, u, [&](int q) { return t[q]; });
+  });
+  std::vector<float2> A(kPvK), B(kPvK);
+  for (int k = 0; k < kPvK; ++k) pv_split(z[zmap(PvRad::pos(k))], z[zmap(PvRad::pos(k == 0 ? 0 : kPvN - k))], &A[k], &B[k]);
+  for (int k = 0; k < kPvK; ++k) { spa[2 * k] = A[k].x; spa[2 * k + 1] = A[k].y; spb[2 * k] = B[k].x; spb[2 * k + 1] = B[k].y; }
+  std::fill(z.begin(), z.end(), make_float2(0.f, 0.f));
+  for (int k = 0; k < kPvK; ++k) {
+    float2 a = A[k], c = B[k], zk, zm;
+    if (k == 0 || k == kPvN / 2) { a.y = 0.f; c.y = 0.f; }
+    pv_pack(a, c, &zk, &zm);
+    z[zmap(PvRad::pos(k))] = zk;
+    if (k > 0 && k < kPvN / 2) z[zmap(PvRad::pos(kPvN - k))] = zm;
+  }
+  static_for<0, PvRad::npass>([&](auto I) {
+    constexpr int i = PvRad::npass - 1 - decltype(I)::value;
+    constexpr int R = PvRad::R(i), L = PvRad::L(i);
+    const float2* t = tw.data() + PvRad::tw_off(i);
+    for (int u = 0; u < kPvN / R; ++u) pass_task<R, true, PvMap>(z.data(), L, u, [&](int q) { return t[q]; });
+  });
+  for (int j = 0; j < kPvN; ++j) { ya[j] = z[zmap(j)].x * (1.0f / kPvN); yb[j] = z[zmap(j)].y * (1.0f / kPvN); }
   return 0;
 }
 

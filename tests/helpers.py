@@ -70,13 +70,14 @@ def philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def philox_draws(seed, first_index, B, n_rir, noise_lens, F, T, nF, nT, rir_prob=0.25, noise_prob=0.5,
-                 freq_mask_prob=0.5, time_mask_prob=0.5, snr_range=(5.0, 20.0), freq_mask_param=15, time_mask_param=35):
+                 freq_mask_prob=0.5, time_mask_prob=0.5, snr_range=(5.0, 20.0), freq_mask_param=15, time_mask_param=35,
+                 stretch_prob=0.0, stretch_range=(0.8, 1.2), pitch_prob=0.0, pitch_range=(-2, 2)):
     """Bit-exact host recomputation of wwf_draw_aug: dict of numpy arrays named like AugParams."""
     idx = np.uint64(first_index) + np.arange(B, dtype=np.uint64)
     c0 = (idx & np.uint64(0xFFFFFFFF)).astype(np.uint32)
     c1 = (idx >> np.uint64(32)).astype(np.uint32)
     k0, k1 = seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF
-    blk = lambda j: philox4x32_10(c0, c1, np.full(B, j, np.uint32), np.zeros(B, np.uint32), k0, k1)
+    blk = lambda j, w=0: philox4x32_10(c0, c1, np.full(B, j, np.uint32), np.full(B, w, np.uint32), k0, k1)
     thr = lambda p: 0 if p <= 0 else (1 << 32) if p >= 1 else int(np.floor(p * 4294967296.0))
     u01 = lambda u: (u >> np.uint32(8)).astype(np.float32) * np.float32(5.9604644775390625e-08)
     pick = lambda u, n: ((u.astype(np.uint64) * np.asarray(n, dtype=np.uint64)) >> np.uint64(32)).astype(np.int64)
@@ -106,4 +107,13 @@ def philox_draws(seed, first_index, B, n_rir, noise_lens, F, T, nF, nT, rir_prob
 
     fs, fl, j = masks(nF, freq_mask_param, F, fon, 2)
     ts, tl, j = masks(nT, time_mask_param, T, ton, j)
-    return dict(rir_idx=rir, noise_idx=noi, noise_off=off, snr_db=snr, fmask_start=fs, fmask_len=fl, tmask_start=ts, tmask_len=tl)
+    out = dict(rir_idx=rir, noise_idx=noi, noise_off=off, snr_db=snr, fmask_start=fs, fmask_len=fl, tmask_start=ts, tmask_len=tl)
+    # time-stretch / pitch-shift: Philox block with counter word 3 = 1, double arithmetic (each op exactly rounded)
+    s = blk(0, 1)
+    slo, shi = np.float64(stretch_range[0]), np.float64(stretch_range[1])
+    rate = slo + (shi - slo) * (s[1].astype(np.float64) * np.float64(2.3283064365386963e-10))
+    out["stretch_rate"] = np.where(s[0].astype(np.uint64) < thr(stretch_prob), rate, 1.0).astype(np.float64)
+    plo, phi = int(pitch_range[0]), int(pitch_range[1])
+    steps = plo + pick(s[3], max(phi - plo + 1, 1))
+    out["pitch_steps"] = np.where(s[2].astype(np.uint64) < thr(pitch_prob), steps, 0).astype(np.int32)
+    return out

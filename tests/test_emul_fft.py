@@ -85,3 +85,16 @@ def test_c_filterbank_close_to_torchaudio(emul):
         emul.emul_mel_fbanks(n_freqs, ctypes.c_float(0.0), ctypes.c_float(8000.0), n_mels, 16000, P(out))
         ref = AF.melscale_fbanks(n_freqs, 0.0, 8000.0, n_mels, 16000).numpy()
         assert np.abs(out - ref).max() <= 2e-5
+
+
+def test_phase_vocoder_analysis_synthesis_pair(emul):
+    """pv_stft_kernel's split and pv_istft_kernel's Hermitian pack + reverse-order inverse passes."""
+    rng = np.random.default_rng(7)
+    fa, fb = rng.standard_normal(512).astype(np.float32), rng.standard_normal(512).astype(np.float32)
+    spa, spb = np.zeros(514, np.float32), np.zeros(514, np.float32)
+    ya, yb = np.zeros(512, np.float32), np.zeros(512, np.float32)
+    assert emul.emul_pv_roundtrip(P(fa), P(fb), P(spa), P(spb), P(ya), P(yb)) == 0
+    for sp, f in ((spa, fa), (spb, fb)):
+        ref = np.fft.rfft(f.astype(np.float64))
+        assert np.abs((sp[0::2] + 1j * sp[1::2]) - ref).max() <= 5e-7 * np.abs(ref).max()
+    assert np.abs(ya - fa).max() <= 2e-6 and np.abs(yb - fb).max() <= 2e-6

@@ -148,8 +148,9 @@ def test_audio_augmentation_class_vs_oracle(ww):
     B, N = 16, 16000
     x = 0.1 * torch.randn(B, N, generator=torch.Generator().manual_seed(1))
     aug = ww.AudioAugmentation(16000, "cuda", background_noise_prob=0.7, noise_snr_range=(0.0, 15.0), rir_prob=0.5,
-                               background_noise=noise, rirs=rirs, seed=9)
+                               background_noise=noise, rirs=rirs, seed=9, time_stretch_prob=0.0, pitch_shift_prob=0.0)
     p = aug.draw(B)
+    assert p.stretch_rate is None and p.pitch_steps is None
     got = aug(x.cuda(), p).cpu()
     want = tao.augment_wave(x, rirs=rirs, rir_idx=p.rir_idx, noise_bank=noise, noise_idx=p.noise_idx,
                             noise_off=p.noise_off, snr_db=p.snr_db)
@@ -487,19 +488,29 @@ def test_device_draws_bit_exact_vs_host_mirror(ww):
     rirs = [torch.randn(2000, generator=gen) * torch.exp(-t / 400.0) for _ in range(7)]
     for (nF, nT, F, N, seed, first, kw) in ((2, 2, 40, 24000, 1234567890123, 0, {}),
                                              (3, 1, 128, 40000, 7, 2 ** 33 + 5, dict(rir_prob=1.0, noise_prob=0.0, freq_mask_prob=1.0)),
-                                             (0, 4, 64, 16000, 2 ** 63 + 11, 999, dict(time_mask_prob=0.9, snr_range=(-5.0, 30.0), time_mask_param=50))):
+                                             (0, 4, 64, 16000, 2 ** 63 + 11, 999, dict(time_mask_prob=0.9, snr_range=(-5.0, 30.0), time_mask_param=50)),
+                                             (2, 2, 40, 24000, 31337, 2 ** 40 + 1, dict(stretch_prob=0.6, stretch_range=(0.8, 1.2), pitch_prob=0.4, pitch_range=(-2, 2))),
+                                             (1, 1, 40, 16000, 5, 77, dict(stretch_prob=1.0, stretch_range=(0.5, 2.0), pitch_prob=1.0, pitch_range=(-12, 12)))):
         plan = ww.FeaturePlan(16000, "mel", F, 40, 1024 if F > 64 else 400, 160, "cuda", n_freq_masks=nF, n_time_masks=nT)
         plan.register_noise(noise); plan.register_rirs(rirs)
         B, T = 4099, N // 160 + 1
         cfg = ww.DrawConfig(seed=seed, **kw)
         got = plan.draw_aug(cfg, first, B, N)
         want = philox_draws(seed, first, B, len(rirs), [len(n) for n in noise], F, T, nF, nT, **kw)
-        for name in ("rir_idx", "noise_idx", "noise_off", "snr_db", "fmask_start", "fmask_len", "tmask_start", "tmask_len"):
+        for name in ("rir_idx", "noise_idx", "noise_off", "snr_db", "fmask_start", "fmask_len", "tmask_start", "tmask_len",
+                     "stretch_rate", "pitch_steps"):
             g = getattr(got, name)
             if g is None:
-                assert want[name].size == 0
+                assert want[name].size == 0 or name in ("stretch_rate", "pitch_steps")
                 continue
             assert np.array_equal(g.cpu().numpy(), want[name]), name
+        if kw.get("stretch_prob", 0) > 0:
+            r, (lo, hi) = got.stretch_rate.cpu().numpy(), kw["stretch_range"]
+            assert ((r == 1.0) | ((r >= lo) & (r < hi))).all() and abs((r != 1.0).mean() - kw["stretch_prob"]) < 0.03
+            assert got.stretch_lo == min(1.0, lo)
+        if kw.get("pitch_prob", 0) > 0:
+            n_, (lo, hi) = got.pitch_steps.cpu().numpy(), kw["pitch_range"]
+            assert n_.min() >= lo and n_.max() <= hi and set(np.unique(n_)) == set(range(lo, hi + 1))
         if nF:
             assert (got.fmask_start >= 0).all() and (got.fmask_start + got.fmask_len <= F).all()
         if nT:
@@ -610,3 +621,162 @@ def test_streamed_featurizer_pcm16_equals_float_path(ww):
     k = sf.submit(pcm.pin_memory(), None)
     got = sf.wait(k).clone()
     assert torch.equal(got, plan.featurize((pcm.float() / 32768.0).cuda()).cpu())
+
+
+# --------------------------------------------------------------------------------------------------
+# time-stretch, pitch-shift, resample
+# --------------------------------------------------------------------------------------------------
+def _rel(a, b):
+    return float((a.double() - b.double()).norm() / b.double().norm())
+
+
+@pytest.mark.parametrize("orig,new", [(44100, 16000), (48000, 16000), (8000, 16000), (22050, 16000), (32000, 16000),
+                                      (17959, 16000), (14254, 16000), (16000, 22050)])
+def test_resample_vs_torchaudio(ww, orig, new):
+    """wwf_resample against F.resample (float32): same kernel arithmetic, so the only difference is the
+    order of the <= 40-term dot product.  Tolerance: max-abs 2e-6 x peak."""
+    from oracle import ta_oracle as tao
+    gen = torch.Generator().manual_seed(orig)
+    x = 0.2 * torch.randn(3, orig // 2 + 17, generator=gen)
+    x[1, : orig // 4] = 0.0
+    plan = ww.FeaturePlan(16000, "mel", 40, 40, 400, 160, "cuda")
+    want = tao.resample(x, orig, new)
+    got = plan.resample(x.cuda(), orig, new).cpu()
+    assert got.shape == want.shape
+    assert (got - want).abs().max() <= 2e-6 * want.abs().max()
+    # cropped and zero-padded output lengths
+    short = plan.resample(x.cuda(), orig, new, n_out=1000).cpu()
+    assert torch.equal(short, got[:, :1000])
+    longer = plan.resample(x.cuda(), orig, new, n_out=want.shape[1] + 50).cpu()
+    assert torch.equal(longer[:, :want.shape[1]], got) and (longer[:, want.shape[1]:] == 0).all()
+
+
+def test_time_stretch_vs_oracle(ww):
+    """wwf_time_stretch against torchaudio's STFT -> phase_vocoder -> iSTFT.
+    torchaudio float32 accumulates the vocoder phase in float32 (ulp 8e-3 rad at 7e4 rad): ITS float32 and
+    float64 results differ by ~1e-3 relative.  The CUDA path accumulates in double, so it is compared
+    (a) tightly with the float64 oracle: relative L2 <= 1e-4, and
+    (b) with the float32 oracle within 1.5 x that oracle's own float32-float64 gap."""
+    from oracle import ta_oracle as tao
+    gen = torch.Generator().manual_seed(42)
+    B, N = 8, 24000
+    x = 0.1 * torch.randn(B, N, generator=gen)
+    t = torch.arange(N) / 16000.0
+    x[2] = 0.5 * torch.sin(2 * torch.pi * 440.0 * t) + 0.2 * torch.sin(2 * torch.pi * 1230.0 * t)
+    x[3, N // 2:] = 0.0
+    rates = torch.tensor([0.8013, 1.1987, 0.9371, 1.0629, 1.0, 0.8642, 1.1318, 1.0], dtype=torch.float64)
+    plan = ww.FeaturePlan(16000, "mel", 40, 40, 400, 160, "cuda")
+    got = plan.time_stretch(x.cuda(), rates).cpu()
+    w64 = tao.time_stretch(x.double(), rates)
+    w32 = tao.time_stretch(x, rates)
+    assert got.shape == x.shape and torch.isfinite(got).all()
+    for b in range(B):
+        if rates[b] == 1.0:
+            assert torch.equal(got[b], x[b])
+            continue
+        gap = _rel(w32[b], w64[b])
+        assert _rel(got[b], w64[b]) <= 1e-4, (b, _rel(got[b], w64[b]))
+        assert _rel(got[b], w32[b]) <= 1.5 * gap + 1e-4, (b, _rel(got[b], w32[b]), gap)
+        if rates[b] > 1.0:                                           # shorter result: zero padding to N
+            assert (got[b, int(round(N / float(rates[b]))):] == 0).all()
+    # in place, strided input, another length
+    y = torch.zeros(B, N + 8, device="cuda")
+    y[:, :N] = x.cuda()
+    v = y[:, :N]
+    plan.time_stretch(v, rates, out=v)
+    assert torch.equal(v.cpu(), got)
+    x2 = 0.1 * torch.randn(2, 7001, generator=gen)
+    r2 = torch.tensor([1.25, 0.75], dtype=torch.float64)
+    assert _rel(plan.time_stretch(x2.cuda(), r2).cpu(), tao.time_stretch(x2.double(), r2)) <= 1e-4
+
+
+def test_pitch_shift_vs_oracle(ww):
+    """wwf_pitch_shift against F.pitch_shift, every semitone of the reference's range and a few beyond.
+    Bounds as in test_time_stretch_vs_oracle; the resampling stage follows torchaudio's float32 kernel
+    arithmetic, whose own float32-float64 gap (4e-4 for ratios like 17959:16000) enters the float64 bound."""
+    from oracle import ta_oracle as tao
+    gen = torch.Generator().manual_seed(43)
+    steps = torch.tensor([-2, -1, 0, 1, 2, 2, -2, 0, 4, -5], dtype=torch.int32)
+    B, N = steps.numel(), 24000
+    x = 0.1 * torch.randn(B, N, generator=gen)
+    t = torch.arange(N) / 16000.0
+    x[4] = 0.5 * torch.sin(2 * torch.pi * 440.0 * t)
+    plan = ww.FeaturePlan(16000, "mel", 40, 40, 400, 160, "cuda")
+    got = plan.pitch_shift(x.cuda(), steps).cpu()
+    w32 = tao.pitch_shift(x, steps, 16000)
+    w64 = tao.pitch_shift(x.double(), steps, 16000)
+    assert got.shape == x.shape and torch.isfinite(got).all()
+    for b in range(B):
+        if steps[b] == 0:
+            assert torch.equal(got[b], x[b])
+            continue
+        gap = _rel(w32[b], w64[b])
+        assert _rel(got[b], w32[b]) <= 1.5 * gap + 1e-4, (b, int(steps[b]), _rel(got[b], w32[b]), gap)
+        assert _rel(got[b], w64[b]) <= 1e-3, (b, int(steps[b]), _rel(got[b], w64[b]))
+    # the tone moved by the requested interval: 440 Hz * 2^(2/12) = 493.9 Hz
+    spec = torch.fft.rfft(got[4, 2000:18000] * torch.hann_window(16000)).abs()
+    assert abs(int(spec.argmax()) - 493.88) <= 1.5
+    # explicit range wider than the values, reused tables, in-place
+    v = x.cuda().clone()
+    plan.pitch_shift(v, steps, step_range=(-12, 12), out=v)
+    assert torch.equal(v.cpu(), got)
+
+
+def test_pipeline_applies_stretch_then_pitch_then_rest(ww):
+    """AugParams.stretch_rate / pitch_steps: featurize() and augment() equal the explicit chain
+    time_stretch -> pitch_shift -> (reverb, noise, features, masks) bit for bit, and the AudioAugmentation
+    class (time_stretch_range / pitch_shift_range kwargs of tests/test_training_pipeline.py:233-234) matches
+    the oracle run on its own draws."""
+    from oracle import ta_oracle as tao
+    noise, rirs = synth_banks(5, 4, 30000, 3, 4000)
+    B, N = 12, 16000
+    x = 0.1 * torch.randn(B, N, generator=torch.Generator().manual_seed(8))
+    plan = ww.FeaturePlan(16000, "mfcc", 40, 40, 400, 160, "cuda", n_freq_masks=2, n_time_masks=2)
+    aug = ww.AudioAugmentation(16000, "cuda", time_stretch_range=(0.8, 1.2), pitch_shift_range=(-2, 2),
+                               background_noise_prob=0.6, rir_prob=0.4, background_noise=noise, rirs=rirs, plan=plan, seed=4,
+                               time_stretch_prob=0.7, pitch_shift_prob=0.7)
+    p = aug.draw(B)
+    assert p.stretch_rate.dtype == torch.float64 and p.pitch_steps.dtype == torch.int32
+    assert ((p.stretch_rate == 1.0) | ((p.stretch_rate >= 0.8) & (p.stretch_rate < 1.2))).all()
+    assert (p.pitch_steps.abs() <= 2).all() and (p.stretch_rate != 1.0).any() and (p.pitch_steps != 0).any()
+    m = ww.SpecAugment(15, 35, 2, 2, seed=1).draw(B, 40, N // 160 + 1)
+    p.fmask_start, p.fmask_len, p.tmask_start, p.tmask_len = m.fmask_start, m.fmask_len, m.tmask_start, m.tmask_len
+    xs = plan.pitch_shift(plan.time_stretch(x.cuda(), p.stretch_rate), p.pitch_steps)
+    rest = ww.AugParams(rir_idx=p.rir_idx, noise_idx=p.noise_idx, noise_off=p.noise_off, snr_db=p.snr_db,
+                        fmask_start=p.fmask_start, fmask_len=p.fmask_len, tmask_start=p.tmask_start, tmask_len=p.tmask_len)
+    assert torch.equal(plan.featurize(x.cuda(), p), plan.featurize(xs, rest))
+    got = aug(x.cuda(), p).cpu()
+    assert torch.equal(got, plan.augment(xs, rest).cpu())
+    w32 = tao.augment_wave(x, rirs=rirs, rir_idx=p.rir_idx, noise_bank=noise, noise_idx=p.noise_idx, noise_off=p.noise_off,
+                           snr_db=p.snr_db, stretch_rate=p.stretch_rate, pitch_steps=p.pitch_steps)
+    w64 = tao.augment_wave(x.double(), rirs=rirs, rir_idx=p.rir_idx, noise_bank=noise, noise_idx=p.noise_idx, noise_off=p.noise_off,
+                           snr_db=p.snr_db.double(), stretch_rate=p.stretch_rate, pitch_steps=p.pitch_steps)
+    for b in range(B):
+        gap = _rel(w32[b], w64[b])
+        assert _rel(got[b], w32[b]) <= 1.5 * gap + 1e-4, (b, _rel(got[b], w32[b]), gap)
+    # the reference's own assertions (shape kept, finite) with its constructor call
+    ref_aug = ww.AudioAugmentation(sample_rate=16000, device="cuda", time_stretch_range=(0.8, 1.2), pitch_shift_range=(-2, 2),
+                                   background_noise_prob=0.5, time_stretch_prob=1.0, pitch_shift_prob=1.0)
+    t_ = torch.randn(1, 16000).cuda()
+    a_ = ref_aug(t_)
+    assert a_.shape == t_.shape and torch.isfinite(a_).all() and not torch.equal(a_, t_)
+
+
+def test_device_loader_with_stretch_and_pitch_draws(ww):
+    """DeviceBatchLoader with on-GPU time-stretch / pitch draws: the waveform it featurizes equals the explicit
+    chain on the host-recomputed draws."""
+    from helpers import philox_draws
+    gen = torch.Generator().manual_seed(23)
+    n, N, B = 96, 16000, 48
+    bank = (0.1 * torch.randn(n, N, generator=gen)).cuda()
+    labels = torch.randint(0, 2, (n,), generator=gen)
+    plan = ww.FeaturePlan(16000, "mel", 40, 40, 400, 160, "cuda")
+    cfg = ww.DrawConfig(seed=11, rir_prob=0.0, noise_prob=0.0, stretch_prob=0.5, pitch_prob=0.5)
+    ld = ww.DeviceBatchLoader(bank, labels, plan, B, draw=cfg, shuffle=False)
+    first = 0
+    for x, y in ld:
+        d = philox_draws(11, first, B, 0, [], 40, 101, 0, 0, rir_prob=0.0, noise_prob=0.0, stretch_prob=0.5, pitch_prob=0.5)
+        sel = torch.arange(first, first + B)
+        xs = plan.pitch_shift(plan.time_stretch(bank[sel], torch.from_numpy(d["stretch_rate"])), torch.from_numpy(d["pitch_steps"]))
+        assert torch.equal(x, plan.featurize(xs))
+        first += B

@@ -50,6 +50,7 @@ class Aug(C.Structure):
         ("rir_idx", C.c_void_p), ("noise_idx", C.c_void_p), ("noise_off", C.c_void_p),
         ("snr_db", C.c_void_p), ("fmask_start", C.c_void_p), ("fmask_len", C.c_void_p),
         ("tmask_start", C.c_void_p), ("tmask_len", C.c_void_p),
+        ("stretch_rate", C.c_void_p), ("pitch_steps", C.c_void_p),
     ]
 
 
@@ -57,7 +58,9 @@ class DrawConfig(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("rir_prob", C.c_double), ("noise_prob", C.c_double),
                 ("freq_mask_prob", C.c_double), ("time_mask_prob", C.c_double),
                 ("snr_lo", C.c_float), ("snr_hi", C.c_float),
-                ("freq_mask_param", C.c_int32), ("time_mask_param", C.c_int32)]
+                ("freq_mask_param", C.c_int32), ("time_mask_param", C.c_int32),
+                ("stretch_prob", C.c_double), ("stretch_lo", C.c_double), ("stretch_hi", C.c_double),
+                ("pitch_prob", C.c_double), ("pitch_lo", C.c_int32), ("pitch_hi", C.c_int32)]
 
 
 class Info(C.Structure):
@@ -84,6 +87,15 @@ SYMBOLS = {
     "wwf_gather_clips": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_void_p,
                                    C.c_int64, C.c_int, C.c_void_p]),
     "wwf_draw_aug": (C.c_int, [C.c_void_p, C.POINTER(DrawConfig), C.c_uint64, C.c_int, C.c_int, C.POINTER(Aug), C.c_void_p]),
+    "wwf_stretch_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_double]),
+    "wwf_time_stretch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_double,
+                                   C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "wwf_pitch_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "wwf_pitch_shift": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int, C.c_int,
+                                  C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "wwf_resample_length": (C.c_int, [C.c_int, C.c_int, C.c_int]),
+    "wwf_resample": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int,
+                               C.c_void_p, C.c_int, C.c_int64, C.c_void_p]),
     "wwf_peak_normalize": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "wwf_spec_augment": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int64,
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,

@@ -5,8 +5,10 @@ tests/test_training_pipeline.py:230-262 and the kwargs dict at src/ui/panel_trai
 Both classes only *draw* parameters on the host (torch.Generator) and hand them, explicit,
 to the CUDA path; ``draw()`` is public so a test can feed the very same draws to the oracle.
 
-Not built in this round: time-stretch / pitch-shift (``time_stretch_range``,
-``pitch_shift_range`` are accepted and stored).
+Time-stretch and pitch-shift (``time_stretch_range``, ``pitch_shift_range``)
+are drawn per clip with probabilities ``time_stretch_prob`` / ``pitch_shift_prob`` - the reference's module
+is absent, so its apply probabilities are unknown; 0.5 is this package's choice - and applied before the
+reverb: time-stretch -> pitch-shift -> RIR -> noise.
 """
 from __future__ import annotations
 
@@ -22,10 +24,11 @@ class AudioAugmentation:
                  pitch_shift_range=(-2, 2), background_noise_prob: float = 0.5, noise_snr_range=(5.0, 20.0),
                  rir_prob: float = 0.25, background_noise: Optional[Sequence[torch.Tensor]] = None,
                  rirs: Optional[Sequence[torch.Tensor]] = None, seed: Optional[int] = None,
-                 plan: Optional[FeaturePlan] = None):
+                 plan: Optional[FeaturePlan] = None, time_stretch_prob: float = 0.5, pitch_shift_prob: float = 0.5):
         self.sample_rate = sample_rate
-        self.time_stretch_range = tuple(time_stretch_range)      # accepted, not applied (next row)
-        self.pitch_shift_range = tuple(pitch_shift_range)        # accepted, not applied (next row)
+        self.time_stretch_range = (float(time_stretch_range[0]), float(time_stretch_range[1]))
+        self.pitch_shift_range = (int(pitch_shift_range[0]), int(pitch_shift_range[1]))   # integer semitones, validator.py:289-294
+        self.time_stretch_prob, self.pitch_shift_prob = float(time_stretch_prob), float(pitch_shift_prob)
         self.background_noise_prob = float(background_noise_prob)
         self.noise_snr_range = tuple(noise_snr_range)
         self.rir_prob = float(rir_prob)
@@ -59,6 +62,18 @@ class AudioAugmentation:
             p.noise_idx = torch.where(on, pick, torch.full_like(pick, -1))
             p.noise_off = (torch.rand(B, generator=g, dtype=torch.float64) * lens).long()
             p.snr_db = (lo + (hi - lo) * torch.rand(B, generator=g)).float()
+        if self.time_stretch_prob > 0:
+            lo, hi = self.time_stretch_range
+            on = torch.rand(B, generator=g) < self.time_stretch_prob
+            rate = lo + (hi - lo) * torch.rand(B, generator=g, dtype=torch.float64)
+            p.stretch_rate = torch.where(on, rate, torch.ones_like(rate))
+            p.stretch_lo = min(1.0, lo)
+        if self.pitch_shift_prob > 0:
+            lo, hi = self.pitch_shift_range
+            on = torch.rand(B, generator=g) < self.pitch_shift_prob
+            steps = torch.randint(lo, hi + 1, (B,), generator=g, dtype=torch.int32)       # random.randint: inclusive
+            p.pitch_steps = torch.where(on, steps, torch.zeros_like(steps))
+            p.pitch_range = (min(0, lo), max(0, hi))
         return p
 
     @torch.no_grad()

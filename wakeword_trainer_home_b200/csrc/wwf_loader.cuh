@@ -40,6 +40,11 @@ struct DrawParams {
   const int64_t* noise_offsets;         // [n_noise + 1] (device) for the offset draw
   int32_t* rir_idx; int32_t* noise_idx; int64_t* noise_off; float* snr_db;
   int32_t* fs; int32_t* fl; int32_t* ts; int32_t* tl;
+  // time-stretch / pitch-shift draws (Philox block with counter word 3 = 1)
+  uint64_t thr_stretch, thr_pitch;
+  double stretch_lo, stretch_hi;
+  int pitch_lo, pitch_hi;
+  double* stretch_rate; int32_t* pitch_steps;
 };
 
 // One (start, len) pair with torchaudio's mask_along_axis arithmetic in float32
@@ -55,6 +60,8 @@ __device__ __forceinline__ void mask_pair(uint32_t ua, uint32_t ub, int param, i
 // Thread i draws everything for sample first_index + i.  Philox counter = (index lo, index hi, j, 0),
 // key = seed; block j = 0: (rir on, rir pick, noise on, noise pick); j = 1: (noise offset, snr,
 // freq-mask gate, time-mask gate); j = 2 + q: two freq masks (value, min) x2; then the time masks.
+// Counter (index lo, index hi, 0, 1): (stretch gate, stretch u, pitch gate, pitch pick) - rate = lo + (hi - lo) * u / 2^32
+// in double (every operation exactly rounded, so the host mirror is bit-identical), semitones = lo + pick(hi - lo + 1).
 __global__ void __launch_bounds__(256) draw_aug_kernel(const DrawParams p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= p.B) return;
@@ -73,6 +80,20 @@ __global__ void __launch_bounds__(256) draw_aug_kernel(const DrawParams p) {
     p.noise_off[i] = off;
   }
   if (p.snr_db) p.snr_db[i] = __fadd_rn(p.snr_lo, __fmul_rn(__fsub_rn(p.snr_hi, p.snr_lo), u01(b.y)));
+  if (p.stretch_rate || p.pitch_steps) {
+    const Philox4 s = philox4x32_10(c0, c1, 0u, 1u, k0, k1);
+    if (p.stretch_rate) {
+      double r = 1.0;
+      if ((uint64_t)s.x < p.thr_stretch)
+        r = __dadd_rn(p.stretch_lo, __dmul_rn(__dsub_rn(p.stretch_hi, p.stretch_lo), __dmul_rn((double)s.y, 2.3283064365386963e-10)));
+      p.stretch_rate[i] = r;
+    }
+    if (p.pitch_steps) {
+      int32_t n = 0;
+      if ((uint64_t)s.z < p.thr_pitch && p.pitch_hi >= p.pitch_lo) n = p.pitch_lo + (int32_t)pick(s.w, (uint32_t)(p.pitch_hi - p.pitch_lo + 1));
+      p.pitch_steps[i] = n;
+    }
+  }
   const bool fon = (uint64_t)b.z < p.thr_fmask, ton = (uint64_t)b.w < p.thr_tmask;
   uint32_t j = 2;
   for (int q = 0; q < p.nF; q += 2, ++j) {

@@ -10,12 +10,14 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "wwf_aux.cuh"
 #include "wwf_conv.cuh"
 #include "wwf_feat.cuh"
 #include "wwf_loader.cuh"
+#include "wwf_pv.cuh"
 #include "wwf_tables.h"
 
 using namespace wwf;
@@ -97,6 +99,13 @@ struct wwf_plan {
   float2* d_fused_tw = nullptr;
   int n_rir = 0, rir_max_len = 0;
   int feat_warps_override = 0;
+  // time-stretch / pitch-shift constants and the resampler coefficient tables (built on first use)
+  std::mutex lazy_mu;
+  float* d_pv_window = nullptr;
+  float* d_pv_pa = nullptr;
+  float2* d_pv_tw = nullptr;
+  struct Resampler { int orig, nw, width, ntaps; float* coef; };
+  std::vector<Resampler> resamplers;
   // optional per-kernel timing (wwf_profile_enable)
   bool prof = false;
   std::vector<cudaEvent_t> prof_events;   // triples: before conv, between, after feat
@@ -150,6 +159,8 @@ extern "C" void wwf_plan_destroy(wwf_plan* p) {
   cudaFree(p->d_noise_prefix); cudaFree(p->d_noise_prefix_offsets);
   for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
   cudaFree(p->d_conv_tw); cudaFree(p->d_fused_l); cudaFree(p->d_fused_tw);
+  cudaFree(p->d_pv_window); cudaFree(p->d_pv_pa); cudaFree(p->d_pv_tw);
+  for (auto& r : p->resamplers) cudaFree(r.coef);
   delete p;
 }
 
@@ -627,6 +638,13 @@ extern "C" int wwf_draw_aug(wwf_plan* p, const wwf_draw_config* dc, uint64_t fir
   dp.noise_offsets = p->d_noise_offsets;
   dp.rir_idx = (int32_t*)out->rir_idx; dp.noise_idx = (int32_t*)out->noise_idx; dp.noise_off = (int64_t*)out->noise_off; dp.snr_db = (float*)out->snr_db;
   dp.fs = (int32_t*)out->fmask_start; dp.fl = (int32_t*)out->fmask_len; dp.ts = (int32_t*)out->tmask_start; dp.tl = (int32_t*)out->tmask_len;
+  dp.thr_stretch = thr(dc->stretch_prob); dp.thr_pitch = thr(dc->pitch_prob);
+  dp.stretch_lo = dc->stretch_lo; dp.stretch_hi = dc->stretch_hi; dp.pitch_lo = dc->pitch_lo; dp.pitch_hi = dc->pitch_hi;
+  dp.stretch_rate = (double*)out->stretch_rate; dp.pitch_steps = (int32_t*)out->pitch_steps;
+  if (dp.stretch_rate && dc->stretch_prob > 0.0 && !(dc->stretch_lo >= 0.1 && dc->stretch_hi >= dc->stretch_lo))
+    return fail(WWF_ERR_INVALID, "wwf_draw_aug: stretch range [%g, %g]", dc->stretch_lo, dc->stretch_hi);
+  if (dp.pitch_steps && dc->pitch_prob > 0.0 && (dc->pitch_lo < -12 || dc->pitch_hi > 12 || dc->pitch_hi < dc->pitch_lo))
+    return fail(WWF_ERR_INVALID, "wwf_draw_aug: pitch range [%d, %d] must lie in [-12, 12]", dc->pitch_lo, dc->pitch_hi);
   draw_aug_kernel<<<(B + 255) / 256, 256, 0, (cudaStream_t)stream>>>(dp);
   g_launches++;
   WWF_CUDA(cudaGetLastError());
@@ -657,6 +675,203 @@ extern "C" int wwf_spec_augment(void* spec, int dtype, int B, int F, int T, int6
   dim3 grid(F < 64 ? F : 64, B);
   if (dtype == WWF_OUT_F32) spec_mask_kernel<float><<<grid, 256, 0, st>>>((float*)spec, B, F, T, clip_stride, fs, fl, nF, ts, tl, nT, mask_value);
   else spec_mask_kernel<__half><<<grid, 256, 0, st>>>((__half*)spec, B, F, T, clip_stride, fs, fl, nF, ts, tl, nT, mask_value);
+  g_launches++;
+  WWF_CUDA(cudaGetLastError());
+  return WWF_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// time-stretch / pitch-shift / resample
+// ------------------------------------------------------------------------------------------
+static int ensure_pv_constants(wwf_plan* p) {
+  std::lock_guard<std::mutex> lk(p->lazy_mu);
+  if (p->d_pv_tw) return WWF_OK;
+  std::vector<float> win(kPvN);
+  for (int i = 0; i < kPvN; ++i) win[i] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * i / kPvN));
+  // torch.linspace(0, math.pi * hop, 257) in float32 (TA/functional/functional.py:1686)
+  std::vector<float> pa = linspace32(0.0f, (float)(M_PI * kPvHop), kPvK);
+  std::vector<float2> tw;
+  build_stft_twiddles<PvRad>(tw);
+  int rc;
+  if ((rc = upload(&p->d_pv_window, win)) || (rc = upload(&p->d_pv_pa, pa))) return rc;
+  return upload(&p->d_pv_tw, tw);
+}
+
+struct PvGeom {
+  int T, Tcap, Lcap;
+  size_t offS, offV, offY, offW, total;
+};
+static PvGeom pv_geometry(int B, int N, double rate_lo) {
+  PvGeom g{};
+  g.T = N / kPvHop + 1;
+  g.Tcap = (int)ceil((double)g.T / rate_lo);
+  g.Lcap = (int)round_up4((int64_t)rint((double)N / rate_lo));
+  g.offS = 0;
+  g.offV = g.offS + (size_t)B * g.T * kPvPitch * sizeof(float2);
+  g.offY = g.offV + (size_t)B * g.Tcap * kPvPitch * sizeof(float2);
+  g.offW = g.offY + (size_t)B * g.Tcap * kPvN * sizeof(float);
+  g.total = g.offW + (size_t)B * g.Lcap * sizeof(float);
+  return g;
+}
+
+extern "C" size_t wwf_stretch_workspace_bytes(int B, int N, double rate_lo) {
+  if (B <= 0 || N <= 0 || !(rate_lo >= 0.1)) return 0;
+  return pv_geometry(B, N, rate_lo).total;
+}
+
+static int check_pv(const wwf_plan* p, const float* wav, int B, int N, int64_t wav_stride, const float* out, int64_t out_stride,
+                    const void* ws, size_t ws_bytes, double rate_lo, const char* who) {
+  if (!p || !wav || !out) return fail(WWF_ERR_INVALID, "%s: null argument", who);
+  if (B <= 0 || wav_stride < N || out_stride < N) return fail(WWF_ERR_INVALID, "%s: bad shape B=%d N=%d", who, B, N);
+  if (N <= kPvN / 2) return fail(WWF_ERR_INVALID, "%s: N=%d must exceed %d (reflect padding of the 512-point STFT)", who, N, kPvN / 2);
+  if (N > (1 << 24)) return fail(WWF_ERR_UNSUPPORTED, "%s: N=%d > 2^24 samples", who, N);
+  if (!(rate_lo >= 0.1)) return fail(WWF_ERR_INVALID, "%s: lower rate bound %g must be >= 0.1", who, rate_lo);
+  const size_t need = wwf_stretch_workspace_bytes(B, N, rate_lo);
+  if (!ws || ws_bytes < need) return fail(WWF_ERR_WORKSPACE, "%s: workspace too small: %zu < %zu bytes", who, ws_bytes, need);
+  if (reinterpret_cast<uintptr_t>(ws) & 15) return fail(WWF_ERR_WORKSPACE, "%s: workspace must be 16-byte aligned", who);
+  return WWF_OK;
+}
+
+// STFT -> phase vocoder -> inverse STFT frames -> overlap-add; the last kernel writes n_out samples per clip to dst
+static int launch_stretch(wwf_plan* p, PvParams& pp, const PvGeom& g, void* ws, cudaStream_t st) {
+  int rc = ensure_pv_constants(p);
+  if (rc) return rc;
+  char* w = (char*)ws;
+  pp.T = g.T; pp.Tcap = g.Tcap; pp.Lcap = g.Lcap;
+  pp.window = p->d_pv_window; pp.phase_adv = p->d_pv_pa; pp.tw = p->d_pv_tw;
+  pp.S = (float2*)(w + g.offS); pp.V = (float2*)(w + g.offV); pp.Y = (float*)(w + g.offY);
+  const int per_cta = 2 * kPvWarps;
+  pv_stft_kernel<<<dim3((g.T + per_cta - 1) / per_cta, pp.B), kPvWarps * 32, 0, st>>>(pp);
+  pv_vocoder_kernel<<<pp.B, 288, 0, st>>>(pp);
+  pv_istft_kernel<<<dim3((g.Tcap + per_cta - 1) / per_cta, pp.B), kPvWarps * 32, 0, st>>>(pp);
+  pv_ola_kernel<<<dim3((pp.n_out + 255) / 256, pp.B), 256, 0, st>>>(pp);
+  g_launches += 4;
+  WWF_CUDA(cudaGetLastError());
+  return WWF_OK;
+}
+
+extern "C" int wwf_time_stretch(wwf_plan* p, const float* wav, int B, int N, int64_t wav_stride, const double* rates, double rate_lo,
+                                float* out, int64_t out_stride, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_pv(p, wav, B, N, wav_stride, out, out_stride, workspace, workspace_bytes, rate_lo, "wwf_time_stretch");
+  if (rc) return rc;
+  if (!rates) return fail(WWF_ERR_INVALID, "wwf_time_stretch: rates is null");
+  DeviceGuard guard(p->device);
+  if (!guard.ok) return fail(WWF_ERR_CUDA, "cudaSetDevice(%d) failed", p->device);
+  const PvGeom g = pv_geometry(B, N, rate_lo);
+  PvParams pp{};
+  pp.wav = wav; pp.wav_stride = wav_stride; pp.B = B; pp.N = N;
+  pp.rate.rates = rates;
+  pp.out = out; pp.out_stride = out_stride; pp.n_out = N; pp.out_pad = 1;
+  return launch_stretch(p, pp, g, workspace, (cudaStream_t)stream);
+}
+
+// coefficient table of one (orig, new) ratio, frequencies already divided by their gcd
+static int get_resampler(wwf_plan* p, int orig, int nw, cudaStream_t st, ResampleDesc* out) {
+  std::lock_guard<std::mutex> lk(p->lazy_mu);
+  for (const auto& r : p->resamplers)
+    if (r.orig == orig && r.nw == nw) { *out = ResampleDesc{r.coef, r.orig, r.nw, r.width, r.ntaps}; return WWF_OK; }
+  // _get_sinc_resample_kernel (TA/functional/functional.py:1343-1350): lowpass_filter_width 6, rolloff 0.99
+  const double base_freq = (double)(orig < nw ? orig : nw) * 0.99;
+  const int width = (int)ceil(6.0 * orig / base_freq);
+  const int ntaps = 2 * width + 1;
+  if ((int64_t)ntaps * nw > (int64_t)64 << 20) return fail(WWF_ERR_UNSUPPORTED, "resample %d:%d needs a %lld-entry table", orig, nw, (long long)ntaps * nw);
+  float* coef = nullptr;
+  WWF_CUDA(cudaMalloc((void**)&coef, (size_t)ntaps * nw * sizeof(float)));
+  resample_table_kernel<<<(ntaps * nw + 255) / 256, 256, 0, st>>>(coef, orig, nw, width, ntaps, (float)base_freq, (float)(base_freq / orig));
+  g_launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) { cudaFree(coef); return fail(WWF_ERR_CUDA, "resample_table_kernel: %s", cudaGetErrorString(e)); }
+  p->resamplers.push_back({orig, nw, width, ntaps, coef});
+  *out = ResampleDesc{coef, orig, nw, width, ntaps};
+  return WWF_OK;
+}
+
+static int gcd_int(int a, int b) { while (b) { const int t = a % b; a = b; b = t; } return a; }
+
+// ceil(new * n / orig) exactly as torchaudio evaluates it: the quotient passes through float32
+// (torch.as_tensor(python float)), TA/functional/functional.py:1427
+static int resample_target(int n_in, int orig, int nw) {
+  return (int)ceilf((float)((double)((int64_t)nw * n_in) / (double)orig));
+}
+
+extern "C" int wwf_resample_length(int n_in, int orig_freq, int new_freq) {
+  if (n_in < 0 || orig_freq <= 0 || new_freq <= 0) return fail(WWF_ERR_INVALID, "wwf_resample_length: bad argument");
+  if (orig_freq == new_freq) return n_in;
+  const int g = gcd_int(orig_freq, new_freq);
+  return resample_target(n_in, orig_freq / g, new_freq / g);
+}
+
+extern "C" int wwf_resample(wwf_plan* p, const float* in, int B, int n_in, int64_t in_stride, int orig_freq, int new_freq,
+                            float* out, int n_out, int64_t out_stride, void* stream) {
+  if (!p || !in || !out) return fail(WWF_ERR_INVALID, "wwf_resample: null argument");
+  if (B <= 0 || n_in <= 0 || n_out <= 0 || in_stride < n_in || out_stride < n_out || orig_freq <= 0 || new_freq <= 0)
+    return fail(WWF_ERR_INVALID, "wwf_resample: bad argument (B=%d n_in=%d n_out=%d %d->%d Hz)", B, n_in, n_out, orig_freq, new_freq);
+  if (in == out) return fail(WWF_ERR_INVALID, "wwf_resample: in-place is not allowed");
+  DeviceGuard guard(p->device);
+  if (!guard.ok) return fail(WWF_ERR_CUDA, "cudaSetDevice(%d) failed", p->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (orig_freq == new_freq) {
+    WWF_CUDA(cudaMemcpy2DAsync(out, out_stride * sizeof(float), in, in_stride * sizeof(float), (size_t)(n_in < n_out ? n_in : n_out) * sizeof(float), B,
+                               cudaMemcpyDeviceToDevice, st));
+    return WWF_OK;
+  }
+  const int g = gcd_int(orig_freq, new_freq);
+  ResampleParams rp{};
+  int rc = get_resampler(p, orig_freq / g, new_freq / g, st, &rp.desc[0]);
+  if (rc) return rc;
+  rp.in = in; rp.in_stride = in_stride; rp.out = out; rp.out_stride = out_stride;
+  rp.B = B; rp.n_in = n_in; rp.n_out = n_out;
+  rp.in_len[0] = n_in;
+  rp.target[0] = resample_target(n_in, orig_freq / g, new_freq / g);    // samples beyond it are written as zeros
+  resample_kernel<<<dim3((n_out + 255) / 256, B), 256, 0, st>>>(rp);
+  g_launches++;
+  WWF_CUDA(cudaGetLastError());
+  return WWF_OK;
+}
+
+static double pitch_rate(int n_steps) { return pow(2.0, -(double)n_steps / 12.0); }   // F.pitch_shift: 2.0 ** (-float(n) / 12)
+
+extern "C" size_t wwf_pitch_workspace_bytes(int B, int N, int step_lo, int step_hi) {
+  if (step_hi < step_lo || step_lo < -12 || step_hi > 12) return 0;
+  return wwf_stretch_workspace_bytes(B, N, pitch_rate(step_hi > 0 ? step_hi : 0));
+}
+
+extern "C" int wwf_pitch_shift(wwf_plan* p, const float* wav, int B, int N, int64_t wav_stride, const int32_t* n_steps, int step_lo, int step_hi,
+                               float* out, int64_t out_stride, void* workspace, size_t workspace_bytes, void* stream) {
+  if (step_hi < step_lo || step_lo < -12 || step_hi > 12) return fail(WWF_ERR_INVALID, "wwf_pitch_shift: step range [%d, %d] must lie in [-12, 12]", step_lo, step_hi);
+  const double rate_lo = pitch_rate(step_hi > 0 ? step_hi : 0);
+  int rc = check_pv(p, wav, B, N, wav_stride, out, out_stride, workspace, workspace_bytes, rate_lo, "wwf_pitch_shift");
+  if (rc) return rc;
+  if (!n_steps) return fail(WWF_ERR_INVALID, "wwf_pitch_shift: n_steps is null");
+  DeviceGuard guard(p->device);
+  if (!guard.ok) return fail(WWF_ERR_CUDA, "cudaSetDevice(%d) failed", p->device);
+  cudaStream_t st = (cudaStream_t)stream;
+  const PvGeom g = pv_geometry(B, N, rate_lo);
+  const int sr = p->cfg.sample_rate, ns = step_hi - step_lo + 1;
+  PvParams pp{};
+  ResampleParams rp{};
+  pp.rate.steps = n_steps; pp.rate.step_lo = step_lo; pp.rate.n_steps = ns;
+  rp.steps = n_steps; rp.step_lo = step_lo; rp.n_steps = ns;
+  for (int i = 0; i < ns; ++i) {
+    const int n = step_lo + i;
+    const double rate = pitch_rate(n);
+    pp.rate.rate_tab[i] = n == 0 ? 1.0 : rate;
+    if (n == 0) continue;                                      // desc[i].coef stays null: clip passes through
+    const int orig = (int)((double)sr / rate);                 // int(sample_rate / rate)
+    const int gg = gcd_int(orig, sr);
+    if ((rc = get_resampler(p, orig / gg, sr / gg, st, &rp.desc[i]))) return rc;
+    rp.in_len[i] = (int)rint((double)N / rate);
+    rp.target[i] = resample_target(rp.in_len[i], orig / gg, sr / gg);
+  }
+  float* W = (float*)((char*)workspace + g.offW);
+  pp.wav = wav; pp.wav_stride = wav_stride; pp.B = B; pp.N = N;
+  pp.out = W; pp.out_stride = g.Lcap; pp.n_out = g.Lcap; pp.out_pad = 0;
+  if ((rc = launch_stretch(p, pp, g, workspace, st))) return rc;
+  rp.in = W; rp.in_stride = g.Lcap; rp.out = out; rp.out_stride = out_stride;
+  rp.B = B; rp.n_in = g.Lcap; rp.n_out = N;
+  rp.wav = wav; rp.wav_stride = wav_stride;
+  resample_kernel<<<dim3((N + 255) / 256, B), 256, 0, st>>>(rp);
   g_launches++;
   WWF_CUDA(cudaGetLastError());
   return WWF_OK;

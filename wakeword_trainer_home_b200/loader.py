@@ -60,7 +60,7 @@ class StreamedFeaturizer:
                 gather_clips(self.d_pcm[k], self._rows, out=self.d_wav[k])
             self.plan.featurize(self.d_wav[k], aug, out=self.d_out[k])
             if aug is not None:                           # keep the draw tensors alive until the kernel ran
-                for f in ("rir_idx", "noise_idx", "noise_off", "snr_db", "fmask_start", "fmask_len", "tmask_start", "tmask_len"):
+                for f in aug.tensor_fields():
                     v = getattr(aug, f)
                     if v is not None:
                         v.record_stream(self.s_run)

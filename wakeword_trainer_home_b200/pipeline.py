@@ -41,6 +41,11 @@ class AugParams:
     snr_db      float32 [B]    target SNR
     fmask_start/fmask_len  int32 [B, n_freq_masks]  masked feature rows [start, start+len)
     tmask_start/tmask_len  int32 [B, n_time_masks]  masked frames       [start, start+len)
+    stretch_rate float64 [B]   time-stretch speed factor (> 1 = faster), exactly 1.0 = untouched
+    pitch_steps int32 [B]      pitch shift in semitones, 0 = untouched
+    stretch_lo / pitch_range   host-side bounds of the two arrays above (they size the workspace);
+                               filled in automatically from host tensors or by the on-GPU draw
+    Order of application: time-stretch -> pitch-shift -> reverb -> noise -> features -> masks.
     """
     rir_idx: Optional[torch.Tensor] = None
     noise_idx: Optional[torch.Tensor] = None
@@ -50,22 +55,36 @@ class AugParams:
     fmask_len: Optional[torch.Tensor] = None
     tmask_start: Optional[torch.Tensor] = None
     tmask_len: Optional[torch.Tensor] = None
+    stretch_rate: Optional[torch.Tensor] = None
+    pitch_steps: Optional[torch.Tensor] = None
+    stretch_lo: Optional[float] = None
+    pitch_range: Optional[tuple] = None
 
     _DTYPES = dict(rir_idx=torch.int32, noise_idx=torch.int32, noise_off=torch.int64, snr_db=torch.float32,
-                   fmask_start=torch.int32, fmask_len=torch.int32, tmask_start=torch.int32, tmask_len=torch.int32)
+                   fmask_start=torch.int32, fmask_len=torch.int32, tmask_start=torch.int32, tmask_len=torch.int32,
+                   stretch_rate=torch.float64, pitch_steps=torch.int32)
+
+    def tensor_fields(self):
+        return [f.name for f in fields(self) if f.name in self._DTYPES]
 
     def to(self, device, non_blocking: bool = False) -> "AugParams":
-        kw = {}
-        for f in fields(self):
-            v = getattr(self, f.name)
+        kw = dict(stretch_lo=self.stretch_lo, pitch_range=self.pitch_range)
+        for name in self.tensor_fields():
+            v = getattr(self, name)
             if v is not None:
-                v = torch.as_tensor(v).to(device=device, dtype=self._DTYPES[f.name], non_blocking=non_blocking).contiguous()
-            kw[f.name] = v
+                v = torch.as_tensor(v)
+                # bounds of the shape-changing draws are taken while the values are still on the host
+                if name == "stretch_rate" and kw["stretch_lo"] is None and not v.is_cuda and v.numel():
+                    kw["stretch_lo"] = float(v.min())
+                if name == "pitch_steps" and kw["pitch_range"] is None and not v.is_cuda and v.numel():
+                    kw["pitch_range"] = (int(v.min()), int(v.max()))
+                v = v.to(device=device, dtype=self._DTYPES[name], non_blocking=non_blocking).contiguous()
+            kw[name] = v
         return AugParams(**kw)
 
     def nbytes(self) -> int:
-        return sum(getattr(self, f.name).numel() * getattr(self, f.name).element_size()
-                   for f in fields(self) if getattr(self, f.name) is not None)
+        return sum(getattr(self, n).numel() * getattr(self, n).element_size()
+                   for n in self.tensor_fields() if getattr(self, n) is not None)
 
 
 @dataclass
@@ -79,6 +98,10 @@ class DrawConfig:
     snr_range: tuple = (5.0, 20.0)
     freq_mask_param: int = 15
     time_mask_param: int = 35
+    stretch_prob: float = 0.0            # time_stretch_min/max, pitch_shift_min/max: src/config/defaults.py:76-79
+    stretch_range: tuple = (0.8, 1.2)
+    pitch_prob: float = 0.0
+    pitch_range: tuple = (-2, 2)
 
 
 def draw_mask_params(gen: Optional[torch.Generator], B: int, size: int, mask_param: int, n_masks: int, p: float = 1.0):
@@ -192,10 +215,18 @@ class FeaturePlan:
         if self.n_time_masks:
             a.tmask_start = torch.empty(B, self.n_time_masks, dtype=torch.int32, device=dev)
             a.tmask_len = torch.empty(B, self.n_time_masks, dtype=torch.int32, device=dev)
+        if cfg.stretch_prob > 0:
+            a.stretch_rate = torch.empty(B, dtype=torch.float64, device=dev)
+            a.stretch_lo = min(1.0, float(cfg.stretch_range[0]))
+        if cfg.pitch_prob > 0:
+            a.pitch_steps = torch.empty(B, dtype=torch.int32, device=dev)
+            a.pitch_range = (min(0, int(cfg.pitch_range[0])), max(0, int(cfg.pitch_range[1])))
         dc = N.DrawConfig(seed=int(cfg.seed) & (2 ** 64 - 1), rir_prob=cfg.rir_prob, noise_prob=cfg.noise_prob,
                           freq_mask_prob=cfg.freq_mask_prob, time_mask_prob=cfg.time_mask_prob,
                           snr_lo=float(cfg.snr_range[0]), snr_hi=float(cfg.snr_range[1]),
-                          freq_mask_param=int(cfg.freq_mask_param), time_mask_param=int(cfg.time_mask_param))
+                          freq_mask_param=int(cfg.freq_mask_param), time_mask_param=int(cfg.time_mask_param),
+                          stretch_prob=cfg.stretch_prob, stretch_lo=float(cfg.stretch_range[0]), stretch_hi=float(cfg.stretch_range[1]),
+                          pitch_prob=cfg.pitch_prob, pitch_lo=int(cfg.pitch_range[0]), pitch_hi=int(cfg.pitch_range[1]))
         st = N.Aug(*[_ptr(getattr(a, f[0])) for f in N.Aug._fields_])
         stream = torch.cuda.current_stream(dev)
         N.check(self.lib.wwf_draw_aug(self._handle, C.byref(dc), C.c_uint64(int(first_index)), B, self.num_frames(n_samples),
@@ -243,7 +274,7 @@ class FeaturePlan:
         if aug is None:
             return None, None
         a = aug.to(self.device)
-        for name in ("rir_idx", "noise_idx", "noise_off", "snr_db"):
+        for name in ("rir_idx", "noise_idx", "noise_off", "snr_db", "stretch_rate", "pitch_steps"):
             v = getattr(a, name)
             if v is not None and v.shape != (B,):
                 raise ValueError(f"AugParams.{name} must have shape ({B},), got {tuple(v.shape)}")
@@ -259,14 +290,83 @@ class FeaturePlan:
         return st, a            # keep `a` alive until the call returns
 
     def _ws(self, B: int, n: int, stream_id: int):
-        need = int(self.lib.wwf_workspace_bytes(self._handle, B, n))
+        return self._ws_bytes(int(self.lib.wwf_workspace_bytes(self._handle, B, n)), stream_id)
+
+    def _ws_bytes(self, need: int, key):
         if need == 0:
             return None, 0
-        ws = self._workspace.get(stream_id)
+        ws = self._workspace.get(key)
         if ws is None or ws.numel() < need:
             ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-            self._workspace[stream_id] = ws
+            self._workspace[key] = ws
         return ws, need
+
+    # ------------------------------------------------------------------ waveform-shape augmentations
+    def time_stretch(self, wav: torch.Tensor, rates: torch.Tensor, rate_lo: Optional[float] = None,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """(B, N) -> (B, N): clip b played rates[b] times faster without changing its pitch (torchaudio's
+        STFT -> phase_vocoder -> iSTFT), cropped / zero-padded to N; rates[b] == 1.0 copies the clip.
+        ``rate_lo`` is a lower bound of the rates (sizes the workspace); it is read from ``rates`` when omitted."""
+        wav = self._check_wav(wav)
+        B, n = wav.shape
+        rates = torch.as_tensor(rates)
+        if rates.shape != (B,):
+            raise ValueError(f"rates must have shape ({B},), got {tuple(rates.shape)}")
+        if rate_lo is None:
+            rate_lo = float(rates.min())                       # synchronises if the rates live on the GPU
+        rates = rates.to(device=self.device, dtype=torch.float64).contiguous()
+        if out is None:
+            out = torch.empty(B, n, dtype=torch.float32, device=self.device)
+        stream = torch.cuda.current_stream(self.device)
+        rate_lo = min(1.0, float(rate_lo))
+        ws, ws_bytes = self._ws_bytes(int(self.lib.wwf_stretch_workspace_bytes(B, n, rate_lo)), (stream.cuda_stream, "pv"))
+        N.check(self.lib.wwf_time_stretch(self._handle, _ptr(wav), B, n, wav.stride(0), _ptr(rates), rate_lo,
+                                          _ptr(out), out.stride(0), _ptr(ws), ws_bytes, C.c_void_p(stream.cuda_stream)))
+        return out
+
+    def pitch_shift(self, wav: torch.Tensor, n_steps: torch.Tensor, step_range: Optional[tuple] = None,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """(B, N) -> (B, N): torchaudio F.pitch_shift by n_steps[b] semitones per clip (0 copies the clip).
+        ``step_range`` = (lo, hi) bounds of n_steps; read from the tensor when omitted."""
+        wav = self._check_wav(wav)
+        B, n = wav.shape
+        n_steps = torch.as_tensor(n_steps)
+        if n_steps.shape != (B,):
+            raise ValueError(f"n_steps must have shape ({B},), got {tuple(n_steps.shape)}")
+        if step_range is None:
+            step_range = (int(n_steps.min()), int(n_steps.max()))
+        lo, hi = min(0, int(step_range[0])), max(0, int(step_range[1]))
+        n_steps = n_steps.to(device=self.device, dtype=torch.int32).contiguous()
+        if out is None:
+            out = torch.empty(B, n, dtype=torch.float32, device=self.device)
+        stream = torch.cuda.current_stream(self.device)
+        ws, ws_bytes = self._ws_bytes(int(self.lib.wwf_pitch_workspace_bytes(B, n, lo, hi)), (stream.cuda_stream, "pv"))
+        N.check(self.lib.wwf_pitch_shift(self._handle, _ptr(wav), B, n, wav.stride(0), _ptr(n_steps), lo, hi,
+                                         _ptr(out), out.stride(0), _ptr(ws), ws_bytes, C.c_void_p(stream.cuda_stream)))
+        return out
+
+    def resample(self, wav: torch.Tensor, orig_freq: int, new_freq: int, n_out: Optional[int] = None) -> torch.Tensor:
+        """(B, n) at orig_freq -> (B, ceil(new * n / orig)) at new_freq, torchaudio F.resample defaults
+        (the AudioProcessor step in front of the path, src/evaluation/evaluator.py:76-79)."""
+        wav = self._check_wav(wav)
+        B, n = wav.shape
+        if n_out is None:
+            n_out = int(self.lib.wwf_resample_length(n, int(orig_freq), int(new_freq)))
+        out = torch.empty(B, n_out, dtype=torch.float32, device=self.device)
+        stream = torch.cuda.current_stream(self.device)
+        N.check(self.lib.wwf_resample(self._handle, _ptr(wav), B, n, wav.stride(0), int(orig_freq), int(new_freq),
+                                      _ptr(out), n_out, out.stride(0), C.c_void_p(stream.cuda_stream)))
+        return out
+
+    def _shape_augs(self, wav: torch.Tensor, a: Optional[AugParams]) -> torch.Tensor:
+        """time-stretch, then pitch-shift, when the draws ask for them (out of place)."""
+        if a is None:
+            return wav
+        if a.stretch_rate is not None:
+            wav = self.time_stretch(wav, a.stretch_rate, a.stretch_lo)
+        if a.pitch_steps is not None:
+            wav = self.pitch_shift(wav, a.pitch_steps, a.pitch_range)
+        return wav
 
     def _check_wav(self, wav: torch.Tensor) -> torch.Tensor:
         if wav.dim() != 2:
@@ -288,6 +388,7 @@ class FeaturePlan:
         elif out.shape != (B, 1, self.n_feat, T) or out.dtype != self.out_dtype or out.device != self.device or not out.is_contiguous():
             raise ValueError("out must be a contiguous (B, 1, n_feat, T) tensor of the plan's dtype on the plan's device")
         st, keep = self._aug_struct(aug, B)
+        wav = self._shape_augs(wav, keep)
         stream = torch.cuda.current_stream(self.device)
         ws, ws_bytes = self._ws(B, n, stream.cuda_stream)
         N.check(self.lib.wwf_featurize(self._handle, _ptr(wav), B, n, wav.stride(0), None if st is None else C.byref(st),
@@ -295,12 +396,13 @@ class FeaturePlan:
         return out
 
     def augment(self, wav: torch.Tensor, aug: Optional[AugParams], out: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Time-domain half only: (B, N) -> (B, N) float32 (reverb, then noise @ SNR)."""
+        """Time-domain half only: (B, N) -> (B, N) float32 ([time-stretch] -> [pitch-shift] -> reverb -> noise @ SNR)."""
         wav = self._check_wav(wav)
         B, n = wav.shape
         if out is None:
             out = torch.empty(B, n, dtype=torch.float32, device=self.device)
         st, keep = self._aug_struct(aug, B)
+        wav = self._shape_augs(wav, keep)
         stream = torch.cuda.current_stream(self.device)
         ws, ws_bytes = self._ws(B, n, stream.cuda_stream)
         N.check(self.lib.wwf_augment(self._handle, _ptr(wav), B, n, wav.stride(0), None if st is None else C.byref(st),
