@@ -267,11 +267,15 @@ def istft(spec: np.ndarray, n_fft: int, hop_length: int, length: int, dtype=np.f
     return (y[:, start:start + length] / env[start:start + length]).astype(dtype)
 
 
-def stretch_core(x: np.ndarray, rate: float, dtype=np.float64) -> np.ndarray:
+def stretch_core(x: np.ndarray, rate: float, dtype=np.float64, window=None) -> np.ndarray:
     """torchaudio's _stretch_waveform (TA/functional/functional.py:1644-1693) with the rate explicit:
-    (B, N) -> (B, round(N / rate))."""
+    (B, N) -> (B, round(N / rate)).
+    ``window`` may inject torch.hann_window(512)'s float32 values: they differ from the correctly rounded
+    Hann window in the last 1-3 ulp, and a stretched PURE TONE is sensitive to exactly that (1e-4 relative,
+    growing along the clip); noise-like signals are not."""
     N = x.shape[1]
-    w32 = hann_periodic(PV_NFFT, np.float32)     # _stretch_waveform builds window / phase_advance in float32 always
+    # _stretch_waveform builds window / phase_advance in float32 whatever the waveform dtype is
+    w32 = hann_periodic(PV_NFFT, np.float32) if window is None else np.asarray(window, np.float32)
     spec = stft_complex(x, PV_NFFT, PV_HOP, dtype, window=w32)
     return istft(phase_vocoder(spec, rate, PV_HOP, dtype), PV_NFFT, PV_HOP, int(round(N / rate)), dtype, window=w32)
 
@@ -281,26 +285,33 @@ def _fix_len(y: np.ndarray, N: int) -> np.ndarray:
     return y[:, :N] if y.shape[1] >= N else np.pad(y, ((0, 0), (0, N - y.shape[1])))
 
 
-def time_stretch(x: np.ndarray, rates, dtype=np.float64) -> np.ndarray:
+def time_stretch(x: np.ndarray, rates, dtype=np.float64, window=None) -> np.ndarray:
     """Per clip stretch_core(rate) cropped / zero-padded back to N; rate == 1.0 = untouched.
     Reference surface: time_stretch_range, tests/test_training_pipeline.py:233."""
     out = np.asarray(x, dtype=dtype).copy()
     for b, r in enumerate([float(v) for v in rates]):
         if r != 1.0:
-            out[b] = _fix_len(stretch_core(out[b:b + 1], r, dtype), x.shape[1])[0]
+            out[b] = _fix_len(stretch_core(out[b:b + 1], r, dtype, window), x.shape[1])[0]
     return out
 
 
 def sinc_resample_kernel(orig_freq: int, new_freq: int, dtype=np.float64, lowpass_filter_width: int = 6,
                          rolloff: float = 0.99):
     """_get_sinc_resample_kernel, 'sinc_interp_hann' (TA/functional/functional.py:1305-1402), frequencies
-    already divided by their gcd.  Returns (kernel [new_freq][2*width + orig_freq], width).
+    already divided by their gcd - restricted to its support: torchaudio's dense kernel [new_freq][2*width +
+    orig_freq] is zero (|t| clamped to the window's edge) except for the <= 2*width + 1 entries around
+    q = phase * orig / new.  Returns (first [new_freq], taps [new_freq][2*width + 1], width) with
+    taps[p][j] = kernel[p][first[p] + j] (0 where that index is outside the dense kernel).
     float32 follows torchaudio's float32 operation order (it builds the kernel in the waveform's dtype)."""
     f = np.float32 if dtype == np.float32 else np.float64
     base_freq = min(orig_freq, new_freq) * rolloff
     width = int(math.ceil(lowpass_filter_width * orig_freq / base_freq))
-    idx = (np.arange(-width, width + orig_freq).astype(f) / f(orig_freq)).astype(f)[None, :]
-    t = ((np.arange(0, -new_freq, -1).astype(f) / f(new_freq)).astype(f)[:, None] + idx).astype(f)
+    ph = np.arange(new_freq)
+    first = (ph * orig_freq) // new_freq                       # kernel column of the first tap (offset -width folded in)
+    col = first[:, None] + np.arange(2 * width + 1)[None, :]   # dense-kernel column index = q + width
+    q = col - width
+    idx = (q.astype(f) / f(orig_freq)).astype(f)
+    t = (((-ph).astype(f) / f(new_freq)).astype(f)[:, None] + idx).astype(f)
     t = (t * f(base_freq)).astype(f)
     t = np.clip(t, f(-lowpass_filter_width), f(lowpass_filter_width))
     window = np.cos(((t * f(math.pi)).astype(f) / f(lowpass_filter_width)).astype(f) / f(2)).astype(f) ** 2
@@ -308,7 +319,9 @@ def sinc_resample_kernel(orig_freq: int, new_freq: int, dtype=np.float64, lowpas
     scale = f(base_freq / orig_freq)
     with np.errstate(invalid="ignore", divide="ignore"):
         k = np.where(t == 0, f(1.0), (np.sin(t).astype(f) / t).astype(f))
-    return (k * (window * scale).astype(f)).astype(f), width
+    k = (k * (window * scale).astype(f)).astype(f)
+    k = np.where(col < 2 * width + orig_freq, k, f(0.0))
+    return first, k, width
 
 
 def resample(x: np.ndarray, orig_freq: int, new_freq: int, dtype=np.float64) -> np.ndarray:
@@ -319,21 +332,20 @@ def resample(x: np.ndarray, orig_freq: int, new_freq: int, dtype=np.float64) -> 
         return x
     g = math.gcd(int(orig_freq), int(new_freq))
     o, n = int(orig_freq) // g, int(new_freq) // g
-    kern, width = sinc_resample_kernel(o, n, dtype)
+    first, taps, width = sinc_resample_kernel(o, n, dtype)
     B, N = x.shape
-    xp = np.pad(x, ((0, 0), (width, width + o))).astype(np.float64)
-    nblk = (xp.shape[1] - kern.shape[1]) // o + 1
+    nblk = N // o + 1
+    xp = np.pad(x, ((0, 0), (width, width + o + 2 * width + 1))).astype(np.float64)
     target = int(np.ceil(np.float32(n * N / o)))             # torch.as_tensor(python float) is float32
     out = np.zeros((B, nblk * n))
-    # only the taps with |t| < lowpass_filter_width matter; use the dense rows for clarity, phase by phase
-    k64 = kern.astype(np.float64)
+    k64 = taps.astype(np.float64)
+    cols = first[:, None] + np.arange(taps.shape[1])[None, :]
     for m in range(nblk):
-        seg = xp[:, m * o:m * o + kern.shape[1]]
-        out[:, m * n:(m + 1) * n] = seg @ k64.T
+        out[:, m * n:(m + 1) * n] = np.einsum("bpj,pj->bp", xp[:, m * o + cols], k64)
     return out[:, :target].astype(dtype)
 
 
-def pitch_shift(x: np.ndarray, n_steps, sample_rate: int = 16000, dtype=np.float64) -> np.ndarray:
+def pitch_shift(x: np.ndarray, n_steps, sample_rate: int = 16000, dtype=np.float64, window=None) -> np.ndarray:
     """F.pitch_shift per clip (TA/functional/functional.py:1596-1641): stretch by rate = 2^(-n/12), resample
     int(sample_rate / rate) -> sample_rate, crop / zero-pad to N.  0 semitones = untouched."""
     out = np.asarray(x, dtype=dtype).copy()
@@ -342,7 +354,7 @@ def pitch_shift(x: np.ndarray, n_steps, sample_rate: int = 16000, dtype=np.float
         if n == 0:
             continue
         rate = 2.0 ** (-float(n) / 12)
-        y = stretch_core(out[b:b + 1], rate, dtype)
+        y = stretch_core(out[b:b + 1], rate, dtype, window)
         out[b] = _fix_len(resample(y, int(sample_rate / rate), sample_rate, dtype), N)[0]
     return out
 

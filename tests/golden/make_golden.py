@@ -88,10 +88,39 @@ def mask_case(name, seed):
     print(name, tuple(out.shape))
 
 
+def shape_aug_case(name, seed, B, N):
+    """Row A3: torchaudio's own stretch stage (F.functional._stretch_waveform), F.pitch_shift and F.resample,
+    float32 and float64.  The float32 stretch is only reproducible to ~1e-3 (float32 phase cumsum), the
+    float64 one to ~1e-9: tests compare tightly with the float64 vectors."""
+    import math
+    g = torch.Generator().manual_seed(seed)
+    x = 0.1 * torch.randn(B, N, generator=g)
+    t = torch.arange(N) / 16000.0
+    x[1] = 0.5 * torch.sin(2 * torch.pi * 440.0 * t)
+    steps = [-2, -1, 1, 2][:B]
+    rates = [2.0 ** (-float(n) / 12) for n in steps]
+    lens = [int(round(N / r)) for r in rates]
+    st32 = np.zeros((B, max(lens)), np.float32)
+    st64 = np.zeros((B, max(lens)), np.float64)
+    ps32 = np.zeros((B, N), np.float32)
+    ps64 = np.zeros((B, N), np.float64)
+    for b, n in enumerate(steps):
+        st32[b, :lens[b]] = AF.functional._stretch_waveform(x[b:b + 1], n)[0].numpy()
+        st64[b, :lens[b]] = AF.functional._stretch_waveform(x[b:b + 1].double(), n)[0].numpy()
+        ps32[b] = AF.pitch_shift(x[b:b + 1], 16000, n)[0].numpy()
+        ps64[b] = AF.pitch_shift(x[b:b + 1].double(), 16000, n)[0].numpy()
+    rs = {f"rs_{o}": AF.resample(x[:2], o, 16000).numpy() for o in (44100, 8000, 17959)}
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), seed=seed, B=B, N=N, steps=np.array(steps), rates=np.array(rates),
+                        lens=np.array(lens), stretch32=st32, stretch64=st64, pitch32=ps32, pitch64=ps64,
+                        torchaudio=torchaudio.__version__, **rs)
+    print(name, st32.shape, ps32.shape)
+
+
 if __name__ == "__main__":
     torch.set_num_threads(1)   # deterministic reductions
     feature_case("feat_cfg1", 0, 6, 24000, 400, 160, 40, 40)          # BASELINE.json configs[0] shape
     feature_case("feat_refdefault", 1, 4, 16000, 1024, 160, 128, 40)  # DataConfig defaults, 1.0 s
     feature_case("feat_n512", 2, 4, 19200, 512, 160, 64, 32)          # Edge-like: 64 mels / 32 mfcc
     aug_case("aug_cfg2", 3, 6, 24000, 8000, 3, 3)                     # BASELINE.json configs[1] shape
+    shape_aug_case("shape_aug", 5, 4, 6000)                           # SURVEY 8a row A3: stretch / pitch / resample
     mask_case("mask_ref", 4)                                          # tests/test_training_pipeline.py:252-262 shape

@@ -655,7 +655,7 @@ def test_time_stretch_vs_oracle(ww):
     """wwf_time_stretch against torchaudio's STFT -> phase_vocoder -> iSTFT.
     torchaudio float32 accumulates the vocoder phase in float32 (ulp 8e-3 rad at 7e4 rad): ITS float32 and
     float64 results differ by ~1e-3 relative.  The CUDA path accumulates in double, so it is compared
-    (a) tightly with the float64 oracle: relative L2 <= 1e-4, and
+    (a) tightly with the float64 oracle: relative L2 <= 3e-5 (measured <= 1.1e-5, pure tones included), and
     (b) with the float32 oracle within 1.5 x that oracle's own float32-float64 gap."""
     from oracle import ta_oracle as tao
     gen = torch.Generator().manual_seed(42)
@@ -664,6 +664,7 @@ def test_time_stretch_vs_oracle(ww):
     t = torch.arange(N) / 16000.0
     x[2] = 0.5 * torch.sin(2 * torch.pi * 440.0 * t) + 0.2 * torch.sin(2 * torch.pi * 1230.0 * t)
     x[3, N // 2:] = 0.0
+    x[5] = 0.5 * torch.sin(2 * torch.pi * 440.0 * t)             # pure tone: sensitive to the window's last ulp
     rates = torch.tensor([0.8013, 1.1987, 0.9371, 1.0629, 1.0, 0.8642, 1.1318, 1.0], dtype=torch.float64)
     plan = ww.FeaturePlan(16000, "mel", 40, 40, 400, 160, "cuda")
     got = plan.time_stretch(x.cuda(), rates).cpu()
@@ -675,7 +676,7 @@ def test_time_stretch_vs_oracle(ww):
             assert torch.equal(got[b], x[b])
             continue
         gap = _rel(w32[b], w64[b])
-        assert _rel(got[b], w64[b]) <= 1e-4, (b, _rel(got[b], w64[b]))
+        assert _rel(got[b], w64[b]) <= 3e-5, (b, _rel(got[b], w64[b]))
         assert _rel(got[b], w32[b]) <= 1.5 * gap + 1e-4, (b, _rel(got[b], w32[b]), gap)
         if rates[b] > 1.0:                                           # shorter result: zero padding to N
             assert (got[b, int(round(N / float(rates[b]))):] == 0).all()
@@ -687,7 +688,7 @@ def test_time_stretch_vs_oracle(ww):
     assert torch.equal(v.cpu(), got)
     x2 = 0.1 * torch.randn(2, 7001, generator=gen)
     r2 = torch.tensor([1.25, 0.75], dtype=torch.float64)
-    assert _rel(plan.time_stretch(x2.cuda(), r2).cpu(), tao.time_stretch(x2.double(), r2)) <= 1e-4
+    assert _rel(plan.time_stretch(x2.cuda(), r2).cpu(), tao.time_stretch(x2.double(), r2)) <= 3e-5
 
 
 def test_pitch_shift_vs_oracle(ww):

@@ -111,3 +111,49 @@ def test_top_db_is_per_clip():
     both = tao.featurize(x, n_fft=400, n_mels=40, hop_length=160)
     alone = tao.featurize(x[1:], n_fft=400, n_mels=40, hop_length=160)
     assert torch.equal(both[1], alone[0])
+
+
+# ---- time-stretch / pitch-shift / resample ------------------------------
+def _shape_aug_inputs(g):
+    N, B = int(g["N"]), int(g["B"])
+    gen = torch.Generator().manual_seed(int(g["seed"]))
+    x = 0.1 * torch.randn(B, N, generator=gen)
+    t = torch.arange(N) / 16000.0
+    x[1] = 0.5 * torch.sin(2 * torch.pi * 440.0 * t)
+    return x
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def test_shape_aug_oracles_reproduce_torchaudio_golden(golden_dir):
+    """Both oracle layers against vectors made by torchaudio's own _stretch_waveform / pitch_shift / resample.
+    float64: tight.  float32: torchaudio's float32 phase cumsum makes its result reproducible only to its own
+    float32-float64 gap (~1e-3), so the float32 comparison is bounded by that gap."""
+    g = np.load(os.path.join(golden_dir, "shape_aug.npz"))
+    x = _shape_aug_inputs(g)
+    N = x.shape[1]
+    w = torch.hann_window(512).numpy()       # the numpy layer is given torch's float32 window (see npo.stretch_core)
+    for b, (n, rate, ln) in enumerate(zip(g["steps"], g["rates"], g["lens"])):
+        n, rate, ln = int(n), float(rate), int(ln)
+        xb = x[b:b + 1]
+        s64 = tao.stretch_core(xb.double(), rate)[0].numpy()
+        assert s64.shape[0] == ln and np.abs(s64 - g["stretch64"][b, :ln]).max() <= 1e-7
+        assert np.abs(npo.stretch_core(xb.numpy(), rate, window=w)[0] - g["stretch64"][b, :ln]).max() <= 2e-6
+        gap = _rel(g["stretch32"][b, :ln], g["stretch64"][b, :ln])
+        assert _rel(tao.stretch_core(xb, rate)[0].numpy(), g["stretch32"][b, :ln]) <= 2 * gap
+        assert _rel(npo.stretch_core(xb.numpy(), rate, np.float32, window=w)[0], g["stretch64"][b, :ln]) <= max(3 * gap, 5e-4)
+        assert np.abs(tao.pitch_shift(xb.double(), [n])[0].numpy() - g["pitch64"][b]).max() <= 1e-7
+        assert np.abs(npo.pitch_shift(xb.numpy(), [n], window=w)[0] - g["pitch64"][b]).max() <= 2e-6
+        assert _rel(tao.pitch_shift(xb, [n])[0].numpy(), g["pitch32"][b]) <= 2 * _rel(g["pitch32"][b], g["pitch64"][b])
+        # time_stretch = stretch_core cropped / zero-padded to N
+        ts = tao.time_stretch(xb.double(), [rate])[0].numpy()
+        assert np.array_equal(ts[:min(N, ln)], s64[:N]) and (ts[ln:] == 0).all()
+    for o in (44100, 8000, 17959):
+        want = g[f"rs_{o}"]
+        assert np.abs(tao.resample(x[:2], o, 16000).numpy() - want).max() <= 1e-6
+        # the numpy float32 layer follows torchaudio's float32 kernel arithmetic (sensitive for 17959:16000)
+        assert np.abs(npo.resample(x[:2].numpy(), o, 16000, np.float32) - want).max() <= 2e-6
+    assert torch.equal(tao.pitch_shift(x, [0] * x.shape[0]), x) and torch.equal(tao.time_stretch(x, [1.0] * x.shape[0]), x)

@@ -683,8 +683,7 @@ extern "C" int wwf_spec_augment(void* spec, int dtype, int B, int F, int T, int6
 // ------------------------------------------------------------------------------------------
 // time-stretch / pitch-shift / resample
 // ------------------------------------------------------------------------------------------
-static int ensure_pv_constants(wwf_plan* p) {
-  std::lock_guard<std::mutex> lk(p->lazy_mu);
+static int ensure_pv_constants_locked(wwf_plan* p) {
   if (p->d_pv_tw) return WWF_OK;
   std::vector<float> win(kPvN);
   for (int i = 0; i < kPvN; ++i) win[i] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * i / kPvN));
@@ -695,6 +694,23 @@ static int ensure_pv_constants(wwf_plan* p) {
   int rc;
   if ((rc = upload(&p->d_pv_window, win)) || (rc = upload(&p->d_pv_pa, pa))) return rc;
   return upload(&p->d_pv_tw, tw);
+}
+static int ensure_pv_constants(wwf_plan* p) {
+  std::lock_guard<std::mutex> lk(p->lazy_mu);
+  return ensure_pv_constants_locked(p);
+}
+
+extern "C" int wwf_set_stretch_tables(wwf_plan* p, const float* window, const float* phase_advance) {
+  if (!p) return fail(WWF_ERR_INVALID, "wwf_set_stretch_tables: null plan");
+  DeviceGuard guard(p->device);
+  if (!guard.ok) return fail(WWF_ERR_CUDA, "cudaSetDevice(%d) failed", p->device);
+  std::lock_guard<std::mutex> lk(p->lazy_mu);
+  int rc = ensure_pv_constants_locked(p);
+  if (rc) return rc;
+  // plain synchronous copies: they are ordered after every kernel already launched on the device
+  if (window) WWF_CUDA(cudaMemcpy(p->d_pv_window, window, kPvN * sizeof(float), cudaMemcpyHostToDevice));
+  if (phase_advance) WWF_CUDA(cudaMemcpy(p->d_pv_pa, phase_advance, kPvK * sizeof(float), cudaMemcpyHostToDevice));
+  return WWF_OK;
 }
 
 struct PvGeom {

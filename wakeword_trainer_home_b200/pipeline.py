@@ -174,6 +174,7 @@ class FeaturePlan:
         info = N.Info()
         N.check(self.lib.wwf_plan_info(self._handle, C.byref(info)))
         self.n_feat, self.n_freq, self.sm_count = info.n_feat, info.n_freq, info.sm_count
+        self._stretch_tables = False   # torch's float32 window / phase_advance are handed over on first use
         self._noise = None          # keeps the borrowed noise bank alive
         self._workspace: dict[int, torch.Tensor] = {}
         self.n_noise = self.n_rir = 0
@@ -319,6 +320,7 @@ class FeaturePlan:
             out = torch.empty(B, n, dtype=torch.float32, device=self.device)
         stream = torch.cuda.current_stream(self.device)
         rate_lo = min(1.0, float(rate_lo))
+        self._ensure_stretch_tables()
         ws, ws_bytes = self._ws_bytes(int(self.lib.wwf_stretch_workspace_bytes(B, n, rate_lo)), (stream.cuda_stream, "pv"))
         N.check(self.lib.wwf_time_stretch(self._handle, _ptr(wav), B, n, wav.stride(0), _ptr(rates), rate_lo,
                                           _ptr(out), out.stride(0), _ptr(ws), ws_bytes, C.c_void_p(stream.cuda_stream)))
@@ -340,6 +342,7 @@ class FeaturePlan:
         if out is None:
             out = torch.empty(B, n, dtype=torch.float32, device=self.device)
         stream = torch.cuda.current_stream(self.device)
+        self._ensure_stretch_tables()
         ws, ws_bytes = self._ws_bytes(int(self.lib.wwf_pitch_workspace_bytes(B, n, lo, hi)), (stream.cuda_stream, "pv"))
         N.check(self.lib.wwf_pitch_shift(self._handle, _ptr(wav), B, n, wav.stride(0), _ptr(n_steps), lo, hi,
                                          _ptr(out), out.stride(0), _ptr(ws), ws_bytes, C.c_void_p(stream.cuda_stream)))
@@ -357,6 +360,13 @@ class FeaturePlan:
         N.check(self.lib.wwf_resample(self._handle, _ptr(wav), B, n, wav.stride(0), int(orig_freq), int(new_freq),
                                       _ptr(out), n_out, out.stride(0), C.c_void_p(stream.cuda_stream)))
         return out
+
+    def _ensure_stretch_tables(self):
+        if not self._stretch_tables:
+            w, pa = K.hann_window(512), K.phase_advance(128, 257)
+            N.check(self.lib.wwf_set_stretch_tables(self._handle, C.cast(w.data_ptr(), C.POINTER(C.c_float)),
+                                                    C.cast(pa.data_ptr(), C.POINTER(C.c_float))))
+            self._stretch_tables = True
 
     def _shape_augs(self, wav: torch.Tensor, a: Optional[AugParams]) -> torch.Tensor:
         """time-stretch, then pitch-shift, when the draws ask for them (out of place)."""
