@@ -214,11 +214,11 @@ int wwf_draw_aug(wwf_plan* plan, const wwf_draw_config* cfg, uint64_t first_inde
  *           tests/test_training_pipeline.py:233; AugmentationConfig.time_stretch_min/max, src/config/defaults.py:76-77).
  */
 size_t wwf_stretch_workspace_bytes(int B, int N, double rate_lo);
-/* Optional: replace the stretch stage's two float32 tables by the caller's (host pointers, copied; NULL keeps
- * the current one): window[512] = torch.hann_window(512), phase_advance[257] = torch.linspace(0, pi * 128, 257).
- * The library's defaults are the correctly rounded values; torch's float32 window differs from them in the
- * last 1-3 ulp, which moves a stretched pure tone by 1e-4 relative - the Python shim passes torch's arrays. */
-int wwf_set_stretch_tables(wwf_plan* plan, const float* window, const float* phase_advance);
+/* Optional: replace the stretch stage's float32 analysis / synthesis window (host pointer, 512 values, copied)
+ * by the caller's, normally torch.hann_window(512).  The library's default is the correctly rounded periodic
+ * Hann window; torch's float32 one differs from it in the last 1-3 ulp, which moves a stretched pure tone by
+ * 1e-4 relative - the Python shim passes torch's array. */
+int wwf_set_stretch_window(wwf_plan* plan, const float* window);
 int wwf_time_stretch(wwf_plan* plan, const float* wav, int B, int N, int64_t wav_stride, const double* rates,
                      double rate_lo, float* out, int64_t out_stride, void* workspace, size_t workspace_bytes,
                      void* stream);

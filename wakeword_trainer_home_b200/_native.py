@@ -88,7 +88,7 @@ SYMBOLS = {
                                    C.c_int64, C.c_int, C.c_void_p]),
     "wwf_draw_aug": (C.c_int, [C.c_void_p, C.POINTER(DrawConfig), C.c_uint64, C.c_int, C.c_int, C.POINTER(Aug), C.c_void_p]),
     "wwf_stretch_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_double]),
-    "wwf_set_stretch_tables": (C.c_int, [C.c_void_p, _fp, _fp]),
+    "wwf_set_stretch_window": (C.c_int, [C.c_void_p, _fp]),
     "wwf_time_stretch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_double,
                                    C.c_void_p, C.c_int64, C.c_void_p, C.c_size_t, C.c_void_p]),
     "wwf_pitch_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -42,8 +42,3 @@ def dct_matrix(n_mfcc: int, n_mels: int) -> torch.Tensor:
     dct *= math.sqrt(2.0 / float(n_mels))
     return dct.t().contiguous()
 
-
-def phase_advance(hop_length: int, n_freq: int) -> torch.Tensor:
-    """Expected phase advance per bin of the phase vocoder, torch.linspace(0, pi * hop, n_freq) float32 -
-    torchaudio/functional/functional.py:1686 (_stretch_waveform)."""
-    return torch.linspace(0, math.pi * hop_length, n_freq).contiguous()

@@ -11,16 +11,15 @@
 //   pv_stft_kernel     wav[N]            -> S[T][272] complex    warp per frame PAIR (two real frames per
 //                                                                complex FFT), same radix-16.8.4 plan and
 //                                                                padded scratch as feat_kernel<512>
-//   pv_vocoder_kernel  S                 -> V[T'][272] complex   thread per (clip, bin): the phase
-//                                                                accumulation is a serial chain over time
-//   pv_istft_kernel    V                 -> Y[T'][512] float     warp per frame pair: Hermitian pack,
-//                                                                inverse FFT, 1/512 and window
-//   pv_ola_kernel      Y                 -> y[len]               4-term overlap-add / window envelope
+//   pv_vocoder_kernel  S                 -> V[T'][272] complex   thread per (clip, bin): the phase accumulation
+//                                                                is a running product of unit phasors over time
+//   pv_synth_kernel    V                 -> y[len]               CTA per 17 hop blocks: Hermitian pack, inverse
+//                                                                FFTs, overlap-add / window envelope from smem
 //   resample_kernel    y (+ coefficient table) -> out[N]
 // Accuracy note: torchaudio accumulates the vocoder phase with a float32 cumsum; at ~7e4 rad one float32
 // ulp is 8e-3 rad, which is why torchaudio's own float32 and float64 results differ by ~1e-3 relative.
-// Here the accumulation runs in double (257 x T' adds per clip) and only the reduced angle is rounded to
-// float32, so the result sits at the float64 oracle; everything else follows the float32 operation order.
+// Here the phase is carried as a unit phasor (see pv_vocoder_kernel), whose error does not grow with the
+// size of the angle, so the result sits at the float64 oracle (1e-5) instead of 1e-3 away from it.
 #pragma once
 #include <stdint.h>
 #include "wwf_feat.cuh"
@@ -67,11 +66,9 @@ struct PvParams {
   int Tcap, Lcap;              // capacity of V / Y rows and of the stretched waveform per clip
   PvRate rate;
   const float* window;         // [512] periodic Hann, float32
-  const float* phase_adv;      // [257] linspace(0, pi * hop, 257), float32
   const float2* tw;            // forward twiddles of Radices<16, 8, 4>
   float2* S; float2* V;        // [B][T][272], [B][Tcap][272]
-  float* Y;                    // [B][Tcap][512]
-  float* out; int64_t out_stride; int n_out;   // pv_ola_kernel destination: n_out samples per clip
+  float* out; int64_t out_stride; int n_out;   // pv_synth_kernel destination: n_out samples per clip
   int out_pad;                 // 1: zero-fill [len, n_out) and copy untouched clips (time-stretch); 0: write len only
 };
 
@@ -139,9 +136,32 @@ __global__ void __launch_bounds__(kPvWarps * 32) pv_stft_kernel(const PvParams p
   }
 }
 
-// ---- phase vocoder: S -> V ------------------------------------------------------------------------
-// One thread per (clip, bin).  Follows F.phase_vocoder line by line: angles, magnitudes and their
-// interpolation in float32, the phase increments and their running sum in double.
+// ---- phase vocoder: S -> V -----------------------------------------------------------------------
+// F.phase_vocoder builds, per bin, phase_acc[j] = angle(S[0]) + sum_{i<j} (pa + wrap(angle(S[i1]) - angle(S[i0]) - pa))
+// and emits mag[j] * exp(i phase_acc[j]).  wrap() only removes multiples of 2 pi and the sum is used solely
+// through cos / sin, so exp(i phase_acc[j+1]) = exp(i phase_acc[j]) * u(S[i1]) * conj(u(S[i0])) with
+// u(z) = z / |z| (u(0) = 1 because torch's angle(0) is 0): the accumulation is a running product of unit
+// complex numbers - no atan2, no sincos, no phase_advance table.  Each product rounds the angle by ~6e-8 rad
+// (a random walk: ~1e-6 rad after 200 frames, 2e-5 after 2^17), far below torchaudio's own float32 cumsum
+// (ulp 8e-3 rad at 7e4 rad); the phasor is renormalised every step.
+// One thread per (clip, bin); the frame loads of kVocU consecutive steps are independent of the running
+// product and are issued together.
+constexpr int kVocU = 8;
+
+// z / |z| and |z| (u = 1, |z| = 0 for z = 0); tiny inputs are rescaled so that x^2 + y^2 cannot underflow
+__device__ __forceinline__ float2 pv_unit(float2 z, float* mag) {
+  const float ax = fmaxf(fabsf(z.x), fabsf(z.y));
+  if (ax == 0.f) { *mag = 0.f; return make_float2(1.f, 0.f); }
+  const bool tiny = ax < 1e-18f;
+  const float sc = tiny ? 1.8446744e19f : 1.0f;               // 2^64
+  const float x = z.x * sc, y = z.y * sc;
+  const float m2 = fmaf(x, x, y * y);
+  const float inv = rsqrtf(m2);
+  const float m = m2 * inv;                                   // sqrt(m2) to ~2 ulp
+  *mag = tiny ? m * 5.4210109e-20f : m;                       // 2^-64
+  return make_float2(x * inv, y * inv);
+}
+
 __global__ void __launch_bounds__(288) pv_vocoder_kernel(const PvParams p) {
   const int b = blockIdx.x, k = threadIdx.x;
   const double rate = pv_clip_rate(p.rate, b);
@@ -150,131 +170,123 @@ __global__ void __launch_bounds__(288) pv_vocoder_kernel(const PvParams p) {
   const int To = pv_out_frames(T, rate, p.Tcap);
   const float2* S = p.S + (size_t)b * T * kPvPitch + k;
   float2* V = p.V + (size_t)b * p.Tcap * kPvPitch + k;
-  const double pa_d = (double)__ldg(p.phase_adv + k);
-  const double two_pi_d = 6.283185307179586476925286766559;
-  // frames >= T are the two zero frames torchaudio pads with: angle(0) = 0, |0| = 0
-  auto load = [&](int t, float& ang, float& nrm) {
-    if (t < T) {
-      const float2 v = S[(size_t)t * kPvPitch];
-      ang = atan2f(v.y, v.x);
-      nrm = hypotf(v.x, v.y);
-    } else { ang = 0.f; nrm = 0.f; }
-  };
-  float a_prev0, n_prev0, a_prev1, n_prev1;
-  int i_prev0 = 0, i_prev1 = 1;
-  load(0, a_prev0, n_prev0);
-  load(1, a_prev1, n_prev1);
-  double acc = (double)a_prev0;                              // phase_0 = angle of frame 0
-  for (int j = 0; j < To; ++j) {
-    const float ts = (float)((double)j * rate);              // arange(0, T, rate) in float32
-    const int i0 = (int)ts, i1 = (int)__fadd_rn(ts, 1.0f);
-    const float alpha = ts - (float)i0;                      // ts % 1.0 (exact for ts >= 0)
-    float a0, n0, a1, n1;
-    // the frame indices advance monotonically and are uniform across the CTA: reuse what is still valid
-    if (i0 == i_prev0) { a0 = a_prev0; n0 = n_prev0; }
-    else if (i0 == i_prev1) { a0 = a_prev1; n0 = n_prev1; }
-    else load(i0, a0, n0);
-    if (i1 == i_prev1) { a1 = a_prev1; n1 = n_prev1; }
-    else load(i1, a1, n1);
-    i_prev0 = i0; a_prev0 = a0; n_prev0 = n0;
-    i_prev1 = i1; a_prev1 = a1; n_prev1 = n1;
-    const float mag = __fadd_rn(__fmul_rn(alpha, n1), __fmul_rn(__fsub_rn(1.0f, alpha), n0));
-    // output j uses the phase accumulated BEFORE this step's increment (torch.cat([phase_0, phase[:-1]]))
-    const double red = acc - two_pi_d * rint(acc / two_pi_d);
-    float sn, cs;
-    sincosf((float)red, &sn, &cs);
-    V[(size_t)j * kPvPitch] = make_float2(mag * cs, mag * sn);
-    // phase increment: wrap(angle1 - angle0 - phase_advance) + phase_advance.  In float32 this rounds at
-    // the magnitude of phase_advance (up to 402 rad, ulp 3e-5) every step, so it is formed in double too.
-    double ph = (double)a1 - (double)a0 - pa_d;
-    ph -= two_pi_d * rint(ph / two_pi_d);
-    acc += ph + pa_d;
+  float m_;
+  float2 E = pv_unit(S[0], &m_);                             // exp(i phase_0), phase_0 = angle of frame 0
+  for (int j0 = 0; j0 < To; j0 += kVocU) {
+    float2 s0[kVocU], s1[kVocU];
+    float al[kVocU];
+#pragma unroll
+    for (int u = 0; u < kVocU; ++u) {
+      const float ts = (float)((double)(j0 + u) * rate);     // arange(0, T, rate) in float32
+      const int i0 = (int)ts, i1 = (int)__fadd_rn(ts, 1.0f);
+      al[u] = ts - (float)i0;                                // ts % 1.0 (exact for ts >= 0)
+      // frames >= T are the two zero frames torchaudio pads with
+      s0[u] = (j0 + u < To && i0 < T) ? S[(size_t)i0 * kPvPitch] : make_float2(0.f, 0.f);
+      s1[u] = (j0 + u < To && i1 < T) ? S[(size_t)i1 * kPvPitch] : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < kVocU; ++u) {
+      if (j0 + u < To) {
+        float m0, m1;
+        const float2 u0 = pv_unit(s0[u], &m0), u1 = pv_unit(s1[u], &m1);
+        const float mag = __fadd_rn(__fmul_rn(al[u], m1), __fmul_rn(__fsub_rn(1.0f, al[u]), m0));
+        // output j uses the phase accumulated BEFORE this step's increment (torch.cat([phase_0, phase[:-1]]))
+        V[(size_t)(j0 + u) * kPvPitch] = make_float2(mag * E.x, mag * E.y);
+        const float2 rot = make_float2(fmaf(u1.x, u0.x, u1.y * u0.y), fmaf(u1.y, u0.x, -u1.x * u0.y));   // u1 * conj(u0)
+        const float2 e = make_float2(fmaf(E.x, rot.x, -E.y * rot.y), fmaf(E.x, rot.y, E.y * rot.x));
+        const float inv = rsqrtf(fmaf(e.x, e.x, e.y * e.y));
+        E = make_float2(e.x * inv, e.y * inv);
+      }
+    }
   }
 }
 
-// ---- inverse STFT frames: V -> Y ----------------------------------------------------------------------
-__global__ void __launch_bounds__(kPvWarps * 32) pv_istft_kernel(const PvParams p) {
-  __shared__ __align__(16) float2 s_z[kPvWarps * kPvZL];
-  __shared__ float2 s_tw[PvRad::tw_total];
-  __shared__ float s_win[kPvN];
+// ---- synthesis: V -> waveform (inverse STFT frames + overlap-add + window envelope, fused) --------------
+// A CTA owns kSynBlocks consecutive hop blocks (128 output samples each) of one clip.  Hop block h is the
+// sum of frames h-3 .. h, so the CTA inverse-transforms the kSynFrames = kSynBlocks + 3 frames it needs
+// (two per warp, packed in one complex FFT), leaves them in its warps' scratch buffers and overlap-adds
+// straight out of shared memory: the windowed frames never travel to HBM.
+constexpr int kSynWarps = 10, kSynFrames = 2 * kSynWarps, kSynBlocks = kSynFrames - 3;
+constexpr int kSynSmemBytes = (kSynWarps * kPvZL + PvRad::tw_total) * (int)sizeof(float2) + kPvN * (int)sizeof(float);
+
+__global__ void __launch_bounds__(kSynWarps * 32) pv_synth_kernel(const PvParams p) {
+  extern __shared__ __align__(16) float2 syn_smem[];
+  float2* s_z = syn_smem;
+  float2* s_tw = s_z + kSynWarps * kPvZL;
+  float* s_win = reinterpret_cast<float*>(s_tw + PvRad::tw_total);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, b = blockIdx.y;
   const double rate = pv_clip_rate(p.rate, b);
-  if (rate == 1.0) return;
-  const int To = pv_out_frames(p.T, rate, p.Tcap);
-  if (2 * blockIdx.x * kPvWarps >= To) return;               // CTA-uniform
-  for (int i = tid; i < kPvN; i += blockDim.x) s_win[i] = __ldg(p.window + i);
-  for (int i = tid; i < PvRad::tw_total; i += blockDim.x) s_tw[i] = __ldg(p.tw + i);
-  __syncthreads();
-  const int ja = 2 * (blockIdx.x * kPvWarps + warp), jb = ja + 1;
-  if (ja >= To) return;
-  const PvMap zmap;
-  float2* z = s_z + warp * kPvZL;
-  const float2* Va = p.V + ((size_t)b * p.Tcap + ja) * kPvPitch;
-  const float2* Vb = Va + kPvPitch;
-  const bool hb = jb < To;
-  // Z = A + i B with Hermitian extension, written where the forward transform would have left bin k
-  // (irfft ignores the imaginary parts of the DC and Nyquist bins)
-  for (int k = lane; k < kPvK; k += 32) {
-    float2 a = Va[k], c = hb ? Vb[k] : make_float2(0.f, 0.f);
-    if (k == 0 || k == kPvN / 2) { a.y = 0.f; c.y = 0.f; }
-    float2 zk, zm;
-    pv_pack(a, c, &zk, &zm);
-    z[zmap(PvRad::pos(k))] = zk;
-    if (k > 0 && k < kPvN / 2) z[zmap(PvRad::pos(kPvN - k))] = zm;
-  }
-  __syncwarp();
-  static_for<0, PvRad::npass>([&](auto I) {
-    constexpr int i = PvRad::npass - 1 - decltype(I)::value;  // inverse (DIT) passes run in reverse order
-    constexpr int R = PvRad::R(i), L = PvRad::L(i), tasks = kPvN / R;
-    const float2* tw = s_tw + PvRad::tw_off(i);
-#pragma unroll 1
-    for (int u = lane; u < tasks; u += 32) pass_task<R, true, PvMap>(z, L, u, [&](int q) { return tw[q]; });
-    __syncwarp();
-  });
-  float* Ya = p.Y + ((size_t)b * p.Tcap + ja) * kPvN;
-  float* Yb = Ya + kPvN;
-#pragma unroll 4
-  for (int j = lane; j < kPvN; j += 32) {
-    const float2 v = z[zmap(j)];
-    const float w = s_win[j];
-    Ya[j] = (v.x * (1.0f / kPvN)) * w;
-    if (hb) Yb[j] = (v.y * (1.0f / kPvN)) * w;
-  }
-}
-
-// ---- overlap-add + window envelope: Y -> waveform ------------------------------------------------------------
-__global__ void __launch_bounds__(256) pv_ola_kernel(const PvParams p) {
-  __shared__ float s_w2[kPvN];
-  const int b = blockIdx.y;
-  const double rate = pv_clip_rate(p.rate, b);
   float* out = p.out + (size_t)b * p.out_stride;
-  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  // hop blocks h0 .. h0 + kSynBlocks - 1; output sample s = 128 h + r - 256 (the first two hop blocks are trimmed)
+  const int h0 = 2 + blockIdx.x * kSynBlocks;
+  const int s_begin = h0 * kPvHop - kPvN / 2, s_end = min(s_begin + kSynBlocks * kPvHop, p.n_out);
+  if (s_begin >= p.n_out) return;
   if (rate == 1.0) {
-    if (p.out_pad && s < p.n_out && s < p.N) out[s] = __ldg(p.wav + (size_t)b * p.wav_stride + s);
+    if (p.out_pad) {
+      const float* x = p.wav + (size_t)b * p.wav_stride;
+      for (int s = s_begin + tid; s < s_end; s += blockDim.x) out[s] = s < p.N ? __ldg(x + s) : 0.f;
+    }
     return;
   }
-  for (int i = threadIdx.x; i < kPvN; i += blockDim.x) { const float w = __ldg(p.window + i); s_w2[i] = w * w; }
-  __syncthreads();
-  if (s >= p.n_out) return;
   const int To = pv_out_frames(p.T, rate, p.Tcap);
   const int len = pv_out_len(p.N, rate, p.Lcap);
-  if (s >= len) {
-    if (p.out_pad) out[s] = 0.f;
+  if (s_begin >= len) {                                        // beyond the stretched signal: zero padding only
+    if (p.out_pad) for (int s = s_begin + tid; s < s_end; s += blockDim.x) out[s] = 0.f;
     return;
   }
-  const int q = s + kPvN / 2;                                // position in the un-trimmed overlap-added signal
-  int j_lo = (q - (kPvN - 1) + kPvHop - 1) / kPvHop;
-  if (q - (kPvN - 1) < 0) j_lo = 0;
-  int j_hi = q / kPvHop;
-  if (j_hi > To - 1) j_hi = To - 1;
-  const float* Y = p.Y + (size_t)b * p.Tcap * kPvN;
-  float acc = 0.f, env = 0.f;
-  for (int j = j_lo; j <= j_hi; ++j) {
-    const int n = q - j * kPvHop;
-    acc += Y[(size_t)j * kPvN + n];
-    env += s_w2[n];
+  for (int i = tid; i < kPvN; i += blockDim.x) s_win[i] = __ldg(p.window + i);
+  for (int i = tid; i < PvRad::tw_total; i += blockDim.x) s_tw[i] = __ldg(p.tw + i);
+  const int jf = h0 - 3;                                       // first frame this CTA needs (may be < 0 ... never: h0 >= 2 -> jf >= -1)
+  const int ja = jf + 2 * warp, jb = ja + 1;
+  const PvMap zmap;
+  float2* z = s_z + warp * kPvZL;
+  const bool ha = ja >= 0 && ja < To, hb = jb >= 0 && jb < To;
+  __syncthreads();
+  if (ha || hb) {
+    const float2* Va = p.V + ((size_t)b * p.Tcap + (ha ? ja : jb)) * kPvPitch;
+    const float2* Vb = p.V + ((size_t)b * p.Tcap + (hb ? jb : ja)) * kPvPitch;
+    // Z = A + i B with Hermitian extension, written where the forward transform would have left bin k
+    // (irfft ignores the imaginary parts of the DC and Nyquist bins)
+    for (int k = lane; k < kPvK; k += 32) {
+      float2 a = ha ? Va[k] : make_float2(0.f, 0.f), c = hb ? Vb[k] : make_float2(0.f, 0.f);
+      if (k == 0 || k == kPvN / 2) { a.y = 0.f; c.y = 0.f; }
+      float2 zk, zm;
+      pv_pack(a, c, &zk, &zm);
+      z[zmap(PvRad::pos(k))] = zk;
+      if (k > 0 && k < kPvN / 2) z[zmap(PvRad::pos(kPvN - k))] = zm;
+    }
+    __syncwarp();
+    static_for<0, PvRad::npass>([&](auto I) {
+      constexpr int i = PvRad::npass - 1 - decltype(I)::value;  // inverse (DIT) passes run in reverse order
+      constexpr int R = PvRad::R(i), L = PvRad::L(i), tasks = kPvN / R;
+      const float2* tw = s_tw + PvRad::tw_off(i);
+#pragma unroll 1
+      for (int u = lane; u < tasks; u += 32) pass_task<R, true, PvMap>(z, L, u, [&](int q) { return tw[q]; });
+      __syncwarp();
+    });
   }
-  out[s] = env > 0.f ? acc / env : 0.f;                      // env == 0 only if the caller's rate bound was wrong
+  __syncthreads();
+  // overlap-add: sample s = 128 h + r - 256 sums frame j = h - d at n = r + 128 d, d = 0..3
+  for (int i = tid; i < kSynBlocks * kPvHop; i += blockDim.x) {
+    const int s = s_begin + i;
+    if (s >= s_end) break;
+    if (s >= len) { if (p.out_pad) out[s] = 0.f; continue; }
+    const int hl = i >> 7, r = i & (kPvHop - 1);               // local hop block, offset inside it
+    float acc = 0.f, env = 0.f;
+#pragma unroll
+    for (int d = 3; d >= 0; --d) {                             // ascending frame index, like the fold
+      const int f = hl + 3 - d;                                // local frame index 0 .. kSynFrames-1
+      const int j = jf + f;
+      if (j >= 0 && j < To) {
+        const int n = r + kPvHop * d;
+        const float2 v = s_z[(f >> 1) * kPvZL + zmap(n)];
+        const float w = s_win[n];
+        acc += (((f & 1) ? v.y : v.x) * (1.0f / kPvN)) * w;
+        env += w * w;
+      }
+    }
+    out[s] = env > 0.f ? acc / env : 0.f;                      // env == 0 only if the caller's rate bound was wrong
+  }
 }
 
 // ---- polyphase windowed-sinc resampling ------------------------------------------------------------------------

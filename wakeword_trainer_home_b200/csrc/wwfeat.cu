@@ -102,7 +102,6 @@ struct wwf_plan {
   // time-stretch / pitch-shift constants and the resampler coefficient tables (built on first use)
   std::mutex lazy_mu;
   float* d_pv_window = nullptr;
-  float* d_pv_pa = nullptr;
   float2* d_pv_tw = nullptr;
   struct Resampler { int orig, nw, width, ntaps; float* coef; };
   std::vector<Resampler> resamplers;
@@ -159,7 +158,7 @@ extern "C" void wwf_plan_destroy(wwf_plan* p) {
   cudaFree(p->d_noise_prefix); cudaFree(p->d_noise_prefix_offsets);
   for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
   cudaFree(p->d_conv_tw); cudaFree(p->d_fused_l); cudaFree(p->d_fused_tw);
-  cudaFree(p->d_pv_window); cudaFree(p->d_pv_pa); cudaFree(p->d_pv_tw);
+  cudaFree(p->d_pv_window); cudaFree(p->d_pv_tw);
   for (auto& r : p->resamplers) cudaFree(r.coef);
   delete p;
 }
@@ -687,12 +686,11 @@ static int ensure_pv_constants_locked(wwf_plan* p) {
   if (p->d_pv_tw) return WWF_OK;
   std::vector<float> win(kPvN);
   for (int i = 0; i < kPvN; ++i) win[i] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * i / kPvN));
-  // torch.linspace(0, math.pi * hop, 257) in float32 (TA/functional/functional.py:1686)
-  std::vector<float> pa = linspace32(0.0f, (float)(M_PI * kPvHop), kPvK);
   std::vector<float2> tw;
   build_stft_twiddles<PvRad>(tw);
   int rc;
-  if ((rc = upload(&p->d_pv_window, win)) || (rc = upload(&p->d_pv_pa, pa))) return rc;
+  if ((rc = upload(&p->d_pv_window, win))) return rc;
+  WWF_CUDA(cudaFuncSetAttribute((const void*)pv_synth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSynSmemBytes));
   return upload(&p->d_pv_tw, tw);
 }
 static int ensure_pv_constants(wwf_plan* p) {
@@ -700,22 +698,21 @@ static int ensure_pv_constants(wwf_plan* p) {
   return ensure_pv_constants_locked(p);
 }
 
-extern "C" int wwf_set_stretch_tables(wwf_plan* p, const float* window, const float* phase_advance) {
-  if (!p) return fail(WWF_ERR_INVALID, "wwf_set_stretch_tables: null plan");
+extern "C" int wwf_set_stretch_window(wwf_plan* p, const float* window) {
+  if (!p || !window) return fail(WWF_ERR_INVALID, "wwf_set_stretch_window: null argument");
   DeviceGuard guard(p->device);
   if (!guard.ok) return fail(WWF_ERR_CUDA, "cudaSetDevice(%d) failed", p->device);
   std::lock_guard<std::mutex> lk(p->lazy_mu);
   int rc = ensure_pv_constants_locked(p);
   if (rc) return rc;
-  // plain synchronous copies: they are ordered after every kernel already launched on the device
-  if (window) WWF_CUDA(cudaMemcpy(p->d_pv_window, window, kPvN * sizeof(float), cudaMemcpyHostToDevice));
-  if (phase_advance) WWF_CUDA(cudaMemcpy(p->d_pv_pa, phase_advance, kPvK * sizeof(float), cudaMemcpyHostToDevice));
+  // plain synchronous copy: ordered after every kernel already launched on the device
+  WWF_CUDA(cudaMemcpy(p->d_pv_window, window, kPvN * sizeof(float), cudaMemcpyHostToDevice));
   return WWF_OK;
 }
 
 struct PvGeom {
   int T, Tcap, Lcap;
-  size_t offS, offV, offY, offW, total;
+  size_t offS, offV, offW, total;
 };
 static PvGeom pv_geometry(int B, int N, double rate_lo) {
   PvGeom g{};
@@ -724,8 +721,7 @@ static PvGeom pv_geometry(int B, int N, double rate_lo) {
   g.Lcap = (int)round_up4((int64_t)rint((double)N / rate_lo));
   g.offS = 0;
   g.offV = g.offS + (size_t)B * g.T * kPvPitch * sizeof(float2);
-  g.offY = g.offV + (size_t)B * g.Tcap * kPvPitch * sizeof(float2);
-  g.offW = g.offY + (size_t)B * g.Tcap * kPvN * sizeof(float);
+  g.offW = g.offV + (size_t)B * g.Tcap * kPvPitch * sizeof(float2);
   g.total = g.offW + (size_t)B * g.Lcap * sizeof(float);
   return g;
 }
@@ -754,14 +750,14 @@ static int launch_stretch(wwf_plan* p, PvParams& pp, const PvGeom& g, void* ws, 
   if (rc) return rc;
   char* w = (char*)ws;
   pp.T = g.T; pp.Tcap = g.Tcap; pp.Lcap = g.Lcap;
-  pp.window = p->d_pv_window; pp.phase_adv = p->d_pv_pa; pp.tw = p->d_pv_tw;
-  pp.S = (float2*)(w + g.offS); pp.V = (float2*)(w + g.offV); pp.Y = (float*)(w + g.offY);
+  pp.window = p->d_pv_window; pp.tw = p->d_pv_tw;
+  pp.S = (float2*)(w + g.offS); pp.V = (float2*)(w + g.offV);
   const int per_cta = 2 * kPvWarps;
   pv_stft_kernel<<<dim3((g.T + per_cta - 1) / per_cta, pp.B), kPvWarps * 32, 0, st>>>(pp);
   pv_vocoder_kernel<<<pp.B, 288, 0, st>>>(pp);
-  pv_istft_kernel<<<dim3((g.Tcap + per_cta - 1) / per_cta, pp.B), kPvWarps * 32, 0, st>>>(pp);
-  pv_ola_kernel<<<dim3((pp.n_out + 255) / 256, pp.B), 256, 0, st>>>(pp);
-  g_launches += 4;
+  const int syn_per_cta = kSynBlocks * kPvHop;
+  pv_synth_kernel<<<dim3((pp.n_out + syn_per_cta - 1) / syn_per_cta, pp.B), kSynWarps * 32, kSynSmemBytes, st>>>(pp);
+  g_launches += 3;
   WWF_CUDA(cudaGetLastError());
   return WWF_OK;
 }

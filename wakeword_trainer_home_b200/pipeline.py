@@ -174,7 +174,7 @@ class FeaturePlan:
         info = N.Info()
         N.check(self.lib.wwf_plan_info(self._handle, C.byref(info)))
         self.n_feat, self.n_freq, self.sm_count = info.n_feat, info.n_freq, info.sm_count
-        self._stretch_tables = False   # torch's float32 window / phase_advance are handed over on first use
+        self._stretch_tables = False   # torch's float32 Hann window of the stretch stage is handed over on first use
         self._noise = None          # keeps the borrowed noise bank alive
         self._workspace: dict[int, torch.Tensor] = {}
         self.n_noise = self.n_rir = 0
@@ -363,9 +363,8 @@ class FeaturePlan:
 
     def _ensure_stretch_tables(self):
         if not self._stretch_tables:
-            w, pa = K.hann_window(512), K.phase_advance(128, 257)
-            N.check(self.lib.wwf_set_stretch_tables(self._handle, C.cast(w.data_ptr(), C.POINTER(C.c_float)),
-                                                    C.cast(pa.data_ptr(), C.POINTER(C.c_float))))
+            w = K.hann_window(512)
+            N.check(self.lib.wwf_set_stretch_window(self._handle, C.cast(w.data_ptr(), C.POINTER(C.c_float))))
             self._stretch_tables = True
 
     def _shape_augs(self, wav: torch.Tensor, a: Optional[AugParams]) -> torch.Tensor:
