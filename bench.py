@@ -163,6 +163,22 @@ def cpu_per_clip_loop(n_clips: int = 24):
     return n_clips / (time.perf_counter() - t0)
 
 
+def cpu_shape_augs(n_stretch: int = 32, n_pitch: int = 8):
+    """torchaudio CPU (oracle/ta_oracle.py) on a bounded sample: time-stretch and F.pitch_shift, clips/s."""
+    from oracle import ta_oracle as tao
+    g = torch.Generator().manual_seed(3)
+    x = 0.1 * torch.randn(max(n_stretch, n_pitch), N_SAMPLES, generator=g)
+    rates = 0.8 + 0.4 * torch.rand(n_stretch, generator=g, dtype=torch.float64)
+    t0 = time.perf_counter()
+    tao.time_stretch(x[:n_stretch], rates)
+    t1 = time.perf_counter()
+    tao.pitch_shift(x[:n_pitch], torch.tensor([-2, -1, 1, 2] * (n_pitch // 4), dtype=torch.int32), 16000)
+    t2 = time.perf_counter()
+    return {"time_stretch": n_stretch / (t1 - t0), "pitch_shift": n_pitch / (t2 - t1), "unit": "clips/s",
+            "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n_stretch} clips time-stretch, {n_pitch} clips F.pitch_shift (1.5 s each), torchaudio CPU"}
+
+
 def run_reference(args, rank: int):
     if rank != 0:
         return
@@ -330,6 +346,31 @@ def main():
     loader_ms = max_over_ranks(e4.elapsed_time(e5))
     loader_value = world * B * args.steps / (loader_ms * 1e-3)
 
+    # ---- supplementary: the waveform-shape augmentations of SURVEY.md section 8a row A3 (not part of configs[1]) ----
+    g = torch.Generator().manual_seed(3)
+    rates = (0.8 + 0.4 * torch.rand(B, generator=g, dtype=torch.float64)).to(dev)
+    semis = torch.randint(-2, 3, (B,), generator=g, dtype=torch.int32).to(dev)
+    acfg = w.DrawConfig(seed=1, rir_prob=1.0, noise_prob=1.0, stretch_prob=0.5, pitch_prob=0.5)
+    shape_ops = {"time_stretch": lambda i: plan.time_stretch(dev_wav[i % RING], rates, rate_lo=0.8, out=wv),
+                 "pitch_shift": lambda i: plan.pitch_shift(dev_wav[i % RING], semis, step_range=(-2, 2), out=wv),
+                 "all_augmentations_pipeline": lambda i: plan.featurize(
+                     dev_wav[i % RING], plan.draw_aug(acfg, i * B, B, N_SAMPLES), out=out)}
+    shape_res = {}
+    for name, fn in shape_ops.items():
+        for i in range(3):
+            fn(i)
+        barrier()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record(stream)
+        for i in range(args.steps):
+            fn(i)
+        eb.record(stream)
+        barrier()
+        ms = max_over_ranks(ea.elapsed_time(eb))
+        shape_res[name] = {"value": world * B * args.steps / (ms * 1e-3), "unit": "clips/s", "ms_per_step": ms / args.steps}
+    shape_res["what"] = ("supplementary: torchaudio-parity time-stretch (rate U[0.8,1.2) on every clip), pitch-shift (randint[-2,2] "
+                         "semitones) and configs[1] with both drawn at probability 0.5 on the GPU in front of reverb + noise")
+
     # keep the GPU under the same load a little longer if the timed loops were too short to sample clocks
     if sampler.ok and len(sampler.samples) < 5:
         t_end = time.perf_counter() + 0.5
@@ -362,6 +403,7 @@ def main():
                          "(torchaudio CPU, batched = the CPU's best case)",
                "per_clip_loop_value": cpu_per_clip_loop(), "per_clip_loop_sample": "24 clips, one call chain per clip "
                "(the reference's __getitem__ pattern)"}
+        shape_res["cpu_baseline"] = cpu_shape_augs()
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world,
@@ -378,6 +420,7 @@ def main():
                 "e2e_pcm16": {"value": pcm_value, "unit": "clips/s", "ms_per_step": pcm_ms / args.steps,
                               "h2d_bytes_per_step": pinned_pcm[0].numel() * 2 + host_aug[0].nbytes(), "d2h_bytes_per_step": d2h,
                               "what": "supplementary: same as e2e but the host clips are int16 PCM (converted on the GPU, exact)"},
+                "shape_augmentations": shape_res,
                 "device_resident_loader": {"value": loader_value, "unit": "clips/s", "ms_per_step": loader_ms / args.steps,
                                            "what": "int16 PCM clip bank in HBM -> wwf_gather_clips -> wwf_draw_aug (on-GPU "
                                                    "Philox draws) -> wwf_featurize; no host->device copy per step"}}
