@@ -781,3 +781,44 @@ def test_device_loader_with_stretch_and_pitch_draws(ww):
         xs = plan.pitch_shift(plan.time_stretch(bank[sel], torch.from_numpy(d["stretch_rate"])), torch.from_numpy(d["pitch_steps"]))
         assert torch.equal(x, plan.featurize(xs))
         first += B
+
+
+def test_stretch_and_pitch_fuzz_over_lengths_and_rates(ww):
+    """Deterministic fuzz: clip lengths from the reflect-padding minimum (257) to 2.5 s, rates over the validator's
+    whole warning-free range [0.5, 2.0] (src/config/validator.py:275-280), batch sizes 1..5, against the float64 oracle."""
+    from oracle import ta_oracle as tao
+    rng = np.random.default_rng(77)
+    gen = torch.Generator().manual_seed(77)
+    plan = ww.FeaturePlan(16000, "mel", 40, 40, 400, 160, "cuda")
+    for case, N in enumerate([257, 300, 513, 1000, 4097, 16000, 24000, 40000]):
+        B = int(rng.integers(1, 6))
+        x = 0.2 * torch.randn(B, N, generator=gen)
+        rates = torch.from_numpy(rng.uniform(0.5, 2.0, B))
+        if case % 3 == 0:
+            rates[0] = 1.0
+        got = plan.time_stretch(x.cuda(), rates).cpu()
+        want = tao.time_stretch(x.double(), rates)
+        assert torch.isfinite(got).all()
+        for b in range(B):
+            if rates[b] == 1.0:
+                assert torch.equal(got[b], x[b])
+            else:
+                assert _rel(got[b], want[b]) <= 3e-5, (N, b, float(rates[b]), _rel(got[b], want[b]))
+    # pitch: a short and a 2.5 s clip, one oracle call per distinct semitone (torchaudio builds a ~1 GB kernel each)
+    for N, steps in ((3000, [3, -3, 0]), (40000, [-1, 5])):
+        x = 0.2 * torch.randn(len(steps), N, generator=gen)
+        st = torch.tensor(steps, dtype=torch.int32)
+        got = plan.pitch_shift(x.cuda(), st).cpu()
+        want = tao.pitch_shift(x.double(), st, 16000)
+        for b in range(len(steps)):
+            if steps[b] == 0:
+                assert torch.equal(got[b], x[b])
+            else:
+                assert _rel(got[b], want[b]) <= 1e-3, (N, steps[b], _rel(got[b], want[b]))
+    # loud refusals: clip shorter than the reflect padding, semitones outside [-12, 12], wrong shapes
+    with pytest.raises(ww.WwfError):
+        plan.time_stretch(torch.zeros(1, 256).cuda(), torch.tensor([1.1], dtype=torch.float64))
+    with pytest.raises(ww.WwfError):
+        plan.pitch_shift(torch.zeros(1, 4000).cuda(), torch.tensor([13], dtype=torch.int32))
+    with pytest.raises(ValueError):
+        plan.time_stretch(torch.zeros(2, 4000).cuda(), torch.tensor([1.1], dtype=torch.float64))
