@@ -185,3 +185,71 @@ def test_philox_mirror_known_answers():
     out = philox4x32_10(np.array([0x243f6a88], np.uint32), np.array([0x85a308d3], np.uint32), np.array([0x13198a2e], np.uint32),
                         np.array([0x03707344], np.uint32), 0xa4093822, 0x299f31d0)
     assert [int(v[0]) for v in out] == [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+def _write_wav(path, x, rate, bits=16, fmt_tag=1):
+    """x: float (channels, frames) in [-1, 1).  Minimal RIFF writer for the decoder test (all depths, float)."""
+    import struct
+    ch, frames = x.shape
+    inter = x.T.reshape(-1)
+    if fmt_tag == 3:
+        body = inter.astype("<f4").tobytes()
+        bits = 32
+    elif bits == 8:
+        body = (np.round(inter * 128.0) + 128).clip(0, 255).astype(np.uint8).tobytes()
+    elif bits == 16:
+        body = np.round(inter * 32768.0).clip(-32768, 32767).astype("<i2").tobytes()
+    elif bits == 24:
+        v = np.round(inter * 8388608.0).clip(-8388608, 8388607).astype(np.int32)
+        body = np.stack([v & 0xFF, (v >> 8) & 0xFF, (v >> 16) & 0xFF], axis=1).astype(np.uint8).tobytes()
+    else:
+        body = np.round(inter.astype(np.float64) * 2147483648.0).clip(-2 ** 31, 2 ** 31 - 1).astype("<i4").tobytes()
+    fmt = struct.pack("<HHIIHH", fmt_tag, ch, rate, rate * ch * bits // 8, ch * bits // 8, bits)
+    junk = b"LIST" + struct.pack("<I", 3) + b"abc" + b"\x00"                  # odd-sized chunk + pad byte
+    data = b"WAVE" + b"fmt " + struct.pack("<I", len(fmt)) + fmt + junk + b"data" + struct.pack("<I", len(body)) + body
+    with open(path, "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", len(data)) + data)
+
+
+def test_wav_decoder_all_sample_formats(tmp_path):
+    """AudioProcessor's host-side container parsing (the numeric part runs on the GPU): every PCM depth and IEEE
+    float, stereo de-interleaving, chunks in front of 'data' - and agreement with the stdlib wave module."""
+    import wave
+    from wakeword_trainer_home_b200.audio_utils import read_wav
+    rng = np.random.default_rng(0)
+    x = (rng.uniform(-0.9, 0.9, (2, 1000))).astype(np.float32)
+    for bits, tag, tol in ((8, 1, 1 / 128), (16, 1, 1 / 32768), (24, 1, 1 / 8388608), (32, 1, 1e-7), (32, 3, 0.0)):
+        p = str(tmp_path / f"t{bits}_{tag}.wav")
+        _write_wav(p, x, 44100, bits, tag)
+        y, rate = read_wav(p)
+        assert rate == 44100 and y.shape == x.shape and y.dtype == np.float32
+        assert np.abs(y - x).max() <= tol + 1e-7
+    p = str(tmp_path / "std.wav")
+    pcm = np.round(x.T.reshape(-1) * 32768.0).astype("<i2")
+    with wave.open(p, "wb") as w:
+        w.setnchannels(2); w.setsampwidth(2); w.setframerate(8000); w.writeframes(pcm.tobytes())
+    y, rate = read_wav(p)
+    assert rate == 8000 and np.array_equal(y, pcm.reshape(-1, 2).T.astype(np.float32) / 32768.0)
+    with pytest.raises(ValueError):
+        (tmp_path / "bad.wav").write_bytes(b"RIFFxxxxWAVEjunk")
+        read_wav(str(tmp_path / "bad.wav"))
+
+
+def test_split_manifest_and_npy_shapes(tmp_path):
+    from wakeword_trainer_home_b200 import formats
+    p = str(tmp_path / "splits" / "train.json")
+    formats.save_split_manifest(p, ["a.wav", "b.wav", "c.wav"], [1, 0, 1], extra={"split": "train"})
+    paths, labels, meta = formats.load_split_manifest(p)
+    assert paths == ["a.wav", "b.wav", "c.wav"] and labels.tolist() == [1, 0, 1] and meta[0]["path"] == "a.wav"
+    for doc, want in (([{"path": "x.wav", "category": "positive"}, {"path": "y.wav", "category": "negative"}], [1, 0]),
+                      ({"samples": [{"path": "x.wav", "label": 0}]}, [0]), (["x.wav", "y.wav"], [-1, -1])):
+        q = tmp_path / "m.json"
+        q.write_text(__import__("json").dumps(doc))
+        assert formats.load_split_manifest(str(q))[1].tolist() == want
+    with pytest.raises(ValueError):
+        (tmp_path / "m2.json").write_text('{"nothing": 1}')
+        formats.load_split_manifest(str(tmp_path / "m2.json"))
+    assert formats.npy_kind(np.zeros((3, 100))) == "audio" and formats.npy_kind(np.zeros((3, 40, 11))) == "features"
+    assert formats.npy_kind(np.zeros((3, 1, 40, 11))) == "features"
+    with pytest.raises(ValueError):
+        formats.npy_kind(np.zeros(5))

@@ -822,3 +822,63 @@ def test_stretch_and_pitch_fuzz_over_lengths_and_rates(ww):
         plan.pitch_shift(torch.zeros(1, 4000).cuda(), torch.tensor([13], dtype=torch.int32))
     with pytest.raises(ValueError):
         plan.time_stretch(torch.zeros(2, 4000).cuda(), torch.tensor([1.1], dtype=torch.float64))
+
+
+def test_audio_processor_files_to_clips(ww, tmp_path):
+    """AudioProcessor(target_sr, target_duration).process_audio(path) (src/evaluation/evaluator.py:76-79,119):
+    stereo 44.1 kHz / 8 kHz / native-rate WAV files -> mono, resampled (torchaudio F.resample parity), padded or
+    trimmed; process_batch equals the per-file results."""
+    from oracle import ta_oracle as tao
+    from test_abi_and_host import _write_wav
+    rng = np.random.default_rng(5)
+    specs = [(44100, 2, 70000, 16), (8000, 1, 9000, 16), (16000, 2, 30000, 24), (48000, 1, 60000, 32), (44100, 1, 20000, 16)]
+    paths, wants = [], []
+    target = 24000
+    for i, (rate, ch, frames, bits) in enumerate(specs):
+        x = rng.uniform(-0.5, 0.5, (ch, frames)).astype(np.float32)
+        p = str(tmp_path / f"f{i}.wav")
+        _write_wav(p, x, rate, bits)
+        dec, _ = ww.read_wav(p)
+        mono = torch.from_numpy(dec).mean(dim=0, keepdim=True)
+        y = tao.resample(mono, rate, 16000) if rate != 16000 else mono
+        y = y[:, :target] if y.shape[1] >= target else torch.nn.functional.pad(y, (0, target - y.shape[1]))
+        paths.append(p); wants.append(y[0])
+    ap = ww.AudioProcessor(target_sr=16000, target_duration=1.5)
+    for p, want in zip(paths, wants):
+        got = ap.process_audio(p)
+        assert isinstance(got, np.ndarray) and got.dtype == np.float32 and got.shape == (target,)
+        assert np.abs(got - want.numpy()).max() <= 2e-6
+    batch = ap.process_batch(paths)
+    assert batch.shape == (len(paths), target) and batch.is_cuda
+    for r, want in enumerate(wants):
+        assert (batch[r].cpu() - want).abs().max() <= 2e-6
+    apn = ww.AudioProcessor(target_sr=16000, target_duration=1.5, normalize=True)
+    g = apn.process_audio(paths[0])
+    assert abs(np.abs(g).max() - 1.0) <= 1e-6
+    fe = ww.FeatureExtractor(16000, "mel", 64, 40, 1024, 160, "cuda")             # evaluator.py:119-128 chain
+    assert fe(torch.from_numpy(ap.process_audio(paths[1])).float()).shape == (1, 64, 151)
+
+
+def test_precomputed_feature_files_and_loader(ww, tmp_path):
+    """.npy formats of src/ui/panel_docs.py:124-130: raw audio (N, samples) -> features (N, F, T) written by the GPU
+    path equal featurize(); NpyFeatureLoader shards and yields (B, 1, F, T) like the DataLoader it replaces."""
+    gen = torch.Generator().manual_seed(12)
+    n, N = 70, 16000
+    clips = (0.1 * torch.randn(n, N, generator=gen)).numpy()
+    np.save(tmp_path / "audio.npy", clips)
+    arr, kind = ww.load_npy(str(tmp_path / "audio.npy"))
+    assert kind == "audio" and arr.shape == (n, N)
+    plan = ww.FeaturePlan(16000, "mfcc", 40, 13, 400, 160, "cuda")
+    feats = ww.precompute_features(plan, arr, str(tmp_path / "mfcc.npy"), batch_size=32)
+    back, kind = ww.load_npy(str(tmp_path / "mfcc.npy"))
+    assert kind == "features" and back.shape == (n, 13, 101)
+    assert np.array_equal(np.asarray(back), plan.featurize(torch.from_numpy(clips).cuda())[:, 0].cpu().numpy())
+    assert np.array_equal(np.asarray(back), feats)
+    labels = torch.arange(n) % 2
+    seen = []
+    for rank in range(2):
+        ld = ww.NpyFeatureLoader(str(tmp_path / "mfcc.npy"), labels, 16, shuffle=True, seed=1, rank=rank, world_size=2)
+        for x, y in ld:
+            assert x.shape[1:] == (1, 13, 101) and x.is_cuda and x.shape[0] == y.shape[0]
+            seen.append(y.cpu())
+    assert torch.cat(seen).numel() == n

@@ -12,8 +12,11 @@ from .feature_extraction import FeatureExtractor  # noqa: F401
 from .augmentation import AudioAugmentation, SpecAugment  # noqa: F401
 from .loader import DeviceBatchLoader, GpuBatchLoader, StreamedFeaturizer  # noqa: F401
 from .sharding import shard_range, shard_seed  # noqa: F401
+from .audio_utils import AudioProcessor, read_wav  # noqa: F401
+from .formats import NpyFeatureLoader, load_npy, load_split_manifest, precompute_features, save_split_manifest  # noqa: F401
 
 __version__ = "0.1.0"
 __all__ = ["FeatureExtractor", "AudioAugmentation", "SpecAugment", "FeaturePlan", "AugParams",
            "draw_mask_params", "spec_augment_", "peak_normalize", "WwfError", "launch_count", "GpuBatchLoader", "DeviceBatchLoader", "StreamedFeaturizer", "DrawConfig", "gather_clips",
-           "shard_range", "shard_seed"]
+           "shard_range", "shard_seed", "AudioProcessor", "read_wav", "NpyFeatureLoader", "load_npy", "load_split_manifest",
+           "precompute_features", "save_split_manifest"]
