@@ -86,7 +86,7 @@ WWF_HD void pv_pack(float2 a, float2 c, float2* zk, float2* zm) {
 }
 
 // ---- STFT: clip -> S ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(kPvWarps * 32) pv_stft_kernel(const PvParams p) {
+__global__ void __launch_bounds__(kPvWarps * 32, 4) pv_stft_kernel(const PvParams p) {
   __shared__ __align__(16) float2 s_z[kPvWarps * kPvZL];
   __shared__ float2 s_tw[PvRad::tw_total];
   __shared__ float s_win[kPvN];
@@ -103,18 +103,28 @@ __global__ void __launch_bounds__(kPvWarps * 32) pv_stft_kernel(const PvParams p
   const float* x = p.wav + (size_t)b * p.wav_stride;
   const int N = p.N;
   const bool inner = ta * kPvHop - kPvN / 2 >= 0 && tb * kPvHop + kPvN / 2 <= N && tb < p.T;
-#pragma unroll 4
-  for (int j = lane; j < kPvN; j += 32) {
-    const float w = s_win[j];
-    float re, im = 0.f;
-    if (inner) {
-      re = __ldg(x + ta * kPvHop - kPvN / 2 + j);
-      im = __ldg(x + tb * kPvHop - kPvN / 2 + j);
-    } else {
-      re = __ldg(x + reflect_index(ta * kPvHop - kPvN / 2 + j, N));
-      if (tb < p.T) im = __ldg(x + reflect_index(tb * kPvHop - kPvN / 2 + j, N));
+  if (inner) {
+    // frame b is frame a shifted by one hop = 4 x 32 samples: both come from one 640-sample span held in
+    // registers in lane-cyclic order, all 20 loads in flight before the first use
+    constexpr int NC = kPvN / 32, SH = kPvHop / 32;
+    float r[NC + SH];
+    const float* xs = x + ta * kPvHop - kPvN / 2 + lane;
+#pragma unroll
+    for (int i = 0; i < NC + SH; ++i) r[i] = __ldg(xs + 32 * i);
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+      const int j = lane + 32 * i;
+      const float w = s_win[j];
+      z[zmap(j)] = make_float2(r[i] * w, r[i + SH] * w);
     }
-    z[zmap(j)] = make_float2(re * w, im * w);
+  } else {
+#pragma unroll 1
+    for (int j = lane; j < kPvN; j += 32) {                   // boundary frames: reflect padding (cold)
+      const float w = s_win[j];
+      float re = __ldg(x + reflect_index(ta * kPvHop - kPvN / 2 + j, N)), im = 0.f;
+      if (tb < p.T) im = __ldg(x + reflect_index(tb * kPvHop - kPvN / 2 + j, N));
+      z[zmap(j)] = make_float2(re * w, im * w);
+    }
   }
   __syncwarp();
   static_for<0, PvRad::npass>([&](auto I) {
@@ -247,13 +257,25 @@ __global__ void __launch_bounds__(kSynWarps * 32) pv_synth_kernel(const PvParams
     const float2* Vb = p.V + ((size_t)b * p.Tcap + (hb ? jb : ja)) * kPvPitch;
     // Z = A + i B with Hermitian extension, written where the forward transform would have left bin k
     // (irfft ignores the imaginary parts of the DC and Nyquist bins)
-    for (int k = lane; k < kPvK; k += 32) {
-      float2 a = ha ? Va[k] : make_float2(0.f, 0.f), c = hb ? Vb[k] : make_float2(0.f, 0.f);
-      if (k == 0 || k == kPvN / 2) { a.y = 0.f; c.y = 0.f; }
-      float2 zk, zm;
-      pv_pack(a, c, &zk, &zm);
-      z[zmap(PvRad::pos(k))] = zk;
-      if (k > 0 && k < kPvN / 2) z[zmap(PvRad::pos(kPvN - k))] = zm;
+    constexpr int NK = (kPvK + 31) / 32;
+    float2 va[NK], vb[NK];
+#pragma unroll
+    for (int i = 0; i < NK; ++i) {                             // all loads in flight before the first use
+      const int k = lane + 32 * i;
+      va[i] = (ha && k < kPvK) ? Va[k] : make_float2(0.f, 0.f);
+      vb[i] = (hb && k < kPvK) ? Vb[k] : make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < NK; ++i) {
+      const int k = lane + 32 * i;
+      if (k < kPvK) {
+        float2 a = va[i], c = vb[i];
+        if (k == 0 || k == kPvN / 2) { a.y = 0.f; c.y = 0.f; }
+        float2 zk, zm;
+        pv_pack(a, c, &zk, &zm);
+        z[zmap(PvRad::pos(k))] = zk;
+        if (k > 0 && k < kPvN / 2) z[zmap(PvRad::pos(kPvN - k))] = zm;
+      }
     }
     __syncwarp();
     static_for<0, PvRad::npass>([&](auto I) {
@@ -352,13 +374,20 @@ __global__ void __launch_bounds__(256) resample_kernel(const ResampleParams p) {
   const float* x = p.in + (size_t)b * p.in_stride;
   const int m = i / rd.nw, ph = i - m * rd.nw;
   const int first = m * rd.orig + (int)(((int64_t)ph * rd.orig) / rd.nw) - rd.width;
-  const float* c = rd.coef + ph;
+  // taps whose sample lies inside the clip: tau in [t0, t1); same ascending summation order as before
+  const int t0 = first < 0 ? -first : 0;
+  const int t1 = min(rd.ntaps, len - first);
+  const float* c = rd.coef + ph + (size_t)t0 * rd.nw;
+  const float* xp = x + first + t0;
+  const int nw = rd.nw;
   float acc = 0.f;
-  for (int tau = 0; tau < rd.ntaps; ++tau) {
-    const int q = first + tau;
-    const float v = (q >= 0 && q < len) ? __ldg(x + q) : 0.f;
-    acc = fmaf(v, __ldg(c + (size_t)tau * rd.nw), acc);
+  int n = t1 - t0;
+  for (; n >= 4; n -= 4, xp += 4, c += 4 * (size_t)nw) {
+    const float v0 = __ldg(xp), v1 = __ldg(xp + 1), v2 = __ldg(xp + 2), v3 = __ldg(xp + 3);
+    const float c0 = __ldg(c), c1 = __ldg(c + nw), c2 = __ldg(c + 2 * (size_t)nw), c3 = __ldg(c + 3 * (size_t)nw);
+    acc = fmaf(v0, c0, acc); acc = fmaf(v1, c1, acc); acc = fmaf(v2, c2, acc); acc = fmaf(v3, c3, acc);
   }
+  for (; n > 0; --n, ++xp, c += nw) acc = fmaf(__ldg(xp), __ldg(c), acc);
   out[i] = acc;
 }
 
