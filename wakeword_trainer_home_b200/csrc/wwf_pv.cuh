@@ -318,7 +318,7 @@ __global__ void __launch_bounds__(kSynWarps * 32) pv_synth_kernel(const PvParams
 // waveform's dtype; for ratios like 17959:16000 float32 rounding of t moves coefficients by ~1e-3, so the
 // order matters for parity).  Taps outside the kernel's extent q in [-width, width + orig) are zero.
 struct ResampleDesc {
-  const float* coef;          // [ntaps][nw]
+  const float* coef;          // [ntaps][nw], followed by int32 first[nw] = floor(p * orig / nw) - width
   int orig, nw, width, ntaps; // frequencies divided by their gcd
 };
 
@@ -327,6 +327,7 @@ __global__ void __launch_bounds__(256) resample_table_kernel(float* coef, int or
   if (idx >= ntaps * nw) return;
   const int tau = idx / nw, ph = idx - tau * nw;
   const int q = (int)(((int64_t)ph * orig) / nw) - width + tau;       // sample offset relative to the block start
+  if (tau == 0) reinterpret_cast<int32_t*>(coef + (size_t)ntaps * nw)[ph] = q;   // first tap of this phase
   float c = 0.f;
   if (q >= -width && q < width + orig) {
     const float idxf = __fdiv_rn((float)q, (float)orig);
@@ -372,8 +373,8 @@ __global__ void __launch_bounds__(256) resample_kernel(const ResampleParams p) {
   if (i >= p.target[d]) { out[i] = 0.f; return; }                       // _fix_waveform_shape zero padding
   const int len = p.in_len[d];
   const float* x = p.in + (size_t)b * p.in_stride;
-  const int m = i / rd.nw, ph = i - m * rd.nw;
-  const int first = m * rd.orig + (int)(((int64_t)ph * rd.orig) / rd.nw) - rd.width;
+  const int m = (int)((unsigned)i / (unsigned)rd.nw), ph = i - m * rd.nw;
+  const int first = m * rd.orig + __ldg(reinterpret_cast<const int32_t*>(rd.coef + (size_t)rd.ntaps * rd.nw) + ph);
   // taps whose sample lies inside the clip: tau in [t0, t1); same ascending summation order as before
   const int t0 = first < 0 ? -first : 0;
   const int t1 = min(rd.ntaps, len - first);

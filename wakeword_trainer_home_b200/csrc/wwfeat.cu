@@ -788,7 +788,7 @@ static int get_resampler(wwf_plan* p, int orig, int nw, cudaStream_t st, Resampl
   const int ntaps = 2 * width + 1;
   if ((int64_t)ntaps * nw > (int64_t)64 << 20) return fail(WWF_ERR_UNSUPPORTED, "resample %d:%d needs a %lld-entry table", orig, nw, (long long)ntaps * nw);
   float* coef = nullptr;
-  WWF_CUDA(cudaMalloc((void**)&coef, (size_t)ntaps * nw * sizeof(float)));
+  WWF_CUDA(cudaMalloc((void**)&coef, ((size_t)ntaps * nw + nw) * sizeof(float)));   // + int32 first[nw]
   resample_table_kernel<<<(ntaps * nw + 255) / 256, 256, 0, st>>>(coef, orig, nw, width, ntaps, (float)base_freq, (float)(base_freq / orig));
   g_launches++;
   cudaError_t e = cudaGetLastError();
