@@ -109,16 +109,41 @@ __global__ void __launch_bounds__(256) draw_aug_kernel(const DrawParams p) {
 }
 
 // out[b][:] = bank[idx[b]][:] (float32) or bank[idx[b]][:] / 32768 (int16 PCM -> float, exact).
-// One CTA per output clip; 16-byte accesses when rows allow it.
+// grid = (chunks, B); 16-byte loads and stores when the rows allow it (vec != 0: N and both strides are
+// multiples of 8 elements and both base pointers are 16-byte aligned - checked by the host).
 template <typename SrcT>
 __global__ void __launch_bounds__(256) gather_clips_kernel(const SrcT* __restrict__ bank, int64_t n_clips, int N, int64_t bank_stride,
-                                                           const int64_t* __restrict__ idx, float* __restrict__ out, int64_t out_stride) {
-  const int b = blockIdx.x;
+                                                           const int64_t* __restrict__ idx, float* __restrict__ out, int64_t out_stride, int vec) {
+  const int b = blockIdx.y;
   int64_t src = idx[b];
   if (src < 0 || src >= n_clips) src = 0;                    // indices are validated by the host for known ranges
   const SrcT* s = bank + src * bank_stride;
   float* d = out + (size_t)b * out_stride;
-  for (int i = threadIdx.x; i < N; i += blockDim.x) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+  if (vec) {
+    if constexpr (sizeof(SrcT) == 2) {
+      const uint4* s8 = reinterpret_cast<const uint4*>(s);     // 8 samples per load
+      float4* d4 = reinterpret_cast<float4*>(d);
+      for (int i = t; i < N / 8; i += nt) {
+        const uint4 v = __ldg(s8 + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          f[2 * j] = (float)(int16_t)(w[j] & 0xffffu) * (1.0f / 32768.0f);
+          f[2 * j + 1] = (float)(int16_t)(w[j] >> 16) * (1.0f / 32768.0f);
+        }
+        d4[2 * i] = make_float4(f[0], f[1], f[2], f[3]);
+        d4[2 * i + 1] = make_float4(f[4], f[5], f[6], f[7]);
+      }
+    } else {
+      const float4* s4 = reinterpret_cast<const float4*>(s);
+      float4* d4 = reinterpret_cast<float4*>(d);
+      for (int i = t; i < N / 4; i += nt) d4[i] = __ldg(s4 + i);
+    }
+    return;
+  }
+  for (int i = t; i < N; i += nt) {
     if constexpr (sizeof(SrcT) == 2) d[i] = (float)s[i] * (1.0f / 32768.0f);
     else d[i] = (float)s[i];
   }

@@ -610,11 +610,20 @@ extern "C" int wwf_gather_clips(const void* bank, int dtype, int64_t n_clips, in
   if (!bank || !idx || !out || B <= 0 || N <= 0 || n_clips <= 0 || bank_stride < N || out_stride < N)
     return fail(WWF_ERR_INVALID, "wwf_gather_clips: bad argument");
   if (dtype != WWF_BANK_F32 && dtype != WWF_BANK_I16) return fail(WWF_ERR_INVALID, "wwf_gather_clips: dtype=%d", dtype);
+  if (B > 65535) return fail(WWF_ERR_UNSUPPORTED, "wwf_gather_clips: B=%d > 65535 clips per call", B);
   DeviceGuard guard(device);
   if (!guard.ok) return fail(WWF_ERR_CUDA, "cudaSetDevice(%d) failed", device);
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == WWF_BANK_F32) gather_clips_kernel<float><<<B, 256, 0, st>>>((const float*)bank, n_clips, N, bank_stride, idx, out, out_stride);
-  else gather_clips_kernel<int16_t><<<B, 256, 0, st>>>((const int16_t*)bank, n_clips, N, bank_stride, idx, out, out_stride);
+  const int vec = N % 8 == 0 && bank_stride % 8 == 0 && out_stride % 8 == 0 && !(reinterpret_cast<uintptr_t>(bank) & 15) &&
+                  !(reinterpret_cast<uintptr_t>(out) & 15);
+  // enough CTAs per clip to fill the GPU at small B, at most 8 elements per thread-iteration
+  int chunks = (N / 8 + 255) / 256;
+  const int want = (4 * 148 + B - 1) / B;
+  if (chunks > want) chunks = want;
+  if (chunks < 1) chunks = 1;
+  const dim3 grid(chunks, B);
+  if (dtype == WWF_BANK_F32) gather_clips_kernel<float><<<grid, 256, 0, st>>>((const float*)bank, n_clips, N, bank_stride, idx, out, out_stride, vec);
+  else gather_clips_kernel<int16_t><<<grid, 256, 0, st>>>((const int16_t*)bank, n_clips, N, bank_stride, idx, out, out_stride, vec);
   g_launches++;
   WWF_CUDA(cudaGetLastError());
   return WWF_OK;
@@ -737,6 +746,7 @@ static int check_pv(const wwf_plan* p, const float* wav, int B, int N, int64_t w
   if (B <= 0 || wav_stride < N || out_stride < N) return fail(WWF_ERR_INVALID, "%s: bad shape B=%d N=%d", who, B, N);
   if (N <= kPvN / 2) return fail(WWF_ERR_INVALID, "%s: N=%d must exceed %d (reflect padding of the 512-point STFT)", who, N, kPvN / 2);
   if (N > (1 << 24)) return fail(WWF_ERR_UNSUPPORTED, "%s: N=%d > 2^24 samples", who, N);
+  if (B > 65535) return fail(WWF_ERR_UNSUPPORTED, "%s: B=%d > 65535 clips per call", who, B);
   if (!(rate_lo >= 0.1)) return fail(WWF_ERR_INVALID, "%s: lower rate bound %g must be >= 0.1", who, rate_lo);
   const size_t need = wwf_stretch_workspace_bytes(B, N, rate_lo);
   if (!ws || ws_bytes < need) return fail(WWF_ERR_WORKSPACE, "%s: workspace too small: %zu < %zu bytes", who, ws_bytes, need);
@@ -820,6 +830,7 @@ extern "C" int wwf_resample(wwf_plan* p, const float* in, int B, int n_in, int64
   if (B <= 0 || n_in <= 0 || n_out <= 0 || in_stride < n_in || out_stride < n_out || orig_freq <= 0 || new_freq <= 0)
     return fail(WWF_ERR_INVALID, "wwf_resample: bad argument (B=%d n_in=%d n_out=%d %d->%d Hz)", B, n_in, n_out, orig_freq, new_freq);
   if (in == out) return fail(WWF_ERR_INVALID, "wwf_resample: in-place is not allowed");
+  if (B > 65535) return fail(WWF_ERR_UNSUPPORTED, "wwf_resample: B=%d > 65535 clips per call", B);
   DeviceGuard guard(p->device);
   if (!guard.ok) return fail(WWF_ERR_CUDA, "cudaSetDevice(%d) failed", p->device);
   cudaStream_t st = (cudaStream_t)stream;
