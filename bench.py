@@ -222,7 +222,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the feature path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    from wakeword_trainer_home_b200.sharding import bind_to_gpu_numa
+    from wakeword_trainer_home_b200.sharding import bind_to_gpu_numa, numa_local
     numa_bound = bind_to_gpu_numa(local_rank) if world > 1 else False   # NUMA-local pinned buffers per rank
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -247,8 +247,15 @@ def main():
     plan.register_noise(noise)
     plan.register_rirs(rirs)
     host = [synth(100 * rank + i, B) for i in range(RING)]
-    pinned_wav = [h[0].pin_memory() for h in host]
-    pinned_draws = [{k: v.pin_memory() for k, v in h[1].items()} for h in host]
+    # pinned host buffers are allocated (and first touched) on the cores next to this GPU's PCIe root; a
+    # single-GPU run gets its full CPU affinity back afterwards so the CPU baseline still uses every core
+    with numa_local(local_rank) as nl:
+        pinned_wav = [h[0].pin_memory() for h in host]
+        pinned_draws = [{k: v.pin_memory() for k, v in h[1].items()} for h in host]
+        sf = w.StreamedFeaturizer(plan, B, N_SAMPLES, depth=2, copy_back=True)
+        pinned_pcm = [(h.clamp(-1, 1) * 32767).to(torch.int16).pin_memory() for h in pinned_wav]
+        sf16 = w.StreamedFeaturizer(plan, B, N_SAMPLES, depth=2, copy_back=True, pcm16=True)
+    numa_bound = numa_bound or nl.bound
     dev_wav = [h.to(dev) for h in pinned_wav]
     dev_aug = [w.AugParams(**d).to(dev) for d in pinned_draws]
     out = torch.empty(B, 1, N_MFCC, T_FRAMES, dtype=torch.float32, device=dev)
@@ -286,7 +293,6 @@ def main():
 
     # ---- end to end through the public API with HOST buffers (pinned), copies inside the timed
     #      region: upload of clips + draws, featurize, download of the features, triple-streamed ----
-    sf = w.StreamedFeaturizer(plan, B, N_SAMPLES, depth=2, copy_back=True)
     host_aug = [w.AugParams(**d) for d in pinned_draws]
     for i in range(4):
         sf.submit(pinned_wav[i % RING], host_aug[i % RING])
@@ -305,10 +311,19 @@ def main():
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
     h2d = pinned_wav[0].numel() * 4 + host_aug[0].nbytes()
     d2h = sf.h_out[0].numel() * sf.h_out[0].element_size()
+    # what the link gives: a bare pinned -> device copy of one clip batch, best of 5 (the e2e path's ceiling)
+    link_ms = 1e9
+    for _ in range(5):
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record(stream)
+        dev_wav[0].copy_(pinned_wav[0], non_blocking=True)
+        eb.record(stream)
+        eb.synchronize()
+        link_ms = min(link_ms, ea.elapsed_time(eb))
+    link_gbs = pinned_wav[0].numel() * 4 / (link_ms * 1e-3) / 1e9
+    e2e_h2d_gbs = h2d / (e2e_ms / args.steps * 1e-3) / 1e9
 
     # ---- supplementary: the same host-fed pipeline with int16 PCM host buffers (half the H2D bytes) ----
-    pinned_pcm = [(h.clamp(-1, 1) * 32767).to(torch.int16).pin_memory() for h in pinned_wav]
-    sf16 = w.StreamedFeaturizer(plan, B, N_SAMPLES, depth=2, copy_back=True, pcm16=True)
     for i in range(4):
         sf16.submit(pinned_pcm[i % RING], host_aug[i % RING])
     sf16.synchronize()
@@ -415,7 +430,10 @@ def main():
                            "l2": f"ring of {RING} distinct input batches ({RING * B * N_SAMPLES * 4 / 1e6:.0f} MB) > 126 MB L2"},
                 "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": e2e_ms / args.steps, "wall_ms_per_step": wall_ms / args.steps,
-                        "numa_bound": numa_bound},
+                        "numa_bound": numa_bound,
+                        "pcie": {"h2d_copy_gbs": link_gbs, "e2e_h2d_gbs": e2e_h2d_gbs, "frac": e2e_h2d_gbs / link_gbs,
+                                 "what": "bare pinned->device copy of one clip batch on this box vs the upload rate the e2e "
+                                         "pipeline sustains: the host-fed path is bound by the PCIe link, not by the kernels"}},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "e2e_pcm16": {"value": pcm_value, "unit": "clips/s", "ms_per_step": pcm_ms / args.steps,
                               "h2d_bytes_per_step": pinned_pcm[0].numel() * 2 + host_aug[0].nbytes(), "d2h_bytes_per_step": d2h,

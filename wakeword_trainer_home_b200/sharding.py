@@ -43,3 +43,30 @@ def bind_to_gpu_numa(local_rank: int) -> bool:
         return True
     except Exception:
         return False
+
+
+class numa_local:
+    """Context manager: run the enclosed block (pinned-buffer allocation + first touch) on the CPU cores nearest
+    to GPU ``local_rank``, then give the process its previous CPU affinity back - so that host-side work outside
+    the block (e.g. a multi-threaded CPU baseline) still sees every core.  ``.bound`` tells whether NVML agreed."""
+
+    def __init__(self, local_rank: int):
+        self.local_rank, self.bound, self._prev = local_rank, False, None
+
+    def __enter__(self):
+        import os
+        try:
+            self._prev = os.sched_getaffinity(0)
+        except Exception:
+            self._prev = None
+        self.bound = bind_to_gpu_numa(self.local_rank)
+        return self
+
+    def __exit__(self, *exc):
+        import os
+        if self.bound and self._prev:
+            try:
+                os.sched_setaffinity(0, self._prev)
+            except Exception:
+                pass
+        return False
