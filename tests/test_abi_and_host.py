@@ -87,6 +87,32 @@ def test_null_and_shape_arguments(native):
     assert lib.wwf_spec_augment(None, 0, 1, 1, 1, 1, None, None, 0, None, None, 0, 0.0, 0, None) == -1
     assert lib.wwf_workspace_bytes(None, 4, 1000) == 0
     lib.wwf_plan_destroy(None)                                            # must be a no-op
+    # time-stretch / pitch-shift / resample entry points: argument errors are reported before any CUDA call
+    assert lib.wwf_time_stretch(None, None, 1, 1000, 1000, None, 0.8, None, 1000, None, 0, None) == -1
+    assert lib.wwf_pitch_shift(None, None, 1, 1000, 1000, None, -2, 2, None, 1000, None, 0, None) == -1
+    assert lib.wwf_pitch_shift(None, None, 1, 1000, 1000, None, -13, 2, None, 1000, None, 0, None) == -1
+    assert lib.wwf_resample(None, None, 1, 1000, 1000, 44100, 16000, None, 363, 363, None) == -1
+    assert lib.wwf_set_stretch_window(None, None) == -1
+    assert lib.wwf_stretch_workspace_bytes(0, 1000, 0.8) == 0 and lib.wwf_stretch_workspace_bytes(4, 1000, 0.01) == 0
+    assert lib.wwf_pitch_workspace_bytes(4, 24000, -13, 2) == 0
+    a, b = lib.wwf_stretch_workspace_bytes(4, 24000, 0.8), lib.wwf_stretch_workspace_bytes(4, 24000, 0.5)
+    assert 0 < a < b and a % 16 == 0                                      # slower rates need more room
+    assert lib.wwf_pitch_workspace_bytes(4, 24000, -2, 2) == lib.wwf_stretch_workspace_bytes(4, 24000, 2.0 ** (-2 / 12))
+
+
+def test_resample_length_matches_torchaudio_rule():
+    """wwf_resample_length = ceil(new * n / orig) with the quotient rounded to float32 first, exactly as
+    torchaudio computes target_length (TA/functional/functional.py:1427)."""
+    import math
+    from wakeword_trainer_home_b200 import _native
+    lib = _native.load()
+    rng = np.random.default_rng(1)
+    for orig, new in ((44100, 16000), (8000, 16000), (17959, 16000), (14254, 16000), (48000, 16000), (16000, 16000), (22050, 44100)):
+        for n in [1, 2, 999, 24000, 26667] + rng.integers(1, 2_000_000, 20).tolist():
+            g = math.gcd(orig, new)
+            want = n if orig == new else int(torch.ceil(torch.as_tensor((new // g) * n / (orig // g))).long())
+            assert lib.wwf_resample_length(int(n), orig, new) == want, (orig, new, n)
+    assert lib.wwf_resample_length(-1, 8000, 16000) == -1 and lib.wwf_resample_length(10, 0, 16000) == -1
 
 
 def test_product_never_touches_the_oracle():
