@@ -35,13 +35,16 @@ def _run(cmd):
     return r.returncode, r.stdout + r.stderr
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, out: str = OUT, defines=()) -> str:
+    """``out`` / ``defines`` build an experimental variant next to the product library (A/B runs load it
+    through the WWF_LIB environment variable)."""
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    if not force and not _stale():
+    if out == OUT and not force and not _stale():
         return OUT
-    os.makedirs(os.path.dirname(OUT), exist_ok=True)
+    OUT_ = out
+    os.makedirs(os.path.dirname(OUT_), exist_ok=True)
     OBJ = tempfile.mkdtemp(prefix="wwfeat_obj_")          # objects stay out of the tree (only the .so ships)
-    extra = ["-Xptxas", "-v"] if verbose else []
+    extra = (["-Xptxas", "-v"] if verbose else []) + [f"-D{d}" for d in defines]
     jobs = [([nvcc] + FLAGS + extra + ["-c", os.path.join(CSRC, "wwfeat.cu"), "-o", os.path.join(OBJ, "wwfeat.o")])]
     for n in N_FFTS:
         jobs.append([nvcc] + FLAGS + extra + [f"-DWWF_INST_NFFT={n}", "-c", os.path.join(CSRC, "wwf_feat_inst.cu"),
@@ -53,15 +56,17 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed building libwwfeat.so")
     objs = [os.path.join(OBJ, "wwfeat.o")] + [os.path.join(OBJ, f"feat_{n}.o") for n in N_FFTS]
-    rc, out = _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT] + objs)
+    rc, msg = _run([nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT_] + objs)
     if rc != 0:
-        sys.stderr.write(out)
+        sys.stderr.write(msg)
         raise RuntimeError("nvcc failed linking libwwfeat.so")
     shutil.rmtree(OBJ, ignore_errors=True)
     if verbose:
         print(log)
-    return OUT
+    return OUT_
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a.split("=", 1)[1] for a in sys.argv[1:] if a.startswith("--out=")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, out=os.path.abspath(outs[0]) if outs else OUT, defines=defs))
