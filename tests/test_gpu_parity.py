@@ -368,6 +368,10 @@ def test_streamed_featurizer_and_batch_loader(ww):
             assert x.shape[1:] == (1, 64, 101) and x.is_cuda and y.shape[0] == x.shape[0] and torch.isfinite(x).all()
             seen += x.shape[0]
     assert seen == n
+    meta = [{"path": f"clip_{i}.wav"} for i in range(n)]                      # evaluator.py:257-268 batches carry metadata
+    ld = ww.GpuBatchLoader(clips.cuda(), labels, plan, B, shuffle=False, metadata=meta)
+    x, y, m = next(iter(ld))
+    assert len(m) == x.shape[0] and m[3]["path"] == "clip_3.wav" and torch.equal(y.cpu(), labels[:B])
     net = torch.nn.Sequential(torch.nn.Conv2d(1, 8, 3, padding=1), torch.nn.ReLU(), torch.nn.AdaptiveAvgPool2d(1),
                               torch.nn.Flatten(), torch.nn.Linear(8, 2)).cuda()
     opt = torch.optim.SGD(net.parameters(), lr=0.01)

@@ -89,17 +89,22 @@ class GpuBatchLoader:
     augment  optional ``AudioAugmentation``-like object with ``draw(B) -> AugParams``
     spec_augment optional ``SpecAugment``-like object with ``draw(B, F, T) -> AugParams``;
              its ``n_freq_masks / n_time_masks`` must match the plan's
+    metadata optional sequence of per-clip dicts; batches then carry a third element, the list of the
+             batch's dicts (the evaluator's ``(features, labels, metadata_list)`` batches)
     """
 
     def __init__(self, clips: torch.Tensor, labels: torch.Tensor, plan: FeaturePlan, batch_size: int,
                  augment=None, spec_augment=None, shuffle: bool = True, seed: int = 0, rank: int = 0,
-                 world_size: int = 1, drop_last: bool = False):
+                 world_size: int = 1, drop_last: bool = False, metadata=None):
         if clips.dim() != 2 or labels.shape[0] != clips.shape[0]:
             raise ValueError("clips must be (n, N) and labels (n,)")
         self.clips, self.labels, self.plan = clips, labels, plan
         self.batch_size, self.shuffle, self.seed = batch_size, shuffle, seed
         self.rank, self.world, self.drop_last = rank, world_size, drop_last
         self.augment, self.spec_augment = augment, spec_augment
+        # per-sample metadata dicts (e.g. {'path': ...}): when given, batches are (inputs, targets, [meta, ...]) like
+        # the collate function of the reference's evaluator (src/evaluation/evaluator.py:257-268, :313)
+        self.metadata = metadata
         self.epoch = 0
         self.step = 0
 
@@ -143,7 +148,11 @@ class GpuBatchLoader:
                 aug.fmask_start, aug.fmask_len, aug.tmask_start, aug.tmask_len = m.fmask_start, m.fmask_len, m.tmask_start, m.tmask_len
             self.step += 1
             feats = self.plan.featurize(wav, aug)
-            yield feats, self.labels.index_select(0, sel.to(self.labels.device)).to(dev, non_blocking=True)
+            targets = self.labels.index_select(0, sel.to(self.labels.device)).to(dev, non_blocking=True)
+            if self.metadata is not None:
+                yield feats, targets, [self.metadata[i] for i in sel.tolist()]
+            else:
+                yield feats, targets
 
 
 class DeviceBatchLoader:
