@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define WWF_VERSION 110 /* 0.1.1: time-stretch / pitch-shift / resample */
+#define WWF_VERSION 120 /* 0.1.2: time-stretch / pitch-shift / resample; large-batch feature path */
 
 typedef enum wwf_status {
   WWF_OK = 0,
@@ -142,7 +142,10 @@ int wwf_num_frames(const wwf_plan* plan, int n_samples);
 int wwf_bank_register(wwf_plan* plan, int kind, const float* data, const int64_t* offsets,
                       int count, void* stream);
 
-/* Scratch bytes wwf_featurize / wwf_augment need for a (B, N) batch (0 if no RIR bank). */
+/* Scratch bytes wwf_featurize / wwf_augment want for a (B, N) batch: the reverberated clips when an RIR bank is
+ * registered, plus the dB tiles of the large-batch path (several rounds of the GPU's CTA slots; without that
+ * part - or with a NULL workspace when no RIR bank is registered - wwf_featurize runs its single-kernel path).
+ * May be 0. */
 size_t wwf_workspace_bytes(const wwf_plan* plan, int B, int N);
 
 /*
@@ -287,6 +290,10 @@ int wwf_check_finite(wwf_plan* plan, void* stream, int* nonfinite);
  */
 int wwf_profile_enable(wwf_plan* plan, int enable);
 int wwf_profile_read(wwf_plan* plan, double* conv_ms, double* feat_ms, int* n_calls);
+/* Same per kernel: kernel_ms[4] = { reverb kernel, feat_prep_kernel, feat_frames_kernel (large-batch path) or the
+ * fused feat_kernel (single-kernel path), feat_epilogue_block_kernel }; n_split = calls that took the large-batch
+ * path (may be NULL).  wwf_profile_read's feat_ms is the sum of the last three. */
+int wwf_profile_read_kernels(wwf_plan* plan, double* kernel_ms, int* n_calls, int* n_split);
 
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 int64_t wwf_launch_count(void);

@@ -104,6 +104,7 @@ SYMBOLS = {
     "wwf_check_finite": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "wwf_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "wwf_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+    "wwf_profile_read_kernels": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "wwf_launch_count": (C.c_int64, []),
 }
 

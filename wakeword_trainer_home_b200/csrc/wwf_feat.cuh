@@ -93,7 +93,23 @@ struct FeatParams {
   // output
   void* out; int64_t out_stride;
   int* nonfinite_flag;                           // plan-owned device int, set to 1 if any feature is NaN/Inf
+  // ---- split path (large batches, see feat_frames_kernel): per-clip intermediates in the caller's workspace ----
+  float* tile_g;                                 // dB values [B][T][mp], frame-major
+  int mp;                                        // n_mels rounded up to 4
+  int* clip_max;                                 // [B] running maximum of the clip's dB values (ordered-int key)
+  float* scale_g;                                // [B] noise-mix scale (0 = no noise)
+  int ngroups;                                   // frame groups per clip
+  // feat_frames_kernel shared memory: window [NFFT] | tw | mel_w | mel_lo | mel_ofs | z float2 [nwarps][G][ZL]
+  int f_off_tw, f_off_melw, f_off_mello, f_off_melofs, f_off_z;
+  int eb_frames, eb_pitch;                       // feat_epilogue_block_kernel: frames per block, odd smem row pitch
 };
+
+// float <-> int key whose signed order equals the float order (for atomicMax on the clip maximum)
+__device__ __forceinline__ int float_key(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
 
 // ---- small device utilities --------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
@@ -582,6 +598,349 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
     if (__any_sync(0xffffffffu, bad) && lane == 0 && p.nonfinite_flag != nullptr) atomicOr(p.nonfinite_flag, 1);
     __syncthreads();   // tile / flags are reused by the next clip
   }
+}
+
+// ==========================================================================================================
+// Split path for large batches: the fused kernel above ties a CTA to a clip, so B clips over S CTA slots run
+// ceil(B / S) rounds and the CTA-wide per-clip phases cost barrier stalls.  Here the frames of ALL clips form
+// one flat queue of warp-sized work items (feat_frames_kernel), the dB tiles go through an L2-resident scratch
+// and a second, fine-grained kernel finishes them (feat_epilogue_block_kernel).
+// ==========================================================================================================
+// ---- per-clip preparation ---------------------------------------------------------------------
+template <int kUnused = 0>   // a template only so that the header can be included by several translation units
+__global__ void __launch_bounds__(256) feat_prep_kernel(const FeatParams p) {
+  __shared__ float red[64];
+  const int b = blockIdx.x;
+  const bool has_rev = p.rev != nullptr && p.rir_idx != nullptr && __ldg(p.rir_idx + b) >= 0;
+  const float* x = has_rev ? p.rev + (size_t)b * p.rev_stride : p.wav + (size_t)b * p.wav_stride;
+  const ClipNoise cn = resolve_noise(p.noise, p.noise_idx, p.noise_off, b);
+  const float scale = clip_mix_scale(cn, x, p.N, has_rev, p.es_part, p.es_nb, b, p.snr_db, red);
+  if (threadIdx.x == 0) {
+    p.scale_g[b] = scale;
+    p.clip_max[b] = float_key(-INFINITY);
+  }
+}
+
+// ---- frames: STFT -> power -> mel -> dB into the global tile (warp-autonomous, flat over clips) ----
+template <int NFFT, int HOP32>
+__global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMinCtas) feat_frames_kernel(const FeatParams p) {
+  using Plan = StftPlan<NFFT>;
+  using Rad = typename Plan::Rad;
+  constexpr int G = Plan::G;
+  constexpr int K = NFFT / 2 + 1;
+  constexpr int NC = (NFFT + 31) / 32;                       // 32-sample columns per frame
+  using Map = typename Plan::Map;
+  constexpr int ZL = stft_zlen<NFFT>();                      // scratch elements per FFT (with padding)
+  const Map zmap;
+  constexpr int NI = (G * K + 31) / 32;                      // split items per lane
+  static_assert(Rad::n == NFFT, "radix plan");
+
+  extern __shared__ __align__(16) float smem[];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int N = p.N, T = p.T, hop = p.hop, M = p.n_mels, mp = p.mp;
+
+  float* s_window = smem;
+  float2* s_tw = reinterpret_cast<float2*>(smem + p.f_off_tw);
+  float* s_melw = smem + p.f_off_melw;
+  int* s_mello = reinterpret_cast<int*>(smem + p.f_off_mello);
+  int* s_melofs = reinterpret_cast<int*>(smem + p.f_off_melofs);
+  float2* z = reinterpret_cast<float2*>(smem + p.f_off_z) + (size_t)warp * G * ZL;
+
+  // ---- constants -> shared memory, once per (persistent) CTA; the only CTA-wide barrier ----
+  for (int i = tid; i < NFFT; i += blockDim.x) s_window[i] = __ldg(p.window + i);
+  for (int i = tid; i < Rad::tw_total; i += blockDim.x) s_tw[i] = __ldg(p.tw + i);
+  for (int i = tid; i < p.n_melw; i += blockDim.x) s_melw[i] = __ldg(p.mel_w + i);
+  for (int i = tid; i < M; i += blockDim.x) s_mello[i] = __ldg(p.mel_lo + i);
+  for (int i = tid; i <= M; i += blockDim.x) s_melofs[i] = __ldg(p.mel_ofs + i);
+  __syncthreads();
+
+  const int ngroups = p.ngroups;
+  const long long total = (long long)p.B * ngroups;
+  // adjacent warps take adjacent groups of the same clip: their sample spans overlap in L1 / L2
+  for (long long item = (long long)blockIdx.x * nwarps + warp; item < total; item += (long long)gridDim.x * nwarps) {
+    const int b = (int)(item / ngroups), grp = (int)(item - (long long)b * ngroups);
+    const bool has_rev = p.rev != nullptr && p.rir_idx != nullptr && __ldg(p.rir_idx + b) >= 0;
+    const float* x = has_rev ? p.rev + (size_t)b * p.rev_stride : p.wav + (size_t)b * p.wav_stride;
+    const float scale = __ldg(p.scale_g + b);
+    const float* nz = nullptr;
+    int noff = 0, nlen = 1;
+    if (scale != 0.f || (p.noise_idx != nullptr && p.noise.data != nullptr)) {
+      const ClipNoise cn = resolve_noise(p.noise, p.noise_idx, p.noise_off, b);
+      nz = cn.nz; noff = cn.off; nlen = cn.len;
+    }
+    const bool mix = nz != nullptr;
+    float vmax = -INFINITY;                                  // maximum of the dB values this lane writes
+    const int f0 = grp * 2 * G;
+    // 1. load + window: z[g][j] = w[j] * (frame(f0+2g)[j] + i frame(f0+2g+1)[j])
+    bool staged = false;
+    if constexpr (HOP32 > 0) {
+      constexpr int NR = (2 * G - 1) * HOP32 + NC;           // registers holding the group's sample span
+      const int s0 = f0 * hop - NFFT / 2;
+      int q0 = 0;                                            // first noise sample of the span (mix only)
+      if (mix && s0 >= 0) { q0 = noff + s0; if (q0 >= nlen) q0 %= nlen; }
+      // fast path: the whole span is inside the clip (no reflection); the noise segment may wrap
+      // around the end of its clip once (needs a noise clip at least as long as the span)
+      if (s0 >= 0 && s0 + 32 * NR <= N && f0 + 2 * G <= T && (!mix || (q0 >= 0 && nlen >= 32 * NR))) {
+        staged = true;
+        // the span is staged in chunks of CH 32-sample columns so that at most (2G-1)*HOP32 + 32
+        // registers are live (n_fft 2048 = 64 columns needs two chunks; everything else one)
+        constexpr int CH = NC < 32 ? NC : 32, NCHUNK = (NC + CH - 1) / CH, NRC = (2 * G - 1) * HOP32 + CH;
+        static_assert(NC % CH == 0, "column chunks");
+#pragma unroll
+        for (int ch = 0; ch < NCHUNK; ++ch) {
+          const int r0 = ch * CH;
+          float sreg[NRC];
+          const float* xs = x + s0 + 32 * r0 + lane;
+#pragma unroll
+          for (int r = 0; r < NRC; ++r) sreg[r] = __ldg(xs + 32 * r);
+          if (mix) {
+            if (q0 + 32 * NR <= nlen) {
+              const float* ns = nz + q0 + 32 * r0 + lane;
+#pragma unroll
+              for (int r = 0; r < NRC; ++r) sreg[r] = fmaf(scale, __ldg(ns + 32 * r), sreg[r]);
+            } else {
+#pragma unroll
+              for (int r = 0; r < NRC; ++r) {
+                int q = q0 + 32 * (r0 + r) + lane;
+                q -= q >= nlen ? nlen : 0;
+                sreg[r] = fmaf(scale, __ldg(nz + q), sreg[r]);
+              }
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < CH; ++c) {
+            const int j = 32 * (r0 + c) + lane;
+            if (NFFT % 32 == 0 || j < NFFT) {
+              const float w = s_window[j];
+#pragma unroll
+              for (int g = 0; g < G; ++g)
+                z[g * ZL + zmap(j)] = make_float2(w * sreg[2 * g * HOP32 + c], w * sreg[(2 * g + 1) * HOP32 + c]);
+            }
+          }
+        }
+      }
+    }
+    if (!staged) {
+      // boundary groups (reflect padding, frames >= T, wrapping noise) and hops that are not a
+      // multiple of 32: plain per-element gather, deliberately not unrolled (cold code)
+#pragma unroll 1
+      for (int idx = lane; idx < G * NFFT; idx += 32) {
+        const int g = idx / NFFT, j = idx - g * NFFT;
+        const int ta = f0 + 2 * g, tb = ta + 1;
+        const float w = s_window[j];
+        float re = 0.f, im = 0.f;
+        if (ta < T) {
+          const int i = reflect_index(ta * hop - NFFT / 2 + j, N);
+          re = __ldg(x + i);
+          if (mix) re = fmaf(scale, noise_at(nz, noff, nlen, i), re);
+        }
+        if (tb < T) {
+          const int i = reflect_index(tb * hop - NFFT / 2 + j, N);
+          im = __ldg(x + i);
+          if (mix) im = fmaf(scale, noise_at(nz, noff, nlen, i), im);
+        }
+        z[g * ZL + zmap(j)] = make_float2(re * w, im * w);
+      }
+    }
+    __syncwarp();
+    // 2. forward FFT passes (in place, digit-reversed result)
+    static_for<0, Rad::npass>([&](auto I) {
+      constexpr int i = decltype(I)::value;
+      constexpr int R = Rad::R(i), L = Rad::L(i), tasks = NFFT / R;
+      const float2* tw = s_tw + Rad::tw_off(i);
+#pragma unroll 1   // one copy of each radix butterfly: the hot loop has to stay inside the instruction cache
+      for (int u = lane; u < G * tasks; u += 32) {
+        const int g = u / tasks, uu = u - g * tasks;
+        pass_task<R, false, Map>(z + g * ZL, L, uu, [&](int q) { return tw[q]; });
+      }
+      __syncwarp();
+    });
+    // 3. split the packed pair into two power spectra (|A[k]|^2, |B[k]|^2): read every (Z[k], Z[n-k])
+    //    first, then store the powers in plain bin order
+    {
+      float2 pw[NI];
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < G * K) {
+          const int g = idx / K, k = idx - g * K;
+          const float2* zz = z + g * ZL;
+          pw[i] = pair_split_power(zz[zmap(Rad::pos(k))], zz[zmap(Rad::pos(k == 0 ? 0 : NFFT - k))]);
+        }
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < NI; ++i) {
+        const int idx = lane + 32 * i;
+        if (idx < G * K) {
+          const int g = idx / K, k = idx - g * K;
+          z[g * ZL + zmap(k)] = pw[i];
+        }
+      }
+    }
+    __syncwarp();
+    // 4. sparse mel rows + dB: one lane per filter, all 2G frames of the group at once
+    float* tg = p.tile_g + ((size_t)b * T + f0) * mp;
+    for (int m = lane; m < M; m += 32) {
+      const int lo = s_mello[m], o0 = s_melofs[m], o1 = s_melofs[m + 1];
+      // two independent accumulator chains per frame pair (even / odd taps) hide the LDS + FFMA2 latency
+      float2 acc[G], acc1[G];
+#pragma unroll
+      for (int g = 0; g < G; ++g) { acc[g] = make_float2(0.f, 0.f); acc1[g] = make_float2(0.f, 0.f); }
+      int o = o0;
+      for (; o + 1 < o1; o += 2) {
+        const float w0 = s_melw[o], w1 = s_melw[o + 1];
+        const int k = lo + (o - o0);
+        const int p0 = zmap(k), p1 = zmap(k + 1);
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+          acc[g] = cfma_s(z[g * ZL + p0], w0, acc[g]);
+          acc1[g] = cfma_s(z[g * ZL + p1], w1, acc1[g]);
+        }
+      }
+      if (o < o1) {
+        const float w0 = s_melw[o];
+        const int p0 = zmap(lo + (o - o0));
+#pragma unroll
+        for (int g = 0; g < G; ++g) acc[g] = cfma_s(z[g * ZL + p0], w0, acc[g]);
+      }
+#pragma unroll
+      for (int g = 0; g < G; ++g) acc[g] = cadd(acc[g], acc1[g]);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int ta = f0 + 2 * g;
+        // frame-major tile: the 32 lanes of a round write 32 consecutive floats of one frame
+        if (ta < T) { const float d = power_to_db(acc[g].x); tg[(size_t)(2 * g) * mp + m] = d; vmax = fmaxf(vmax, d); }
+        if (ta + 1 < T) { const float d = power_to_db(acc[g].y); tg[(size_t)(2 * g + 1) * mp + m] = d; vmax = fmaxf(vmax, d); }
+      }
+    }
+    vmax = warp_max(vmax);
+    if (lane == 0 && vmax > -INFINITY) atomicMax(p.clip_max + b, float_key(vmax));
+    __syncwarp();
+  }
+}
+
+// ---- block epilogue of the split path: top_db floor -> [DCT-II] -> [SpecAugment] -> store ----------------
+// One CTA per (clip, block of eb_frames frames).  The block's rows of the frame-major tile are one contiguous
+// span of global memory: read with 16-byte coalesced loads, written transposed into shared memory
+// [n_mels][pitch], then the same 8-coefficient x 4-frame register tiles as the fused kernel's DCT phase.
+// Many small CTAs with short dependent phases: the grid is 2-3 k CTAs, 8+ resident per SM.
+// exact i / d for 0 <= i < 2^16, 1 <= d < 2^10 without an integer division
+__device__ __forceinline__ int small_div(int i, float inv_d) { return __float2int_rd(((float)i + 0.5f) * inv_d); }
+
+template <typename OutT>
+__global__ void __launch_bounds__(256) feat_epilogue_block_kernel(const FeatParams p) {
+  extern __shared__ __align__(16) float smem[];               // tile [n_mels][pitch] | dct [n_mels][c8]
+  __shared__ unsigned char s_rowmask[128];
+  __shared__ unsigned char s_colmask[256];
+  const int tid = threadIdx.x;
+  const int T = p.T, M = p.n_mels, F = p.n_feat, mp = p.mp, pitch = p.eb_pitch, c8 = p.c8;
+  const int nblk = (T + p.eb_frames - 1) / p.eb_frames;
+  float* tile = smem;
+  float* s_dct = smem + ((M * pitch + 3) & ~3);
+  const int mq = mp / 4, cq = c8 / 4;
+  const float inv_mq = 1.0f / (float)mq;
+  if (p.is_mfcc) {                                            // DCT matrix: once per (persistent) CTA
+    const float inv_cq = 1.0f / (float)cq;
+    for (int i = tid; i < M * cq; i += blockDim.x) {          // c8 is a multiple of 8: rows in float4 units
+      const int m = small_div(i, inv_cq), c = 4 * (i - m * cq);
+      const float* src = p.dct + (size_t)m * p.n_mfcc + c;
+      reinterpret_cast<float4*>(s_dct)[i] = make_float4(c < p.n_mfcc ? __ldg(src) : 0.f, c + 1 < p.n_mfcc ? __ldg(src + 1) : 0.f,
+                                                        c + 2 < p.n_mfcc ? __ldg(src + 2) : 0.f, c + 3 < p.n_mfcc ? __ldg(src + 3) : 0.f);
+    }
+  }
+  const OutT mv = to_out<OutT>(p.mask_value);
+  float chk = 0.f;                                            // v * 0 accumulates to NaN iff some v is NaN / Inf
+  const int total = p.B * nblk;
+  for (int item = blockIdx.x; item < total; item += gridDim.x) {
+    const int b = item / nblk, t0 = (item - b * nblk) * p.eb_frames;
+    const int nf = min(p.eb_frames, T - t0);                  // frames in this block
+    for (int i = tid; i < F + nf; i += blockDim.x) {          // SpecAugment flags: feature rows, then this block's frames
+      const bool is_row = i < F;
+      const int q = is_row ? i : t0 + (i - F);
+      const int32_t* st = is_row ? p.fs : p.ts;
+      const int32_t* ln = is_row ? p.fl : p.tl;
+      const int nm = is_row ? p.nF : p.nT;
+      bool mk = false;
+      if (st != nullptr)
+        for (int j = 0; j < nm; ++j) {
+          const int s0 = __ldg(st + (size_t)b * nm + j), l = __ldg(ln + (size_t)b * nm + j);
+          mk |= (q >= s0) && (q < s0 + l);
+        }
+      (is_row ? s_rowmask : s_colmask)[is_row ? i : i - F] = mk ? 1 : 0;
+    }
+    float cutoff = -INFINITY;
+    if (p.top_db >= 0.f) cutoff = key_float(p.clip_max[b]) - p.top_db;
+    // the block's rows of the frame-major tile are one contiguous span: coalesced 16-byte loads, transposed into smem
+    const float4* tg = reinterpret_cast<const float4*>(p.tile_g + ((size_t)b * T + t0) * mp);
+    for (int i = tid; i < nf * mq; i += blockDim.x) {
+      const int tl = small_div(i, inv_mq), m = 4 * (i - tl * mq);
+      const float4 v = tg[i];
+      tile[m * pitch + tl] = fmaxf(v.x, cutoff);
+      if (m + 1 < M) tile[(m + 1) * pitch + tl] = fmaxf(v.y, cutoff);
+      if (m + 2 < M) tile[(m + 2) * pitch + tl] = fmaxf(v.z, cutoff);
+      if (m + 3 < M) tile[(m + 3) * pitch + tl] = fmaxf(v.w, cutoff);
+    }
+    __syncthreads();
+    OutT* out = reinterpret_cast<OutT*>(p.out) + (size_t)b * p.out_stride + t0;
+    if (!p.is_mfcc) {
+      const float inv_nf = 1.0f / (float)nf;
+      for (int i = tid; i < M * nf; i += blockDim.x) {
+        const int m = small_div(i, inv_nf), tl = i - m * nf;
+        const float v = tile[m * pitch + tl];
+        chk = fmaf(v, 0.f, chk);
+        out[(size_t)m * T + tl] = (s_rowmask[m] || s_colmask[tl]) ? mv : to_out<OutT>(v);
+      }
+    } else {
+      // DCT-II in 8-coefficient x 4-frame register tiles (frames tb, tb+TB, tb+2TB, tb+3TB: a warp reads
+      // consecutive tile columns; each 16-byte broadcast load of coefficients feeds eight FFMA2)
+      const int C = F, ncg = c8 / 8, TB = (nf + 3) / 4;
+      const float inv_tb = 1.0f / (float)TB;
+      for (int idx = tid; idx < ncg * TB; idx += blockDim.x) {
+        const int cg = small_div(idx, inv_tb), tb = idx - cg * TB, c0 = cg * 8;
+        // frames beyond the block read a neighbouring (finite) tile entry and are never stored
+        const int o1 = tb + TB < nf ? TB : 0, o2 = tb + 2 * TB < nf ? 2 * TB : 0, o3 = tb + 3 * TB < nf ? 3 * TB : 0;
+        float2 acc2[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc2[i][j] = make_float2(0.f, 0.f);
+        const float* d = s_dct + c0;
+        const float* row = tile + tb;
+#pragma unroll 2
+        for (int m = 0; m < M; ++m, d += c8, row += pitch) {
+          const float4 d0 = *reinterpret_cast<const float4*>(d);
+          const float4 d1 = *reinterpret_cast<const float4*>(d + 4);
+          const float a[4] = {row[0], row[o1], row[o2], row[o3]};
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            acc2[i][0] = cfma_s(make_float2(d0.x, d0.y), a[i], acc2[i][0]);
+            acc2[i][1] = cfma_s(make_float2(d0.z, d0.w), a[i], acc2[i][1]);
+            acc2[i][2] = cfma_s(make_float2(d1.x, d1.y), a[i], acc2[i][2]);
+            acc2[i][3] = cfma_s(make_float2(d1.z, d1.w), a[i], acc2[i][3]);
+          }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int tl = tb + i * TB;
+          if (tl < nf) {
+            const bool cm = s_colmask[tl] != 0;
+            OutT* o = out + (size_t)c0 * T + tl;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float v = (j & 1) ? acc2[i][j >> 1].y : acc2[i][j >> 1].x;
+              if (c0 + j < C) {
+                chk = fmaf(v, 0.f, chk);
+                o[(size_t)j * T] = (cm || s_rowmask[c0 + j]) ? mv : to_out<OutT>(v);
+              }
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();                                          // tile and flags are reused by the next block
+  }
+  if (__any_sync(0xffffffffu, chk != 0.f) && (tid & 31) == 0 && p.nonfinite_flag != nullptr) atomicOr(p.nonfinite_flag, 1);
 }
 
 }  // namespace wwf

@@ -26,7 +26,8 @@ using namespace wwf;
 namespace wwf {
 #define WWF_EXT(N, H)                                                                  \
   extern template __global__ void feat_kernel<N, H, float>(const FeatParams);          \
-  extern template __global__ void feat_kernel<N, H, __half>(const FeatParams);
+  extern template __global__ void feat_kernel<N, H, __half>(const FeatParams);         \
+  extern template __global__ void feat_frames_kernel<N, H>(const FeatParams);
 WWF_EXT(256, 0) WWF_EXT(256, 4) WWF_EXT(256, 5)
 WWF_EXT(400, 0) WWF_EXT(400, 4) WWF_EXT(400, 5) WWF_EXT(400, 8)
 WWF_EXT(512, 0) WWF_EXT(512, 4) WWF_EXT(512, 5) WWF_EXT(512, 8)
@@ -76,7 +77,9 @@ struct wwf_plan {
   wwf_config cfg;
   int device = 0, sm_count = 0, max_smem = 0;
   int K = 0, n_feat = 0, G = 1, zlen = 0, tw_total = 0, n_melw = 0, max_warps = 16;
-  FeatKernel kernel = nullptr;
+  FeatKernel kernel = nullptr;          // fused per-clip kernel
+  FeatKernel frames = nullptr;          // split path: flat frames kernel (same n_fft / hop variant)
+  FeatKernel epilogue_block = nullptr;  // split path: feat_epilogue_block_kernel<float | __half>
   // device constants
   float* d_window = nullptr;
   float2* d_tw = nullptr;
@@ -107,7 +110,10 @@ struct wwf_plan {
   std::vector<Resampler> resamplers;
   // optional per-kernel timing (wwf_profile_enable)
   bool prof = false;
-  std::vector<cudaEvent_t> prof_events;   // triples: before conv, between, after feat
+  // five events per profiled call: before reverb | after reverb | after prep | after frames | after epilogue
+  // (the single-kernel path records the last three at the same point: its time shows up under "frames")
+  std::vector<cudaEvent_t> prof_events;
+  std::vector<int> prof_split;            // per call: 1 = split path
 };
 
 template <typename T>
@@ -132,14 +138,20 @@ static void select_kernel(wwf_plan* p, std::vector<float2>& tw) {
   p->tw_total = Plan::Rad::tw_total;
   const bool f16 = p->cfg.out_dtype == WWF_OUT_F16;
   p->kernel = f16 ? (FeatKernel)feat_kernel<NFFT, 0, __half> : (FeatKernel)feat_kernel<NFFT, 0, float>;
+  p->frames = (FeatKernel)feat_frames_kernel<NFFT, 0>;
+  p->epilogue_block = f16 ? (FeatKernel)feat_epilogue_block_kernel<__half> : (FeatKernel)feat_epilogue_block_kernel<float>;
   {
     // register-staged frame loads for hops that are a multiple of 32 and instantiated: 128, 160, 256
     if (!getenv("WWF_FEAT_GENERIC_LOAD")) {
       switch (p->cfg.hop_length) {
-        case 128: p->kernel = f16 ? (FeatKernel)feat_kernel<NFFT, 4, __half> : (FeatKernel)feat_kernel<NFFT, 4, float>; break;
-        case 160: p->kernel = f16 ? (FeatKernel)feat_kernel<NFFT, 5, __half> : (FeatKernel)feat_kernel<NFFT, 5, float>; break;
-        case 256: if constexpr (NFFT > 256) p->kernel = f16 ? (FeatKernel)feat_kernel<NFFT, 8, __half> : (FeatKernel)feat_kernel<NFFT, 8, float>; break;
-        case 512: if constexpr (NFFT >= 1024) p->kernel = f16 ? (FeatKernel)feat_kernel<NFFT, 16, __half> : (FeatKernel)feat_kernel<NFFT, 16, float>; break;
+        case 128: p->kernel = f16 ? (FeatKernel)feat_kernel<NFFT, 4, __half> : (FeatKernel)feat_kernel<NFFT, 4, float>;
+                  p->frames = (FeatKernel)feat_frames_kernel<NFFT, 4>; break;
+        case 160: p->kernel = f16 ? (FeatKernel)feat_kernel<NFFT, 5, __half> : (FeatKernel)feat_kernel<NFFT, 5, float>;
+                  p->frames = (FeatKernel)feat_frames_kernel<NFFT, 5>; break;
+        case 256: if constexpr (NFFT > 256) { p->kernel = f16 ? (FeatKernel)feat_kernel<NFFT, 8, __half> : (FeatKernel)feat_kernel<NFFT, 8, float>;
+                                              p->frames = (FeatKernel)feat_frames_kernel<NFFT, 8>; } break;
+        case 512: if constexpr (NFFT >= 1024) { p->kernel = f16 ? (FeatKernel)feat_kernel<NFFT, 16, __half> : (FeatKernel)feat_kernel<NFFT, 16, float>;
+                                                p->frames = (FeatKernel)feat_frames_kernel<NFFT, 16>; } break;
         default: break;
       }
     }
@@ -256,6 +268,8 @@ extern "C" int wwf_plan_create(const wwf_config* cfg, int device, wwf_plan** out
     return fail(WWF_ERR_NOMEM, "cudaMalloc(nonfinite flag) failed");
   }
   cudaError_t e = cudaFuncSetAttribute((const void*)p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem - 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)p->frames, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem - 1024);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)p->epilogue_block, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem - 2048);
   if (e != cudaSuccess) {
     wwf_plan_destroy(p);
     return fail(WWF_ERR_CUDA, "cudaFuncSetAttribute(feat_kernel): %s (is libwwfeat.so built for this GPU?)", cudaGetErrorString(e));
@@ -282,24 +296,43 @@ extern "C" int wwf_profile_enable(wwf_plan* p, int enable) {
   return WWF_OK;
 }
 
-extern "C" int wwf_profile_read(wwf_plan* p, double* conv_ms, double* feat_ms, int* n_calls) {
-  if (!p || !conv_ms || !feat_ms || !n_calls) return fail(WWF_ERR_INVALID, "wwf_profile_read: null argument");
+static int profile_collect(wwf_plan* p, double ms[4], int* n_calls, int* n_split) {
   DeviceGuard guard(p->device);
-  const int n = (int)(p->prof_events.size() / 3);
-  double c = 0.0, f = 0.0;
+  const int n = (int)(p->prof_events.size() / 5);
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
   cudaError_t err = cudaSuccess;
   for (int i = 0; i < n && err == cudaSuccess; ++i) {
-    float a = 0.f, b = 0.f;
-    err = cudaEventSynchronize(p->prof_events[3 * i + 2]);
-    if (err == cudaSuccess) err = cudaEventElapsedTime(&a, p->prof_events[3 * i], p->prof_events[3 * i + 1]);
-    if (err == cudaSuccess) err = cudaEventElapsedTime(&b, p->prof_events[3 * i + 1], p->prof_events[3 * i + 2]);
-    c += a; f += b;
+    err = cudaEventSynchronize(p->prof_events[5 * i + 4]);
+    for (int k = 0; k < 4 && err == cudaSuccess; ++k) {
+      float v = 0.f;
+      err = cudaEventElapsedTime(&v, p->prof_events[5 * i + k], p->prof_events[5 * i + k + 1]);
+      acc[k] += v;
+    }
   }
+  int ns = 0;
+  for (int v : p->prof_split) ns += v;
   for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
   p->prof_events.clear();
+  p->prof_split.clear();
   if (err != cudaSuccess) return fail(WWF_ERR_CUDA, "wwf_profile_read: %s", cudaGetErrorString(err));
-  *conv_ms = n ? c / n : 0.0; *feat_ms = n ? f / n : 0.0; *n_calls = n;
+  for (int k = 0; k < 4; ++k) ms[k] = n ? acc[k] / n : 0.0;
+  *n_calls = n;
+  if (n_split) *n_split = ns;
   return WWF_OK;
+}
+
+extern "C" int wwf_profile_read(wwf_plan* p, double* conv_ms, double* feat_ms, int* n_calls) {
+  if (!p || !conv_ms || !feat_ms || !n_calls) return fail(WWF_ERR_INVALID, "wwf_profile_read: null argument");
+  double ms[4];
+  int rc = profile_collect(p, ms, n_calls, nullptr);
+  if (rc) return rc;
+  *conv_ms = ms[0]; *feat_ms = ms[1] + ms[2] + ms[3];
+  return WWF_OK;
+}
+
+extern "C" int wwf_profile_read_kernels(wwf_plan* p, double* kernel_ms, int* n_calls, int* n_split) {
+  if (!p || !kernel_ms || !n_calls) return fail(WWF_ERR_INVALID, "wwf_profile_read_kernels: null argument");
+  return profile_collect(p, kernel_ms, n_calls, n_split);
 }
 
 extern "C" int wwf_plan_info(const wwf_plan* p, wwf_info* out) {
@@ -427,12 +460,35 @@ static void conv_geometry(const wwf_plan* p, int N, int* hist, int* valid, int* 
   }
 }
 
-// workspace = reverberated clips [B][roundup4(N)] + their per-block energies [B][nb]
-extern "C" size_t wwf_workspace_bytes(const wwf_plan* p, int B, int N) {
-  if (!p || B <= 0 || N <= 0 || p->n_rir == 0) return 0;
+// workspace = [reverb part: reverberated clips [B][roundup4(N)] + their per-block energies [B][nb]] (RIR bank only)
+//           + [split-path part: dB tiles [B][T][roundup4(n_mels)] + clip maxima [B] + mix scales [B]] (large batches only)
+static size_t conv_ws_bytes(const wwf_plan* p, int B, int N) {
+  if (p->n_rir == 0) return 0;
   int hist, valid, nb;
   conv_geometry(p, N, &hist, &valid, &nb);
   return ((size_t)B * (size_t)round_up4(N) + (size_t)round_up4((int64_t)B * nb)) * sizeof(float);
+}
+// The split path (flat frames kernel + block epilogue) pays off once the batch spans several rounds of the fused
+// kernel's CTA slots: measured break-even around 450 clips of 1.5 s (profiles/README.md).  WWF_FEAT_PATH=fused|split
+// forces one of them (tests run both).
+static bool use_split(const wwf_plan* p, int B, int N) {
+  if (p->cfg.cmvn) return false;                               // CMVN needs whole rows of a clip in one CTA
+  if (const char* e = getenv("WWF_FEAT_PATH")) {
+    if (!strcmp(e, "fused")) return false;
+    if (!strcmp(e, "split")) return true;
+  }
+  const int T = N / p->cfg.hop_length + 1;
+  const long long groups = (long long)B * ((T + 2 * p->G - 1) / (2 * p->G));
+  return groups >= 6ll * 20 * p->sm_count;
+}
+static size_t split_ws_bytes(const wwf_plan* p, int B, int N) {
+  if (!use_split(p, B, N)) return 0;
+  const int T = N / p->cfg.hop_length + 1;
+  return ((size_t)B * T * (size_t)round_up4(p->cfg.n_mels) + 2 * (size_t)round_up4(B)) * sizeof(float);
+}
+extern "C" size_t wwf_workspace_bytes(const wwf_plan* p, int B, int N) {
+  if (!p || B <= 0 || N <= 0) return 0;
+  return conv_ws_bytes(p, B, N) + split_ws_bytes(p, B, N);
 }
 
 static bool wants_reverb(const wwf_plan* p, const wwf_aug* aug) { return aug && aug->rir_idx && p->n_rir > 0; }
@@ -446,7 +502,7 @@ static int launch_conv(wwf_plan* p, const float* wav, int B, int N, int64_t wav_
   *es_part = nullptr;
   *es_nb = 0;
   if (!wants_reverb(p, aug)) return WWF_OK;
-  const size_t need = wwf_workspace_bytes(p, B, N);
+  const size_t need = conv_ws_bytes(p, B, N);
   if (!workspace || workspace_bytes < need) return fail(WWF_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
   if (reinterpret_cast<uintptr_t>(workspace) & 15) return fail(WWF_ERR_WORKSPACE, "workspace must be 16-byte aligned");
   ConvParams cp{};
@@ -490,7 +546,7 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
   if (!guard.ok) return fail(WWF_ERR_CUDA, "cudaSetDevice(%d) failed", p->device);
   cudaStream_t st = (cudaStream_t)stream;
 
-  cudaEvent_t pe[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t pe[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   if (p->prof) {
     for (auto& e : pe) WWF_CUDA(cudaEventCreate(&e));
     WWF_CUDA(cudaEventRecord(pe[0], st));
@@ -564,12 +620,82 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
   fp.es_part = es_part; fp.es_nb = es_nb;
   fp.out = out; fp.out_stride = out_stride;
   fp.nonfinite_flag = p->d_nonfinite;
+  // ---- split path: prep -> flat frames -> block epilogue (large batches with room in the workspace) ----
+  const size_t conv_bytes = conv_ws_bytes(p, B, N), split_bytes = split_ws_bytes(p, B, N);
+  if (split_bytes > 0 && workspace && workspace_bytes >= conv_bytes + split_bytes && !(reinterpret_cast<uintptr_t>(workspace) & 15)) {
+    fp.mp = (int)round_up4(M);
+    fp.tile_g = (float*)((char*)workspace + conv_bytes);
+    fp.clip_max = (int*)(fp.tile_g + (size_t)B * T * fp.mp);
+    fp.scale_g = (float*)(fp.clip_max + round_up4(B));
+    fp.ngroups = (T + 2 * p->G - 1) / (2 * p->G);
+    int fo = al4(nfft);
+    fp.f_off_tw = fo;       fo += al4(2 * p->tw_total);
+    fp.f_off_melw = fo;     fo += al4(p->n_melw);
+    fp.f_off_mello = fo;    fo += al4(M);
+    fp.f_off_melofs = fo;   fo += al4(M + 1);
+    fp.f_off_z = fo;
+    const size_t f_fixed = (size_t)fo * sizeof(float);
+    int fw = 0, fc = 1, fbest = -1;
+    for (int c : cands) {
+      if (c > p->max_warps) continue;
+      const size_t sm = f_fixed + (size_t)c * per_warp;
+      if (sm > budget) continue;
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)p->frames, c * 32, sm) != cudaSuccess || nb < 1) continue;
+      if (nb * c > fbest) { fbest = nb * c; fw = c; fc = nb; }
+    }
+    // block epilogue: frames per block and threads per CTA chosen so that the 8-coefficient x 4-frame DCT tasks
+    // fill the CTA's threads (T = 151, 40 coefficients: 2 blocks of 76 frames -> 95 tasks on 96 threads)
+    int eb_threads = 128;
+    fp.eb_frames = 64;
+    {
+      const int ncg = mfcc ? fp.c8 / 8 : 1;
+      double best_eff = -1.0;
+      for (int nblk = 1; nblk <= (T + 31) / 32; ++nblk) {
+        const int eb = (((T + nblk - 1) / nblk) + 3) & ~3;
+        if (eb > 256) continue;
+        for (int th = 64; th <= 256; th += 32) {
+          const int tasks = ncg * (eb / 4), rounds = (tasks + th - 1) / th;
+          double eff = (double)tasks / ((double)rounds * th) * ((double)T / ((double)nblk * eb));
+          eff -= 0.02 * rounds;                                 // prefer short CTAs (more of them resident)
+          if (eff > best_eff) { best_eff = eff; fp.eb_frames = eb; eb_threads = th; }
+        }
+      }
+    }
+    fp.eb_pitch = fp.eb_frames | 1;
+    const size_t eb_smem = ((size_t)((M * fp.eb_pitch + 3) & ~3) + (mfcc ? (size_t)M * fp.c8 : 0)) * sizeof(float);
+    if (fw > 0 && eb_smem <= budget - 1024) {
+      const long long items = (long long)B * fp.ngroups;
+      long long fgrid = (long long)p->sm_count * fc;
+      if (fgrid > (items + fw - 1) / fw) fgrid = (items + fw - 1) / fw;
+      feat_prep_kernel<0><<<B, 256, 0, st>>>(fp);
+      if (p->prof) WWF_CUDA(cudaEventRecord(pe[2], st));
+      p->frames<<<(unsigned)fgrid, fw * 32, f_fixed + (size_t)fw * per_warp, st>>>(fp);
+      if (p->prof) WWF_CUDA(cudaEventRecord(pe[3], st));
+      const long long eitems = (long long)B * ((T + fp.eb_frames - 1) / fp.eb_frames);
+      int eocc = 1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eocc, (const void*)p->epilogue_block, eb_threads, eb_smem);
+      const long long egrid = std::min(eitems, (long long)p->sm_count * std::max(eocc, 1));
+      p->epilogue_block<<<(unsigned)egrid, eb_threads, eb_smem, st>>>(fp);
+      g_launches += 3;
+      WWF_CUDA(cudaGetLastError());
+      if (p->prof) {
+        WWF_CUDA(cudaEventRecord(pe[4], st));
+        p->prof_events.insert(p->prof_events.end(), pe, pe + 5);
+        p->prof_split.push_back(1);
+      }
+      return WWF_OK;
+    }
+  }
+  if (p->prof) WWF_CUDA(cudaEventRecord(pe[2], st));
   p->kernel<<<grid, nwarps * 32, smem, st>>>(fp);
   g_launches++;
   WWF_CUDA(cudaGetLastError());
   if (p->prof) {
-    WWF_CUDA(cudaEventRecord(pe[2], st));
-    p->prof_events.insert(p->prof_events.end(), pe, pe + 3);
+    WWF_CUDA(cudaEventRecord(pe[3], st));
+    WWF_CUDA(cudaEventRecord(pe[4], st));
+    p->prof_events.insert(p->prof_events.end(), pe, pe + 5);
+    p->prof_split.push_back(0);
   }
   return WWF_OK;
 }

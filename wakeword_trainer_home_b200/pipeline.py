@@ -252,6 +252,15 @@ class FeaturePlan:
         N.check(self.lib.wwf_profile_read(self._handle, C.byref(c), C.byref(f), C.byref(n)))
         return c.value, f.value, n.value
 
+    def profile_read_kernels(self):
+        """({'conv_kernel', 'feat_prep_kernel', 'feat_frames_kernel' | 'feat_kernel', 'feat_epilogue_block_kernel'}
+        -> average ms per call, calls, calls that took the large-batch path) since the last read."""
+        ms, n, ns = (C.c_double * 4)(), C.c_int(), C.c_int()
+        N.check(self.lib.wwf_profile_read_kernels(self._handle, ms, C.byref(n), C.byref(ns)))
+        split = n.value > 0 and ns.value == n.value
+        names = ["conv_kernel", "feat_prep_kernel", "feat_frames_kernel" if split else "feat_kernel", "feat_epilogue_block_kernel"]
+        return {k: v for k, v in zip(names, ms) if v > 0.0 or k == "conv_kernel"}, n.value, ns.value
+
     # ------------------------------------------------------------------ banks
     def _register(self, kind: int, clips: Sequence[torch.Tensor]):
         flat, offs = _flatten_bank(clips, self.device)
