@@ -614,6 +614,7 @@ __global__ void __launch_bounds__(256) feat_prep_kernel(const FeatParams p) {
   const bool has_rev = p.rev != nullptr && p.rir_idx != nullptr && __ldg(p.rir_idx + b) >= 0;
   const float* x = has_rev ? p.rev + (size_t)b * p.rev_stride : p.wav + (size_t)b * p.wav_stride;
   const ClipNoise cn = resolve_noise(p.noise, p.noise_idx, p.noise_off, b);
+  pdl_wait();                            // conv_kernel's clips and energy partials (PDL)
   const float scale = clip_mix_scale(cn, x, p.N, has_rev, p.es_part, p.es_nb, b, p.snr_db, red);
   if (threadIdx.x == 0) {
     p.scale_g[b] = scale;
@@ -652,6 +653,9 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
   for (int i = tid; i < p.n_melw; i += blockDim.x) s_melw[i] = __ldg(p.mel_w + i);
   for (int i = tid; i < M; i += blockDim.x) s_mello[i] = __ldg(p.mel_lo + i);
   for (int i = tid; i <= M; i += blockDim.x) s_melofs[i] = __ldg(p.mel_ofs + i);
+  // programmatic dependent launch: everything above only reads plan constants and overlapped with the tail of
+  // the previous kernel; its results (mix scales, reverberated clips) are needed from here on
+  pdl_wait();
   __syncthreads();
 
   const int ngroups = p.ngroups;
@@ -849,6 +853,7 @@ __global__ void __launch_bounds__(256) feat_epilogue_block_kernel(const FeatPara
                                                         c + 2 < p.n_mfcc ? __ldg(src + 2) : 0.f, c + 3 < p.n_mfcc ? __ldg(src + 3) : 0.f);
     }
   }
+  pdl_wait();                            // the tiles and maxima of feat_frames_kernel (PDL)
   const OutT mv = to_out<OutT>(p.mask_value);
   float chk = 0.f;                                            // v * 0 accumulates to NaN iff some v is NaN / Inf
   const int total = p.B * nblk;

@@ -21,6 +21,18 @@
 
 namespace wwf {
 
+// Programmatic dependent launch (sm_90+): a kernel launched with the programmatic-stream-serialization attribute
+// may start while its predecessor drains; it must call pdl_wait() before touching the predecessor's results.
+// (Triggering the early start explicitly from inside the predecessor was measured slower: the waiting CTAs take
+// registers and shared memory from the kernel that is still running.)  A no-op for a normal launch and for the
+// host-side emulation build of the tests.
+__device__ __forceinline__ void pdl_wait() {
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 900)
+  cudaGridDependencySynchronize();
+#endif
+}
+
+
 // ----------------------------------------------------------------------------------------
 // compile-time helpers
 // ----------------------------------------------------------------------------------------

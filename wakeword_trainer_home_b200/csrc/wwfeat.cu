@@ -668,15 +668,27 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
       const long long items = (long long)B * fp.ngroups;
       long long fgrid = (long long)p->sm_count * fc;
       if (fgrid > (items + fw - 1) / fw) fgrid = (items + fw - 1) / fw;
-      feat_prep_kernel<0><<<B, 256, 0, st>>>(fp);
+      // the three kernels are chained with programmatic dependent launch: each may start its prologue (constants
+      // into shared memory) while its predecessor drains and waits in cudaGridDependencySynchronize() for its data
+      const bool pdl = !p->prof && !getenv("WWF_NO_PDL");
+      auto launch = [&](FeatKernel k, unsigned g, unsigned b, size_t sm) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(g); cfg.blockDim = dim3(b); cfg.dynamicSmemBytes = sm; cfg.stream = st;
+        cudaLaunchAttribute at{};
+        at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at.val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = &at; cfg.numAttrs = pdl ? 1 : 0;
+        return cudaLaunchKernelEx(&cfg, k, fp);
+      };
+      WWF_CUDA(launch((FeatKernel)feat_prep_kernel<0>, (unsigned)B, 256, 0));
       if (p->prof) WWF_CUDA(cudaEventRecord(pe[2], st));
-      p->frames<<<(unsigned)fgrid, fw * 32, f_fixed + (size_t)fw * per_warp, st>>>(fp);
+      WWF_CUDA(launch(p->frames, (unsigned)fgrid, (unsigned)(fw * 32), f_fixed + (size_t)fw * per_warp));
       if (p->prof) WWF_CUDA(cudaEventRecord(pe[3], st));
       const long long eitems = (long long)B * ((T + fp.eb_frames - 1) / fp.eb_frames);
       int eocc = 1;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eocc, (const void*)p->epilogue_block, eb_threads, eb_smem);
       const long long egrid = std::min(eitems, (long long)p->sm_count * std::max(eocc, 1));
-      p->epilogue_block<<<(unsigned)egrid, eb_threads, eb_smem, st>>>(fp);
+      WWF_CUDA(launch(p->epilogue_block, (unsigned)egrid, (unsigned)eb_threads, eb_smem));
       g_launches += 3;
       WWF_CUDA(cudaGetLastError());
       if (p->prof) {
