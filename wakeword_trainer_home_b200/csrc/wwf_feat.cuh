@@ -301,6 +301,7 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
       const int m = i / p.c8, c = i - m * p.c8;
       s_dct[i] = c < p.n_mfcc ? __ldg(p.dct + (size_t)m * p.n_mfcc + c) : 0.f;
     }
+  pdl_wait();   // programmatic dependent launch: the constants above were staged while conv_kernel drained
 
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
     // ---- per-clip setup -------------------------------------------------------------
@@ -610,11 +611,11 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
 template <int kUnused = 0>   // a template only so that the header can be included by several translation units
 __global__ void __launch_bounds__(256) feat_prep_kernel(const FeatParams p) {
   __shared__ float red[64];
+  pdl_wait();   // launched behind conv_kernel with programmatic dependent launch: nothing is read before this
   const int b = blockIdx.x;
   const bool has_rev = p.rev != nullptr && p.rir_idx != nullptr && __ldg(p.rir_idx + b) >= 0;
   const float* x = has_rev ? p.rev + (size_t)b * p.rev_stride : p.wav + (size_t)b * p.wav_stride;
   const ClipNoise cn = resolve_noise(p.noise, p.noise_idx, p.noise_off, b);
-  pdl_wait();                            // conv_kernel's clips and energy partials (PDL)
   const float scale = clip_mix_scale(cn, x, p.N, has_rev, p.es_part, p.es_nb, b, p.snr_db, red);
   if (threadIdx.x == 0) {
     p.scale_g[b] = scale;

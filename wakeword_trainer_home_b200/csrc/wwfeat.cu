@@ -302,10 +302,15 @@ static int profile_collect(wwf_plan* p, double ms[4], int* n_calls, int* n_split
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   cudaError_t err = cudaSuccess;
   for (int i = 0; i < n && err == cudaSuccess; ++i) {
-    err = cudaEventSynchronize(p->prof_events[5 * i + 4]);
+    cudaEvent_t* e = &p->prof_events[5 * i];
+    const bool split = i < (int)p->prof_split.size() && p->prof_split[i] != 0;
+    err = cudaEventSynchronize(e[split ? 4 : 3]);
+    // the single-kernel path records only events 0, 1, 3 (no extra records between its two kernels)
+    const int pairs[4][2] = {{0, 1}, {1, 2}, {split ? 2 : 1, 3}, {3, 4}};
     for (int k = 0; k < 4 && err == cudaSuccess; ++k) {
+      if (!split && (k == 1 || k == 3)) continue;
       float v = 0.f;
-      err = cudaEventElapsedTime(&v, p->prof_events[5 * i + k], p->prof_events[5 * i + k + 1]);
+      err = cudaEventElapsedTime(&v, e[pairs[k][0]], e[pairs[k][1]]);
       acc[k] += v;
     }
   }
@@ -671,24 +676,25 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
       // the three kernels are chained with programmatic dependent launch: each may start its prologue (constants
       // into shared memory) while its predecessor drains and waits in cudaGridDependencySynchronize() for its data
       const bool pdl = !p->prof && !getenv("WWF_NO_PDL");
-      auto launch = [&](FeatKernel k, unsigned g, unsigned b, size_t sm) {
+      // (only behind one of OUR kernels: what runs before the first of them may still be producing the inputs)
+      auto launch = [&](FeatKernel k, unsigned g, unsigned b, size_t sm, bool behind_ours) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(g); cfg.blockDim = dim3(b); cfg.dynamicSmemBytes = sm; cfg.stream = st;
         cudaLaunchAttribute at{};
         at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at.val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = &at; cfg.numAttrs = pdl ? 1 : 0;
+        cfg.attrs = &at; cfg.numAttrs = (pdl && behind_ours) ? 1 : 0;
         return cudaLaunchKernelEx(&cfg, k, fp);
       };
-      WWF_CUDA(launch((FeatKernel)feat_prep_kernel<0>, (unsigned)B, 256, 0));
+      WWF_CUDA(launch((FeatKernel)feat_prep_kernel<0>, (unsigned)B, 256, 0, rev != nullptr));
       if (p->prof) WWF_CUDA(cudaEventRecord(pe[2], st));
-      WWF_CUDA(launch(p->frames, (unsigned)fgrid, (unsigned)(fw * 32), f_fixed + (size_t)fw * per_warp));
+      WWF_CUDA(launch(p->frames, (unsigned)fgrid, (unsigned)(fw * 32), f_fixed + (size_t)fw * per_warp, true));
       if (p->prof) WWF_CUDA(cudaEventRecord(pe[3], st));
       const long long eitems = (long long)B * ((T + fp.eb_frames - 1) / fp.eb_frames);
       int eocc = 1;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eocc, (const void*)p->epilogue_block, eb_threads, eb_smem);
       const long long egrid = std::min(eitems, (long long)p->sm_count * std::max(eocc, 1));
-      WWF_CUDA(launch(p->epilogue_block, (unsigned)egrid, (unsigned)eb_threads, eb_smem));
+      WWF_CUDA(launch(p->epilogue_block, (unsigned)egrid, (unsigned)eb_threads, eb_smem, true));
       g_launches += 3;
       WWF_CUDA(cudaGetLastError());
       if (p->prof) {
@@ -699,13 +705,19 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
       return WWF_OK;
     }
   }
-  if (p->prof) WWF_CUDA(cudaEventRecord(pe[2], st));
-  p->kernel<<<grid, nwarps * 32, smem, st>>>(fp);
+  {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(nwarps * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at{};
+    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &at; cfg.numAttrs = (rev != nullptr && !p->prof && !getenv("WWF_NO_PDL")) ? 1 : 0;   // behind conv_kernel only
+    WWF_CUDA(cudaLaunchKernelEx(&cfg, p->kernel, fp));
+  }
   g_launches++;
   WWF_CUDA(cudaGetLastError());
   if (p->prof) {
     WWF_CUDA(cudaEventRecord(pe[3], st));
-    WWF_CUDA(cudaEventRecord(pe[4], st));
     p->prof_events.insert(p->prof_events.end(), pe, pe + 5);
     p->prof_split.push_back(0);
   }
