@@ -155,7 +155,11 @@ size_t wwf_workspace_bytes(const wwf_plan* plan, int B, int N);
  *   aug         NULL = no augmentation (FeatureExtractor.__call__ only)
  *   out         dev [B][1][n_feat][T] (float32 or float16 per plan), clip stride out_stride
  *               elements (>= n_feat*T)
- *   workspace   dev, >= wwf_workspace_bytes(plan,B,N), 16-byte aligned (may be NULL if 0)
+ *   workspace   dev, >= wwf_workspace_bytes(plan,B,N), 16-byte aligned.  The reverb part is mandatory when
+ *               aug->rir_idx is used; the rest only enables the large-batch kernels (a smaller or NULL
+ *               workspace selects the single-kernel path, same results)
+ * Kernels: conv_kernel (reverb) -> feat_kernel, or for large batches feat_prep_kernel -> feat_frames_kernel ->
+ * feat_epilogue_block_kernel; all enqueued on `stream`, no allocation, no synchronisation (graph-capturable).
  * Replaces: WakewordDataset.__getitem__'s  AudioAugmentation(wave) -> FeatureExtractor(wave)
  *           -> SpecAugment(feat) chain (src/evaluation/evaluator.py:125,204;
  *           src/evaluation/inference.py:197), batched.
