@@ -157,7 +157,8 @@ size_t wwf_workspace_bytes(const wwf_plan* plan, int B, int N);
  *               elements (>= n_feat*T)
  *   workspace   dev, >= wwf_workspace_bytes(plan,B,N), 16-byte aligned.  The reverb part is mandatory when
  *               aug->rir_idx is used; the rest only enables the large-batch kernels (a smaller or NULL
- *               workspace selects the single-kernel path, same results)
+ *               workspace selects the single-kernel path; results are bit-identical between the two, except
+ *               that the energy of a dry (un-reverberated) clip that gets noise is summed in a different order)
  * Kernels: conv_kernel (reverb) -> feat_kernel, or for large batches feat_prep_kernel -> feat_frames_kernel ->
  * feat_epilogue_block_kernel; all enqueued on `stream`, no allocation, no synchronisation (graph-capturable).
  * Replaces: WakewordDataset.__getitem__'s  AudioAugmentation(wave) -> FeatureExtractor(wave)
