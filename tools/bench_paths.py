@@ -1,0 +1,37 @@
+"""Feature stage, fused kernel vs large-batch path (WWF_FEAT_PATH), for a few configurations and batch sizes."""
+import os
+import subprocess
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+CASES = [("mfcc", 40, 40, 400, 160, 24000), ("mfcc", 128, 40, 1024, 160, 40000), ("mel", 128, 40, 1024, 160, 24000),
+         ("mel", 64, 40, 512, 160, 32000), ("mfcc", 40, 13, 2048, 512, 24000)]
+
+if len(sys.argv) > 1 and sys.argv[1] == "child":
+    import torch
+    import wakeword_trainer_home_b200 as w
+    for (ft, M, C, nfft, hop, N) in CASES:
+        plan = w.FeaturePlan(16000, ft, M, C, nfft, hop, "cuda")
+        for B in (128, 256, 512, 1024, 2048):
+            x = (0.1 * torch.randn(B, N, generator=torch.Generator().manual_seed(0))).cuda()
+            out = plan.featurize(x)
+            for _ in range(3):
+                plan.featurize(x, out=out)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(20):
+                plan.featurize(x, out=out)
+            b.record()
+            torch.cuda.synchronize()
+            print(f"{ft} M={M} C={C} n_fft={nfft} hop={hop} N={N} B={B}: {a.elapsed_time(b) / 20 * 1e3:8.1f} us")
+else:
+    for path in ("fused", "split", "auto"):
+        env = dict(os.environ)
+        if path != "auto":
+            env["WWF_FEAT_PATH"] = path
+        else:
+            env.pop("WWF_FEAT_PATH", None)
+        print("==", path)
+        print(subprocess.run([sys.executable, __file__, "child"], env=env, capture_output=True, text=True).stdout)

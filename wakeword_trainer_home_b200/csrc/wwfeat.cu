@@ -484,7 +484,14 @@ static bool use_split(const wwf_plan* p, int B, int N) {
   }
   const int T = N / p->cfg.hop_length + 1;
   const long long groups = (long long)B * ((T + 2 * p->G - 1) / (2 * p->G));
-  return groups >= 6ll * 20 * p->sm_count;
+  // break-even measured with tools/bench_paths.py: n_fft 256 / 400 keep 3 fused CTAs per SM and need ~6 frame groups
+  // per resident warp before the flat queue wins; the larger FFTs run one fused CTA per SM and lose from ~2
+  // Log-mel has no DCT to amortise the tile's round trip: the flat queue only pays for the large FFTs (-4 % at
+  // n_fft 1024, +6 % at n_fft 512), so smaller ones stay on the fused kernel.
+  const bool mfcc = p->cfg.feature_type == WWF_FEAT_MFCC;
+  if (!mfcc && p->cfg.n_fft < 1024) return false;
+  const long long per_warp = !mfcc ? 4 : p->cfg.n_fft <= 400 ? 6 : 2;
+  return groups >= per_warp * 20 * p->sm_count;
 }
 static size_t split_ws_bytes(const wwf_plan* p, int B, int N) {
   if (!use_split(p, B, N)) return 0;
@@ -651,9 +658,9 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
     }
     // block epilogue: frames per block and threads per CTA chosen so that the 8-coefficient x 4-frame DCT tasks
     // fill the CTA's threads (T = 151, 40 coefficients: 2 blocks of 76 frames -> 95 tasks on 96 threads)
-    int eb_threads = 128;
-    fp.eb_frames = 64;
-    {
+    int eb_threads = 256;
+    fp.eb_frames = 64;                                          // log-mel: a plain clamp + mask + transpose, 64 frames per CTA
+    if (mfcc) {
       const int ncg = mfcc ? fp.c8 / 8 : 1;
       double best_eff = -1.0;
       for (int nblk = 1; nblk <= (T + 31) / 32; ++nblk) {
