@@ -933,3 +933,46 @@ def test_featurize_is_cuda_graph_capturable(ww):
         step()
         s.synchronize()
         assert torch.equal(out, replayed) and not torch.equal(out, eager)
+
+
+def test_fused_and_large_batch_feature_paths_agree(ww, monkeypatch):
+    """wwf_featurize has two launch shapes (one fused kernel per call; prep + flat frames + block epilogue for large
+    batches).  The library picks by batch size, so most small parity cases above exercise the fused
+    kernel: here both are forced on the same inputs - every n_fft family, log-mel and MFCC, float16 output, masks,
+    reverb + noise - and must agree BIT FOR BIT, which carries the oracle parity of one over to the other.
+    (Only a dry clip that gets noise may differ in the last ulp of its mix scale: its energy is summed by CTAs of
+    different width.)"""
+    noise, rirs = synth_banks(41, 4, 30000, 3, 4000)
+    gen = torch.Generator().manual_seed(41)
+    cases = [(256, 128, 40, 13, "mfcc", 9000, torch.float32), (400, 160, 40, 40, "mfcc", 24000, torch.float32),
+             (400, 160, 40, 40, "mel", 16000, torch.float16), (512, 160, 64, 32, "mfcc", 12345, torch.float16),
+             (1024, 160, 128, 40, "mel", 16000, torch.float32), (1024, 256, 80, 40, "mfcc", 20000, torch.float32),
+             (2048, 512, 128, 20, "mfcc", 30000, torch.float32), (1024, 200, 64, 64, "mfcc", 7000, torch.float32)]
+    for (n_fft, hop, M, C, ft, N, dt) in cases:
+        B = 7
+        T = N // hop + 1
+        F = C if ft == "mfcc" else M
+        x = (0.1 * torch.randn(B, N, generator=gen)).cuda()
+        x[1] = 0.0
+        plan = ww.FeaturePlan(16000, ft, M, C, n_fft, hop, "cuda", out_dtype=dt, n_freq_masks=2, n_time_masks=1)
+        plan.register_noise(noise); plan.register_rirs(rirs)
+        fs, fl = ww.draw_mask_params(gen, B, F, 15, 2)
+        ts, tl = ww.draw_mask_params(gen, B, T, 35, 1)
+        p = ww.AugParams(rir_idx=torch.tensor([0, 1, 2, 0, 1, 2, 0], dtype=torch.int32),          # all reverberated
+                         noise_idx=torch.tensor([0, -1, 2, 3, -1, 1, 0], dtype=torch.int32),
+                         noise_off=torch.randint(0, 30000, (B,), generator=gen), snr_db=5.0 + 15.0 * torch.rand(B, generator=gen),
+                         fmask_start=fs, fmask_len=fl, tmask_start=ts, tmask_len=tl)
+        outs = {}
+        for path in ("fused", "split"):
+            monkeypatch.setenv("WWF_FEAT_PATH", path)
+            outs[path] = (plan.featurize(x, p).clone(), plan.featurize(x).clone())
+        for a, b in zip(outs["fused"], outs["split"]):
+            assert torch.equal(a, b), (n_fft, hop, M, C, ft, N, dt)
+        # dry clips with noise: equal up to the summation order of the clip energy
+        p.rir_idx = torch.tensor([-1, 0, -1, 1, -1, 2, -1], dtype=torch.int32)
+        monkeypatch.setenv("WWF_FEAT_PATH", "fused")
+        a = plan.featurize(x, p).float()
+        monkeypatch.setenv("WWF_FEAT_PATH", "split")
+        b = plan.featurize(x, p).float()
+        assert (a - b).abs().max() <= (2e-3 if dt == torch.float16 else 2e-4), (n_fft, ft, float((a - b).abs().max()))
+    monkeypatch.delenv("WWF_FEAT_PATH")
