@@ -473,23 +473,26 @@ static size_t conv_ws_bytes(const wwf_plan* p, int B, int N) {
   conv_geometry(p, N, &hist, &valid, &nb);
   return ((size_t)B * (size_t)round_up4(N) + (size_t)round_up4((int64_t)B * nb)) * sizeof(float);
 }
-// The split path (flat frames kernel + block epilogue) pays off once the batch spans several rounds of the fused
-// kernel's CTA slots: measured break-even around 450 clips of 1.5 s (profiles/README.md).  WWF_FEAT_PATH=fused|split
-// forces one of them (tests run both).
+// Which launch shape?  Measured with tools/bench_paths.py and tools/bench_small.py (profiles/README.md):
+//  * few clips (at most one per two SMs): the fused kernel would put each clip on ONE CTA and leave the rest of the GPU
+//    idle - the flat queue spreads a clip's frame groups over every SM (1 clip, n_fft 1024, 2.5 s: 142 -> 37 us);
+//  * many clips: the flat queue wins once there are several frame groups per resident warp (no per-clip barriers, no
+//    clip-granular grid quantisation): from ~6 for n_fft 256 / 400, whose fused kernel keeps 3 CTAs per SM, from ~2
+//    for the larger FFTs, whose fused kernel fits one CTA per SM;
+//  * in between the fused kernel (one launch, no intermediate) is faster.  Log-mel has no DCT to amortise the tile's
+//    round trip: below n_fft 1024 it only takes the flat queue in the few-clips case.
+// WWF_FEAT_PATH=fused|split forces one of them (the GPU tests run both).
 static bool use_split(const wwf_plan* p, int B, int N) {
   if (p->cfg.cmvn) return false;                               // CMVN needs whole rows of a clip in one CTA
   if (const char* e = getenv("WWF_FEAT_PATH")) {
     if (!strcmp(e, "fused")) return false;
     if (!strcmp(e, "split")) return true;
   }
-  const int T = N / p->cfg.hop_length + 1;
-  const long long groups = (long long)B * ((T + 2 * p->G - 1) / (2 * p->G));
-  // break-even measured with tools/bench_paths.py: n_fft 256 / 400 keep 3 fused CTAs per SM and need ~6 frame groups
-  // per resident warp before the flat queue wins; the larger FFTs run one fused CTA per SM and lose from ~2
-  // Log-mel has no DCT to amortise the tile's round trip: the flat queue only pays for the large FFTs (-4 % at
-  // n_fft 1024, +6 % at n_fft 512), so smaller ones stay on the fused kernel.
+  if (2 * B <= p->sm_count) return true;
   const bool mfcc = p->cfg.feature_type == WWF_FEAT_MFCC;
   if (!mfcc && p->cfg.n_fft < 1024) return false;
+  const int T = N / p->cfg.hop_length + 1;
+  const long long groups = (long long)B * ((T + 2 * p->G - 1) / (2 * p->G));
   const long long per_warp = !mfcc ? 4 : p->cfg.n_fft <= 400 ? 6 : 2;
   return groups >= per_warp * 20 * p->sm_count;
 }
