@@ -976,3 +976,24 @@ def test_fused_and_large_batch_feature_paths_agree(ww, monkeypatch):
         b = plan.featurize(x, p).float()
         assert (a - b).abs().max() <= (2e-3 if dt == torch.float16 else 2e-4), (n_fft, ft, float((a - b).abs().max()))
     monkeypatch.delenv("WWF_FEAT_PATH")
+
+
+def test_long_clips_run_on_the_flat_path(ww):
+    """Clips whose [n_mels][T] tile does not fit in shared memory (128 mels: beyond ~4 s) used to be refused; the flat
+    path has no per-clip tile, so they are featurized and match the oracle.  CMVN plans (which need whole rows of a
+    clip in one CTA) still refuse loudly."""
+    from oracle import ta_oracle as tao
+    gen = torch.Generator().manual_seed(77)
+    for (N, n_fft, hop, M, C, ft) in ((160000, 1024, 160, 128, 40, "mfcc"), (100000, 400, 160, 128, 40, "mel"), (480000, 512, 256, 64, 20, "mfcc")):
+        B = 3
+        x = 0.1 * torch.randn(B, N, generator=gen)
+        x[1, N // 3:] = 0.0
+        plan = ww.FeaturePlan(16000, ft, M, C, n_fft, hop, "cuda")
+        got = plan.featurize(x.cuda()).cpu().numpy()
+        ref = tao.featurize(x.double(), sample_rate=16000, feature_type=ft, n_mels=M, n_mfcc=C, n_fft=n_fft, hop_length=hop,
+                            dtype=torch.float64).numpy()
+        assert got.shape == ref.shape
+        assert_features_close(got, ref, f"long clip N={N} n_fft={n_fft} {ft}")
+    with pytest.raises(ww.WwfError) as ei:
+        ww.FeaturePlan(16000, "mfcc", 128, 40, 1024, 160, "cuda", cmvn=True).featurize(torch.zeros(1, 160000).cuda())
+    assert ei.value.code == -2 and "shared-memory tile" in str(ei.value)

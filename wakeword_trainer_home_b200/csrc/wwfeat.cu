@@ -473,6 +473,22 @@ static size_t conv_ws_bytes(const wwf_plan* p, int B, int N) {
   conv_geometry(p, N, &hist, &valid, &nb);
   return ((size_t)B * (size_t)round_up4(N) + (size_t)round_up4((int64_t)B * nb)) * sizeof(float);
 }
+// Does the fused kernel's shared-memory layout (the clip's [n_mels][T] tile + tables + one warp's FFT scratch) fit?
+static size_t fused_fixed_bytes(const wwf_plan* p, int N) {
+  auto al4 = [](long long v) { return (v + 3) & ~3ll; };
+  const bool mfcc = p->cfg.feature_type == WWF_FEAT_MFCC;
+  const int T = N / p->cfg.hop_length + 1, M = p->cfg.n_mels, F = p->n_feat, pitch = T | 1;
+  const int c8 = mfcc ? ((F + 7) & ~7) : 0;
+  long long o = al4((long long)M * pitch);
+  o += (mfcc && p->cfg.cmvn) ? al4((long long)F * pitch) : 0;
+  o += al4(p->cfg.n_fft) + al4(2 * p->tw_total) + al4(p->n_melw) + (mfcc ? (long long)M * c8 : 0) + al4(M) + al4(M + 1) +
+       al4((F + 3) / 4) + al4((T + 3) / 4);
+  return (size_t)o * sizeof(float);
+}
+static bool fused_fits(const wwf_plan* p, int N) {
+  return fused_fixed_bytes(p, N) + (size_t)p->G * p->zlen * sizeof(float2) <= (size_t)p->max_smem - 1024;
+}
+
 // Which launch shape?  Measured with tools/bench_paths.py and tools/bench_small.py (profiles/README.md):
 //  * few clips (at most one per two SMs): the fused kernel would put each clip on ONE CTA and leave the rest of the GPU
 //    idle - the flat queue spreads a clip's frame groups over every SM (1 clip, n_fft 1024, 2.5 s: 142 -> 37 us);
@@ -488,6 +504,7 @@ static bool use_split(const wwf_plan* p, int B, int N) {
     if (!strcmp(e, "fused")) return false;
     if (!strcmp(e, "split")) return true;
   }
+  if (!fused_fits(p, N)) return true;                          // long clips: only the flat path has no per-clip tile
   if (2 * B <= p->sm_count) return true;
   const bool mfcc = p->cfg.feature_type == WWF_FEAT_MFCC;
   if (!mfcc && p->cfg.n_fft < 1024) return false;
@@ -594,8 +611,7 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
   const size_t fixed_bytes = (size_t)o * sizeof(float);
   const size_t per_warp = (size_t)p->G * p->zlen * sizeof(float2);
   const size_t budget = (size_t)p->max_smem - 1024;   // static smem of the kernel is 256 B
-  if (fixed_bytes + per_warp > budget)
-    return fail(WWF_ERR_UNSUPPORTED, "clip too long for the in-shared-memory tile: %zu bytes of tiles/tables (N=%d, T=%d, n_mels=%d)", fixed_bytes, N, T, M);
+  const bool fused_ok = fixed_bytes + per_warp <= budget;     // else: only the flat path (no per-clip tile) can run
   // CTA shape: the candidate (warps per CTA) that keeps the most warps resident per SM
   int nwarps = 0, ctas_per_sm = 1, best = -1;
   const int cands[] = {16, 12, 11, 10, 8, 6, 4, 2, 1};
@@ -612,7 +628,7 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
     const int score = nb_eff * c + (nb_eff >= 3 ? 3 : 0);
     if (score > best) { best = score; nwarps = c; ctas_per_sm = nb; }
   }
-  if (nwarps == 0) return fail(WWF_ERR_CUDA, "feat_kernel does not fit on this device (%zu + %zu bytes of shared memory)", fixed_bytes, per_warp);
+  if (nwarps == 0 && fused_ok) return fail(WWF_ERR_CUDA, "feat_kernel does not fit on this device (%zu + %zu bytes of shared memory)", fixed_bytes, per_warp);
   const size_t smem = fixed_bytes + (size_t)nwarps * per_warp;
   int grid = p->sm_count * ctas_per_sm;
   if (grid > B) grid = B;
@@ -715,6 +731,10 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
       return WWF_OK;
     }
   }
+  if (!fused_ok)
+    return fail(WWF_ERR_UNSUPPORTED, "clip too long for the in-shared-memory tile of the single-kernel path: %zu bytes of tiles/tables "
+                "(N=%d, T=%d, n_mels=%d)%s", fixed_bytes, N, T, M,
+                p->cfg.cmvn ? "; CMVN plans have no other path" : "; pass a workspace of wwf_workspace_bytes() to use the flat path");
   {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(nwarps * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
