@@ -110,6 +110,10 @@ __device__ __forceinline__ int float_key(float f) {
   return i >= 0 ? i : i ^ 0x7fffffff;
 }
 __device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+// Identity of the running maximum when it is initialised by a byte-wise memset (no noise: feat_prep_kernel is
+// skipped): 0x80808080 orders below the key of every float except -inf / NaN payloads and reads back as -inf.
+constexpr int kMaxKeyMemset = (int)0x80808080;
+__device__ __forceinline__ float clip_max_value(int k) { return k == kMaxKeyMemset ? -INFINITY : key_float(k); }
 
 // ---- small device utilities --------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
@@ -876,7 +880,7 @@ __global__ void __launch_bounds__(256) feat_epilogue_block_kernel(const FeatPara
       (is_row ? s_rowmask : s_colmask)[is_row ? i : i - F] = mk ? 1 : 0;
     }
     float cutoff = -INFINITY;
-    if (p.top_db >= 0.f) cutoff = key_float(p.clip_max[b]) - p.top_db;
+    if (p.top_db >= 0.f) cutoff = clip_max_value(p.clip_max[b]) - p.top_db;
     // the block's rows of the frame-major tile are one contiguous span: coalesced 16-byte loads, transposed into smem
     const float4* tg = reinterpret_cast<const float4*>(p.tile_g + ((size_t)b * T + t0) * mp);
     for (int i = tid; i < nf * mq; i += blockDim.x) {

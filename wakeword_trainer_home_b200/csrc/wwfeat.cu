@@ -712,16 +712,19 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
         cfg.attrs = &at; cfg.numAttrs = (pdl && behind_ours) ? 1 : 0;
         return cudaLaunchKernelEx(&cfg, k, fp);
       };
-      WWF_CUDA(launch((FeatKernel)feat_prep_kernel<0>, (unsigned)B, 256, 0, rev != nullptr));
+      // without noise there is no mix scale to prepare: the clip maxima are initialised by a memset instead
+      const bool need_prep = fp.noise_idx != nullptr;
+      if (need_prep) WWF_CUDA(launch((FeatKernel)feat_prep_kernel<0>, (unsigned)B, 256, 0, rev != nullptr));
+      else WWF_CUDA(cudaMemsetAsync(fp.clip_max, 0x80, (size_t)B * sizeof(int), st));
       if (p->prof) WWF_CUDA(cudaEventRecord(pe[2], st));
-      WWF_CUDA(launch(p->frames, (unsigned)fgrid, (unsigned)(fw * 32), f_fixed + (size_t)fw * per_warp, true));
+      WWF_CUDA(launch(p->frames, (unsigned)fgrid, (unsigned)(fw * 32), f_fixed + (size_t)fw * per_warp, need_prep));
       if (p->prof) WWF_CUDA(cudaEventRecord(pe[3], st));
       const long long eitems = (long long)B * ((T + fp.eb_frames - 1) / fp.eb_frames);
       int eocc = 1;
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eocc, (const void*)p->epilogue_block, eb_threads, eb_smem);
       const long long egrid = std::min(eitems, (long long)p->sm_count * std::max(eocc, 1));
       WWF_CUDA(launch(p->epilogue_block, (unsigned)egrid, (unsigned)eb_threads, eb_smem, true));
-      g_launches += 3;
+      g_launches += need_prep ? 3 : 2;
       WWF_CUDA(cudaGetLastError());
       if (p->prof) {
         WWF_CUDA(cudaEventRecord(pe[4], st));
