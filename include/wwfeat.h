@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define WWF_VERSION 120 /* 0.1.2: time-stretch / pitch-shift / resample; large-batch feature path */
+#define WWF_VERSION 130 /* 0.1.3: tensor-core DCT epilogue, mel lane schedule, launch cache, wwf_plan_set_option */
 
 typedef enum wwf_status {
   WWF_OK = 0,
@@ -45,6 +45,8 @@ enum { WWF_FEAT_LOGMEL = 0, WWF_FEAT_MFCC = 1 };
 enum { WWF_OUT_F32 = 0, WWF_OUT_F16 = 1 };
 enum { WWF_BANK_NOISE = 0, WWF_BANK_RIR = 1 };
 enum { WWF_BANK_F32 = 0, WWF_BANK_I16 = 1 }; /* element type of a device-resident clip bank */
+enum { WWF_OPT_FEAT_PATH = 0, WWF_OPT_PDL = 1 };              /* wwf_plan_set_option */
+enum { WWF_PATH_AUTO = 0, WWF_PATH_FUSED = 1, WWF_PATH_FLAT = 2 };
 
 /*
  * Feature configuration = the reference's FeatureExtractor constructor arguments
@@ -295,10 +297,21 @@ int wwf_check_finite(wwf_plan* plan, void* stream, int* nonfinite);
  */
 int wwf_profile_enable(wwf_plan* plan, int enable);
 int wwf_profile_read(wwf_plan* plan, double* conv_ms, double* feat_ms, int* n_calls);
-/* Same per kernel: kernel_ms[4] = { reverb kernel, feat_prep_kernel, feat_frames_kernel (large-batch path) or the
- * fused feat_kernel (single-kernel path), feat_epilogue_block_kernel }; n_split = calls that took the large-batch
- * path (may be NULL).  wwf_profile_read's feat_ms is the sum of the last three. */
+/* Same per kernel: kernel_ms[4] = { reverb kernel, feat_prep_kernel (per-clip mix records; only when noise is mixed),
+ * feat_frames_kernel (flat path) or the fused feat_kernel (single-kernel path), the flat path's epilogue
+ * (feat_epilogue_mma_kernel / feat_epilogue_block_kernel) }; n_split = calls that took the flat path (may be NULL).
+ * wwf_profile_read's feat_ms is the sum of the last three. */
 int wwf_profile_read_kernels(wwf_plan* plan, double* kernel_ms, int* n_calls, int* n_split);
+
+/*
+ * Launch options of a plan.  WWF_OPT_FEAT_PATH: WWF_PATH_AUTO (default: the library picks per batch shape),
+ * WWF_PATH_FUSED (one kernel per call) or WWF_PATH_FLAT (flat frame queue + epilogue; needs the workspace);
+ * WWF_OPT_PDL: 1 (default) chains the kernels of a call with programmatic dependent launch, 0 = plain launches.
+ * The same two can be preset through the environment (WWF_FEAT_PATH=fused|split, WWF_NO_PDL), which is read
+ * once, at wwf_plan_create.  Changing an option drops the plan's cached launch shapes; call it between, not
+ * concurrently with, wwf_featurize calls.  No reference counterpart: test / measurement control only.
+ */
+int wwf_plan_set_option(wwf_plan* plan, int option, int value);
 
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 int64_t wwf_launch_count(void);

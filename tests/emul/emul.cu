@@ -6,7 +6,9 @@
 // - one "thread" after the other, one pass after the other - and compared with numpy by
 // tests/test_emul_fft.py.  Nothing in the product loads this library.
 #include <cstdint>
+#include <algorithm>
 #include <cstring>
+#include <functional>
 #include <vector>
 #include "../../wakeword_trainer_home_b200/csrc/wwf_feat.cuh"
 #include "../../wakeword_trainer_home_b200/csrc/wwf_conv.cuh"
@@ -228,6 +230,73 @@ int emul_pv_roundtrip(const float* fa, const float* fb, float* spa, float* spb, 
     for (int u = 0; u < kPvN / R; ++u) pass_task<R, true, PvMap>(z.data(), L, u, [&](int q) { return t[q]; });
   });
   for (int j = 0; j < kPvN; ++j) { ya[j] = z[zmap(j)].x * (1.0f / kPvN); yb[j] = z[zmap(j)].y * (1.0f / kPvN); }
+  return 0;
+}
+
+// Mel lane schedule (build_mel_schedule, wwf_tables.h) evaluated exactly like step 4 of frame_group_to_db: rounds of 32
+// lanes, two-tap iterations, partner halves joined by lane ^ 1.  fb = dense [n_freqs][n_mels] filterbank, power =
+// [n_freqs]; out_mel = [n_mels].  stats[0] = rounds, [1] = two-tap iterations, [2] = worst number of distinct bank
+// residues collisions in a half-warp's first load (1 = conflict-free), [3] = number of split filters.
+// Returns 0, or a negative code when the schedule is malformed (a filter without exactly one owner, ...).
+int emul_mel_schedule(int n_fft, int n_freqs, int n_mels, const float* fb, const float* power, float* out_mel, int* stats) {
+  std::vector<int> lo(n_mels), ofs(n_mels + 1);
+  std::vector<float> w;
+  for (int m = 0; m < n_mels; ++m) {
+    int first = -1, last = -1;
+    for (int k = 0; k < n_freqs; ++k)
+      if (fb[(size_t)k * n_mels + m] != 0.f) { if (first < 0) first = k; last = k; }
+    ofs[m] = (int)w.size();
+    lo[m] = first < 0 ? 0 : first;
+    if (first >= 0) for (int k = first; k <= last; ++k) w.push_back(fb[(size_t)k * n_mels + m]);
+  }
+  ofs[n_mels] = (int)w.size();
+  if (w.empty()) w.push_back(0.f);
+  std::function<int(int)> zmap;
+  if (n_fft == 400) zmap = [](int i) { return IdentityMap()(i); };
+  else zmap = [](int i) { return PadMap2()(i); };
+  const MelSchedule s = build_mel_schedule(lo, ofs, w, zmap);
+  std::vector<int> owners(n_mels, 0);
+  int worst = 1, nsplit = 0;
+  for (int r = 0; r < s.rounds; ++r) {
+    float acc[32];
+    for (int lane = 0; lane < 32; ++lane) {
+      const int2 t = s.tasks[(size_t)r * 32 + lane];
+      const int k0 = t.x & 0xffff, n = (int)((unsigned)t.x >> 16);
+      const float* wr = s.w.data() + (size_t)(t.y & 0xffff) * 32 + lane;
+      float a0 = 0.f, a1 = 0.f;
+      int i = 0;
+      for (; i + 1 < n; i += 2) { a0 = fmaf(power[k0 + i], wr[32 * i], a0); a1 = fmaf(power[k0 + i + 1], wr[32 * i + 32], a1); }
+      if (i < n) a0 = fmaf(power[k0 + i], wr[32 * i], a0);
+      acc[lane] = a0 + a1;
+      if (n > 0 && k0 + n > n_freqs) return -1;
+    }
+    for (int h = 0; h < 2; ++h) {
+      int cnt[16] = {};
+      for (int l = 0; l < 16; ++l) {
+        const int2 t = s.tasks[(size_t)r * 32 + 16 * h + l];
+        if (((unsigned)t.x >> 16) > 0) worst = std::max(worst, ++cnt[zmap(t.x & 0xffff) & 15]);
+      }
+    }
+    for (int lane = 0; lane < 32; ++lane) {
+      const int2 t = s.tasks[(size_t)r * 32 + lane];
+      const unsigned flags = (unsigned)t.y >> 24;
+      float v = acc[lane];
+      if (flags & kMelPartner) {
+        const int2 o = s.tasks[(size_t)r * 32 + (lane ^ 1)];
+        if (((o.y >> 16) & 0xff) != ((t.y >> 16) & 0xff) || (((unsigned)o.y >> 24) & kMelOwner)) return -2;
+        v += acc[lane ^ 1];
+        ++nsplit;
+      }
+      if (flags & kMelOwner) {
+        const int m = (t.y >> 16) & 0xff;
+        if (m >= n_mels) return -3;
+        owners[m]++;
+        out_mel[m] = v;
+      }
+    }
+  }
+  for (int m = 0; m < n_mels; ++m) if (owners[m] != 1) return -4;
+  stats[0] = s.rounds; stats[1] = s.iterations; stats[2] = worst; stats[3] = nsplit;
   return 0;
 }
 

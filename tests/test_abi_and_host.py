@@ -36,7 +36,7 @@ def test_library_exports_every_declared_symbol(native):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/wwfeat.h but not exported"
     assert set(names) == set(native.SYMBOLS), "ctypes binding and header disagree"
-    assert native.load().wwf_version() == 120
+    assert native.load().wwf_version() == 130
 
 
 def test_library_is_sm100a_native_code(native):

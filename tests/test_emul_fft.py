@@ -98,3 +98,27 @@ def test_phase_vocoder_analysis_synthesis_pair(emul):
         ref = np.fft.rfft(f.astype(np.float64))
         assert np.abs((sp[0::2] + 1j * sp[1::2]) - ref).max() <= 5e-7 * np.abs(ref).max()
     assert np.abs(ya - fa).max() <= 2e-6 and np.abs(yb - fb).max() <= 2e-6
+
+
+@pytest.mark.parametrize("n_fft,n_mels", [(400, 40), (400, 128), (256, 40), (512, 64), (1024, 128), (1024, 80), (2048, 128), (400, 13), (2048, 32)])
+def test_mel_lane_schedule_equals_dense_filterbank(emul, n_fft, n_mels):
+    """The lane schedule of the sparse mel projection (wwf_tables.h: filters cut in halves, sorted into rounds of 32
+    lanes, weights interleaved) visits every non-zero of torchaudio's filterbank exactly once: evaluated on the CPU in
+    the kernel's order it equals the dense matmul, every filter has one owner lane, split halves sit on adjacent lanes."""
+    import torchaudio.functional as AF
+    K = n_fft // 2 + 1
+    fb = AF.melscale_fbanks(K, 0.0, 8000.0, n_mels, 16000).numpy().astype(np.float32)
+    rng = np.random.default_rng(n_fft + n_mels)
+    power = (rng.standard_normal(K) ** 2).astype(np.float32)
+    out = np.zeros(n_mels, np.float32)
+    stats = (ctypes.c_int * 4)()
+    rc = emul.emul_mel_schedule(n_fft, K, n_mels, P(np.ascontiguousarray(fb)), P(power), P(out), stats)
+    assert rc == 0
+    ref = power.astype(np.float64) @ fb.astype(np.float64)
+    assert np.abs(out - ref).max() <= 2e-6 * max(1.0, np.abs(ref).max())
+    rounds, iters, worst, nsplit = list(stats)
+    naive = sum(-(-max((int(np.count_nonzero(fb[:, m])) and (np.nonzero(fb[:, m])[0][-1] - np.nonzero(fb[:, m])[0][0] + 1))
+                       for m in range(r, min(r + 32, n_mels))) // 2) for r in range(0, n_mels, 32))
+    assert iters <= naive, (iters, naive)
+    print(f"n_fft {n_fft} n_mels {n_mels}: rounds {rounds}, two-tap iterations {iters} (filter-per-lane order: {naive}), "
+          f"worst half-warp residue multiplicity {worst}, split filters {nsplit}")

@@ -14,9 +14,13 @@ from .loader import DeviceBatchLoader, GpuBatchLoader, StreamedFeaturizer  # noq
 from .sharding import shard_range, shard_seed  # noqa: F401
 from .audio_utils import AudioProcessor, read_wav  # noqa: F401
 from .formats import NpyFeatureLoader, load_npy, load_split_manifest, precompute_features, save_split_manifest  # noqa: F401
+from .dataset import WakewordDataset, load_dataset_splits  # noqa: F401
+from . import config_adapter  # noqa: F401
+from .config_adapter import draw_config_from, plan_from_config  # noqa: F401
 
-__version__ = "0.1.0"
+__version__ = "0.2.0"
 __all__ = ["FeatureExtractor", "AudioAugmentation", "SpecAugment", "FeaturePlan", "AugParams",
            "draw_mask_params", "spec_augment_", "peak_normalize", "WwfError", "launch_count", "GpuBatchLoader", "DeviceBatchLoader", "StreamedFeaturizer", "DrawConfig", "gather_clips",
            "shard_range", "shard_seed", "AudioProcessor", "read_wav", "NpyFeatureLoader", "load_npy", "load_split_manifest",
-           "precompute_features", "save_split_manifest"]
+           "precompute_features", "save_split_manifest", "WakewordDataset", "load_dataset_splits", "config_adapter",
+           "plan_from_config", "draw_config_from"]

@@ -134,8 +134,12 @@ class AudioProcessor:
             x = batch.to(self.device)
             if rate != self.target_sr:
                 x = self.plan.resample(x, rate, self.target_sr)
+            if self.normalize:
+                # like process_waveform: the peak is taken over the WHOLE file, before the trim to target_duration
+                # (rows are zero-padded to the longest file of the group, which does not move a peak)
+                x = peak_normalize(x.contiguous())
             n = min(x.shape[1], self.target_samples)
             for r, (i, w) in enumerate(items):
                 keep = min(n, -(-w.numel() * self.target_sr // rate))      # ceil(new * len / orig): this file's own length
                 out[i, :keep] = x[r, :keep]
-        return peak_normalize(out, out=out) if self.normalize else out
+        return out

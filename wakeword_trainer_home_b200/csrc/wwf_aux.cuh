@@ -13,7 +13,7 @@ struct MixParams {
   NoiseBankDev noise;
   const float* es_part; int es_nb;
   float* out; int64_t out_stride;
-  int B, N;
+  int B, N, n_rir;
 };
 
 // One CTA per clip: y = src + scale * noise, scale from the two clip energies
@@ -21,7 +21,7 @@ struct MixParams {
 __global__ void __launch_bounds__(512) mix_kernel(const MixParams p) {
   __shared__ float red[64];
   const int b = blockIdx.x;
-  const bool has_rev = p.rev != nullptr && p.rir_idx != nullptr && __ldg(p.rir_idx + b) >= 0;
+  const bool has_rev = clip_has_rev(p.rev, p.rir_idx, p.n_rir, b);
   const float* x = has_rev ? p.rev + (size_t)b * p.rev_stride : p.wav + (size_t)b * p.wav_stride;
   float* y = p.out + (size_t)b * p.out_stride;
   const ClipNoise cn = resolve_noise(p.noise, p.noise_idx, p.noise_off, b);

@@ -23,6 +23,7 @@
 #pragma once
 #include <stdint.h>
 #include "wwf_fft.cuh"
+#include "wwf_mix.cuh"
 
 namespace wwf {
 
@@ -270,6 +271,10 @@ __device__ __forceinline__ void conv_fused_middle(float2* zc, const float4* __re
 }
 
 // Persistent: grid = min(#SMs, work items); work item = (clip b, overlap-save block blk).
+// (The flat feature path's per-clip mix records were produced here for a while - at the end of each item, then warp-
+// parallel at the end of the kernel, then with the noise side resolved up front: every variant made THIS kernel
+// 10-12 us slower per 1024 clips, the hot loop is at the 128-register limit and does not take passengers.  They come
+// from feat_prep_kernel, whose noise side runs in the shadow of this kernel's tail.)
 __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams p) {
   extern __shared__ __align__(16) float2 zc[];
   __shared__ float red[kConvThreads / 32];
@@ -280,7 +285,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams 
   for (int item = blockIdx.x; item < p.B * nblk; item += gridDim.x) {
     const int b = item / nblk, blk = item - b * nblk;
     const int r = __ldg(p.rir_idx + b);
-    if (r < 0 || r >= p.n_rir) continue;                     // dry clip (CTA-uniform)
+    if (!rir_in_range(r, p.n_rir)) continue;                 // dry clip (CTA-uniform)
     const float* x = p.wav + (size_t)b * p.wav_stride;
     const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
     __syncthreads();                                          // previous item's stores / table copy done

@@ -23,6 +23,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include "wwf_fft.cuh"
+#include "wwf_mix.cuh"
 
 namespace wwf {
 
@@ -43,26 +44,6 @@ template <int NFFT> constexpr int stft_zlen() {
   return (typename StftPlan<NFFT>::Map()(NFFT - 1) + 2) & ~1;
 }
 
-constexpr int kNoiseBlk = 128;   // granularity of the noise bank's squared-sample prefix sums
-
-// Registered background-noise bank (device view).  sq_prefix holds, per clip, the running sum
-// (double) of squared samples at every kNoiseBlk boundary: P[j] = sum_{q < j*128} n[q]^2, with a
-// final entry for the whole clip, so the energy of ANY segment costs two table reads plus at
-// most 2*127 edge samples instead of a pass over the segment.
-struct NoiseBankDev {
-  const float* data;              // all clips back to back (borrowed from the caller)
-  const int64_t* offsets;         // [count+1] sample offsets
-  const double* sq_prefix;        // concatenated per-clip prefix tables
-  const int64_t* prefix_offsets;  // [count] start of clip i's table
-  int count;
-};
-
-struct ClipNoise {
-  const float* nz;     // nullptr = this clip has no noise
-  const double* P;
-  int len, off;
-};
-
 struct FeatParams {
   // inputs
   const float* wav;        int64_t wav_stride;   // original clips [B][N]
@@ -74,58 +55,50 @@ struct FeatParams {
   int tile_pitch;                                // odd row pitch of the shared tile (>= T)
   // dynamic shared-memory layout, offsets in floats from the start (each a multiple of 4):
   //   tile [n_mels][pitch] | res [n_feat][pitch] (mfcc && cmvn only) | window [NFFT] | tw float2[tw_total]
-  //   | mel_w | dct [n_mels][c8] | mel_lo int[n_mels] | mel_ofs int[n_mels+1] | rowmask u8[n_feat]
-  //   | colmask u8[T] | z float2 [nwarps][G][NFFT]
-  int off_res, off_window, off_tw, off_melw, off_dct, off_mello, off_melofs, off_rowmask, off_colmask, off_z;
-  int n_melw, c8;                                // mel weight count; n_mfcc rounded up to 8
+  //   | mel_w (lane-interleaved) | dct [n_mels][c8] | mel tasks int2[mel_rounds*32] | rowmask u8[n_feat]
+  //   | colmask u8[T] | z float2 [nwarps][G][ZL]
+  int off_res, off_window, off_tw, off_melw, off_dct, off_meltasks, off_rowmask, off_colmask, off_z;
+  int n_melw, mel_rounds, c8;                    // interleaved mel weight count, schedule rounds; n_mfcc rounded up to 8
   // device constants (plan-owned)
   const float* window;                           // [NFFT]
   const float2* tw;                              // concatenated per-pass twiddle tables
-  const int* mel_lo;                             // [n_mels] first FFT bin of each filter
-  const int* mel_ofs;                            // [n_mels+1] CSR offsets into mel_w
-  const float* mel_w;                            // filter weights, bin-contiguous per filter
+  const int2* mel_tasks;                         // [mel_rounds*32] lane schedule of the sparse mel rows (wwf_tables.h)
+  const float* mel_w;                            // filter weights, interleaved per round: [(base + tap) * 32 + lane]
   const float* dct;                              // [n_mels][n_mfcc]
+  const uint4* dct_frag;                         // the same matrix as split-TF32 mma.sync B fragments (build_dct_fragments)
+  const float* dct_colsum;                       // [c8] column sums of dct (float of the double sum), 0 beyond n_mfcc
   // augmentation draws (device, nullable)
-  const int32_t* rir_idx; const int32_t* noise_idx; const int64_t* noise_off; const float* snr_db;
+  const int32_t* rir_idx; int n_rir;             // a clip is reverberated iff rir_in_range(rir_idx[b], n_rir)
+  const int32_t* noise_idx; const int64_t* noise_off; const float* snr_db;
   NoiseBankDev noise;
   const float* es_part; int es_nb;               // per-clip energy partials written by conv_kernel [B][es_nb]
   const int32_t* fs; const int32_t* fl; const int32_t* ts; const int32_t* tl; int nF, nT;
   // output
   void* out; int64_t out_stride;
   int* nonfinite_flag;                           // plan-owned device int, set to 1 if any feature is NaN/Inf
-  // ---- split path (large batches, see feat_frames_kernel): per-clip intermediates in the caller's workspace ----
-  float* tile_g;                                 // dB values [B][T][mp], frame-major
+  // ---- flat path (few clips / large batches, see feat_frames_kernel): per-clip intermediates in the caller's workspace ----
+  float* tile_g;                                 // dB values [B][T][mp], frame-major (= one flat matrix of B*T rows)
   int mp;                                        // n_mels rounded up to 4
   int* clip_max;                                 // [B] running maximum of the clip's dB values (ordered-int key)
-  float* scale_g;                                // [B] noise-mix scale (0 = no noise)
+  ClipMix* mix_g;                                // [B] noise-mix records (nullptr: no noise in this call)
   int ngroups;                                   // frame groups per clip
-  // feat_frames_kernel shared memory: window [NFFT] | tw | mel_w | mel_lo | mel_ofs | z float2 [nwarps][G][ZL]
-  int f_off_tw, f_off_melw, f_off_mello, f_off_melofs, f_off_z;
+  // feat_frames_kernel shared memory: window [NFFT] | tw | mel_w | mel tasks | z float2 [nwarps][G][ZL]
+  int f_off_tw, f_off_melw, f_off_meltasks, f_off_z;
   int eb_frames, eb_pitch;                       // feat_epilogue_block_kernel: frames per block, odd smem row pitch
+  int em_k8, em_ap;                              // feat_epilogue_mma_kernel: n_mels rounded up to 8, smem pitch of A
 };
 
-// float <-> int key whose signed order equals the float order (for atomicMax on the clip maximum)
+// float <-> int key whose signed order equals the float order (for atomicMax on the clip maximum); every NaN maps to
+// the largest key, so a NaN dB value makes the clip maximum NaN (torch.amax semantics)
 __device__ __forceinline__ int float_key(float f) {
   const int i = __float_as_int(f);
-  return i >= 0 ? i : i ^ 0x7fffffff;
+  return f != f ? 0x7fffffff : i >= 0 ? i : i ^ 0x7fffffff;
 }
 __device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
-// Identity of the running maximum when it is initialised by a byte-wise memset (no noise: feat_prep_kernel is
-// skipped): 0x80808080 orders below the key of every float except -inf / NaN payloads and reads back as -inf.
+// Identity of the running maximum: the maxima are initialised by a byte-wise memset; 0x80808080 orders below the key
+// of every float except -inf / NaN payloads and reads back as -inf.
 constexpr int kMaxKeyMemset = (int)0x80808080;
 __device__ __forceinline__ float clip_max_value(int k) { return k == kMaxKeyMemset ? -INFINITY : key_float(k); }
-
-// ---- small device utilities --------------------------------------------------------------
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
 
 // torch reflect padding index (edge sample not repeated): i in [-N+1, 2N-2] -> [0, N)
 WWF_HD int reflect_index(int i, int N) {
@@ -142,16 +115,6 @@ WWF_HD float2 pair_split_power(float2 a, float2 c) {
   return make_float2(0.25f * fmaf(s.x, s.x, s.y * s.y), 0.25f * fmaf(d.x, d.x, d.y * d.y));
 }
 
-// noise sample for clip position i: bank[(off + i) mod len]
-__device__ __forceinline__ float noise_at(const float* nz, int noff, int nlen, int i) {
-  int q = noff + i;
-  if (q >= nlen) {
-    q -= nlen;
-    if (q >= nlen) q %= nlen;
-  }
-  return __ldg(nz + q);
-}
-
 // 10*log10(max(x, 1e-10)) = (10/log2(10)) * log2(.) through MUFU.LG2 (lg2.approx: max abs error
 // 2^-22.6 on log2 => < 5e-7 dB; the argument is >= 1e-10, never denormal).
 __device__ __forceinline__ float power_to_db(float x) {
@@ -159,121 +122,248 @@ __device__ __forceinline__ float power_to_db(float x) {
   return x <= 1e-10f ? -100.0f : 3.01029995663981195f * __log2f(x);
 }
 
-// scale of F.add_noise (TA/functional/functional.py:2376-2378), float32 like the oracle
-__device__ __forceinline__ float snr_scale(float es, float en, float snr_db) {
-  const float snr0 = 10.0f * (log10f(es) - log10f(en));
-  return exp10f((snr0 - snr_db) / 20.0f);
+// max that PROPAGATES NaN like torch.max / torch.amax (fmaxf returns the other operand): one FMNMX.NAN.
+// A clip with a NaN sample gets a NaN maximum, hence a NaN top_db floor, hence NaN features - exactly what
+// AmplitudeToDB does (TA/functional/functional.py:393-402) - and the non-finite flag is raised.
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 800)
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+  return r;
+#else
+  return (a != a || b != b) ? NAN : fmaxf(a, b);
+#endif
 }
-
-// Noise clip, wrapped start offset and prefix table of batch item b (nz == nullptr: no noise).
-__device__ __forceinline__ ClipNoise resolve_noise(const NoiseBankDev& bank, const int32_t* noise_idx,
-                                                   const int64_t* noise_off, int b) {
-  ClipNoise c{nullptr, nullptr, 1, 0};
-  if (noise_idx == nullptr || bank.data == nullptr) return c;
-  const int ni = __ldg(noise_idx + b);
-  if (ni < 0 || ni >= bank.count) return c;
-  const int64_t o0 = __ldg(bank.offsets + ni), o1 = __ldg(bank.offsets + ni + 1);
-  c.len = (int)(o1 - o0);
-  c.nz = bank.data + o0;
-  c.P = bank.sq_prefix + __ldg(bank.prefix_offsets + ni);
-  int64_t off = noise_off ? __ldg(noise_off + b) : 0;
-  off %= c.len;
-  if (off < 0) off += c.len;
-  c.off = (int)off;
-  return c;
-}
-
-// sum of nz[q]^2 over [a, b), 0 <= a <= b <= len: prefix table for whole 128-blocks, direct sum
-// of the (< 128-sample) edges.  Executed by a full warp; every lane returns the result.
-static __device__ __noinline__ double warp_seg_energy(const ClipNoise& c, int a, int b) {
-  const int lane = threadIdx.x & 31;
-  const int lo = (a + kNoiseBlk - 1) / kNoiseBlk, hi = b / kNoiseBlk;
-  float e = 0.f;
-  double mid = 0.0;
-  if (lo <= hi) {
-    mid = c.P[hi] - c.P[lo];
-    for (int q = a + lane; q < lo * kNoiseBlk; q += 32) { const float v = __ldg(c.nz + q); e = fmaf(v, v, e); }
-    for (int q = hi * kNoiseBlk + lane; q < b; q += 32) { const float v = __ldg(c.nz + q); e = fmaf(v, v, e); }
-  } else {
-    for (int q = a + lane; q < b; q += 32) { const float v = __ldg(c.nz + q); e = fmaf(v, v, e); }
-  }
-  return mid + (double)warp_sum(e);
-}
-
-// Energy of the N-sample noise segment nz[(off + i) mod len], i < N.
-__device__ __forceinline__ float warp_noise_energy(const ClipNoise& c, int N) {
-  const int first = min(N, c.len - c.off);
-  double e = warp_seg_energy(c, c.off, c.off + first);
-  int rem = N - first;
-  if (rem > 0) {
-    const int loops = rem / c.len;
-    rem -= loops * c.len;
-    if (loops > 0) e += (double)loops * c.P[(c.len + kNoiseBlk - 1) / kNoiseBlk];
-    if (rem > 0) e += warp_seg_energy(c, 0, rem);
-  }
-  return (float)e;
-}
-
-// Block-wide sum of x[i]^2, i < N (8 independent loads in flight per thread); result in all
-// threads.  red: >= 32 floats of shared memory.  Contains __syncthreads().
-static __device__ __noinline__ float block_energy(const float* __restrict__ x, int N, float* red) {
-  const int tid = threadIdx.x, nt = blockDim.x;
-  float acc[8];
+__device__ __forceinline__ float warp_max_nan(float v) {
 #pragma unroll
-  for (int u = 0; u < 8; ++u) acc[u] = 0.f;
-  int i = tid;
-  for (; i + 7 * nt < N; i += 8 * nt) {
-    float v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = __ldg(x + i + u * nt);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) acc[u] = fmaf(v[u], v[u], acc[u]);
-  }
-  for (; i < N; i += nt) { const float v = __ldg(x + i); acc[0] = fmaf(v, v, acc[0]); }
-  float s = ((acc[0] + acc[1]) + (acc[2] + acc[3])) + ((acc[4] + acc[5]) + (acc[6] + acc[7]));
-  const int lane = tid & 31, warp = tid >> 5, nw = (nt + 31) >> 5;
-  s = warp_sum(s);
-  __syncthreads();
-  if (lane == 0) red[warp] = s;
-  __syncthreads();
-  s = lane < nw ? red[lane] : 0.f;
-  return warp_sum(s);
-}
-
-// Mix scale of batch item b (0 if it has no noise): energies of the (possibly reverberated)
-// clip and of its noise segment -> F.add_noise's scale.  CTA-uniform control flow.
-__device__ __forceinline__ float clip_mix_scale(const ClipNoise& cn, const float* x, int N, bool has_rev,
-                                                const float* es_part, int es_nb, int b, const float* snr_db, float* red) {
-  if (cn.nz == nullptr) return 0.f;
-  float es = 0.f;
-  if (has_rev && es_part != nullptr) {
-    for (int i = 0; i < es_nb; ++i) es += __ldg(es_part + (size_t)b * es_nb + i);   // fixed order: deterministic
-  } else {
-    es = block_energy(x, N, red);
-  }
-  const float en = warp_noise_energy(cn, N);
-  return snr_scale(es, en, snr_db ? __ldg(snr_db + b) : 0.f);
+  for (int o = 16; o > 0; o >>= 1) v = fmax_nan(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
 }
 
 template <typename OutT> __device__ __forceinline__ OutT to_out(float v);
 template <> __device__ __forceinline__ float to_out<float>(float v) { return v; }
 template <> __device__ __forceinline__ __half to_out<__half>(float v) { return __float2half_rn(v); }
 
-// ---- the kernel ------------------------------------------------------------------------
+// SpecAugment flag of row / column q of clip b: inside any of the clip's nm explicit (start, length) masks
+__device__ __forceinline__ bool in_masks(const int32_t* st, const int32_t* ln, int nm, int b, int q) {
+  bool mk = false;
+  if (st != nullptr)
+    for (int j = 0; j < nm; ++j) {
+      const int s0 = __ldg(st + (size_t)b * nm + j), l = __ldg(ln + (size_t)b * nm + j);
+      mk |= (q >= s0) && (q < s0 + l);
+    }
+  return mk;
+}
+
+// ==========================================================================================================
+// One frame group = 2G consecutive frames of one clip, processed by ONE warp in its private scratch z:
+//   load + [noise mix] + window -> FFT (two real frames per complex transform) -> power spectra -> sparse mel -> dB.
+// The single body behind both launch shapes (feat_kernel and feat_frames_kernel), so their results are bit-identical.
+// sink(m, i, d): dB value d of mel filter m for frame f0 + i (called for frames < T only).  Returns the NaN-propagating
+// maximum of the values this lane produced.
+// ==========================================================================================================
+struct MelTables {          // shared-memory copies
+  const float* window;      // [NFFT]
+  const float2* tw;         // pass twiddles
+  const float* melw;        // lane-interleaved filter weights
+  const int2* tasks;        // [rounds*32] mel lane schedule
+  int rounds;
+};
+
+template <int NFFT, int HOP32, class Sink>
+__device__ __forceinline__ float frame_group_to_db(const float* __restrict__ x, int N, int T, int hop,
+                                                   const float* __restrict__ nz, int noff, int nlen, float scale,
+                                                   int f0, float2* z, const MelTables& tb, Sink sink) {
+  using Plan = StftPlan<NFFT>;
+  using Rad = typename Plan::Rad;
+  using Map = typename Plan::Map;
+  constexpr int G = Plan::G;
+  constexpr int K = NFFT / 2 + 1;
+  constexpr int NC = (NFFT + 31) / 32;                       // 32-sample columns per frame
+  constexpr int ZL = stft_zlen<NFFT>();                      // scratch elements per FFT (with padding)
+  constexpr int NI = (G * K + 31) / 32;                      // split items per lane
+  static_assert(Rad::n == NFFT, "radix plan");
+  const Map zmap;
+  const int lane = threadIdx.x & 31;
+  const bool mix = nz != nullptr;
+  const float* s_window = tb.window;
+
+  // 1. load + window: z[g][j] = w[j] * (frame(f0+2g)[j] + i frame(f0+2g+1)[j])
+  bool staged = false;
+  if constexpr (HOP32 > 0) {
+    constexpr int NR = (2 * G - 1) * HOP32 + NC;             // registers holding the group's sample span
+    const int s0 = f0 * hop - NFFT / 2;
+    int q0 = 0;                                              // first noise sample of the span (mix only)
+    if (mix && s0 >= 0) { q0 = noff + s0; if (q0 >= nlen) q0 %= nlen; }
+    // fast path: the whole span is inside the clip (no reflection); the noise segment may wrap
+    // around the end of its clip once (needs a noise clip at least as long as the span)
+    if (s0 >= 0 && s0 + 32 * NR <= N && f0 + 2 * G <= T && (!mix || (q0 >= 0 && nlen >= 32 * NR))) {
+      staged = true;
+      // the span is staged in chunks of CH 32-sample columns so that at most (2G-1)*HOP32 + 32
+      // registers are live (n_fft 2048 = 64 columns needs two chunks; everything else one)
+      constexpr int CH = NC < 32 ? NC : 32, NCHUNK = (NC + CH - 1) / CH, NRC = (2 * G - 1) * HOP32 + CH;
+      static_assert(NC % CH == 0, "column chunks");
+#pragma unroll
+      for (int ch = 0; ch < NCHUNK; ++ch) {
+        const int r0 = ch * CH;
+        float sreg[NRC];
+        const float* xs = x + s0 + 32 * r0 + lane;
+#pragma unroll
+        for (int r = 0; r < NRC; ++r) sreg[r] = __ldg(xs + 32 * r);
+        if (mix) {
+          if (q0 + 32 * NR <= nlen) {
+            const float* ns = nz + q0 + 32 * r0 + lane;
+#pragma unroll
+            for (int r = 0; r < NRC; ++r) sreg[r] = fmaf(scale, __ldg(ns + 32 * r), sreg[r]);
+          } else {
+#pragma unroll
+            for (int r = 0; r < NRC; ++r) {
+              int q = q0 + 32 * (r0 + r) + lane;
+              q -= q >= nlen ? nlen : 0;
+              sreg[r] = fmaf(scale, __ldg(nz + q), sreg[r]);
+            }
+          }
+        }
+#pragma unroll
+        for (int c = 0; c < CH; ++c) {
+          const int j = 32 * (r0 + c) + lane;
+          if (NFFT % 32 == 0 || j < NFFT) {
+            const float w = s_window[j];
+#pragma unroll
+            for (int g = 0; g < G; ++g)
+              z[g * ZL + zmap(j)] = make_float2(w * sreg[2 * g * HOP32 + c], w * sreg[(2 * g + 1) * HOP32 + c]);
+          }
+        }
+      }
+    }
+  }
+  if (!staged) {
+    // boundary groups (reflect padding, frames >= T, wrapping noise) and hops that are not a
+    // multiple of 32: plain per-element gather, deliberately not unrolled (cold code)
+#pragma unroll 1
+    for (int idx = lane; idx < G * NFFT; idx += 32) {
+      const int g = idx / NFFT, j = idx - g * NFFT;
+      const int ta = f0 + 2 * g, tb_ = ta + 1;
+      const float w = s_window[j];
+      float re = 0.f, im = 0.f;
+      if (ta < T) {
+        const int i = reflect_index(ta * hop - NFFT / 2 + j, N);
+        re = __ldg(x + i);
+        if (mix) re = fmaf(scale, noise_at(nz, noff, nlen, i), re);
+      }
+      if (tb_ < T) {
+        const int i = reflect_index(tb_ * hop - NFFT / 2 + j, N);
+        im = __ldg(x + i);
+        if (mix) im = fmaf(scale, noise_at(nz, noff, nlen, i), im);
+      }
+      z[g * ZL + zmap(j)] = make_float2(re * w, im * w);
+    }
+  }
+  __syncwarp();
+  // 2. forward FFT passes (in place, digit-reversed result)
+  static_for<0, Rad::npass>([&](auto I) {
+    constexpr int i = decltype(I)::value;
+    constexpr int R = Rad::R(i), L = Rad::L(i), tasks = NFFT / R;
+    const float2* tw = tb.tw + Rad::tw_off(i);
+    // tasks of the G FFTs share the rounds of 32 lanes, unless one FFT per round costs no extra round (n_fft 400:
+    // 25 radix-16 tasks per FFT, 2 rounds either way) - then no half-warp straddles two FFTs (no bank conflicts
+    // between their columns or twiddles) and the task index needs no division
+    constexpr bool kPerFft = tasks < 32 && G * ((tasks + 31) / 32) == (G * tasks + 31) / 32;
+    if constexpr (kPerFft) {
+#pragma unroll 1   // one copy of each radix butterfly: the hot loop has to stay inside the instruction cache
+      for (int g = 0; g < G; ++g)
+        if (lane < tasks) pass_task<R, false, Map>(z + g * ZL, L, lane, [&](int q) { return tw[q]; });
+    } else {
+#pragma unroll 1
+      for (int u = lane; u < G * tasks; u += 32) {
+        const int g = u / tasks, uu = u - g * tasks;
+        pass_task<R, false, Map>(z + g * ZL, L, uu, [&](int q) { return tw[q]; });
+      }
+    }
+    __syncwarp();
+  });
+  // 3. split the packed pair into two power spectra (|A[k]|^2, |B[k]|^2): read every (Z[k], Z[n-k])
+  //    first, then store the powers in plain bin order
+  {
+    float2 pw[NI];
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < G * K) {
+        const int g = idx / K, k = idx - g * K;
+        const float2* zz = z + g * ZL;
+        pw[i] = pair_split_power(zz[zmap(Rad::pos(k))], zz[zmap(Rad::pos(k == 0 ? 0 : NFFT - k))]);
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      const int idx = lane + 32 * i;
+      if (idx < G * K) {
+        const int g = idx / K, k = idx - g * K;
+        z[g * ZL + zmap(k)] = pw[i];
+      }
+    }
+  }
+  __syncwarp();
+  // 4. sparse mel rows + dB through the lane schedule (build_mel_schedule, wwf_tables.h): per round one task per
+  //    lane = a run of consecutive bins of one filter, all 2G frames of the group at once
+  float vmax = -INFINITY;
+  for (int r = 0; r < tb.rounds; ++r) {
+    const int2 task = tb.tasks[r * 32 + lane];
+    const int k0 = task.x & 0xffff, n = (int)((unsigned)task.x >> 16);
+    const unsigned flags = (unsigned)task.y >> 24;
+    const float* wr = tb.melw + (task.y & 0xffff) * 32 + lane;
+    // two independent accumulator chains per frame pair (even / odd taps) hide the LDS + FFMA2 latency
+    float2 acc[G], acc1[G];
+#pragma unroll
+    for (int g = 0; g < G; ++g) { acc[g] = make_float2(0.f, 0.f); acc1[g] = make_float2(0.f, 0.f); }
+    int i = 0;
+    for (; i + 1 < n; i += 2) {
+      const float w0 = wr[32 * i], w1 = wr[32 * i + 32];
+      const int p0 = zmap(k0 + i), p1 = zmap(k0 + i + 1);
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        acc[g] = cfma_s(z[g * ZL + p0], w0, acc[g]);
+        acc1[g] = cfma_s(z[g * ZL + p1], w1, acc1[g]);
+      }
+    }
+    if (i < n) {
+      const float w0 = wr[32 * i];
+      const int p0 = zmap(k0 + i);
+#pragma unroll
+      for (int g = 0; g < G; ++g) acc[g] = cfma_s(z[g * ZL + p0], w0, acc[g]);
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) acc[g] = cadd(acc[g], acc1[g]);
+    if (__any_sync(0xffffffffu, flags & kMelPartner)) {        // a filter cut in two: its halves sit on adjacent lanes
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float ox = __shfl_xor_sync(0xffffffffu, acc[g].x, 1), oy = __shfl_xor_sync(0xffffffffu, acc[g].y, 1);
+        if (flags & kMelPartner) acc[g] = cadd(acc[g], make_float2(ox, oy));
+      }
+    }
+    if (flags & kMelOwner) {
+      const int m = (task.y >> 16) & 0xff;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const int ta = f0 + 2 * g;
+        if (ta < T) { const float d = power_to_db(acc[g].x); sink(m, 2 * g, d); vmax = fmax_nan(vmax, d); }
+        if (ta + 1 < T) { const float d = power_to_db(acc[g].y); sink(m, 2 * g + 1, d); vmax = fmax_nan(vmax, d); }
+      }
+    }
+  }
+  __syncwarp();
+  return vmax;
+}
+
+// ---- the single-kernel path ------------------------------------------------------------------------
 template <int NFFT, int HOP32, typename OutT>
 __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMinCtas) feat_kernel(const FeatParams p) {
   using Plan = StftPlan<NFFT>;
   using Rad = typename Plan::Rad;
   constexpr int G = Plan::G;
-  constexpr int K = NFFT / 2 + 1;
-  constexpr int NC = (NFFT + 31) / 32;                       // 32-sample columns per frame
-  constexpr bool kNatural = true;                            // power spectra re-stored in bin order (false: left
-                                                             // at their digit-reversed slots, mel reads through pos())
-  using Map = typename Plan::Map;
   constexpr int ZL = stft_zlen<NFFT>();                      // scratch elements per FFT (with padding)
-  const Map zmap;
-  constexpr int NI = (G * K + 31) / 32;                      // split items per lane
-  static_assert(Rad::n == NFFT, "radix plan");
 
   extern __shared__ __align__(16) float smem[];
   __shared__ float red[64];
@@ -288,18 +378,17 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
   float2* s_tw = reinterpret_cast<float2*>(smem + p.off_tw);
   float* s_melw = smem + p.off_melw;
   float* s_dct = smem + p.off_dct;
-  int* s_mello = reinterpret_cast<int*>(smem + p.off_mello);
-  int* s_melofs = reinterpret_cast<int*>(smem + p.off_melofs);
+  int2* s_tasks = reinterpret_cast<int2*>(smem + p.off_meltasks);
   unsigned char* s_rowmask = reinterpret_cast<unsigned char*>(smem + p.off_rowmask);
   unsigned char* s_colmask = reinterpret_cast<unsigned char*>(smem + p.off_colmask);
   float2* z = reinterpret_cast<float2*>(smem + p.off_z) + (size_t)warp * G * ZL;
+  const MelTables tb{s_window, s_tw, s_melw, s_tasks, p.mel_rounds};
 
   // ---- constants -> shared memory, once per (persistent) CTA ---------------------------
   for (int i = tid; i < NFFT; i += blockDim.x) s_window[i] = __ldg(p.window + i);
   for (int i = tid; i < Rad::tw_total; i += blockDim.x) s_tw[i] = __ldg(p.tw + i);
   for (int i = tid; i < p.n_melw; i += blockDim.x) s_melw[i] = __ldg(p.mel_w + i);
-  for (int i = tid; i < M; i += blockDim.x) s_mello[i] = __ldg(p.mel_lo + i);
-  for (int i = tid; i <= M; i += blockDim.x) s_melofs[i] = __ldg(p.mel_ofs + i);
+  for (int i = tid; i < p.mel_rounds * 32; i += blockDim.x) s_tasks[i] = __ldg(p.mel_tasks + i);
   if (p.is_mfcc)
     for (int i = tid; i < M * p.c8; i += blockDim.x) {
       const int m = i / p.c8, c = i - m * p.c8;
@@ -309,30 +398,19 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
 
   for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
     // ---- per-clip setup -------------------------------------------------------------
-    const bool has_rev = p.rev != nullptr && p.rir_idx != nullptr && __ldg(p.rir_idx + b) >= 0;
+    const bool has_rev = clip_has_rev(p.rev, p.rir_idx, p.n_rir, b);
     const float* x = has_rev ? p.rev + (size_t)b * p.rev_stride : p.wav + (size_t)b * p.wav_stride;
 
     // SpecAugment flags: one byte per feature row / frame
     for (int i = tid; i < F + T; i += blockDim.x) {
       const bool is_row = i < F;
       const int q = is_row ? i : i - F;
-      const int32_t* st = is_row ? p.fs : p.ts;
-      const int32_t* ln = is_row ? p.fl : p.tl;
-      const int nm = is_row ? p.nF : p.nT;
-      bool mk = false;
-      if (st != nullptr)
-        for (int j = 0; j < nm; ++j) {
-          const int s0 = __ldg(st + (size_t)b * nm + j), l = __ldg(ln + (size_t)b * nm + j);
-          mk |= (q >= s0) && (q < s0 + l);
-        }
+      const bool mk = is_row ? in_masks(p.fs, p.fl, p.nF, b, q) : in_masks(p.ts, p.tl, p.nT, b, q);
       (is_row ? s_rowmask : s_colmask)[q] = mk ? 1 : 0;
     }
 
     const ClipNoise cn = resolve_noise(p.noise, p.noise_idx, p.noise_off, b);
-    const float* nz = cn.nz;
-    const int noff = cn.off, nlen = cn.len;
     const float scale = clip_mix_scale(cn, x, N, has_rev, p.es_part, p.es_nb, b, p.snr_db, red);
-    const bool mix = nz != nullptr;
     if (tid == 0) s_next_group = 0;
     __syncthreads();   // constants + mask flags + group queue visible
 
@@ -347,166 +425,18 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
       grp = __shfl_sync(0xffffffffu, grp, 0);
       if (grp >= ngroups) break;
       const int f0 = grp * 2 * G;
-      // 1. load + window: z[g][j] = w[j] * (frame(f0+2g)[j] + i frame(f0+2g+1)[j])
-      bool staged = false;
-      if constexpr (HOP32 > 0) {
-        constexpr int NR = (2 * G - 1) * HOP32 + NC;         // registers holding the group's sample span
-        const int s0 = f0 * hop - NFFT / 2;
-        int q0 = 0;                                          // first noise sample of the span (mix only)
-        if (mix && s0 >= 0) { q0 = noff + s0; if (q0 >= nlen) q0 %= nlen; }
-        // fast path: the whole span is inside the clip (no reflection); the noise segment may wrap
-        // around the end of its clip once (needs a noise clip at least as long as the span)
-        if (s0 >= 0 && s0 + 32 * NR <= N && f0 + 2 * G <= T && (!mix || (q0 >= 0 && nlen >= 32 * NR))) {
-          staged = true;
-          // the span is staged in chunks of CH 32-sample columns so that at most (2G-1)*HOP32 + 32
-          // registers are live (n_fft 2048 = 64 columns needs two chunks; everything else one)
-          constexpr int CH = NC < 32 ? NC : 32, NCHUNK = (NC + CH - 1) / CH, NRC = (2 * G - 1) * HOP32 + CH;
-          static_assert(NC % CH == 0, "column chunks");
-#pragma unroll
-          for (int ch = 0; ch < NCHUNK; ++ch) {
-            const int r0 = ch * CH;
-            float sreg[NRC];
-            const float* xs = x + s0 + 32 * r0 + lane;
-#pragma unroll
-            for (int r = 0; r < NRC; ++r) sreg[r] = __ldg(xs + 32 * r);
-            if (mix) {
-              if (q0 + 32 * NR <= nlen) {
-                const float* ns = nz + q0 + 32 * r0 + lane;
-#pragma unroll
-                for (int r = 0; r < NRC; ++r) sreg[r] = fmaf(scale, __ldg(ns + 32 * r), sreg[r]);
-              } else {
-#pragma unroll
-                for (int r = 0; r < NRC; ++r) {
-                  int q = q0 + 32 * (r0 + r) + lane;
-                  q -= q >= nlen ? nlen : 0;
-                  sreg[r] = fmaf(scale, __ldg(nz + q), sreg[r]);
-                }
-              }
-            }
-#pragma unroll
-            for (int c = 0; c < CH; ++c) {
-              const int j = 32 * (r0 + c) + lane;
-              if (NFFT % 32 == 0 || j < NFFT) {
-                const float w = s_window[j];
-#pragma unroll
-                for (int g = 0; g < G; ++g)
-                  z[g * ZL + zmap(j)] = make_float2(w * sreg[2 * g * HOP32 + c], w * sreg[(2 * g + 1) * HOP32 + c]);
-              }
-            }
-          }
-        }
-      }
-      if (!staged) {
-        // boundary groups (reflect padding, frames >= T, wrapping noise) and hops that are not a
-        // multiple of 32: plain per-element gather, deliberately not unrolled (cold code)
-#pragma unroll 1
-        for (int idx = lane; idx < G * NFFT; idx += 32) {
-          const int g = idx / NFFT, j = idx - g * NFFT;
-          const int ta = f0 + 2 * g, tb = ta + 1;
-          const float w = s_window[j];
-          float re = 0.f, im = 0.f;
-          if (ta < T) {
-            const int i = reflect_index(ta * hop - NFFT / 2 + j, N);
-            re = __ldg(x + i);
-            if (mix) re = fmaf(scale, noise_at(nz, noff, nlen, i), re);
-          }
-          if (tb < T) {
-            const int i = reflect_index(tb * hop - NFFT / 2 + j, N);
-            im = __ldg(x + i);
-            if (mix) im = fmaf(scale, noise_at(nz, noff, nlen, i), im);
-          }
-          z[g * ZL + zmap(j)] = make_float2(re * w, im * w);
-        }
-      }
-      __syncwarp();
-      // 2. forward FFT passes (in place, digit-reversed result)
-      static_for<0, Rad::npass>([&](auto I) {
-        constexpr int i = decltype(I)::value;
-        constexpr int R = Rad::R(i), L = Rad::L(i), tasks = NFFT / R;
-        const float2* tw = s_tw + Rad::tw_off(i);
-#pragma unroll 1   // one copy of each radix butterfly: the hot loop has to stay inside the instruction cache
-        for (int u = lane; u < G * tasks; u += 32) {
-          const int g = u / tasks, uu = u - g * tasks;
-          pass_task<R, false, Map>(z + g * ZL, L, uu, [&](int q) { return tw[q]; });
-        }
-        __syncwarp();
-      });
-      // 3. split the packed pair into two power spectra (|A[k]|^2, |B[k]|^2)
-      if constexpr (kNatural) {
-        // read every (Z[k], Z[n-k]) first, then store the powers in plain bin order
-        float2 pw[NI];
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-          const int idx = lane + 32 * i;
-          if (idx < G * K) {
-            const int g = idx / K, k = idx - g * K;
-            const float2* zz = z + g * ZL;
-            pw[i] = pair_split_power(zz[zmap(Rad::pos(k))], zz[zmap(Rad::pos(k == 0 ? 0 : NFFT - k))]);
-          }
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < NI; ++i) {
-          const int idx = lane + 32 * i;
-          if (idx < G * K) {
-            const int g = idx / K, k = idx - g * K;
-            z[g * ZL + zmap(k)] = pw[i];
-          }
-        }
-      } else {
-        // in place at Z[k]'s slot (only bin k's lane touches it)
-        for (int idx = lane; idx < G * K; idx += 32) {
-          const int g = idx / K, k = idx - g * K;
-          float2* zz = z + g * ZL;
-          const int pk = zmap(Rad::pos(k)), pm = zmap(Rad::pos(k == 0 ? 0 : NFFT - k));
-          zz[pk] = pair_split_power(zz[pk], zz[pm]);
-        }
-      }
-      __syncwarp();
-      // 4. sparse mel rows + dB: one lane per filter, all 2G frames of the group at once
-      for (int m = lane; m < M; m += 32) {
-        const int lo = s_mello[m], o0 = s_melofs[m], o1 = s_melofs[m + 1];
-        // two independent accumulator chains per frame pair (even / odd taps) hide the LDS + FFMA2 latency
-        float2 acc[G], acc1[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) { acc[g] = make_float2(0.f, 0.f); acc1[g] = make_float2(0.f, 0.f); }
-        int o = o0;
-        for (; o + 1 < o1; o += 2) {
-          const float w0 = s_melw[o], w1 = s_melw[o + 1];
-          const int k = lo + (o - o0);
-          const int p0 = zmap(kNatural ? k : Rad::pos(k)), p1 = zmap(kNatural ? k + 1 : Rad::pos(k + 1));
-#pragma unroll
-          for (int g = 0; g < G; ++g) {
-            acc[g] = cfma_s(z[g * ZL + p0], w0, acc[g]);
-            acc1[g] = cfma_s(z[g * ZL + p1], w1, acc1[g]);
-          }
-        }
-        if (o < o1) {
-          const float w0 = s_melw[o];
-          const int k = lo + (o - o0);
-          const int p0 = zmap(kNatural ? k : Rad::pos(k));
-#pragma unroll
-          for (int g = 0; g < G; ++g) acc[g] = cfma_s(z[g * ZL + p0], w0, acc[g]);
-        }
-#pragma unroll
-        for (int g = 0; g < G; ++g) acc[g] = cadd(acc[g], acc1[g]);
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          const int ta = f0 + 2 * g;
-          if (ta < T) { const float d = power_to_db(acc[g].x); tile[m * pitch + ta] = d; vmax = fmaxf(vmax, d); }
-          if (ta + 1 < T) { const float d = power_to_db(acc[g].y); tile[m * pitch + ta + 1] = d; vmax = fmaxf(vmax, d); }
-        }
-      }
-      __syncwarp();
+      float* tcol = tile + f0;
+      vmax = fmax_nan(vmax, frame_group_to_db<NFFT, HOP32>(x, N, T, hop, cn.nz, cn.off, cn.len, scale, f0, z, tb,
+                                                           [&](int m, int i, float d) { tcol[m * pitch + i] = d; }));
     }
     // ---- per-clip top_db floor: max over the tile, gathered while it was written ------------
-    vmax = warp_max(vmax);
+    vmax = warp_max_nan(vmax);
     if (lane == 0) red[warp] = vmax;
     __syncthreads();
     float cutoff = -INFINITY;
     if (p.top_db >= 0.f) {
       float mx = lane < nwarps ? red[lane] : -INFINITY;
-      cutoff = warp_max(mx) - p.top_db;
+      cutoff = warp_max_nan(mx) - p.top_db;
     }
 
     OutT* out = reinterpret_cast<OutT*>(p.out) + (size_t)b * p.out_stride;
@@ -520,7 +450,7 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
         for (int m = warp; m < M; m += nwarps) {
           const bool rm = s_rowmask[m] != 0;
           for (int t = lane; t < T; t += 32) {
-            const float v = fmaxf(tile[m * pitch + t], cutoff);
+            const float v = fmax_nan(tile[m * pitch + t], cutoff);
             bad |= !isfinite(v);
             out[(size_t)m * T + t] = (rm || s_colmask[t]) ? mv : to_out<OutT>(v);
           }
@@ -528,7 +458,7 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
         done = true;
       } else {
         for (int m = warp; m < M; m += nwarps)
-          for (int t = lane; t < T; t += 32) tile[m * pitch + t] = fmaxf(tile[m * pitch + t], cutoff);
+          for (int t = lane; t < T; t += 32) tile[m * pitch + t] = fmax_nan(tile[m * pitch + t], cutoff);
       }
     } else {
       // DCT-II: out[c][t] = sum_m dct[m][c] * max(tile[m][t], cutoff).  One task = 8 coefficients x 4
@@ -536,7 +466,7 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
       // 16-byte broadcast load of DCT coefficients feeds eight FFMA2.
       const int C = F, c8 = p.c8, ncg = c8 / 8, TB = (T + 3) / 4;
       for (int idx = tid; idx < ncg * TB; idx += blockDim.x) {
-        const int cg = idx / TB, tb = idx - cg * TB, c0 = cg * 8;
+        const int cg = idx / TB, tb0 = idx - cg * TB, c0 = cg * 8;
         float2 acc2[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -547,11 +477,11 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
         for (int m = 0; m < M; ++m) {
           const float4 d0 = *reinterpret_cast<const float4*>(d + m * c8);
           const float4 d1 = *reinterpret_cast<const float4*>(d + m * c8 + 4);
-          const float* row = tile + m * pitch + tb;
+          const float* row = tile + m * pitch + tb0;
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             // frames beyond T read a neighbouring (finite) tile entry and are never stored
-            const float a = fmaxf(row[tb + i * TB < T ? i * TB : 0], cutoff);
+            const float a = fmax_nan(row[tb0 + i * TB < T ? i * TB : 0], cutoff);
             acc2[i][0] = cfma_s(make_float2(d0.x, d0.y), a, acc2[i][0]);   // FFMA2: two coefficients per instruction
             acc2[i][1] = cfma_s(make_float2(d0.z, d0.w), a, acc2[i][1]);
             acc2[i][2] = cfma_s(make_float2(d1.x, d1.y), a, acc2[i][2]);
@@ -560,7 +490,7 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int t = tb + i * TB;
+          const int t = tb0 + i * TB;
           if (t < T) {
             const bool cm = s_colmask[t] != 0;
 #pragma unroll
@@ -606,25 +536,42 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
 }
 
 // ==========================================================================================================
-// Split path for large batches: the fused kernel above ties a CTA to a clip, so B clips over S CTA slots run
-// ceil(B / S) rounds and the CTA-wide per-clip phases cost barrier stalls.  Here the frames of ALL clips form
+// Flat path (few clips, large batches): the fused kernel above ties a CTA to a clip, so B clips over S CTA slots run
+// ceil(B / S) rounds and the CTA-wide per-clip phases cost barrier stalls.  Here the frame groups of ALL clips form
 // one flat queue of warp-sized work items (feat_frames_kernel), the dB tiles go through an L2-resident scratch
-// and a second, fine-grained kernel finishes them (feat_epilogue_block_kernel).
+// and a second, fine-grained kernel finishes them (feat_epilogue_mma_kernel for MFCC: the DCT on the tensor cores;
+// feat_epilogue_block_kernel for log-mel).  The per-clip noise-mix records come from feat_prep_kernel.
 // ==========================================================================================================
-// ---- per-clip preparation ---------------------------------------------------------------------
+// ---- per-clip preparation: the noise-mix record (only when the call mixes noise) ----------------------------
+// One CTA per clip.  Everything that does not depend on the reverb kernel - the bank lookups and the energy of the
+// noise segment, three levels of dependent loads - happens BEFORE the programmatic-launch wait, i.e. in the shadow
+// of conv_kernel's last wave; after it only the clip's energy is fetched (the per-block partials conv_kernel left,
+// or a pass over a dry clip) and the record is written.
 template <int kUnused = 0>   // a template only so that the header can be included by several translation units
 __global__ void __launch_bounds__(256) feat_prep_kernel(const FeatParams p) {
   __shared__ float red[64];
-  pdl_wait();   // launched behind conv_kernel with programmatic dependent launch: nothing is read before this
   const int b = blockIdx.x;
-  const bool has_rev = p.rev != nullptr && p.rir_idx != nullptr && __ldg(p.rir_idx + b) >= 0;
-  const float* x = has_rev ? p.rev + (size_t)b * p.rev_stride : p.wav + (size_t)b * p.wav_stride;
-  const ClipNoise cn = resolve_noise(p.noise, p.noise_idx, p.noise_off, b);
-  const float scale = clip_mix_scale(cn, x, p.N, has_rev, p.es_part, p.es_nb, b, p.snr_db, red);
-  if (threadIdx.x == 0) {
-    p.scale_g[b] = scale;
-    p.clip_max[b] = float_key(-INFINITY);
+  const ClipNoise cn = resolve_noise(p.noise, p.noise_idx, p.noise_off, b);        // CTA-uniform
+  ClipMix m{0.f, 0, 0, 1, 0, 0};
+  float en = 0.f, snr = 0.f;
+  if (cn.nz != nullptr) {
+    if (threadIdx.x < 32) en = warp_noise_energy(cn, p.N);
+    snr = p.snr_db ? __ldg(p.snr_db + b) : 0.f;
+    m.has_noise = 1; m.noff = cn.off; m.nlen = cn.len; m.nz_off = (long long)(cn.nz - p.noise.data);
   }
+  const bool has_rev = clip_has_rev(p.rev, p.rir_idx, p.n_rir, b);
+  pdl_wait();
+  if (cn.nz != nullptr) {
+    float es = 0.f;
+    if (has_rev && p.es_part != nullptr) {
+      for (int i = 0; i < p.es_nb; ++i) es += __ldcg(p.es_part + (size_t)b * p.es_nb + i);   // fixed order: deterministic
+    } else {
+      const float* x = has_rev ? p.rev + (size_t)b * p.rev_stride : p.wav + (size_t)b * p.wav_stride;
+      es = block_energy(x, p.N, red);
+    }
+    m.scale = snr_scale(es, en, snr);
+  }
+  if (threadIdx.x == 0) p.mix_g[b] = m;
 }
 
 // ---- frames: STFT -> power -> mel -> dB into the global tile (warp-autonomous, flat over clips) ----
@@ -633,231 +580,79 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
   using Plan = StftPlan<NFFT>;
   using Rad = typename Plan::Rad;
   constexpr int G = Plan::G;
-  constexpr int K = NFFT / 2 + 1;
-  constexpr int NC = (NFFT + 31) / 32;                       // 32-sample columns per frame
-  using Map = typename Plan::Map;
   constexpr int ZL = stft_zlen<NFFT>();                      // scratch elements per FFT (with padding)
-  const Map zmap;
-  constexpr int NI = (G * K + 31) / 32;                      // split items per lane
-  static_assert(Rad::n == NFFT, "radix plan");
 
   extern __shared__ __align__(16) float smem[];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const int N = p.N, T = p.T, hop = p.hop, M = p.n_mels, mp = p.mp;
+  const int N = p.N, T = p.T, hop = p.hop, mp = p.mp;
 
   float* s_window = smem;
   float2* s_tw = reinterpret_cast<float2*>(smem + p.f_off_tw);
   float* s_melw = smem + p.f_off_melw;
-  int* s_mello = reinterpret_cast<int*>(smem + p.f_off_mello);
-  int* s_melofs = reinterpret_cast<int*>(smem + p.f_off_melofs);
+  int2* s_tasks = reinterpret_cast<int2*>(smem + p.f_off_meltasks);
   float2* z = reinterpret_cast<float2*>(smem + p.f_off_z) + (size_t)warp * G * ZL;
+  const MelTables tb{s_window, s_tw, s_melw, s_tasks, p.mel_rounds};
 
   // ---- constants -> shared memory, once per (persistent) CTA; the only CTA-wide barrier ----
   for (int i = tid; i < NFFT; i += blockDim.x) s_window[i] = __ldg(p.window + i);
   for (int i = tid; i < Rad::tw_total; i += blockDim.x) s_tw[i] = __ldg(p.tw + i);
   for (int i = tid; i < p.n_melw; i += blockDim.x) s_melw[i] = __ldg(p.mel_w + i);
-  for (int i = tid; i < M; i += blockDim.x) s_mello[i] = __ldg(p.mel_lo + i);
-  for (int i = tid; i <= M; i += blockDim.x) s_melofs[i] = __ldg(p.mel_ofs + i);
+  for (int i = tid; i < p.mel_rounds * 32; i += blockDim.x) s_tasks[i] = __ldg(p.mel_tasks + i);
   // programmatic dependent launch: everything above only reads plan constants and overlapped with the tail of
-  // the previous kernel; its results (mix scales, reverberated clips) are needed from here on
+  // the previous kernel; its results (mix records, reverberated clips) are needed from here on
   pdl_wait();
   __syncthreads();
 
+  // Flat queue of (clip, group) items, adjacent warps on adjacent groups of the same clip (their sample spans overlap
+  // in L1 / L2).  The (clip, group) pair is advanced incrementally: no division in the loop.
   const int ngroups = p.ngroups;
-  const long long total = (long long)p.B * ngroups;
-  // adjacent warps take adjacent groups of the same clip: their sample spans overlap in L1 / L2
-  for (long long item = (long long)blockIdx.x * nwarps + warp; item < total; item += (long long)gridDim.x * nwarps) {
-    const int b = (int)(item / ngroups), grp = (int)(item - (long long)b * ngroups);
-    const bool has_rev = p.rev != nullptr && p.rir_idx != nullptr && __ldg(p.rir_idx + b) >= 0;
+  const int stride = (int)gridDim.x * nwarps;
+  const int sb = stride / ngroups, sg = stride - sb * ngroups;
+  const int first = (int)blockIdx.x * nwarps + warp;
+  int b = first / ngroups, grp = first - b * ngroups;
+  while (b < p.B) {
+    const bool has_rev = clip_has_rev(p.rev, p.rir_idx, p.n_rir, b);
     const float* x = has_rev ? p.rev + (size_t)b * p.rev_stride : p.wav + (size_t)b * p.wav_stride;
-    const float scale = __ldg(p.scale_g + b);
     const float* nz = nullptr;
     int noff = 0, nlen = 1;
-    if (scale != 0.f || (p.noise_idx != nullptr && p.noise.data != nullptr)) {
-      const ClipNoise cn = resolve_noise(p.noise, p.noise_idx, p.noise_off, b);
-      nz = cn.nz; noff = cn.off; nlen = cn.len;
+    float scale = 0.f;
+    if (p.mix_g != nullptr) {
+      const int4 m0 = __ldg(reinterpret_cast<const int4*>(p.mix_g + b));
+      if (m0.y != 0) {
+        nz = p.noise.data + __ldg(reinterpret_cast<const long long*>(p.mix_g + b) + 2);
+        scale = __int_as_float(m0.x); noff = m0.z; nlen = m0.w;
+      }
     }
-    const bool mix = nz != nullptr;
-    float vmax = -INFINITY;                                  // maximum of the dB values this lane writes
     const int f0 = grp * 2 * G;
-    // 1. load + window: z[g][j] = w[j] * (frame(f0+2g)[j] + i frame(f0+2g+1)[j])
-    bool staged = false;
-    if constexpr (HOP32 > 0) {
-      constexpr int NR = (2 * G - 1) * HOP32 + NC;           // registers holding the group's sample span
-      const int s0 = f0 * hop - NFFT / 2;
-      int q0 = 0;                                            // first noise sample of the span (mix only)
-      if (mix && s0 >= 0) { q0 = noff + s0; if (q0 >= nlen) q0 %= nlen; }
-      // fast path: the whole span is inside the clip (no reflection); the noise segment may wrap
-      // around the end of its clip once (needs a noise clip at least as long as the span)
-      if (s0 >= 0 && s0 + 32 * NR <= N && f0 + 2 * G <= T && (!mix || (q0 >= 0 && nlen >= 32 * NR))) {
-        staged = true;
-        // the span is staged in chunks of CH 32-sample columns so that at most (2G-1)*HOP32 + 32
-        // registers are live (n_fft 2048 = 64 columns needs two chunks; everything else one)
-        constexpr int CH = NC < 32 ? NC : 32, NCHUNK = (NC + CH - 1) / CH, NRC = (2 * G - 1) * HOP32 + CH;
-        static_assert(NC % CH == 0, "column chunks");
-#pragma unroll
-        for (int ch = 0; ch < NCHUNK; ++ch) {
-          const int r0 = ch * CH;
-          float sreg[NRC];
-          const float* xs = x + s0 + 32 * r0 + lane;
-#pragma unroll
-          for (int r = 0; r < NRC; ++r) sreg[r] = __ldg(xs + 32 * r);
-          if (mix) {
-            if (q0 + 32 * NR <= nlen) {
-              const float* ns = nz + q0 + 32 * r0 + lane;
-#pragma unroll
-              for (int r = 0; r < NRC; ++r) sreg[r] = fmaf(scale, __ldg(ns + 32 * r), sreg[r]);
-            } else {
-#pragma unroll
-              for (int r = 0; r < NRC; ++r) {
-                int q = q0 + 32 * (r0 + r) + lane;
-                q -= q >= nlen ? nlen : 0;
-                sreg[r] = fmaf(scale, __ldg(nz + q), sreg[r]);
-              }
-            }
-          }
-#pragma unroll
-          for (int c = 0; c < CH; ++c) {
-            const int j = 32 * (r0 + c) + lane;
-            if (NFFT % 32 == 0 || j < NFFT) {
-              const float w = s_window[j];
-#pragma unroll
-              for (int g = 0; g < G; ++g)
-                z[g * ZL + zmap(j)] = make_float2(w * sreg[2 * g * HOP32 + c], w * sreg[(2 * g + 1) * HOP32 + c]);
-            }
-          }
-        }
-      }
-    }
-    if (!staged) {
-      // boundary groups (reflect padding, frames >= T, wrapping noise) and hops that are not a
-      // multiple of 32: plain per-element gather, deliberately not unrolled (cold code)
-#pragma unroll 1
-      for (int idx = lane; idx < G * NFFT; idx += 32) {
-        const int g = idx / NFFT, j = idx - g * NFFT;
-        const int ta = f0 + 2 * g, tb = ta + 1;
-        const float w = s_window[j];
-        float re = 0.f, im = 0.f;
-        if (ta < T) {
-          const int i = reflect_index(ta * hop - NFFT / 2 + j, N);
-          re = __ldg(x + i);
-          if (mix) re = fmaf(scale, noise_at(nz, noff, nlen, i), re);
-        }
-        if (tb < T) {
-          const int i = reflect_index(tb * hop - NFFT / 2 + j, N);
-          im = __ldg(x + i);
-          if (mix) im = fmaf(scale, noise_at(nz, noff, nlen, i), im);
-        }
-        z[g * ZL + zmap(j)] = make_float2(re * w, im * w);
-      }
-    }
-    __syncwarp();
-    // 2. forward FFT passes (in place, digit-reversed result)
-    static_for<0, Rad::npass>([&](auto I) {
-      constexpr int i = decltype(I)::value;
-      constexpr int R = Rad::R(i), L = Rad::L(i), tasks = NFFT / R;
-      const float2* tw = s_tw + Rad::tw_off(i);
-#pragma unroll 1   // one copy of each radix butterfly: the hot loop has to stay inside the instruction cache
-      for (int u = lane; u < G * tasks; u += 32) {
-        const int g = u / tasks, uu = u - g * tasks;
-        pass_task<R, false, Map>(z + g * ZL, L, uu, [&](int q) { return tw[q]; });
-      }
-      __syncwarp();
-    });
-    // 3. split the packed pair into two power spectra (|A[k]|^2, |B[k]|^2): read every (Z[k], Z[n-k])
-    //    first, then store the powers in plain bin order
-    {
-      float2 pw[NI];
-#pragma unroll
-      for (int i = 0; i < NI; ++i) {
-        const int idx = lane + 32 * i;
-        if (idx < G * K) {
-          const int g = idx / K, k = idx - g * K;
-          const float2* zz = z + g * ZL;
-          pw[i] = pair_split_power(zz[zmap(Rad::pos(k))], zz[zmap(Rad::pos(k == 0 ? 0 : NFFT - k))]);
-        }
-      }
-      __syncwarp();
-#pragma unroll
-      for (int i = 0; i < NI; ++i) {
-        const int idx = lane + 32 * i;
-        if (idx < G * K) {
-          const int g = idx / K, k = idx - g * K;
-          z[g * ZL + zmap(k)] = pw[i];
-        }
-      }
-    }
-    __syncwarp();
-    // 4. sparse mel rows + dB: one lane per filter, all 2G frames of the group at once
     float* tg = p.tile_g + ((size_t)b * T + f0) * mp;
-    for (int m = lane; m < M; m += 32) {
-      const int lo = s_mello[m], o0 = s_melofs[m], o1 = s_melofs[m + 1];
-      // two independent accumulator chains per frame pair (even / odd taps) hide the LDS + FFMA2 latency
-      float2 acc[G], acc1[G];
-#pragma unroll
-      for (int g = 0; g < G; ++g) { acc[g] = make_float2(0.f, 0.f); acc1[g] = make_float2(0.f, 0.f); }
-      int o = o0;
-      for (; o + 1 < o1; o += 2) {
-        const float w0 = s_melw[o], w1 = s_melw[o + 1];
-        const int k = lo + (o - o0);
-        const int p0 = zmap(k), p1 = zmap(k + 1);
-#pragma unroll
-        for (int g = 0; g < G; ++g) {
-          acc[g] = cfma_s(z[g * ZL + p0], w0, acc[g]);
-          acc1[g] = cfma_s(z[g * ZL + p1], w1, acc1[g]);
-        }
-      }
-      if (o < o1) {
-        const float w0 = s_melw[o];
-        const int p0 = zmap(lo + (o - o0));
-#pragma unroll
-        for (int g = 0; g < G; ++g) acc[g] = cfma_s(z[g * ZL + p0], w0, acc[g]);
-      }
-#pragma unroll
-      for (int g = 0; g < G; ++g) acc[g] = cadd(acc[g], acc1[g]);
-#pragma unroll
-      for (int g = 0; g < G; ++g) {
-        const int ta = f0 + 2 * g;
-        // frame-major tile: the 32 lanes of a round write 32 consecutive floats of one frame
-        if (ta < T) { const float d = power_to_db(acc[g].x); tg[(size_t)(2 * g) * mp + m] = d; vmax = fmaxf(vmax, d); }
-        if (ta + 1 < T) { const float d = power_to_db(acc[g].y); tg[(size_t)(2 * g + 1) * mp + m] = d; vmax = fmaxf(vmax, d); }
-      }
-    }
-    vmax = warp_max(vmax);
-    if (lane == 0 && vmax > -INFINITY) atomicMax(p.clip_max + b, float_key(vmax));
-    __syncwarp();
+    // frame-major tile: the 32 lanes of a round write 32 consecutive floats of one frame
+    float vmax = frame_group_to_db<NFFT, HOP32>(x, N, T, hop, nz, noff, nlen, scale, f0, z, tb,
+                                                [&](int m, int i, float d) { tg[(size_t)i * mp + m] = d; });
+    vmax = warp_max_nan(vmax);
+    if (lane == 0 && !(vmax == -INFINITY)) atomicMax(p.clip_max + b, float_key(vmax));
+    grp += sg; b += sb;
+    if (grp >= ngroups) { grp -= ngroups; ++b; }
   }
 }
 
-// ---- block epilogue of the split path: top_db floor -> [DCT-II] -> [SpecAugment] -> store ----------------
+// ---- log-mel epilogue of the flat path: top_db floor -> [SpecAugment] -> transposed store ----------------
 // One CTA per (clip, block of eb_frames frames).  The block's rows of the frame-major tile are one contiguous
 // span of global memory: read with 16-byte coalesced loads, written transposed into shared memory
-// [n_mels][pitch], then the same 8-coefficient x 4-frame register tiles as the fused kernel's DCT phase.
-// Many small CTAs with short dependent phases: the grid is 2-3 k CTAs, 8+ resident per SM.
+// [n_mels][pitch], stored row by row.  Many small CTAs with short dependent phases.
 // exact i / d for 0 <= i < 2^16, 1 <= d < 2^10 without an integer division
 __device__ __forceinline__ int small_div(int i, float inv_d) { return __float2int_rd(((float)i + 0.5f) * inv_d); }
 
 template <typename OutT>
 __global__ void __launch_bounds__(256) feat_epilogue_block_kernel(const FeatParams p) {
-  extern __shared__ __align__(16) float smem[];               // tile [n_mels][pitch] | dct [n_mels][c8]
+  extern __shared__ __align__(16) float smem[];               // tile [n_mels][pitch]
   __shared__ unsigned char s_rowmask[128];
   __shared__ unsigned char s_colmask[256];
   const int tid = threadIdx.x;
-  const int T = p.T, M = p.n_mels, F = p.n_feat, mp = p.mp, pitch = p.eb_pitch, c8 = p.c8;
+  const int T = p.T, M = p.n_mels, F = p.n_feat, mp = p.mp, pitch = p.eb_pitch;
   const int nblk = (T + p.eb_frames - 1) / p.eb_frames;
   float* tile = smem;
-  float* s_dct = smem + ((M * pitch + 3) & ~3);
-  const int mq = mp / 4, cq = c8 / 4;
+  const int mq = mp / 4;
   const float inv_mq = 1.0f / (float)mq;
-  if (p.is_mfcc) {                                            // DCT matrix: once per (persistent) CTA
-    const float inv_cq = 1.0f / (float)cq;
-    for (int i = tid; i < M * cq; i += blockDim.x) {          // c8 is a multiple of 8: rows in float4 units
-      const int m = small_div(i, inv_cq), c = 4 * (i - m * cq);
-      const float* src = p.dct + (size_t)m * p.n_mfcc + c;
-      reinterpret_cast<float4*>(s_dct)[i] = make_float4(c < p.n_mfcc ? __ldg(src) : 0.f, c + 1 < p.n_mfcc ? __ldg(src + 1) : 0.f,
-                                                        c + 2 < p.n_mfcc ? __ldg(src + 2) : 0.f, c + 3 < p.n_mfcc ? __ldg(src + 3) : 0.f);
-    }
-  }
   pdl_wait();                            // the tiles and maxima of feat_frames_kernel (PDL)
   const OutT mv = to_out<OutT>(p.mask_value);
   float chk = 0.f;                                            // v * 0 accumulates to NaN iff some v is NaN / Inf
@@ -867,16 +662,7 @@ __global__ void __launch_bounds__(256) feat_epilogue_block_kernel(const FeatPara
     const int nf = min(p.eb_frames, T - t0);                  // frames in this block
     for (int i = tid; i < F + nf; i += blockDim.x) {          // SpecAugment flags: feature rows, then this block's frames
       const bool is_row = i < F;
-      const int q = is_row ? i : t0 + (i - F);
-      const int32_t* st = is_row ? p.fs : p.ts;
-      const int32_t* ln = is_row ? p.fl : p.tl;
-      const int nm = is_row ? p.nF : p.nT;
-      bool mk = false;
-      if (st != nullptr)
-        for (int j = 0; j < nm; ++j) {
-          const int s0 = __ldg(st + (size_t)b * nm + j), l = __ldg(ln + (size_t)b * nm + j);
-          mk |= (q >= s0) && (q < s0 + l);
-        }
+      const bool mk = is_row ? in_masks(p.fs, p.fl, p.nF, b, i) : in_masks(p.ts, p.tl, p.nT, b, t0 + (i - F));
       (is_row ? s_rowmask : s_colmask)[is_row ? i : i - F] = mk ? 1 : 0;
     }
     float cutoff = -INFINITY;
@@ -886,71 +672,220 @@ __global__ void __launch_bounds__(256) feat_epilogue_block_kernel(const FeatPara
     for (int i = tid; i < nf * mq; i += blockDim.x) {
       const int tl = small_div(i, inv_mq), m = 4 * (i - tl * mq);
       const float4 v = tg[i];
-      tile[m * pitch + tl] = fmaxf(v.x, cutoff);
-      if (m + 1 < M) tile[(m + 1) * pitch + tl] = fmaxf(v.y, cutoff);
-      if (m + 2 < M) tile[(m + 2) * pitch + tl] = fmaxf(v.z, cutoff);
-      if (m + 3 < M) tile[(m + 3) * pitch + tl] = fmaxf(v.w, cutoff);
+      tile[m * pitch + tl] = fmax_nan(v.x, cutoff);
+      if (m + 1 < M) tile[(m + 1) * pitch + tl] = fmax_nan(v.y, cutoff);
+      if (m + 2 < M) tile[(m + 2) * pitch + tl] = fmax_nan(v.z, cutoff);
+      if (m + 3 < M) tile[(m + 3) * pitch + tl] = fmax_nan(v.w, cutoff);
     }
     __syncthreads();
     OutT* out = reinterpret_cast<OutT*>(p.out) + (size_t)b * p.out_stride + t0;
-    if (!p.is_mfcc) {
-      const float inv_nf = 1.0f / (float)nf;
-      for (int i = tid; i < M * nf; i += blockDim.x) {
-        const int m = small_div(i, inv_nf), tl = i - m * nf;
-        const float v = tile[m * pitch + tl];
-        chk = fmaf(v, 0.f, chk);
-        out[(size_t)m * T + tl] = (s_rowmask[m] || s_colmask[tl]) ? mv : to_out<OutT>(v);
-      }
-    } else {
-      // DCT-II in 8-coefficient x 4-frame register tiles (frames tb, tb+TB, tb+2TB, tb+3TB: a warp reads
-      // consecutive tile columns; each 16-byte broadcast load of coefficients feeds eight FFMA2)
-      const int C = F, ncg = c8 / 8, TB = (nf + 3) / 4;
-      const float inv_tb = 1.0f / (float)TB;
-      for (int idx = tid; idx < ncg * TB; idx += blockDim.x) {
-        const int cg = small_div(idx, inv_tb), tb = idx - cg * TB, c0 = cg * 8;
-        // frames beyond the block read a neighbouring (finite) tile entry and are never stored
-        const int o1 = tb + TB < nf ? TB : 0, o2 = tb + 2 * TB < nf ? 2 * TB : 0, o3 = tb + 3 * TB < nf ? 3 * TB : 0;
-        float2 acc2[4][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc2[i][j] = make_float2(0.f, 0.f);
-        const float* d = s_dct + c0;
-        const float* row = tile + tb;
-#pragma unroll 2
-        for (int m = 0; m < M; ++m, d += c8, row += pitch) {
-          const float4 d0 = *reinterpret_cast<const float4*>(d);
-          const float4 d1 = *reinterpret_cast<const float4*>(d + 4);
-          const float a[4] = {row[0], row[o1], row[o2], row[o3]};
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            acc2[i][0] = cfma_s(make_float2(d0.x, d0.y), a[i], acc2[i][0]);
-            acc2[i][1] = cfma_s(make_float2(d0.z, d0.w), a[i], acc2[i][1]);
-            acc2[i][2] = cfma_s(make_float2(d1.x, d1.y), a[i], acc2[i][2]);
-            acc2[i][3] = cfma_s(make_float2(d1.z, d1.w), a[i], acc2[i][3]);
-          }
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int tl = tb + i * TB;
-          if (tl < nf) {
-            const bool cm = s_colmask[tl] != 0;
-            OutT* o = out + (size_t)c0 * T + tl;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float v = (j & 1) ? acc2[i][j >> 1].y : acc2[i][j >> 1].x;
-              if (c0 + j < C) {
-                chk = fmaf(v, 0.f, chk);
-                o[(size_t)j * T] = (cm || s_rowmask[c0 + j]) ? mv : to_out<OutT>(v);
-              }
-            }
-          }
-        }
-      }
+    const float inv_nf = 1.0f / (float)nf;
+    for (int i = tid; i < M * nf; i += blockDim.x) {
+      const int m = small_div(i, inv_nf), tl = i - m * nf;
+      const float v = tile[m * pitch + tl];
+      chk = fmaf(v, 0.f, chk);
+      out[(size_t)m * T + tl] = (s_rowmask[m] || s_colmask[tl]) ? mv : to_out<OutT>(v);
     }
     __syncthreads();                                          // tile and flags are reused by the next block
   }
   if (__any_sync(0xffffffffu, chk != 0.f) && (tid & 31) == 0 && p.nonfinite_flag != nullptr) atomicOr(p.nonfinite_flag, 1);
+}
+
+// ---- MFCC epilogue of the flat path on the tensor cores: top_db floor -> DCT-II -> [SpecAugment] -> store ----------
+// The frame-major dB tiles of all clips are ONE row-major matrix A of B*T rows x n_mels columns, and
+//     mfcc[row][c] = sum_m max(A[row][m], cutoff(clip(row))) * dct[m][c]
+// is a [B*T x n_mels] x [n_mels x n_mfcc] GEMM (oracle: torchaudio MFCC's
+// matmul(mel_db.T, create_dct(...)), TA/transforms/_transforms.py:672-719).  The scalar version spent 4x the FFMA
+// minimum in issue slots (profiles/r01_ncu_split_path_summary.txt); here a CTA takes 128 consecutive rows, clamps
+// them into shared memory with 16-byte loads and every warp multiplies a 16-row slab with legacy mma.sync
+// m16n8k8 TF32 tiles.  1e-3 dB needs more than TF32's 10 mantissa bits: both operands are split hi + lo
+// (x = tf32(x) + tf32(x - tf32(x))) and three products are accumulated in float32 (lo*hi + hi*lo + hi*hi), which
+// carries ~21 bits - measured against the float64 oracle in tests/test_gpu_parity.py.  The tensor core's float32
+// accumulator rounds toward zero, a bias proportional to the running sum (7e-4 on c0 of a 128-mel clip, measured
+// against the FFMA kernel), so the rows are centred first: after the floor every value of a clip lies in
+// [max - top_db, max]; with mu = max - top_db / 2 the kernel multiplies (x - mu), |x - mu| <= top_db / 2, and adds
+// mu * colsum(dct)[c] in float32 at the end (the DCT is linear) - sums 3-25x smaller, silence exact.  The DCT matrix arrives
+// already split and laid out fragment by fragment (one 16-byte shared-memory load per lane, k-step and tile,
+// build_dct_fragments in wwf_tables.h).  The D fragment gives every lane (row, coefficient) pairs, so the
+// [n_mfcc][T] output is written straight from registers (8 consecutive frames per coefficient = one 32-byte sector
+// per lane group).  A rows sit at a pitch = 4 (mod 8) floats: conflict-free fragment loads.
+constexpr int kEmRows = 128;          // rows per CTA (8 warps x one 16-row m-tile)
+constexpr int kEmThreads = 256;
+constexpr int kEmMaxSlots = kEmRows + 1;       // clips a CTA's rows can touch (T >= 1)
+constexpr int kEmNT = 5;              // n-tiles (8 coefficients each) accumulated per pass over A
+
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+  uint32_t r = 0;
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 800)
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+#endif
+  return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 800)
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+#endif
+}
+
+template <typename OutT>
+__global__ void __launch_bounds__(kEmThreads) feat_epilogue_mma_kernel(const FeatParams p) {
+  extern __shared__ __align__(16) float smem[];               // A [128][ap] | B fragments uint4 [k8/8][c8/8][32]
+  __shared__ float s_cut[kEmRows], s_mu[kEmRows];             // per row: top_db floor and centre of its clip's value range
+  __shared__ float s_colsum[128];
+  __shared__ int s_clip[kEmRows];                             // clip of each row (-1 beyond the last row)
+  __shared__ int s_frame[kEmRows];
+  __shared__ unsigned char s_colmask[kEmRows];
+  __shared__ uint32_t s_rowbits[kEmMaxSlots][4];              // per clip slot: bit c set = feature row c is masked
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int T = p.T, M = p.n_mels, C = p.n_feat, mp = p.mp, k8 = p.em_k8, ap = p.em_ap, c8 = p.c8;
+  const int ntiles = c8 / 8, nfrag = (k8 / 8) * ntiles * 32;
+  float* sA = smem;
+  uint4* sB = reinterpret_cast<uint4*>(smem + kEmRows * ap);
+  // plan constants (staged before the PDL wait): the DCT fragments; the padding columns of A are zeroed once
+  for (int i = tid; i < nfrag; i += kEmThreads) sB[i] = __ldg(p.dct_frag + i);
+  for (int i = tid; i < c8; i += kEmThreads) s_colsum[i] = __ldg(p.dct_colsum + i);
+  for (int i = tid; i < kEmRows * (ap - mp); i += kEmThreads) {
+    const int row = i / (ap - mp);
+    sA[row * ap + mp + (i - row * (ap - mp))] = 0.f;
+  }
+  pdl_wait();                                                 // the tiles and maxima of feat_frames_kernel
+  const OutT mv = to_out<OutT>(p.mask_value);
+  const long long rows = (long long)p.B * T;
+  const int mq = mp / 4;
+  const float inv_mq = 1.0f / (float)mq;
+  const bool has_fmask = p.fs != nullptr && p.nF > 0;         // CTA-uniform
+  float chk = 0.f;                                            // v * 0 accumulates to NaN iff some v is NaN / Inf
+  constexpr int NL = 5;                                       // 16-byte tile loads in flight per thread
+  for (long long r0 = (long long)blockIdx.x * kEmRows; r0 < rows; r0 += (long long)gridDim.x * kEmRows) {
+    __syncthreads();                                          // A and the row tables of the previous block are free
+    const int b_first = (int)(r0 / T);
+    const int nrows = (int)min((long long)kEmRows, rows - r0);
+    // A: 128 rows x mp floats are one contiguous span of the flat tile matrix.  All loads of a pass are issued
+    // before anything waits on them (the first version waited per load: 21 % of its stall samples).
+    const float4* tg = reinterpret_cast<const float4*>(p.tile_g + (size_t)r0 * mp);
+    const int nload = nrows * mq;
+    for (int base = 0; base < kEmRows * mq; base += kEmThreads * NL) {
+      float4 v[NL];
+#pragma unroll
+      for (int u = 0; u < NL; ++u) {
+        const int i = base + u * kEmThreads + tid;
+        v[u] = i < nload ? __ldcg(tg + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      if (base == 0) {
+        if (tid < kEmRows) {                                  // per-row clip, frame, floor and column flag
+          const long long r = r0 + tid;
+          int b = -1, t = 0;
+          float cut = -INFINITY, mu = 0.f;
+          bool cm = false;
+          if (r < rows) {
+            b = b_first + (tid + (int)(r0 - (long long)b_first * T)) / T;
+            t = (int)(r - (long long)b * T);
+            const float mx = clip_max_value(__ldcg(p.clip_max + b));
+            if (p.top_db >= 0.f) cut = mx - p.top_db;
+            mu = mx - (p.top_db >= 0.f ? 0.5f * p.top_db : 40.0f);
+            cm = in_masks(p.ts, p.tl, p.nT, b, t);
+          }
+          s_clip[tid] = b; s_frame[tid] = t; s_cut[tid] = cut; s_mu[tid] = mu; s_colmask[tid] = cm ? 1 : 0;
+        }
+        if (has_fmask) {
+          const int nslots = min(kEmMaxSlots, min(p.B - b_first, (kEmRows + T - 1) / T + 1));
+          for (int i = tid; i < nslots * 4; i += kEmThreads) {
+            const int slot = i >> 2, w0 = (i & 3) * 32, b = b_first + slot;
+            uint32_t bits = 0;
+            for (int j = 0; j < p.nF; ++j) {
+              const int s0 = __ldg(p.fs + (size_t)b * p.nF + j), l = __ldg(p.fl + (size_t)b * p.nF + j);
+              const int lo = max(s0, w0) - w0, hi = min(s0 + l, w0 + 32) - w0;      // bit range inside this word
+              if (hi > lo) bits |= (hi - lo >= 32 ? 0xffffffffu : ((1u << (hi - lo)) - 1u) << lo);
+            }
+            s_rowbits[slot][i & 3] = bits;
+          }
+        }
+        __syncthreads();
+      }
+#pragma unroll
+      for (int u = 0; u < NL; ++u) {
+        const int i = base + u * kEmThreads + tid;
+        if (i < kEmRows * mq) {
+          const int row = small_div(i, inv_mq), m = 4 * (i - row * mq);
+          const float cut = s_cut[row], mu = s_mu[row];        // rows beyond the last: zeros, floor -inf, centre 0
+          float4 w = v[u];
+          w.x = fmax_nan(w.x, cut) - mu;
+          w.y = m + 1 < M ? fmax_nan(w.y, cut) - mu : 0.f;
+          w.z = m + 2 < M ? fmax_nan(w.z, cut) - mu : 0.f;
+          w.w = m + 3 < M ? fmax_nan(w.w, cut) - mu : 0.f;
+          *reinterpret_cast<float4*>(sA + row * ap + m) = w;
+        }
+      }
+    }
+    __syncthreads();
+    // one 16-row slab per warp; D fragment: c0/c1 = (row g, coefficients 2t, 2t+1), c2/c3 = (row g + 8, same)
+    const int g = lane >> 2, t4 = lane & 3;
+    const int rowA = warp * 16 + g, rowB = rowA + 8;
+    const int bA = s_clip[rowA], bB = s_clip[rowB];
+    const float* arow0 = sA + rowA * ap + t4;
+    const float* arow1 = sA + rowB * ap + t4;
+    // element (row, coefficient c) lives at out[clip][c][frame]: base pointers per row, 32-bit offsets c * T
+    OutT* outA = reinterpret_cast<OutT*>(p.out) + (size_t)max(bA, 0) * p.out_stride + s_frame[rowA];
+    OutT* outB = reinterpret_cast<OutT*>(p.out) + (size_t)max(bB, 0) * p.out_stride + s_frame[rowB];
+    const bool okA = bA >= 0, okB = bB >= 0;
+    const bool cmA = s_colmask[rowA] != 0, cmB = s_colmask[rowB] != 0;
+    const float muA = s_mu[rowA], muB = s_mu[rowB];
+    const uint32_t* bitsA = s_rowbits[min(max(bA - b_first, 0), kEmMaxSlots - 1)];
+    const uint32_t* bitsB = s_rowbits[min(max(bB - b_first, 0), kEmMaxSlots - 1)];
+    // warp-uniform: every row of the slab exists, nothing of it is masked, no padded coefficient -> plain stores
+    const bool plain = !has_fmask && C == c8 && __all_sync(0xffffffffu, okA && okB && !cmA && !cmB);
+    for (int n0 = 0; n0 < ntiles; n0 += kEmNT) {
+      const int nt = min(kEmNT, ntiles - n0);                  // tiles of this pass (warp-uniform)
+      float acc[kEmNT][4];
+#pragma unroll
+      for (int j = 0; j < kEmNT; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+      const uint4* bf = sB + (size_t)n0 * 32 + lane;
+      for (int k0 = 0; k0 < k8; k0 += 8, bf += ntiles * 32) {
+        const float av[4] = {arow0[k0], arow1[k0], arow0[k0 + 4], arow1[k0 + 4]};
+        uint32_t ah[4], al[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { ah[i] = tf32_rna(av[i]); al[i] = tf32_rna(av[i] - __uint_as_float(ah[i])); }
+        uint4 b[kEmNT];                                        // (hi k, hi k+4, lo k, lo k+4) of this lane's B fragment
+#pragma unroll
+        for (int j = 0; j < kEmNT; ++j) b[j] = j < nt ? bf[j * 32] : make_uint4(0u, 0u, 0u, 0u);
+        // the three products of a tile form a dependent chain: interleave the tiles, small terms first
+#pragma unroll
+        for (int j = 0; j < kEmNT; ++j) if (j < nt) mma_tf32_16x8x8(acc[j], al, b[j].x, b[j].y);
+#pragma unroll
+        for (int j = 0; j < kEmNT; ++j) if (j < nt) mma_tf32_16x8x8(acc[j], ah, b[j].z, b[j].w);
+#pragma unroll
+        for (int j = 0; j < kEmNT; ++j) if (j < nt) mma_tf32_16x8x8(acc[j], ah, b[j].x, b[j].y);
+      }
+#pragma unroll
+      for (int j = 0; j < kEmNT; ++j) {
+        if (j < nt) {
+          const int c = (n0 + j) * 8 + 2 * t4;                 // this lane's coefficient pair of the tile: c, c + 1
+          const float2 cs = *reinterpret_cast<const float2*>(s_colsum + c);
+          acc[j][0] = fmaf(muA, cs.x, acc[j][0]); acc[j][1] = fmaf(muA, cs.y, acc[j][1]);   // un-centre: + mu * colsum[c]
+          acc[j][2] = fmaf(muB, cs.x, acc[j][2]); acc[j][3] = fmaf(muB, cs.y, acc[j][3]);
+          chk = fmaf(acc[j][0], 0.f, fmaf(acc[j][1], 0.f, fmaf(acc[j][2], 0.f, fmaf(acc[j][3], 0.f, chk))));
+          const int o0 = c * T, o1 = o0 + T;
+          if (plain) {
+            outA[o0] = to_out<OutT>(acc[j][0]); outA[o1] = to_out<OutT>(acc[j][1]);
+            outB[o0] = to_out<OutT>(acc[j][2]); outB[o1] = to_out<OutT>(acc[j][3]);
+          } else {
+            bool m0A = cmA, m1A = cmA, m0B = cmB, m1B = cmB;
+            if (has_fmask) {
+              const uint32_t wa = bitsA[c >> 5] >> (c & 31), wb = bitsB[c >> 5] >> (c & 31);   // c is even: c + 1 is in the same word
+              m0A |= wa & 1u; m1A |= (wa >> 1) & 1u; m0B |= wb & 1u; m1B |= (wb >> 1) & 1u;
+            }
+            if (okA && c < C) outA[o0] = m0A ? mv : to_out<OutT>(acc[j][0]);
+            if (okA && c + 1 < C) outA[o1] = m1A ? mv : to_out<OutT>(acc[j][1]);
+            if (okB && c < C) outB[o0] = m0B ? mv : to_out<OutT>(acc[j][2]);
+            if (okB && c + 1 < C) outB[o1] = m1B ? mv : to_out<OutT>(acc[j][3]);
+          }
+        }
+      }
+    }
+  }
+  if (__any_sync(0xffffffffu, chk != 0.f) && lane == 0 && p.nonfinite_flag != nullptr) atomicOr(p.nonfinite_flag, 1);
 }
 
 }  // namespace wwf

@@ -46,6 +46,10 @@ WWF_HD void static_for(F&& f) {
 
 constexpr double kPi = 3.14159265358979323846264338327950288;
 
+// flag bits of a mel lane-schedule task (built on the host in wwf_tables.h, consumed in wwf_feat.cuh)
+constexpr int kMelOwner = 1;      // this lane finalises the filter (dB, store)
+constexpr int kMelPartner = 2;    // add the partial sum of lane ^ 1 first
+
 // sin/cos by Taylor series around 0 after folding the argument into [-pi/4, pi/4];
 // evaluated only at compile time (double precision, then rounded to float once).
 constexpr double cx_sin_core(double x) {

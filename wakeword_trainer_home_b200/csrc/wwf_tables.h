@@ -1,8 +1,11 @@
 // wwf_tables.h - host-side builders of the constant tables the kernels read (FFT twiddles,
 // mel filterbank).  Shared by wwfeat.cu (plan creation) and tests/emul (CPU index-math checks).
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstring>
+#include <functional>
 #include <vector>
 #include "wwf_conv.cuh"
 #include "wwf_fft.cuh"
@@ -71,6 +74,167 @@ inline std::vector<float> mel_fbanks32(int n_freqs, float f_min, float f_max, in
       fb[(size_t)k * n_mels + m] = fmaxf(0.f, fminf(down, up));
     }
   return fb;
+}
+
+
+// ------------------------------------------------------------------------------------------------------------------
+// Lane schedule of the sparse mel projection.
+//
+// The filterbank has at most two non-zeros per FFT bin, so each filter is a short run of consecutive bins
+// (2 .. ~30 taps).  One lane per filter in filter order leaves the warp waiting for its widest filter (21 two-tap
+// iterations for 40 mels at n_fft 400, 25 of 32 lanes active on average) and reads bins lo[m] + i whose bank
+// residues collide (1.9 wavefronts per load, ncu round 1).  The schedule built here instead
+//   * cuts filters wider than a threshold W into two halves on ADJACENT lanes (one __shfl_xor joins them),
+//   * sorts the resulting tasks by length and fills rounds of 32 lanes, so the lanes of a round finish together,
+//   * places tasks inside a round so that the 16 lanes of a half-warp start at bins with distinct bank residues,
+//   * stores the weights interleaved per round (w[(base + i) * 32 + lane]): conflict-free by construction.
+// W is chosen by minimising the modelled issue cost (two-tap iterations of each round's longest task + a fixed
+// per-round overhead).  A task is an int2: x = first bin | ntaps << 16,  y = weight base (in rows of 32 floats)
+// | filter << 16 | flags << 24.
+// ------------------------------------------------------------------------------------------------------------------
+struct MelSchedule {
+  int rounds = 0;
+  std::vector<int2> tasks;        // [rounds * 32]
+  std::vector<float> w;           // interleaved weights, rows of 32
+  int iterations = 0;             // two-tap iterations summed over the rounds (for reports)
+};
+
+// lo[m] / ofs[m] / w: CSR rows of the filterbank (first bin, offsets into w); zmap: scratch index map of the kernel
+inline MelSchedule build_mel_schedule(const std::vector<int>& lo, const std::vector<int>& ofs, const std::vector<float>& w,
+                                      const std::function<int(int)>& zmap) {
+  const int M = (int)lo.size();
+  struct Task { int m, k0, o, n, flags; };
+  struct Unit { Task a, b; bool pair; int len() const { return pair ? std::max(a.n, b.n) : a.n; } };
+  struct Round { std::vector<std::pair<int, Task>> placed; int mx = 0; };
+  // all units of a threshold W, longest first, placed round by round: a unit goes to the half-warp (of the current
+  // round) that has room and the fewest tasks starting on the same bank residue; pairs fill a half from lane 0 upwards
+  // (even aligned), singles from lane 15 downwards; when neither half has room the round is closed
+  auto layout = [&](int W) {
+    std::vector<Unit> u;
+    for (int m = 0; m < M; ++m) {
+      const int n = ofs[m + 1] - ofs[m];
+      if (n > W && n >= 2) {
+        const int n1 = (n + 1) / 2;
+        u.push_back({{m, lo[m], ofs[m], n1, kMelOwner | kMelPartner}, {m, lo[m] + n1, ofs[m] + n1, n - n1, 0}, true});
+      } else {
+        u.push_back({{m, lo[m], ofs[m], n, kMelOwner}, {}, false});
+      }
+    }
+    std::stable_sort(u.begin(), u.end(), [](const Unit& x, const Unit& y) { return x.len() > y.len(); });
+    std::vector<Round> rounds(1);
+    int pair_cur[2] = {0, 0}, single_cur[2] = {15, 15};
+    int resid[2][16] = {};
+    for (const Unit& x : u) {
+      const int need = x.pair ? 2 : 1;
+      int best_h = -1;
+      for (int attempt = 0; attempt < 2 && best_h < 0; ++attempt) {
+        int best_col = 1 << 30, best_free = -1;
+        for (int h = 0; h < 2; ++h) {
+          const int free_l = single_cur[h] - pair_cur[h] + 1;
+          if (free_l < need) continue;
+          int col = resid[h][zmap(x.a.k0) & 15];
+          if (x.pair) col += resid[h][zmap(x.b.k0) & 15];
+          if (col < best_col || (col == best_col && free_l > best_free)) { best_h = h; best_col = col; best_free = free_l; }
+        }
+        if (best_h < 0) {                                        // no room: next round
+          rounds.emplace_back();
+          pair_cur[0] = pair_cur[1] = 0; single_cur[0] = single_cur[1] = 15;
+          for (auto& rr : resid) for (int& v : rr) v = 0;
+        }
+      }
+      Round& r = rounds.back();
+      r.mx = std::max(r.mx, x.len());
+      if (x.pair) {
+        const int l = 16 * best_h + pair_cur[best_h];
+        pair_cur[best_h] += 2;
+        r.placed.push_back({l, x.a});
+        r.placed.push_back({l + 1, x.b});
+        resid[best_h][zmap(x.a.k0) & 15]++;
+        resid[best_h][zmap(x.b.k0) & 15]++;
+      } else {
+        r.placed.push_back({16 * best_h + single_cur[best_h]--, x.a});
+        resid[best_h][zmap(x.a.k0) & 15]++;
+      }
+    }
+    return rounds;
+  };
+  auto cost = [](const std::vector<Round>& r) {                  // issue slots: two-tap iterations + per-round overhead
+    int c = 0;
+    for (const Round& rr : r) c += 14 * ((rr.mx + 1) / 2) + 45;
+    return c;
+  };
+  int maxw = 1;
+  for (int m = 0; m < M; ++m) maxw = std::max(maxw, ofs[m + 1] - ofs[m]);
+  int bestW = maxw, bestC = -1;
+  for (int W = maxw; W >= 1; --W) {                              // ties: the least splitting
+    const int c = cost(layout(W));
+    if (bestC < 0 || c < bestC) { bestC = c; bestW = W; }
+  }
+  const std::vector<Round> rounds = layout(bestW);
+  MelSchedule s;
+  s.rounds = (int)rounds.size();
+  s.tasks.assign((size_t)s.rounds * 32, make_int2(0, 0xff << 16));
+  int wbase = 0;
+  for (int r = 0; r < s.rounds; ++r) {
+    const int mx = rounds[r].mx;
+    s.w.resize((size_t)(wbase + mx) * 32, 0.f);
+    for (const auto& pl : rounds[r].placed) {
+      const Task& t = pl.second;
+      for (int i = 0; i < t.n; ++i) s.w[(size_t)(wbase + i) * 32 + pl.first] = w[t.o + i];
+      s.tasks[(size_t)r * 32 + pl.first] = make_int2(t.k0 | (t.n << 16), wbase | (t.m << 16) | (t.flags << 24));
+    }
+    wbase += mx;
+    s.iterations += (mx + 1) / 2;
+  }
+  if (s.w.empty()) s.w.push_back(0.f);
+  return s;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// DCT matrix as split-TF32 mma.sync.m16n8k8 B fragments (feat_epilogue_mma_kernel, wwf_feat.cuh).
+// dct: [n_mels][n_mfcc] float32 (torchaudio's create_dct values).  Output: uint4 per (k-step ks, n-tile j, lane):
+//   x = hi(D[8 ks + t][8 j + g]), y = hi(D[8 ks + t + 4][8 j + g]), z / w = the lo halves, g = lane / 4, t = lane % 4,
+// zero beyond the matrix.  hi(x) = x rounded to TF32 (round to nearest, ties away: cvt.rna), lo(x) = hi(x - hi(x)).
+// ------------------------------------------------------------------------------------------------------------------
+inline uint32_t tf32_rna_host(float x) {
+  uint32_t u;
+  memcpy(&u, &x, 4);
+  if ((u & 0x7f800000u) == 0x7f800000u) return u;             // inf / nan pass through
+  u += 0x1000u;                                                // half an ulp of the 13 dropped bits, in magnitude
+  return u & 0xffffe000u;
+}
+inline std::vector<uint4> build_dct_fragments(const std::vector<float>& dct, int n_mels, int n_mfcc) {
+  const int k8 = (n_mels + 7) & ~7, c8 = (n_mfcc + 7) & ~7, ksteps = k8 / 8, ntiles = c8 / 8;
+  std::vector<uint4> out((size_t)ksteps * ntiles * 32);
+  auto at = [&](int m, int c) { return (m < n_mels && c < n_mfcc) ? dct[(size_t)m * n_mfcc + c] : 0.f; };
+  auto split = [](float v, uint32_t& hi, uint32_t& lo) {
+    hi = tf32_rna_host(v);
+    float h;
+    memcpy(&h, &hi, 4);
+    lo = tf32_rna_host(v - h);
+  };
+  for (int ks = 0; ks < ksteps; ++ks)
+    for (int j = 0; j < ntiles; ++j)
+      for (int lane = 0; lane < 32; ++lane) {
+        const int g = lane >> 2, t = lane & 3;
+        uint4 f;
+        split(at(8 * ks + t, 8 * j + g), f.x, f.z);
+        split(at(8 * ks + t + 4, 8 * j + g), f.y, f.w);
+        out[((size_t)ks * ntiles + j) * 32 + lane] = f;
+      }
+  return out;
+}
+
+// column sums of the DCT matrix (double accumulation, rounded once), padded with zeros to a multiple of 8 columns:
+// the un-centring term of feat_epilogue_mma_kernel
+inline std::vector<float> dct_column_sums(const std::vector<float>& dct, int n_mels, int n_mfcc) {
+  std::vector<float> out((size_t)((n_mfcc + 7) & ~7), 0.f);
+  for (int c = 0; c < n_mfcc; ++c) {
+    double s = 0.0;
+    for (int m = 0; m < n_mels; ++m) s += (double)dct[(size_t)m * n_mfcc + c];
+    out[c] = (float)s;
+  }
+  return out;
 }
 
 

@@ -9,7 +9,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
+#include <functional>
 #include <mutex>
 #include <vector>
 
@@ -72,22 +74,32 @@ struct DeviceGuard {
 // plan
 // ------------------------------------------------------------------------------------------
 typedef void (*FeatKernel)(const FeatParams);
+constexpr int kEpStaticSmem = 6144;   // upper bound of the epilogue kernels' static shared memory (row tables, mask bits)
+struct FeatLaunch;
+static void free_launch(FeatLaunch* l);
 
 struct wwf_plan {
   wwf_config cfg;
   int device = 0, sm_count = 0, max_smem = 0;
-  int K = 0, n_feat = 0, G = 1, zlen = 0, tw_total = 0, n_melw = 0, max_warps = 16;
+  int K = 0, n_feat = 0, G = 1, zlen = 0, tw_total = 0, n_melw = 0, mel_rounds = 0, max_warps = 16;
   FeatKernel kernel = nullptr;          // fused per-clip kernel
-  FeatKernel frames = nullptr;          // split path: flat frames kernel (same n_fft / hop variant)
-  FeatKernel epilogue_block = nullptr;  // split path: feat_epilogue_block_kernel<float | __half>
+  FeatKernel frames = nullptr;          // flat path: flat frames kernel (same n_fft / hop variant)
+  FeatKernel epilogue_block = nullptr;  // flat path, log-mel: feat_epilogue_block_kernel<float | __half>
+  FeatKernel epilogue_mma = nullptr;    // flat path, MFCC: feat_epilogue_mma_kernel<float | __half>
+  std::function<int(int)> zmap;         // index map of the feature kernels' FFT scratch (for the mel lane schedule)
   // device constants
   float* d_window = nullptr;
   float2* d_tw = nullptr;
-  int* d_mel_lo = nullptr;
-  int* d_mel_ofs = nullptr;
+  int2* d_mel_tasks = nullptr;
   int* d_nonfinite = nullptr;
   float* d_mel_w = nullptr;
   float* d_dct = nullptr;
+  uint4* d_dct_frag = nullptr;
+  float* d_dct_colsum = nullptr;
+  // options (environment at plan creation, wwf_plan_set_option afterwards) and the per-(B, N) launch cache
+  int opt_path = WWF_PATH_AUTO, opt_pdl = 1;
+  std::mutex cache_mu;
+  std::vector<struct FeatLaunch*> launches;
   // noise bank (borrowed data, owned offsets)
   const float* noise_data = nullptr;
   int64_t* d_noise_offsets = nullptr;
@@ -102,6 +114,7 @@ struct wwf_plan {
   float2* d_fused_tw = nullptr;
   int n_rir = 0, rir_max_len = 0;
   int feat_warps_override = 0;
+  bool generic_load = false;
   // time-stretch / pitch-shift constants and the resampler coefficient tables (built on first use)
   std::mutex lazy_mu;
   float* d_pv_window = nullptr;
@@ -140,9 +153,11 @@ static void select_kernel(wwf_plan* p, std::vector<float2>& tw) {
   p->kernel = f16 ? (FeatKernel)feat_kernel<NFFT, 0, __half> : (FeatKernel)feat_kernel<NFFT, 0, float>;
   p->frames = (FeatKernel)feat_frames_kernel<NFFT, 0>;
   p->epilogue_block = f16 ? (FeatKernel)feat_epilogue_block_kernel<__half> : (FeatKernel)feat_epilogue_block_kernel<float>;
+  p->epilogue_mma = f16 ? (FeatKernel)feat_epilogue_mma_kernel<__half> : (FeatKernel)feat_epilogue_mma_kernel<float>;
+  p->zmap = [](int i) { return typename Plan::Map()(i); };
   {
     // register-staged frame loads for hops that are a multiple of 32 and instantiated: 128, 160, 256
-    if (!getenv("WWF_FEAT_GENERIC_LOAD")) {
+    if (!p->generic_load) {
       switch (p->cfg.hop_length) {
         case 128: p->kernel = f16 ? (FeatKernel)feat_kernel<NFFT, 4, __half> : (FeatKernel)feat_kernel<NFFT, 4, float>;
                   p->frames = (FeatKernel)feat_frames_kernel<NFFT, 4>; break;
@@ -165,8 +180,9 @@ extern "C" int64_t wwf_launch_count(void) { return g_launches.load(); }
 extern "C" void wwf_plan_destroy(wwf_plan* p) {
   if (!p) return;
   DeviceGuard g(p->device);
-  cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_mel_lo); cudaFree(p->d_mel_ofs);
-  cudaFree(p->d_mel_w); cudaFree(p->d_dct); cudaFree(p->d_nonfinite); cudaFree(p->d_noise_offsets); cudaFree(p->d_spec);
+  cudaFree(p->d_window); cudaFree(p->d_tw); cudaFree(p->d_mel_tasks);
+  for (FeatLaunch* l : p->launches) free_launch(l);
+  cudaFree(p->d_mel_w); cudaFree(p->d_dct); cudaFree(p->d_dct_frag); cudaFree(p->d_dct_colsum); cudaFree(p->d_nonfinite); cudaFree(p->d_noise_offsets); cudaFree(p->d_spec);
   cudaFree(p->d_noise_prefix); cudaFree(p->d_noise_prefix_offsets);
   for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
   cudaFree(p->d_conv_tw); cudaFree(p->d_fused_l); cudaFree(p->d_fused_tw);
@@ -210,7 +226,11 @@ extern "C" int wwf_plan_create(const wwf_config* cfg, int device, wwf_plan** out
   p->max_smem = (int)prop.sharedMemPerBlockOptin;
   p->K = K;
   p->n_feat = cfg->feature_type == WWF_FEAT_MFCC ? cfg->n_mfcc : cfg->n_mels;
+  // environment overrides are read ONCE, here (experiments and the A/B tools); wwf_plan_set_option changes them later
   if (const char* e = getenv("WWF_FEAT_WARPS")) p->feat_warps_override = atoi(e);
+  if (const char* e = getenv("WWF_FEAT_PATH")) p->opt_path = !strcmp(e, "fused") ? WWF_PATH_FUSED : !strcmp(e, "split") ? WWF_PATH_FLAT : WWF_PATH_AUTO;
+  p->opt_pdl = getenv("WWF_NO_PDL") ? 0 : 1;
+  p->generic_load = getenv("WWF_FEAT_GENERIC_LOAD") != nullptr;
 
   std::vector<float2> tw;
   switch (n) {
@@ -240,8 +260,10 @@ extern "C" int wwf_plan_create(const wwf_config* cfg, int device, wwf_plan** out
     if (first >= 0) for (int k = first; k <= last; ++k) w.push_back(fb[(size_t)k * M + m]);
   }
   ofs[M] = (int)w.size();
-  p->n_melw = (int)w.size();
   if (w.empty()) w.push_back(0.f);
+  const MelSchedule sched = build_mel_schedule(lo, ofs, w, p->zmap);
+  p->n_melw = (int)sched.w.size();
+  p->mel_rounds = sched.rounds;
 
   std::vector<float> dct;
   if (cfg->feature_type == WWF_FEAT_MFCC) {
@@ -258,8 +280,10 @@ extern "C" int wwf_plan_create(const wwf_config* cfg, int device, wwf_plan** out
   }
 
   int rc;
-  if ((rc = upload(&p->d_window, window)) || (rc = upload(&p->d_tw, tw)) || (rc = upload(&p->d_mel_lo, lo)) ||
-      (rc = upload(&p->d_mel_ofs, ofs)) || (rc = upload(&p->d_mel_w, w)) || (rc = upload(&p->d_dct, dct))) {
+  if ((rc = upload(&p->d_window, window)) || (rc = upload(&p->d_tw, tw)) || (rc = upload(&p->d_mel_tasks, sched.tasks)) ||
+      (rc = upload(&p->d_mel_w, sched.w)) || (rc = upload(&p->d_dct, dct)) ||
+      (rc = upload(&p->d_dct_frag, dct.empty() ? std::vector<uint4>() : build_dct_fragments(dct, M, cfg->n_mfcc))) ||
+      (rc = upload(&p->d_dct_colsum, dct.empty() ? std::vector<float>() : dct_column_sums(dct, M, cfg->n_mfcc)))) {
     wwf_plan_destroy(p);
     return rc;
   }
@@ -270,6 +294,7 @@ extern "C" int wwf_plan_create(const wwf_config* cfg, int device, wwf_plan** out
   cudaError_t e = cudaFuncSetAttribute((const void*)p->kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem - 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)p->frames, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem - 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)p->epilogue_block, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem - 2048);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)p->epilogue_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem - kEpStaticSmem);
   if (e != cudaSuccess) {
     wwf_plan_destroy(p);
     return fail(WWF_ERR_CUDA, "cudaFuncSetAttribute(feat_kernel): %s (is libwwfeat.so built for this GPU?)", cudaGetErrorString(e));
@@ -466,28 +491,34 @@ static void conv_geometry(const wwf_plan* p, int N, int* hist, int* valid, int* 
 }
 
 // workspace = [reverb part: reverberated clips [B][roundup4(N)] + their per-block energies [B][nb]] (RIR bank only)
-//           + [split-path part: dB tiles [B][T][roundup4(n_mels)] + clip maxima [B] + mix scales [B]] (large batches only)
+//           + [flat-path part: dB tiles [B][T][roundup4(n_mels)] | clip maxima int[B4] | ClipMix[B]]
 static size_t conv_ws_bytes(const wwf_plan* p, int B, int N) {
   if (p->n_rir == 0) return 0;
   int hist, valid, nb;
   conv_geometry(p, N, &hist, &valid, &nb);
   return ((size_t)B * (size_t)round_up4(N) + (size_t)round_up4((int64_t)B * nb)) * sizeof(float);
 }
-// Does the fused kernel's shared-memory layout (the clip's [n_mels][T] tile + tables + one warp's FFT scratch) fit?
-static size_t fused_fixed_bytes(const wwf_plan* p, int N) {
-  auto al4 = [](long long v) { return (v + 3) & ~3ll; };
-  const bool mfcc = p->cfg.feature_type == WWF_FEAT_MFCC;
-  const int T = N / p->cfg.hop_length + 1, M = p->cfg.n_mels, F = p->n_feat, pitch = T | 1;
-  const int c8 = mfcc ? ((F + 7) & ~7) : 0;
-  long long o = al4((long long)M * pitch);
-  o += (mfcc && p->cfg.cmvn) ? al4((long long)F * pitch) : 0;
-  o += al4(p->cfg.n_fft) + al4(2 * p->tw_total) + al4(p->n_melw) + (mfcc ? (long long)M * c8 : 0) + al4(M) + al4(M + 1) +
-       al4((F + 3) / 4) + al4((T + 3) / 4);
-  return (size_t)o * sizeof(float);
-}
-static bool fused_fits(const wwf_plan* p, int N) {
-  return fused_fixed_bytes(p, N) + (size_t)p->G * p->zlen * sizeof(float2) <= (size_t)p->max_smem - 1024;
-}
+
+// Everything about a wwf_featurize call that depends only on (plan, options, B, N): shared-memory layouts, CTA shapes
+// (the occupancy queries), grids and workspace sizes.  Built once per shape and cached in the plan, so a call costs
+// a mutex, a struct copy and the launches (the 1-clip inference path is host-bound).
+struct FeatLaunch {
+  int B = 0, N = 0, T = 0;
+  FeatParams fp{};               // configuration, plan constants and layout offsets; per-call pointers are filled per call
+  // single-kernel path
+  bool fused_ok = false;
+  int fused_warps = 0, fused_grid = 0;
+  size_t fused_smem = 0, fused_fixed = 0;
+  // flat path
+  bool flat_wanted = false, flat_ok = false;
+  size_t flat_bytes = 0, off_clipmax = 0, off_mix = 0;   // (the reverb part of the workspace depends on the RIR bank: per call)
+  int frames_warps = 0;
+  unsigned frames_grid = 0, ep_grid = 0;
+  size_t frames_smem = 0, ep_smem = 0;
+  int ep_threads = 0;
+  FeatKernel ep_kernel = nullptr;   // feat_epilogue_mma_kernel (MFCC) or feat_epilogue_block_kernel (log-mel)
+};
+static void free_launch(FeatLaunch* l) { delete l; }
 
 // Which launch shape?  Measured with tools/bench_paths.py and tools/bench_small.py (profiles/README.md):
 //  * few clips (at most one per two SMs): the fused kernel would put each clip on ONE CTA and leave the rest of the GPU
@@ -497,14 +528,12 @@ static bool fused_fits(const wwf_plan* p, int N) {
 //    for the larger FFTs, whose fused kernel fits one CTA per SM;
 //  * in between the fused kernel (one launch, no intermediate) is faster.  Log-mel has no DCT to amortise the tile's
 //    round trip: below n_fft 1024 it only takes the flat queue in the few-clips case.
-// WWF_FEAT_PATH=fused|split forces one of them (the GPU tests run both).
-static bool use_split(const wwf_plan* p, int B, int N) {
+// WWF_FEAT_PATH=fused|split at plan creation or wwf_plan_set_option(WWF_OPT_FEAT_PATH) forces one (the GPU tests run both).
+static bool want_flat(const wwf_plan* p, int B, int N, bool fused_ok) {
   if (p->cfg.cmvn) return false;                               // CMVN needs whole rows of a clip in one CTA
-  if (const char* e = getenv("WWF_FEAT_PATH")) {
-    if (!strcmp(e, "fused")) return false;
-    if (!strcmp(e, "split")) return true;
-  }
-  if (!fused_fits(p, N)) return true;                          // long clips: only the flat path has no per-clip tile
+  if (p->opt_path == WWF_PATH_FUSED) return false;
+  if (p->opt_path == WWF_PATH_FLAT) return true;
+  if (!fused_ok) return true;                                  // long clips: only the flat path has no per-clip tile
   if (2 * B <= p->sm_count) return true;
   const bool mfcc = p->cfg.feature_type == WWF_FEAT_MFCC;
   if (!mfcc && p->cfg.n_fft < 1024) return false;
@@ -513,19 +542,159 @@ static bool use_split(const wwf_plan* p, int B, int N) {
   const long long per_warp = !mfcc ? 4 : p->cfg.n_fft <= 400 ? 6 : 2;
   return groups >= per_warp * 20 * p->sm_count;
 }
-static size_t split_ws_bytes(const wwf_plan* p, int B, int N) {
-  if (!use_split(p, B, N)) return 0;
+
+static FeatLaunch* build_launch(wwf_plan* p, int B, int N) {
+  FeatLaunch* l = new FeatLaunch();
+  l->B = B; l->N = N;
   const int T = N / p->cfg.hop_length + 1;
-  return ((size_t)B * T * (size_t)round_up4(p->cfg.n_mels) + 2 * (size_t)round_up4(B)) * sizeof(float);
+  l->T = T;
+  const int F = p->n_feat, M = p->cfg.n_mels;
+  const bool mfcc = p->cfg.feature_type == WWF_FEAT_MFCC;
+  const int pitch = T | 1;
+  const int nfft = p->cfg.n_fft;
+  auto al4 = [](long long v) { return (v + 3) & ~3ll; };
+  FeatParams& fp = l->fp;
+  fp.c8 = mfcc ? ((F + 7) & ~7) : 0;
+  fp.n_melw = p->n_melw;
+  fp.mel_rounds = p->mel_rounds;
+  // ---- single-kernel path: shared-memory layout (64-bit: very long clips must not wrap) ----
+  long long o = al4((long long)M * pitch);
+  const long long off_res = o;      o += (mfcc && p->cfg.cmvn) ? al4((long long)F * pitch) : 0;
+  const long long off_window = o;   o += al4(nfft);
+  const long long off_tw = o;       o += al4(2 * p->tw_total);
+  const long long off_melw = o;     o += al4(p->n_melw);
+  const long long off_dct = o;      o += mfcc ? (long long)M * fp.c8 : 0;
+  const long long off_meltasks = o; o += 2ll * 32 * p->mel_rounds;
+  const long long off_rowmask = o;  o += al4((F + 3) / 4);
+  const long long off_colmask = o;  o += al4((T + 3) / 4);
+  const long long off_z = o;
+  const size_t per_warp = (size_t)p->G * p->zlen * sizeof(float2);
+  const size_t budget = (size_t)p->max_smem - 1024;   // static smem of the kernel is 256 B
+  l->fused_fixed = (size_t)o * sizeof(float);
+  l->fused_ok = l->fused_fixed + per_warp <= budget;           // else: only the flat path (no per-clip tile) can run
+  const int cands[] = {16, 12, 11, 10, 8, 6, 4, 2, 1};
+  if (l->fused_ok) {
+    fp.off_res = (int)off_res; fp.off_window = (int)off_window; fp.off_tw = (int)off_tw; fp.off_melw = (int)off_melw;
+    fp.off_dct = (int)off_dct; fp.off_meltasks = (int)off_meltasks; fp.off_rowmask = (int)off_rowmask;
+    fp.off_colmask = (int)off_colmask; fp.off_z = (int)off_z;
+    // CTA shape: the candidate (warps per CTA) that keeps the most warps resident per SM
+    int ctas_per_sm = 1, best = -1;
+    for (int c : cands) {
+      if (c > p->max_warps || (p->feat_warps_override > 0 && c != p->feat_warps_override)) continue;
+      const size_t sm = l->fused_fixed + (size_t)c * per_warp;
+      if (sm > budget) continue;
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)p->kernel, c * 32, sm) != cudaSuccess || nb < 1) continue;
+      // resident warps, plus a bonus for a third CTA: the per-clip CTA-wide phases (max, DCT, store)
+      // of one CTA then overlap with the frame phases of two others (measured: 3x6 warps beats 2x10).
+      // A small batch cannot fill several CTAs per SM: count only the CTAs it will actually place.
+      const int nb_eff = std::min(nb, (B + p->sm_count - 1) / p->sm_count);
+      const int score = nb_eff * c + (nb_eff >= 3 ? 3 : 0);
+      if (score > best) { best = score; l->fused_warps = c; ctas_per_sm = nb; }
+    }
+    if (l->fused_warps == 0) l->fused_ok = false;
+    l->fused_smem = l->fused_fixed + (size_t)l->fused_warps * per_warp;
+    l->fused_grid = std::min(B, p->sm_count * ctas_per_sm);
+  }
+  fp.B = B; fp.N = N; fp.T = T; fp.hop = p->cfg.hop_length;
+  fp.n_mels = M; fp.n_mfcc = p->cfg.n_mfcc; fp.n_feat = F; fp.is_mfcc = mfcc;
+  fp.cmvn = p->cfg.cmvn != 0; fp.top_db = p->cfg.top_db; fp.cmvn_eps = p->cfg.cmvn_eps; fp.mask_value = p->cfg.mask_value;
+  fp.tile_pitch = pitch;
+  fp.window = p->d_window; fp.tw = p->d_tw; fp.mel_tasks = p->d_mel_tasks; fp.mel_w = p->d_mel_w; fp.dct = p->d_dct; fp.dct_frag = p->d_dct_frag; fp.dct_colsum = p->d_dct_colsum;
+  fp.nonfinite_flag = p->d_nonfinite;
+  // ---- flat path: [prep] -> flat frames -> epilogue ----
+  l->flat_wanted = want_flat(p, B, N, l->fused_ok);
+  if (l->flat_wanted) {
+    fp.mp = (int)round_up4(M);
+    fp.ngroups = (T + 2 * p->G - 1) / (2 * p->G);
+    const size_t tile_bytes = (size_t)B * T * fp.mp * sizeof(float);
+    l->off_clipmax = tile_bytes;
+    l->off_mix = l->off_clipmax + (size_t)round_up4(B) * sizeof(int);          // 16-byte aligned
+    l->flat_bytes = l->off_mix + (size_t)B * sizeof(ClipMix);
+    long long fo = al4(nfft);
+    fp.f_off_tw = (int)fo;       fo += al4(2 * p->tw_total);
+    fp.f_off_melw = (int)fo;     fo += al4(p->n_melw);
+    fp.f_off_meltasks = (int)fo; fo += 2ll * 32 * p->mel_rounds;
+    fp.f_off_z = (int)fo;
+    const size_t f_fixed = (size_t)fo * sizeof(float);
+    int fc = 1, fbest = -1;
+    for (int c : cands) {
+      if (c > p->max_warps) continue;
+      const size_t sm = f_fixed + (size_t)c * per_warp;
+      if (sm > budget) continue;
+      int nb = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)p->frames, c * 32, sm) != cudaSuccess || nb < 1) continue;
+      if (nb * c > fbest) { fbest = nb * c; l->frames_warps = c; fc = nb; }
+    }
+    l->frames_smem = f_fixed + (size_t)l->frames_warps * per_warp;
+    const long long items = (long long)B * fp.ngroups;
+    if (l->frames_warps > 0) l->frames_grid = (unsigned)std::min<long long>((long long)p->sm_count * fc, (items + l->frames_warps - 1) / l->frames_warps);
+    long long eitems = 0;
+    if (mfcc) {
+      // tensor-core DCT: 128 rows of the flat [B*T][n_mels] tile matrix per CTA
+      fp.em_k8 = (M + 7) & ~7;
+      fp.em_ap = fp.em_k8 + 4;
+      l->ep_kernel = p->epilogue_mma;
+      l->ep_threads = kEmThreads;
+      l->ep_smem = (size_t)kEmRows * fp.em_ap * sizeof(float) + (size_t)(fp.em_k8 / 8) * (fp.c8 / 8) * 32 * sizeof(uint4);
+      eitems = ((long long)B * T + kEmRows - 1) / kEmRows;
+    } else {
+      // log-mel: a plain clamp + mask + transpose, 64 frames per CTA
+      fp.eb_frames = 64;
+      fp.eb_pitch = fp.eb_frames | 1;
+      l->ep_kernel = p->epilogue_block;
+      l->ep_threads = 256;
+      l->ep_smem = (size_t)((M * fp.eb_pitch + 3) & ~3) * sizeof(float);
+      eitems = (long long)B * ((T + fp.eb_frames - 1) / fp.eb_frames);
+    }
+    int eocc = 0;
+    if (l->ep_smem <= (size_t)p->max_smem - kEpStaticSmem &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eocc, (const void*)l->ep_kernel, l->ep_threads, l->ep_smem) == cudaSuccess && eocc >= 1)
+      l->ep_grid = (unsigned)std::min<long long>(eitems, (long long)p->sm_count * eocc);
+    l->flat_ok = l->frames_warps > 0 && l->frames_grid > 0 && l->ep_grid > 0 && (long long)B * fp.ngroups < (1ll << 31) - (1 << 20);
+  }
+  cudaGetLastError();   // a failed occupancy query must not poison the next launch check
+  return l;
 }
+
+static FeatLaunch* get_launch(wwf_plan* p, int B, int N) {
+  std::lock_guard<std::mutex> lk(p->cache_mu);
+  for (FeatLaunch* l : p->launches)
+    if (l->B == B && l->N == N) return l;
+  if (p->launches.size() >= 64) {                              // bounded: drop the oldest shape
+    free_launch(p->launches.front());
+    p->launches.erase(p->launches.begin());
+  }
+  p->launches.push_back(build_launch(p, B, N));
+  return p->launches.back();
+}
+
+extern "C" int wwf_plan_set_option(wwf_plan* p, int option, int value) {
+  if (!p) return fail(WWF_ERR_INVALID, "wwf_plan_set_option: null plan");
+  std::lock_guard<std::mutex> lk(p->cache_mu);
+  if (option == WWF_OPT_FEAT_PATH) {
+    if (value != WWF_PATH_AUTO && value != WWF_PATH_FUSED && value != WWF_PATH_FLAT) return fail(WWF_ERR_INVALID, "wwf_plan_set_option: path %d", value);
+    p->opt_path = value;
+  } else if (option == WWF_OPT_PDL) {
+    p->opt_pdl = value != 0;
+  } else {
+    return fail(WWF_ERR_INVALID, "wwf_plan_set_option: unknown option %d", option);
+  }
+  for (FeatLaunch* l : p->launches) free_launch(l);            // cached shapes were built for the old options
+  p->launches.clear();
+  return WWF_OK;
+}
+
 extern "C" size_t wwf_workspace_bytes(const wwf_plan* p, int B, int N) {
   if (!p || B <= 0 || N <= 0) return 0;
-  return conv_ws_bytes(p, B, N) + split_ws_bytes(p, B, N);
+  DeviceGuard guard(p->device);
+  const FeatLaunch* l = get_launch(const_cast<wwf_plan*>(p), B, N);
+  return conv_ws_bytes(p, B, N) + (l->flat_ok ? l->flat_bytes : 0);
 }
 
 static bool wants_reverb(const wwf_plan* p, const wwf_aug* aug) { return aug && aug->rir_idx && p->n_rir > 0; }
 
-// Overlap-save reverb of the clips that have rir_idx >= 0 into the workspace.
+// Overlap-save reverb of the clips whose rir_idx addresses the bank into the workspace.
 static int launch_conv(wwf_plan* p, const float* wav, int B, int N, int64_t wav_stride, const wwf_aug* aug,
                        void* workspace, size_t workspace_bytes, cudaStream_t st, float** rev, int64_t* rev_stride,
                        const float** es_part, int* es_nb) {
@@ -566,17 +735,52 @@ static int check_batch(const wwf_plan* p, const void* wav, int B, int N, int64_t
   return WWF_OK;
 }
 
+static cudaError_t launch_feat(FeatKernel k, const FeatParams& fp, unsigned grid, unsigned block, size_t smem, cudaStream_t st, bool pdl) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at{};
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, k, fp);
+}
+
 extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_t wav_stride, const wwf_aug* aug,
                              void* out, int64_t out_stride, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = check_batch(p, wav, B, N, wav_stride, "wwf_featurize");
   if (rc) return rc;
   if (!out) return fail(WWF_ERR_INVALID, "wwf_featurize: out is null");
-  const int T = N / p->cfg.hop_length + 1;
-  const int F = p->n_feat, M = p->cfg.n_mels;
-  if (out_stride < (int64_t)F * T) return fail(WWF_ERR_INVALID, "wwf_featurize: out_stride=%lld < n_feat*T=%d", (long long)out_stride, F * T);
   DeviceGuard guard(p->device);
   if (!guard.ok) return fail(WWF_ERR_CUDA, "cudaSetDevice(%d) failed", p->device);
+  const FeatLaunch* l = get_launch(p, B, N);
+  const int T = l->T, F = p->n_feat, M = p->cfg.n_mels;
+  if (out_stride < (int64_t)F * T) return fail(WWF_ERR_INVALID, "wwf_featurize: out_stride=%lld < n_feat*T=%d", (long long)out_stride, F * T);
   cudaStream_t st = (cudaStream_t)stream;
+
+  FeatParams fp = l->fp;
+  fp.wav = wav; fp.wav_stride = wav_stride;
+  fp.out = out; fp.out_stride = out_stride;
+  const bool reverb = wants_reverb(p, aug);
+  if (aug) {
+    if (reverb) { fp.rir_idx = aug->rir_idx; fp.n_rir = p->n_rir; }
+    if (aug->noise_idx && p->n_noise > 0) {
+      fp.noise_idx = aug->noise_idx; fp.noise_off = aug->noise_off; fp.snr_db = aug->snr_db;
+      fp.noise = p->noise_dev();
+    }
+    if (aug->fmask_start && aug->fmask_len && p->cfg.n_freq_masks > 0) { fp.fs = aug->fmask_start; fp.fl = aug->fmask_len; fp.nF = p->cfg.n_freq_masks; }
+    if (aug->tmask_start && aug->tmask_len && p->cfg.n_time_masks > 0) { fp.ts = aug->tmask_start; fp.tl = aug->tmask_len; fp.nT = p->cfg.n_time_masks; }
+  }
+  const size_t conv_bytes = conv_ws_bytes(p, B, N);
+  const bool flat = l->flat_ok && workspace && workspace_bytes >= conv_bytes + l->flat_bytes && !(reinterpret_cast<uintptr_t>(workspace) & 15);
+  if (flat) {
+    char* fw = (char*)workspace + conv_bytes;
+    fp.tile_g = (float*)fw;
+    fp.clip_max = (int*)(fw + l->off_clipmax);
+    fp.mix_g = fp.noise_idx ? (ClipMix*)(fw + l->off_mix) : nullptr;
+    // identity of the clip maxima: a byte-wise memset, BEFORE the reverb launch so that the kernels of the step
+    // stay chained (programmatic dependent launch)
+    WWF_CUDA(cudaMemsetAsync(fp.clip_max, 0x80, (size_t)round_up4(B) * sizeof(int), st));
+  }
 
   cudaEvent_t pe[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   if (p->prof) {
@@ -589,164 +793,33 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
   int es_nb = 0;
   if ((rc = launch_conv(p, wav, B, N, wav_stride, aug, workspace, workspace_bytes, st, &rev, &rev_stride, &es_part, &es_nb))) return rc;
   if (p->prof) WWF_CUDA(cudaEventRecord(pe[1], st));
-
-  const bool mfcc = p->cfg.feature_type == WWF_FEAT_MFCC;
-  const int pitch = T | 1;
-  const int nfft = p->cfg.n_fft;
-  auto al4 = [](int v) { return (v + 3) & ~3; };
-  FeatParams fp{};
-  fp.c8 = mfcc ? ((F + 7) & ~7) : 0;
-  fp.n_melw = p->n_melw;
-  int o = al4(M * pitch);
-  fp.off_res = o;      o += (mfcc && p->cfg.cmvn) ? al4(F * pitch) : 0;
-  fp.off_window = o;   o += al4(nfft);
-  fp.off_tw = o;       o += al4(2 * p->tw_total);
-  fp.off_melw = o;     o += al4(p->n_melw);
-  fp.off_dct = o;      o += mfcc ? M * fp.c8 : 0;
-  fp.off_mello = o;    o += al4(M);
-  fp.off_melofs = o;   o += al4(M + 1);
-  fp.off_rowmask = o;  o += al4((F + 3) / 4);
-  fp.off_colmask = o;  o += al4((T + 3) / 4);
-  fp.off_z = o;
-  const size_t fixed_bytes = (size_t)o * sizeof(float);
-  const size_t per_warp = (size_t)p->G * p->zlen * sizeof(float2);
-  const size_t budget = (size_t)p->max_smem - 1024;   // static smem of the kernel is 256 B
-  const bool fused_ok = fixed_bytes + per_warp <= budget;     // else: only the flat path (no per-clip tile) can run
-  // CTA shape: the candidate (warps per CTA) that keeps the most warps resident per SM
-  int nwarps = 0, ctas_per_sm = 1, best = -1;
-  const int cands[] = {16, 12, 11, 10, 8, 6, 4, 2, 1};
-  for (int c : cands) {
-    if (c > p->max_warps || (p->feat_warps_override > 0 && c != p->feat_warps_override)) continue;
-    const size_t sm = fixed_bytes + (size_t)c * per_warp;
-    if (sm > budget) continue;
-    int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)p->kernel, c * 32, sm) != cudaSuccess || nb < 1) continue;
-    // resident warps, plus a bonus for a third CTA: the per-clip CTA-wide phases (max, DCT, store)
-    // of one CTA then overlap with the frame phases of two others (measured: 3x6 warps beats 2x10).
-    // A small batch cannot fill several CTAs per SM: count only the CTAs it will actually place.
-    const int nb_eff = std::min(nb, (B + p->sm_count - 1) / p->sm_count);
-    const int score = nb_eff * c + (nb_eff >= 3 ? 3 : 0);
-    if (score > best) { best = score; nwarps = c; ctas_per_sm = nb; }
-  }
-  if (nwarps == 0 && fused_ok) return fail(WWF_ERR_CUDA, "feat_kernel does not fit on this device (%zu + %zu bytes of shared memory)", fixed_bytes, per_warp);
-  const size_t smem = fixed_bytes + (size_t)nwarps * per_warp;
-  int grid = p->sm_count * ctas_per_sm;
-  if (grid > B) grid = B;
-
-  fp.wav = wav; fp.wav_stride = wav_stride; fp.rev = rev; fp.rev_stride = rev_stride;
-  fp.B = B; fp.N = N; fp.T = T; fp.hop = p->cfg.hop_length;
-  fp.n_mels = M; fp.n_mfcc = p->cfg.n_mfcc; fp.n_feat = F; fp.is_mfcc = mfcc;
-  fp.cmvn = p->cfg.cmvn != 0; fp.top_db = p->cfg.top_db; fp.cmvn_eps = p->cfg.cmvn_eps; fp.mask_value = p->cfg.mask_value;
-  fp.tile_pitch = pitch;
-  fp.window = p->d_window; fp.tw = p->d_tw; fp.mel_lo = p->d_mel_lo; fp.mel_ofs = p->d_mel_ofs; fp.mel_w = p->d_mel_w; fp.dct = p->d_dct;
-  if (aug) {
-    fp.rir_idx = rev ? aug->rir_idx : nullptr;
-    if (aug->noise_idx && p->n_noise > 0) {
-      fp.noise_idx = aug->noise_idx; fp.noise_off = aug->noise_off; fp.snr_db = aug->snr_db;
-      fp.noise = p->noise_dev();
-    }
-    if (aug->fmask_start && aug->fmask_len && p->cfg.n_freq_masks > 0) { fp.fs = aug->fmask_start; fp.fl = aug->fmask_len; fp.nF = p->cfg.n_freq_masks; }
-    if (aug->tmask_start && aug->tmask_len && p->cfg.n_time_masks > 0) { fp.ts = aug->tmask_start; fp.tl = aug->tmask_len; fp.nT = p->cfg.n_time_masks; }
-  }
+  fp.rev = rev; fp.rev_stride = rev_stride;
+  if (!rev) { fp.rir_idx = nullptr; fp.n_rir = 0; }
   fp.es_part = es_part; fp.es_nb = es_nb;
-  fp.out = out; fp.out_stride = out_stride;
-  fp.nonfinite_flag = p->d_nonfinite;
-  // ---- split path: prep -> flat frames -> block epilogue (large batches with room in the workspace) ----
-  const size_t conv_bytes = conv_ws_bytes(p, B, N), split_bytes = split_ws_bytes(p, B, N);
-  if (split_bytes > 0 && workspace && workspace_bytes >= conv_bytes + split_bytes && !(reinterpret_cast<uintptr_t>(workspace) & 15)) {
-    fp.mp = (int)round_up4(M);
-    fp.tile_g = (float*)((char*)workspace + conv_bytes);
-    fp.clip_max = (int*)(fp.tile_g + (size_t)B * T * fp.mp);
-    fp.scale_g = (float*)(fp.clip_max + round_up4(B));
-    fp.ngroups = (T + 2 * p->G - 1) / (2 * p->G);
-    int fo = al4(nfft);
-    fp.f_off_tw = fo;       fo += al4(2 * p->tw_total);
-    fp.f_off_melw = fo;     fo += al4(p->n_melw);
-    fp.f_off_mello = fo;    fo += al4(M);
-    fp.f_off_melofs = fo;   fo += al4(M + 1);
-    fp.f_off_z = fo;
-    const size_t f_fixed = (size_t)fo * sizeof(float);
-    int fw = 0, fc = 1, fbest = -1;
-    for (int c : cands) {
-      if (c > p->max_warps) continue;
-      const size_t sm = f_fixed + (size_t)c * per_warp;
-      if (sm > budget) continue;
-      int nb = 0;
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, (const void*)p->frames, c * 32, sm) != cudaSuccess || nb < 1) continue;
-      if (nb * c > fbest) { fbest = nb * c; fw = c; fc = nb; }
+  const bool pdl = p->opt_pdl && !p->prof;   // (only behind one of OUR kernels: what runs before the first of them may still be producing the inputs)
+
+  if (flat) {
+    // noise: the per-clip mix records (one CTA per clip; its noise side runs before the programmatic-launch wait)
+    const bool need_prep = fp.mix_g != nullptr;
+    if (need_prep) WWF_CUDA(launch_feat((FeatKernel)feat_prep_kernel<0>, fp, (unsigned)B, 256, 0, st, pdl && rev != nullptr));
+    if (p->prof) WWF_CUDA(cudaEventRecord(pe[2], st));
+    WWF_CUDA(launch_feat(p->frames, fp, l->frames_grid, (unsigned)(l->frames_warps * 32), l->frames_smem, st, pdl && (need_prep || rev != nullptr)));
+    if (p->prof) WWF_CUDA(cudaEventRecord(pe[3], st));
+    WWF_CUDA(launch_feat(l->ep_kernel, fp, l->ep_grid, (unsigned)l->ep_threads, l->ep_smem, st, pdl));
+    g_launches += need_prep ? 3 : 2;
+    WWF_CUDA(cudaGetLastError());
+    if (p->prof) {
+      WWF_CUDA(cudaEventRecord(pe[4], st));
+      p->prof_events.insert(p->prof_events.end(), pe, pe + 5);
+      p->prof_split.push_back(1);
     }
-    // block epilogue: frames per block and threads per CTA chosen so that the 8-coefficient x 4-frame DCT tasks
-    // fill the CTA's threads (T = 151, 40 coefficients: 2 blocks of 76 frames -> 95 tasks on 96 threads)
-    int eb_threads = 256;
-    fp.eb_frames = 64;                                          // log-mel: a plain clamp + mask + transpose, 64 frames per CTA
-    if (mfcc) {
-      const int ncg = mfcc ? fp.c8 / 8 : 1;
-      double best_eff = -1.0;
-      for (int nblk = 1; nblk <= (T + 31) / 32; ++nblk) {
-        const int eb = (((T + nblk - 1) / nblk) + 3) & ~3;
-        if (eb > 256) continue;
-        for (int th = 64; th <= 256; th += 32) {
-          const int tasks = ncg * (eb / 4), rounds = (tasks + th - 1) / th;
-          double eff = (double)tasks / ((double)rounds * th) * ((double)T / ((double)nblk * eb));
-          eff -= 0.02 * rounds;                                 // prefer short CTAs (more of them resident)
-          if (eff > best_eff) { best_eff = eff; fp.eb_frames = eb; eb_threads = th; }
-        }
-      }
-    }
-    fp.eb_pitch = fp.eb_frames | 1;
-    const size_t eb_smem = ((size_t)((M * fp.eb_pitch + 3) & ~3) + (mfcc ? (size_t)M * fp.c8 : 0)) * sizeof(float);
-    if (fw > 0 && eb_smem <= budget - 1024) {
-      const long long items = (long long)B * fp.ngroups;
-      long long fgrid = (long long)p->sm_count * fc;
-      if (fgrid > (items + fw - 1) / fw) fgrid = (items + fw - 1) / fw;
-      // the three kernels are chained with programmatic dependent launch: each may start its prologue (constants
-      // into shared memory) while its predecessor drains and waits in cudaGridDependencySynchronize() for its data
-      const bool pdl = !p->prof && !getenv("WWF_NO_PDL");
-      // (only behind one of OUR kernels: what runs before the first of them may still be producing the inputs)
-      auto launch = [&](FeatKernel k, unsigned g, unsigned b, size_t sm, bool behind_ours) {
-        cudaLaunchConfig_t cfg{};
-        cfg.gridDim = dim3(g); cfg.blockDim = dim3(b); cfg.dynamicSmemBytes = sm; cfg.stream = st;
-        cudaLaunchAttribute at{};
-        at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at.val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = &at; cfg.numAttrs = (pdl && behind_ours) ? 1 : 0;
-        return cudaLaunchKernelEx(&cfg, k, fp);
-      };
-      // without noise there is no mix scale to prepare: the clip maxima are initialised by a memset instead
-      const bool need_prep = fp.noise_idx != nullptr;
-      if (need_prep) WWF_CUDA(launch((FeatKernel)feat_prep_kernel<0>, (unsigned)B, 256, 0, rev != nullptr));
-      else WWF_CUDA(cudaMemsetAsync(fp.clip_max, 0x80, (size_t)B * sizeof(int), st));
-      if (p->prof) WWF_CUDA(cudaEventRecord(pe[2], st));
-      WWF_CUDA(launch(p->frames, (unsigned)fgrid, (unsigned)(fw * 32), f_fixed + (size_t)fw * per_warp, need_prep));
-      if (p->prof) WWF_CUDA(cudaEventRecord(pe[3], st));
-      const long long eitems = (long long)B * ((T + fp.eb_frames - 1) / fp.eb_frames);
-      int eocc = 1;
-      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eocc, (const void*)p->epilogue_block, eb_threads, eb_smem);
-      const long long egrid = std::min(eitems, (long long)p->sm_count * std::max(eocc, 1));
-      WWF_CUDA(launch(p->epilogue_block, (unsigned)egrid, (unsigned)eb_threads, eb_smem, true));
-      g_launches += need_prep ? 3 : 2;
-      WWF_CUDA(cudaGetLastError());
-      if (p->prof) {
-        WWF_CUDA(cudaEventRecord(pe[4], st));
-        p->prof_events.insert(p->prof_events.end(), pe, pe + 5);
-        p->prof_split.push_back(1);
-      }
-      return WWF_OK;
-    }
+    return WWF_OK;
   }
-  if (!fused_ok)
+  if (!l->fused_ok)
     return fail(WWF_ERR_UNSUPPORTED, "clip too long for the in-shared-memory tile of the single-kernel path: %zu bytes of tiles/tables "
-                "(N=%d, T=%d, n_mels=%d)%s", fixed_bytes, N, T, M,
+                "(N=%d, T=%d, n_mels=%d)%s", l->fused_fixed, N, T, M,
                 p->cfg.cmvn ? "; CMVN plans have no other path" : "; pass a workspace of wwf_workspace_bytes() to use the flat path");
-  {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(nwarps * 32); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-    cudaLaunchAttribute at{};
-    at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    at.val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = &at; cfg.numAttrs = (rev != nullptr && !p->prof && !getenv("WWF_NO_PDL")) ? 1 : 0;   // behind conv_kernel only
-    WWF_CUDA(cudaLaunchKernelEx(&cfg, p->kernel, fp));
-  }
+  WWF_CUDA(launch_feat(p->kernel, fp, (unsigned)l->fused_grid, (unsigned)(l->fused_warps * 32), l->fused_smem, st, pdl && rev != nullptr));   // behind conv_kernel only
   g_launches++;
   WWF_CUDA(cudaGetLastError());
   if (p->prof) {
@@ -774,7 +847,7 @@ extern "C" int wwf_augment(wwf_plan* p, const float* wav, int B, int N, int64_t 
   MixParams mp{};
   mp.wav = wav; mp.wav_stride = wav_stride; mp.rev = rev; mp.rev_stride = rev_stride;
   if (aug) {
-    mp.rir_idx = rev ? aug->rir_idx : nullptr;
+    mp.rir_idx = rev ? aug->rir_idx : nullptr; mp.n_rir = p->n_rir;
     if (aug->noise_idx && p->n_noise > 0) {
       mp.noise_idx = aug->noise_idx; mp.noise_off = aug->noise_off; mp.snr_db = aug->snr_db;
       mp.noise = p->noise_dev();
@@ -801,7 +874,9 @@ extern "C" int wwf_gather_clips(const void* bank, int dtype, int64_t n_clips, in
                   !(reinterpret_cast<uintptr_t>(out) & 15);
   // enough CTAs per clip to fill the GPU at small B, at most 8 elements per thread-iteration
   int chunks = (N / 8 + 255) / 256;
-  const int want = (4 * 148 + B - 1) / B;
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sms <= 0) sms = 148;
+  const int want = (4 * sms + B - 1) / B;
   if (chunks > want) chunks = want;
   if (chunks < 1) chunks = 1;
   const dim3 grid(chunks, B);

@@ -59,6 +59,7 @@ class AugParams:
     pitch_steps: Optional[torch.Tensor] = None
     stretch_lo: Optional[float] = None
     pitch_range: Optional[tuple] = None
+    resident_on: Optional[torch.device] = None   # set by .to(): every tensor already has the ABI's dtype on that device
 
     _DTYPES = dict(rir_idx=torch.int32, noise_idx=torch.int32, noise_off=torch.int64, snr_db=torch.float32,
                    fmask_start=torch.int32, fmask_len=torch.int32, tmask_start=torch.int32, tmask_len=torch.int32,
@@ -80,7 +81,19 @@ class AugParams:
                     kw["pitch_range"] = (int(v.min()), int(v.max()))
                 v = v.to(device=device, dtype=self._DTYPES[name], non_blocking=non_blocking).contiguous()
             kw[name] = v
+        moved = [kw[n] for n in self.tensor_fields() if kw.get(n) is not None]
+        kw["resident_on"] = moved[0].device if moved else torch.device(device)    # "cuda" -> "cuda:0"
         return AugParams(**kw)
+
+    def is_resident(self, device) -> bool:
+        """Every tensor already lives on ``device`` with the ABI's dtype (nothing to convert before a call)."""
+        if self.resident_on != device:
+            return False
+        for name in self.tensor_fields():
+            v = getattr(self, name)
+            if v is not None and (v.device != device or v.dtype != self._DTYPES[name] or not v.is_contiguous()):
+                return False
+        return True
 
     def nbytes(self) -> int:
         return sum(getattr(self, n).numel() * getattr(self, n).element_size()
@@ -209,7 +222,7 @@ class FeaturePlan:
         a = AugParams(rir_idx=torch.empty(B, dtype=torch.int32, device=dev),
                       noise_idx=torch.empty(B, dtype=torch.int32, device=dev),
                       noise_off=torch.empty(B, dtype=torch.int64, device=dev),
-                      snr_db=torch.empty(B, dtype=torch.float32, device=dev))
+                      snr_db=torch.empty(B, dtype=torch.float32, device=dev), resident_on=dev)
         if self.n_freq_masks:
             a.fmask_start = torch.empty(B, self.n_freq_masks, dtype=torch.int32, device=dev)
             a.fmask_len = torch.empty(B, self.n_freq_masks, dtype=torch.int32, device=dev)
@@ -253,12 +266,13 @@ class FeaturePlan:
         return c.value, f.value, n.value
 
     def profile_read_kernels(self):
-        """({'conv_kernel', 'feat_prep_kernel', 'feat_frames_kernel' | 'feat_kernel', 'feat_epilogue_block_kernel'}
-        -> average ms per call, calls, calls that took the large-batch path) since the last read."""
+        """({'conv_kernel', 'feat_prep_kernel', 'feat_frames_kernel' | 'feat_kernel', 'feat_epilogue_mma_kernel' |
+        'feat_epilogue_block_kernel'} -> average ms per call, calls, calls that took the flat path) since the last read."""
         ms, n, ns = (C.c_double * 4)(), C.c_int(), C.c_int()
         N.check(self.lib.wwf_profile_read_kernels(self._handle, ms, C.byref(n), C.byref(ns)))
         split = n.value > 0 and ns.value == n.value
-        names = ["conv_kernel", "feat_prep_kernel", "feat_frames_kernel" if split else "feat_kernel", "feat_epilogue_block_kernel"]
+        names = ["conv_kernel", "feat_prep_kernel", "feat_frames_kernel" if split else "feat_kernel",
+                 "feat_epilogue_mma_kernel" if self.feature_type == "mfcc" else "feat_epilogue_block_kernel"]
         return {k: v for k, v in zip(names, ms) if v > 0.0 or k == "conv_kernel"}, n.value, ns.value
 
     # ------------------------------------------------------------------ banks
@@ -283,7 +297,8 @@ class FeaturePlan:
     def _aug_struct(self, aug: Optional[AugParams], B: int):
         if aug is None:
             return None, None
-        a = aug.to(self.device)
+        # draws made on the GPU (draw_aug) or moved once with .to(plan.device) are passed through untouched
+        a = aug if aug.is_resident(self.device) else aug.to(self.device)
         for name in ("rir_idx", "noise_idx", "noise_off", "snr_db", "stretch_rate", "pitch_steps"):
             v = getattr(a, name)
             if v is not None and v.shape != (B,):
@@ -305,11 +320,29 @@ class FeaturePlan:
     def _ws_bytes(self, need: int, key):
         if need == 0:
             return None, 0
-        ws = self._workspace.get(key)
+        ws = self._workspace.pop(key, None)
         if ws is None or ws.numel() < need:
             ws = torch.empty(need, dtype=torch.uint8, device=self.device)
-            self._workspace[key] = ws
+        self._workspace[key] = ws                               # most recently used last
+        while len(self._workspace) > self.MAX_WORKSPACES:       # short-lived streams must not pin their buffers forever
+            self._workspace.pop(next(iter(self._workspace)))
         return ws, need
+
+    MAX_WORKSPACES = 8
+
+    def release_workspaces(self):
+        """Drop the cached per-stream scratch buffers (they are re-created on demand)."""
+        self._workspace.clear()
+
+    def set_path(self, path: str = "auto"):
+        """Force the launch shape of ``featurize``: 'fused' (one kernel), 'flat' (flat frame queue + epilogue) or
+        'auto' (the library picks per batch shape).  Test / measurement control (wwf_plan_set_option)."""
+        code = {"auto": N.PATH_AUTO, "fused": N.PATH_FUSED, "flat": N.PATH_FLAT, "split": N.PATH_FLAT}[path]
+        N.check(self.lib.wwf_plan_set_option(self._handle, N.OPT_FEAT_PATH, code))
+
+    def set_pdl(self, enable: bool = True):
+        """Chain the kernels of a call with programmatic dependent launch (default on)."""
+        N.check(self.lib.wwf_plan_set_option(self._handle, N.OPT_PDL, int(bool(enable))))
 
     # ------------------------------------------------------------------ waveform-shape augmentations
     def time_stretch(self, wav: torch.Tensor, rates: torch.Tensor, rate_lo: Optional[float] = None,
