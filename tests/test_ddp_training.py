@@ -35,7 +35,7 @@ def test_reference_config_and_model_import_without_gpu():
     cfg = dt.default_config()
     assert cfg.model.architecture == "resnet18" and cfg.training.batch_size == 128 and cfg.data.n_fft == 1024
     edge = dt.default_config("edge")
-    assert edge.model.architecture == "mobilenetv3" and edge.data.n_mels == 64
+    assert edge.model.architecture == "mobilenetv3" and edge.data.audio_duration == 1.2      # presets.py (BASELINE.json's "2 s, 64 mels" is not what ships: SURVEY App. C)
     compat.install_as_src_data()
     from src.models.architectures import create_model
     m = create_model("resnet18", num_classes=2, pretrained=False, input_channels=1)
