@@ -165,7 +165,6 @@ def _main():
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
     cfg = default_config()
     cfg.training.batch_size = int(os.environ.get("WWF_DDP_BATCH", "32"))
-    cfg.training.epochs = 1
     cfg.data.audio_duration = 1.5
     steps = int(os.environ.get("WWF_DDP_STEPS", "4"))
     plan, train, val = build_plan_and_loaders(cfg, dev, rank=rank, world_size=world,
