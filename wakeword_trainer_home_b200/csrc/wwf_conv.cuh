@@ -70,15 +70,11 @@ struct ConvParams {
 // ------------------------------------------------------------------------------------------
 // radix-32 pass with derived twiddles (pass 0).  tw5[b*s + j] = w_L^{j 2^b}, b = 0..4.
 // ------------------------------------------------------------------------------------------
-template <bool INV, class Map, class TwLoad>
-WWF_HD void pass32_derived(float2* z, int L, int u, TwLoad tw5, Map map = Map()) {
+// register-level core: v[q] = element j + q s of a length-L sub-transform (s = L / 32); forward: DFT_32 then the
+// output twiddles w_L^{j r}; inverse: their conjugates, then the inverse DFT_32.
+template <bool INV, class TwLoad>
+WWF_HD void pass32_core(float2 (&v)[32], int s, int j, TwLoad tw5) {
   constexpr int R = 32;
-  const int s = L / R;
-  const int blk = u / s, j = u - blk * s;
-  const int base = blk * L + j;
-  float2 v[R];
-#pragma unroll
-  for (int q = 0; q < R; ++q) v[q] = z[map(base + q * s)];
   const float2 w1 = tw5(j), w2 = tw5(s + j), w4 = tw5(2 * s + j), w8 = tw5(3 * s + j), w16 = tw5(4 * s + j);
   const float2 w24 = cmul(w16, w8);
   auto apply = [&](float2 x, float2 w) { return INV ? cmulc(x, w) : cmul(x, w); };
@@ -100,6 +96,18 @@ WWF_HD void pass32_derived(float2* z, int L, int u, TwLoad tw5, Map map = Map())
     v[24 + r2] = apply(v[24 + r2], r2 == 0 ? w24 : cmul(lo, w24));
   });
   if constexpr (INV) dft<R, true>(v);
+}
+
+template <bool INV, class Map, class TwLoad>
+WWF_HD void pass32_derived(float2* z, int L, int u, TwLoad tw5, Map map = Map()) {
+  constexpr int R = 32;
+  const int s = L / R;
+  const int blk = u / s, j = u - blk * s;
+  const int base = blk * L + j;
+  float2 v[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) v[q] = z[map(base + q * s)];
+  pass32_core<INV>(v, s, j, tw5);
 #pragma unroll
   for (int q = 0; q < R; ++q) z[map(base + q * s)] = v[q];
 }
@@ -270,28 +278,98 @@ __device__ __forceinline__ void conv_fused_middle(float2* zc, const float4* __re
   }
 }
 
+// ---- the passes of conv_kernel in pointer form ------------------------------------------------------------------
+// pad(i) = i + (i >> 4) and every stride of the radix-32 passes is a multiple of 16, so element base + q s sits at
+// pad(base) + q (s + s / 16): one address per task, compile-time offsets per element (the generic pass_task recomputed
+// the pad map per access: a quarter of the kernel's instructions were LEA / LOP3 / IADD3).
+constexpr int kConvStride0 = ConvRad::S(0) + ConvRad::S(0) / 16;   // 544: pass 0, elements u + 512 q
+constexpr int kConvStride1 = ConvRad::S(1) + ConvRad::S(1) / 16;   // 17:  pass 1, elements 512 blk + j + 16 q
+
+// second radix-32 pass (sub-transforms of length 512, full twiddle table in shared memory), in place
+template <bool INV>
+__device__ __forceinline__ void conv_pass1(float2* z, const float2* t1) {
+  const int u = threadIdx.x, blk = u >> 4, j = u & 15;
+  float2* zp = z + blk * (512 + 32) + j;                         // pad(512 blk + j), j < 16
+  float2 v[32];
+#pragma unroll
+  for (int q = 0; q < 32; ++q) v[q] = zp[kConvStride1 * q];
+  if constexpr (!INV) {
+    dft<32, false>(v);
+#pragma unroll
+    for (int r = 1; r < 32; ++r) v[r] = cmul(v[r], t1[(r - 1) * 16 + j]);
+  } else {
+#pragma unroll
+    for (int r = 1; r < 32; ++r) v[r] = cmulc(v[r], t1[(r - 1) * 16 + j]);
+    dft<32, true>(v);
+  }
+#pragma unroll
+  for (int q = 0; q < 32; ++q) zp[kConvStride1 * q] = v[q];
+}
+
+// Inputs of the FIRST pass straight from global memory: task u combines complex elements u + 512 q, i.e. the sample
+// pairs (x[start + 2 (u + 512 q)], +1) - consecutive threads read consecutive 8-byte pairs, fully coalesced - so the
+// block never makes the load -> shared memory -> registers round trip.  Samples outside [0, N) are zero (the
+// zero padding of the linear convolution / the history before the clip) and are not read at all.
+__device__ __forceinline__ void conv_load_pass0(float2 (&v)[32], const float* __restrict__ x, int N, int start, bool al8) {
+  const int n0 = start + 2 * (int)threadIdx.x;
+  if (start >= 0 && al8 && !(N & 1)) {
+    // the common case (CTA-uniform): the block starts inside the clip, even length, aligned rows - every pair is
+    // either wholly inside or wholly outside: one predicated 8-byte load per element, no branches
+#pragma unroll
+    for (int q = 0; q < 32; ++q) {
+      const int n = n0 + 2 * ConvRad::S(0) * q;
+      float2 t = make_float2(0.f, 0.f);
+      if (n < N) t = __ldg(reinterpret_cast<const float2*>(x + n));
+      v[q] = t;
+    }
+    return;
+  }
+#pragma unroll
+  for (int q = 0; q < 32; ++q) {
+    const int n = n0 + 2 * ConvRad::S(0) * q;
+    float2 t = make_float2(0.f, 0.f);
+    if (n >= 0 && n < N) t.x = __ldg(x + n);
+    if (n + 1 >= 0 && n + 1 < N) t.y = __ldg(x + n + 1);
+    v[q] = t;
+  }
+}
+
 // Persistent: grid = min(#SMs, work items); work item = (clip b, overlap-save block blk).
+// Shared-memory round trips per block: pass 0 (store only: its inputs come from global memory) | pass 1 | fused middle
+// | inverse pass 1 | inverse pass 0 (load only: its results go straight to global memory) = 4 stores + 4 loads of the
+// block (was 6 + 6 with a staging copy at either end) and 5 CTA barriers (was 9).
 // (The flat feature path's per-clip mix records were produced here for a while - at the end of each item, then warp-
 // parallel at the end of the kernel, then with the noise side resolved up front: every variant made THIS kernel
 // 10-12 us slower per 1024 clips, the hot loop is at the 128-register limit and does not take passengers.  They come
-// from feat_prep_kernel, whose noise side runs in the shadow of this kernel's tail.)
+// from feat_prep_kernel, which runs BEFORE this kernel.)
 __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams p) {
   extern __shared__ __align__(16) float2 zc[];
   __shared__ float red[kConvThreads / 32];
   float2* s_tw = zc + kConvSmemElems;
   conv_load_tables(s_tw, p.tw);
-  PadMap pad;
+  const int u = threadIdx.x;
+  const float2* t0 = s_tw + kConvTw0;
+  const float2* t1 = s_tw + kConvTw1;
+  float2* zp0 = zc + u + (u >> 4);                               // pad(u): pass-0 elements at zp0[544 q]
   const int nblk = p.es_nb;
+  __syncthreads();                                               // twiddle tables visible
   for (int item = blockIdx.x; item < p.B * nblk; item += gridDim.x) {
     const int b = item / nblk, blk = item - b * nblk;
     const int r = __ldg(p.rir_idx + b);
-    if (!rir_in_range(r, p.n_rir)) continue;                 // dry clip (CTA-uniform)
+    if (!rir_in_range(r, p.n_rir)) continue;                     // dry clip (CTA-uniform)
     const float* x = p.wav + (size_t)b * p.wav_stride;
-    const bool vec_ok = ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
-    __syncthreads();                                          // previous item's stores / table copy done
-    conv_load_block(zc, x, p.N, blk * p.valid - p.hist, vec_ok);
+    {
+      float2 v[32];
+      conv_load_pass0(v, x, p.N, blk * p.valid - p.hist, (reinterpret_cast<uintptr_t>(x) & 7) == 0);
+      pass32_core<false>(v, ConvRad::S(0), u, [&](int q) { return t0[q]; });
+      // (no barrier needed here: every completed item ends with the barrier of its energy reduction, which all
+      // threads pass only after their last shared-memory loads of that item)
+#pragma unroll
+      for (int q = 0; q < 32; ++q) zp0[kConvStride0 * q] = v[q];
+    }
     __syncthreads();
-    conv_smem_passes<false>(zc, s_tw);
+    conv_pass1<false>(zc, t1);
+    __syncthreads();
     conv_fused_middle(zc, p.spec + (size_t)r * kSpecPerRir, p.fused_l, p.fused_tw);
     __syncthreads();
     {  // pull the next work item's samples into L2 while this block's inverse passes run (no registers held)
@@ -306,30 +384,45 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams 
         }
       }
     }
-    conv_smem_passes<true>(zc, s_tw);
-
-    // store the valid outputs: block sample i in [hist, P) -> clip sample blk*valid + i - hist
-    float* y = p.rev + (size_t)b * p.rev_stride;
-    const bool st_ok = ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+    conv_pass1<true>(zc, t1);
+    __syncthreads();
+    // last inverse pass: results leave the registers for global memory.  Element u + 512 q = block samples
+    // i = 2 (u + 512 q), i + 1 -> clip sample blk * valid + i - hist (hist, valid are multiples of 4: n is even and
+    // the row base is 16-byte aligned, so the pair is one 8-byte store).  The energy of the stored samples is
+    // accumulated on the way for the SNR mix that follows (fixed order: deterministic).
     float e0 = 0.f, e1 = 0.f;
-    for (int q = threadIdx.x; q < kConvP / 4; q += kConvThreads) {
-      const int i = 4 * q;
-      if (i < p.hist) continue;
-      const int n = blk * p.valid + i - p.hist;
-      if (n >= p.N) continue;
-      const float2 a = zc[pad(2 * q)], c = zc[pad(2 * q + 1)];
-      if (n + 3 < p.N && st_ok) {
-        *reinterpret_cast<float4*>(y + n) = make_float4(a.x, a.y, c.x, c.y);
-        e0 = fmaf(a.x, a.x, fmaf(a.y, a.y, e0));
-        e1 = fmaf(c.x, c.x, fmaf(c.y, c.y, e1));
+    {
+      float2 v[32];
+#pragma unroll
+      for (int q = 0; q < 32; ++q) v[q] = zp0[kConvStride0 * q];
+      pass32_core<true>(v, ConvRad::S(0), u, [&](int q) { return t0[q]; });
+      float* y = p.rev + (size_t)b * p.rev_stride;
+      const int nbase = blk * p.valid - p.hist + 2 * u;
+      if (p.hist == 0 && !(p.N & 1) && (reinterpret_cast<uintptr_t>(y) & 7) == 0) {
+        // single-block clips of even length (CTA-uniform): predicated 8-byte stores, no branches
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const int n = nbase + 2 * ConvRad::S(0) * q;
+          const bool in = n < p.N;
+          if (in) *reinterpret_cast<float2*>(y + n) = v[q];
+          const float ax = in ? v[q].x : 0.f, ay = in ? v[q].y : 0.f;
+          if (q & 1) e1 = fmaf(ax, ax, fmaf(ay, ay, e1));
+          else e0 = fmaf(ax, ax, fmaf(ay, ay, e0));
+        }
       } else {
-        y[n] = a.x; e0 = fmaf(a.x, a.x, e0);
-        if (n + 1 < p.N) { y[n + 1] = a.y; e0 = fmaf(a.y, a.y, e0); }
-        if (n + 2 < p.N) { y[n + 2] = c.x; e1 = fmaf(c.x, c.x, e1); }
-        if (n + 3 < p.N) { y[n + 3] = c.y; e1 = fmaf(c.y, c.y, e1); }
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const int i = 2 * (u + ConvRad::S(0) * q), n = nbase + 2 * ConvRad::S(0) * q;
+          const bool in0 = i >= p.hist && n < p.N, in1 = i >= p.hist && n + 1 < p.N;
+          if (in0) y[n] = v[q].x;
+          if (in1) y[n + 1] = v[q].y;
+          const float ax = in0 ? v[q].x : 0.f, ay = in1 ? v[q].y : 0.f;
+          if (q & 1) e1 = fmaf(ax, ax, fmaf(ay, ay, e1));
+          else e0 = fmaf(ax, ax, fmaf(ay, ay, e0));
+        }
       }
     }
-    // energy of this block's output samples, for the SNR mix that follows (fixed reduction order)
+    // energy of this block's output samples (fixed reduction order)
     float e = e0 + e1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
