@@ -106,7 +106,7 @@ int emul_cfft(int nfft, const float* in, float* out) {
   return -1;
 }
 
-// the 511 run pairs + 2 self-paired runs must cover every run exactly once
+// the 511 run pairs + the self-paired run l = 512 (task 511) + the run l = 0 must cover every run exactly once
 int emul_pair_task_coverage(void) {
   std::vector<float2> tw, ftw;
   std::vector<uint16_t> fl;
@@ -114,12 +114,11 @@ int emul_pair_task_coverage(void) {
   std::vector<int> seen(kRuns, 0);
   for (int t = 0; t < kFusedTasks; ++t) {
     const int l = fl[t];
-    if (l <= 0 || l >= kRuns || l == kRuns / 2) return -1;
+    if (l <= 0 || l > kRuns / 2 || (l == kRuns / 2) != (t == kFusedTasks - 1)) return -1;
     seen[run_of(l)]++;
-    seen[run_of(kRuns - l)]++;
+    if (l != kRuns / 2) seen[run_of(kRuns - l)]++;
   }
   seen[run_of(0)]++;
-  seen[run_of(kRuns / 2)]++;
   for (int a = 0; a < kRuns; ++a) if (seen[a] != 1) return -2 - a;
   return 0;
 }
@@ -163,7 +162,7 @@ int emul_rir_conv(const float* x, int N, const float* h, int L, int lmax, float*
   };
   for (int rr = 0; rr < 16; ++rr)
     for (int t = 0; t < kFusedTasks; ++t) spec[rr * 512 + t] = entry((int)fl[t] + 1024 * rr);
-  for (int i = 0; i < 17; ++i) spec[kSpecSpecial + i] = entry(i < 9 ? 1024 * i : 512 + 1024 * (i - 9));
+  for (int i = 0; i < 9; ++i) spec[kSpecSpecial + i] = entry(1024 * i);
   // blocks (conv_kernel)
   int hist = 0, valid = kConvP, nb = 1;
   if ((int64_t)N + lmax - 1 > kConvP) { hist = (lmax - 1 + 3) & ~3; valid = kConvP - hist; nb = (N + valid - 1) / valid; }
@@ -174,7 +173,7 @@ int emul_rir_conv(const float* x, int N, const float* h, int L, int lmax, float*
       const float4* sp = spec.data() + t;
       fused_pair_task(z.data(), (int)fl[t], ftw[t], [&](int r) { return sp[r * 512]; });
     }
-    fused_special_task(z.data(), [&](int i) { return spec[kSpecSpecial + i]; });
+    fused_dc_task(z.data(), [&](int i) { return spec[kSpecSpecial + i]; });
     conv_passes<true>(z.data(), tw.data());
     for (int m = 0; m < kConvM; ++m) {
       for (int c = 0; c < 2; ++c) {

@@ -34,7 +34,8 @@ constexpr int kConvThreads = 512;
 using ConvRad = Radices<32, 32, 16>;
 constexpr int kRunLen = 16;                  // last radix: 16 contiguous positions = one run
 constexpr int kRuns = kConvM / kRunLen;      // 1024 runs, run(l) for l = k mod 1024
-constexpr int kFusedTasks = kRuns / 2 - 1;   // 511 run pairs {l, 1024-l}; l = 0 and l = 512 are self-paired
+constexpr int kFusedTasks = kRuns / 2;       // 511 run pairs {l, 1024-l}, 0 < l < 512, + the self-paired run l = 512 (task 511);
+                                             // the other self-paired run, l = 0 (DC / Nyquist), is fused_dc_task
 
 constexpr int kConvSmemElems = kConvM + (kConvM >> 4);
 
@@ -48,10 +49,10 @@ constexpr int kConvTwTotal = kConvTw1 + 31 * ConvRad::S(1);
 constexpr size_t kConvSmemBytes = (size_t)(kConvSmemElems + kConvTwTotal) * sizeof(float2);
 
 // Per-RIR spectrum layout consumed by the fused task (float4 = (H''[k], H''[M-k]), H'' = rfft(h,P)/(4M)):
-//   general  [r*512 + t]      k = l(t) + 1024 r,  t < 511 (task order), r < 16
-//   special  [16*512 + i]     i < 9: k = 1024 i;  i >= 9: k = 512 + 1024 (i - 9)
+//   general  [r*512 + t]      k = l(t) + 1024 r,  t < 512 (task order), r < 16
+//   special  [16*512 + i]     i < 9: k = 1024 i   (the run l = 0)
 constexpr int kSpecSpecial = 16 * 512;
-constexpr int kSpecPerRir = kSpecSpecial + 17;
+constexpr int kSpecPerRir = kSpecSpecial + 9;
 
 struct ConvParams {
   const float* wav; int64_t wav_stride;      // [B][N]
@@ -63,8 +64,8 @@ struct ConvParams {
   int valid;                                 // V = P - H0 output samples per block
   const float4* spec;                        // [n_rir][kSpecPerRir]
   const float2* tw;                          // pass tables (kConvTwTotal)
-  const uint16_t* fused_l;                   // [511] l of fused task t (bank-conflict-free order)
-  const float2* fused_tw;                    // [511] w_P^{l(t)}
+  const uint16_t* fused_l;                   // [512] l of fused task t (bank-conflict-free order)
+  const float2* fused_tw;                    // [512] w_P^{l(t)}
 };
 
 // ------------------------------------------------------------------------------------------
@@ -142,8 +143,10 @@ WWF_HD void pair_convolve(float2& zk, float2& zm, float2 w, float4 h) {
 
 WWF_HD int run_of(int l) { return ConvRad::pos(l) >> 4; }   // run holding frequencies l + 1024 d2
 
-// General fused task: runs of l and 1024 - l (l not in {0, 512}).  wl = w_P^l;
-// spec(r) = (H''[k], H''[M-k]) for k = l + 1024 r.
+// Fused task: runs of l and 1024 - l, 0 < l <= 512.  wl = w_P^l; spec(r) = (H''[k], H''[M-k]) for k = l + 1024 r.
+// l = 512 pairs the run with itself (k = 512 + 1024 r <-> 512 + 1024 (15 - r)): u and v are then two copies of the same
+// run, every pair is simply computed from both ends, and both copies are written back to the same place - the same
+// straight-line code as every other task, so the warp that owns it does not diverge.
 template <class SpecLoad>
 WWF_HD void fused_pair_task(float2* z, int l, float2 wl, SpecLoad spec) {
   const int a = run_of(l), ap = run_of(kRuns - l);
@@ -165,47 +168,32 @@ WWF_HD void fused_pair_task(float2* z, int l, float2 wl, SpecLoad spec) {
   for (int q = 0; q < 16; ++q) { zu[q] = u[q]; zv[q] = v[q]; }
 }
 
-// The two self-paired runs.  spec(i): i < 9 -> k = 1024 i; i >= 9 -> k = 512 + 1024 (i - 9).
+// The run l = 0: k = 1024 r pairs with 1024 (16 - r); r = 0 carries DC and Nyquist, r = 8 is its own partner.
+// spec(i): k = 1024 i, i < 9.
 template <class SpecLoad>
-WWF_HD void fused_special_task(float2* z, SpecLoad spec) {
-  {  // l = 0: k = 1024 r pairs with 1024 (16 - r); r = 0 carries DC and Nyquist, r = 8 is its own partner
-    float2* zu = z + 17 * run_of(0);
-    float2 u[16];
+WWF_HD void fused_dc_task(float2* z, SpecLoad spec) {
+  float2* zu = z + 17 * run_of(0);
+  float2 u[16];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) u[q] = zu[q];
-    dft<16, false>(u);
-    {
-      float2 a = u[0], b = u[0];
-      pair_convolve(a, b, make_float2(1.f, 0.f), spec(0));
-      u[0] = a;
-    }
-    static_for<1, 8>([&](auto Rr) {
-      constexpr int r = decltype(Rr)::value;
-      pair_convolve(u[r], u[16 - r], make_float2(TwC<r, 32>::c, -TwC<r, 32>::s), spec(r));
-    });
-    {
-      float2 a = u[8], b = u[8];
-      pair_convolve(a, b, make_float2(0.f, -1.f), spec(8));   // w_32^8 = -i
-      u[8] = a;
-    }
-    dft<16, true>(u);
-#pragma unroll
-    for (int q = 0; q < 16; ++q) zu[q] = u[q];
+  for (int q = 0; q < 16; ++q) u[q] = zu[q];
+  dft<16, false>(u);
+  {
+    float2 a = u[0], b = u[0];
+    pair_convolve(a, b, make_float2(1.f, 0.f), spec(0));
+    u[0] = a;
   }
-  {  // l = 512: k = 512 + 1024 r pairs with 512 + 1024 (15 - r); w_P^k = w_64^{1 + 2r}
-    float2* zu = z + 17 * run_of(kRuns / 2);
-    float2 u[16];
-#pragma unroll
-    for (int q = 0; q < 16; ++q) u[q] = zu[q];
-    dft<16, false>(u);
-    static_for<0, 8>([&](auto Rr) {
-      constexpr int r = decltype(Rr)::value;
-      pair_convolve(u[r], u[15 - r], make_float2(TwC<1 + 2 * r, 64>::c, -TwC<1 + 2 * r, 64>::s), spec(9 + r));
-    });
-    dft<16, true>(u);
-#pragma unroll
-    for (int q = 0; q < 16; ++q) zu[q] = u[q];
+  static_for<1, 8>([&](auto Rr) {
+    constexpr int r = decltype(Rr)::value;
+    pair_convolve(u[r], u[16 - r], make_float2(TwC<r, 32>::c, -TwC<r, 32>::s), spec(r));
+  });
+  {
+    float2 a = u[8], b = u[8];
+    pair_convolve(a, b, make_float2(0.f, -1.f), spec(8));   // w_32^8 = -i
+    u[8] = a;
   }
+  dft<16, true>(u);
+#pragma unroll
+  for (int q = 0; q < 16; ++q) zu[q] = u[q];
 }
 
 #if defined(__CUDACC__)
@@ -265,16 +253,17 @@ __device__ __forceinline__ void conv_load_block(float2* z, const float* __restri
   }
 }
 
-// fused middle of one block: thread t < 511 owns run pair l(t); thread 511 the two self-paired runs
+// fused middle of one block: thread t owns run pair l(t) (t = 511: the self-paired run l = 512); thread 511 then
+// also does the run l = 0 - the only divergent stretch, half a task long (it used to do BOTH self-paired runs on a
+// separate path while its warp waited: that warp spent two task times in this phase and everyone else at the barrier)
 __device__ __forceinline__ void conv_fused_middle(float2* zc, const float4* __restrict__ spec,
                                                   const uint16_t* __restrict__ fused_l, const float2* __restrict__ fused_tw) {
   const int t = threadIdx.x;
-  if (t < kFusedTasks) {
-    const float4* sp = spec + t;
-    fused_pair_task(zc, (int)__ldg(fused_l + t), __ldg(fused_tw + t), [&](int r) { return __ldg(sp + r * 512); });
-  } else {
-    const float4* sp = spec + kSpecSpecial;
-    fused_special_task(zc, [&](int i) { return __ldg(sp + i); });
+  const float4* sp = spec + t;
+  fused_pair_task(zc, (int)__ldg(fused_l + t), __ldg(fused_tw + t), [&](int r) { return __ldg(sp + r * 512); });
+  if (t == kFusedTasks - 1) {
+    const float4* sd = spec + kSpecSpecial;
+    fused_dc_task(zc, [&](int i) { return __ldg(sd + i); });
   }
 }
 
@@ -475,10 +464,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) rir_spectrum_kernel(const Spe
     const int rr = i / kFusedTasks, t = i - rr * kFusedTasks;
     spec[rr * 512 + t] = entry((int)p.fused_l[t] + 1024 * rr);
   }
-  if (threadIdx.x < 17) {
-    const int i = threadIdx.x;
-    spec[kSpecSpecial + i] = entry(i < 9 ? 1024 * i : 512 + 1024 * (i - 9));
-  }
+  if (threadIdx.x < 9) spec[kSpecSpecial + threadIdx.x] = entry(1024 * (int)threadIdx.x);
 }
 #endif  // __CUDACC__
 

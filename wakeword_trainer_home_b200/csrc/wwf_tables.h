@@ -44,7 +44,8 @@ inline void build_conv_tables(std::vector<float2>& tw, std::vector<uint16_t>& fu
   fused_l.resize(kFusedTasks);
   fused_tw.resize(kFusedTasks);
   for (int t = 0; t < kFusedTasks; ++t) {
-    const int tt = t + 1, l = (tt >> 4) + 32 * (tt & 15);
+    // (t = 511: tt = 512 -> the self-paired run l = 512, run residue 0 next to the residues 1..15 of its half-warp)
+    const int tt = t + 1, l = tt == kRuns / 2 ? kRuns / 2 : (tt >> 4) + 32 * (tt & 15);
     fused_l[t] = (uint16_t)l;
     fused_tw[t] = W(l, kConvP);
   }
