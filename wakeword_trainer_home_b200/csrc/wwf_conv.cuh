@@ -66,7 +66,12 @@ struct ConvParams {
   const float2* tw;                          // pass tables (kConvTwTotal)
   const uint16_t* fused_l;                   // [512] l of fused task t (bank-conflict-free order)
   const float2* fused_tw;                    // [512] w_P^{l(t)}
+  // noise-mix records of the flat feature path made HERE (single-block clips, at most kConvMaxOwn items per CTA), or
+  // mix_g == nullptr: feat_prep_kernel makes them
+  ClipMix* mix_g;                            // [B]
+  NoiseBankDev noise; const int32_t* noise_idx; const int64_t* noise_off; const float* snr_db;
 };
+constexpr int kConvMaxOwn = 16;              // items per CTA whose records fit the shared-memory staging area
 
 // ------------------------------------------------------------------------------------------
 // radix-32 pass with derived twiddles (pass 0).  tw5[b*s + j] = w_L^{j 2^b}, b = 0..4.
@@ -327,13 +332,43 @@ __device__ __forceinline__ void conv_load_pass0(float2 (&v)[32], const float* __
 // Shared-memory round trips per block: pass 0 (store only: its inputs come from global memory) | pass 1 | fused middle
 // | inverse pass 1 | inverse pass 0 (load only: its results go straight to global memory) = 4 stores + 4 loads of the
 // block (was 6 + 6 with a staging copy at either end) and 5 CTA barriers (was 9).
-// (The flat feature path's per-clip mix records were produced here for a while - at the end of each item, then warp-
-// parallel at the end of the kernel, then with the noise side resolved up front: every variant made THIS kernel
-// 10-12 us slower per 1024 clips, the hot loop is at the 128-register limit and does not take passengers.  They come
-// from feat_prep_kernel, which runs BEFORE this kernel.)
+// The flat feature path's per-clip noise-mix records (ClipMix) are produced here too (MIX): in the prologue every warp
+// resolves the noise side of one of the CTA's own clips (bank lookups + segment energy: a chain of dependent loads
+// that overlaps the table staging) and parks it in SHARED memory; when a clip's block is done, thread 0 turns the
+// block's energy into F.add_noise's scale and writes the record.  Nothing is carried in registers through the hot
+// loop - it sits at the 128-register limit and its code generation is touchy: variants that kept anything live across
+// it, or merely shared one instantiation with the plain kernel, cost 6-12 us per 1024 clips - so the record code lives
+// in two __noinline__ helpers and the kernel is a template.  No kernel of its own (feat_prep_kernel: 16 us of mostly
+// launch and load latency per step) sits in front of the frames kernel any more.  Measured (B = 1024): plain kernel
+// 127.2 us, with the records 135.8 us - 6.7 us of it the prologue's pointer chase (three dependent global loads per
+// clip), which is serial latency wherever it is put (as its own kernel in front of this one: 8 us) - against 16 us.
+static __device__ __noinline__ void conv_mix_prologue(const ConvParams& p, ClipMix* s_mix) {
+  const int warp = threadIdx.x >> 5;
+  for (int k = warp; k < kConvMaxOwn; k += kConvThreads / 32) {
+    const int b = blockIdx.x + k * gridDim.x;                    // (single-block clips: item = clip)
+    if (b >= p.B) break;
+    const ClipNoise cn = resolve_noise(p.noise, p.noise_idx, p.noise_off, b);   // warp-uniform
+    ClipMix m{0.f, 0, 0, 1, 0, 0.f, 0.f};
+    if (cn.nz != nullptr) {
+      m.en = warp_noise_energy(cn, p.N);
+      m.snr = p.snr_db ? __ldg(p.snr_db + b) : 0.f;
+      m.has_noise = 1; m.noff = cn.off; m.nlen = cn.len; m.nz_off = (long long)(cn.nz - p.noise.data);
+    }
+    if ((threadIdx.x & 31) == 0) s_mix[k] = m;
+  }
+}
+// record of clip b (the CTA's item number (b - blockIdx.x) / gridDim.x) once its energy es is known; one thread
+static __device__ __noinline__ void conv_mix_finish(const ConvParams& p, const ClipMix* s_mix, int b, float es) {
+  ClipMix m = s_mix[(b - (int)blockIdx.x) / (int)gridDim.x];
+  if (m.has_noise) m.scale = snr_scale(es, m.en, m.snr);
+  p.mix_g[b] = m;
+}
+
+template <bool MIX>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams p) {
   extern __shared__ __align__(16) float2 zc[];
-  __shared__ float red[kConvThreads / 32];
+  __shared__ float red[32];
+  __shared__ ClipMix s_mix[MIX ? kConvMaxOwn : 1];
   float2* s_tw = zc + kConvSmemElems;
   conv_load_tables(s_tw, p.tw);
   const int u = threadIdx.x;
@@ -341,12 +376,22 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams 
   const float2* t1 = s_tw + kConvTw1;
   float2* zp0 = zc + u + (u >> 4);                               // pad(u): pass-0 elements at zp0[544 q]
   const int nblk = p.es_nb;
+  pdl_wait();                                                    // the clips may come from a kernel of ours (gather / stretch)
   __syncthreads();                                               // twiddle tables visible
+  // (after the barrier: the warps that chase the noise-side pointers arrive late at the first barrier of the item loop
+  // while the others already run their first pass; the records are first read at the end of the first item)
+  if constexpr (MIX) conv_mix_prologue(p, s_mix);
   for (int item = blockIdx.x; item < p.B * nblk; item += gridDim.x) {
     const int b = item / nblk, blk = item - b * nblk;
     const int r = __ldg(p.rir_idx + b);
-    if (!rir_in_range(r, p.n_rir)) continue;                     // dry clip (CTA-uniform)
     const float* x = p.wav + (size_t)b * p.wav_stride;
+    if (!rir_in_range(r, p.n_rir)) {                             // dry clip (CTA-uniform): only its mix record
+      if constexpr (MIX) {
+        const float es = s_mix[(b - (int)blockIdx.x) / (int)gridDim.x].has_noise ? block_energy(x, p.N, red) : 0.f;
+        if (threadIdx.x == 0) conv_mix_finish(p, s_mix, b, es);
+      }
+      continue;
+    }
     {
       float2 v[32];
       conv_load_pass0(v, x, p.N, blk * p.valid - p.hist, (reinterpret_cast<uintptr_t>(x) & 7) == 0);
@@ -421,7 +466,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams 
       e = threadIdx.x < kConvThreads / 32 ? red[threadIdx.x] : 0.f;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-      if (threadIdx.x == 0 && p.es_part != nullptr) p.es_part[(size_t)b * nblk + blk] = e;
+      if (threadIdx.x == 0) {
+        if (p.es_part != nullptr) p.es_part[(size_t)b * nblk + blk] = e;
+        if constexpr (MIX) conv_mix_finish(p, s_mix, b, e);     // F.add_noise's scale, now that the clip's energy is known
+      }
     }
   }
 }

@@ -543,20 +543,20 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
 // feat_epilogue_block_kernel for log-mel).  The per-clip noise-mix records come from feat_prep_kernel.
 // ==========================================================================================================
 // ---- per-clip preparation: the noise-mix record (only when the call mixes noise) ----------------------------
-// One CTA per clip.  Everything that does not depend on the reverb kernel - the bank lookups and the energy of the
-// noise segment, three levels of dependent loads - happens BEFORE the programmatic-launch wait, i.e. in the shadow
-// of conv_kernel's last wave; after it only the clip's energy is fetched (the per-block partials conv_kernel left,
-// or a pass over a dry clip) and the record is written.
+// conv_kernel makes these records itself when it can (wwf_conv.cuh); this kernel serves calls without reverb and clips
+// of several overlap-save blocks (their energy partials come from several CTAs).  One CTA per clip.  Everything that
+// does not depend on the reverb kernel - the bank lookups and the energy of the noise segment, three levels of
+// dependent loads - happens BEFORE the programmatic-launch wait, i.e. in the shadow of conv_kernel's last wave; after
+// it only the clip's energy is fetched (the per-block partials conv_kernel left, or a pass over a dry clip).
 template <int kUnused = 0>   // a template only so that the header can be included by several translation units
 __global__ void __launch_bounds__(256) feat_prep_kernel(const FeatParams p) {
   __shared__ float red[64];
   const int b = blockIdx.x;
   const ClipNoise cn = resolve_noise(p.noise, p.noise_idx, p.noise_off, b);        // CTA-uniform
-  ClipMix m{0.f, 0, 0, 1, 0, 0};
-  float en = 0.f, snr = 0.f;
+  ClipMix m{0.f, 0, 0, 1, 0, 0.f, 0.f};
   if (cn.nz != nullptr) {
-    if (threadIdx.x < 32) en = warp_noise_energy(cn, p.N);
-    snr = p.snr_db ? __ldg(p.snr_db + b) : 0.f;
+    if (threadIdx.x < 32) m.en = warp_noise_energy(cn, p.N);
+    m.snr = p.snr_db ? __ldg(p.snr_db + b) : 0.f;
     m.has_noise = 1; m.noff = cn.off; m.nlen = cn.len; m.nz_off = (long long)(cn.nz - p.noise.data);
   }
   const bool has_rev = clip_has_rev(p.rev, p.rir_idx, p.n_rir, b);
@@ -569,7 +569,7 @@ __global__ void __launch_bounds__(256) feat_prep_kernel(const FeatParams p) {
       const float* x = has_rev ? p.rev + (size_t)b * p.rev_stride : p.wav + (size_t)b * p.wav_stride;
       es = block_energy(x, p.N, red);
     }
-    m.scale = snr_scale(es, en, snr);
+    m.scale = snr_scale(es, m.en, m.snr);
   }
   if (threadIdx.x == 0) p.mix_g[b] = m;
 }

@@ -28,13 +28,14 @@ struct ClipNoise {
   int len, off;
 };
 
-// What the flat frames kernel needs to know about one clip's noise mix; written once per clip by feat_prep_kernel.
+// What the flat frames kernel needs to know about one clip's noise mix; written once per clip by feat_prep_kernel
+// (a reverberated clip's scale by conv_kernel, from en / snr, when the records are made before the reverb).
 struct alignas(16) ClipMix {
   float scale;          // F.add_noise's scale
   int has_noise;        // 0: the clip is not mixed
   int noff, nlen;       // start offset inside the noise clip (already wrapped), its length
   long long nz_off;     // sample offset of the noise clip inside the bank
-  long long pad_;
+  float en, snr;        // energy of the noise segment, target SNR (what the scale is made of besides the clip's energy)
 };
 
 // A clip is reverberated iff its RIR index addresses the registered bank; the SAME predicate in the producer

@@ -123,10 +123,10 @@ struct wwf_plan {
   std::vector<Resampler> resamplers;
   // optional per-kernel timing (wwf_profile_enable)
   bool prof = false;
-  // five events per profiled call: before reverb | after reverb | after prep | after frames | after epilogue
-  // (the single-kernel path records the last three at the same point: its time shows up under "frames")
-  std::vector<cudaEvent_t> prof_events;
-  std::vector<int> prof_split;            // per call: 1 = split path
+  // per profiled call: one event before the first kernel and one after every kernel, plus which kernel each interval
+  // timed (slot 0 conv_kernel | 1 feat_prep_kernel | 2 feat_frames_kernel / feat_kernel | 3 epilogue kernel)
+  struct ProfCall { std::vector<cudaEvent_t> ev; std::vector<int> slot; bool split; };
+  std::vector<ProfCall> prof_calls;
 };
 
 template <typename T>
@@ -184,7 +184,7 @@ extern "C" void wwf_plan_destroy(wwf_plan* p) {
   for (FeatLaunch* l : p->launches) free_launch(l);
   cudaFree(p->d_mel_w); cudaFree(p->d_dct); cudaFree(p->d_dct_frag); cudaFree(p->d_dct_colsum); cudaFree(p->d_nonfinite); cudaFree(p->d_noise_offsets); cudaFree(p->d_spec);
   cudaFree(p->d_noise_prefix); cudaFree(p->d_noise_prefix_offsets);
-  for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
+  for (auto& c : p->prof_calls) for (cudaEvent_t e : c.ev) cudaEventDestroy(e);
   cudaFree(p->d_conv_tw); cudaFree(p->d_fused_l); cudaFree(p->d_fused_tw);
   cudaFree(p->d_pv_window); cudaFree(p->d_pv_tw);
   for (auto& r : p->resamplers) cudaFree(r.coef);
@@ -323,27 +323,21 @@ extern "C" int wwf_profile_enable(wwf_plan* p, int enable) {
 
 static int profile_collect(wwf_plan* p, double ms[4], int* n_calls, int* n_split) {
   DeviceGuard guard(p->device);
-  const int n = (int)(p->prof_events.size() / 5);
+  const int n = (int)p->prof_calls.size();
   double acc[4] = {0.0, 0.0, 0.0, 0.0};
   cudaError_t err = cudaSuccess;
-  for (int i = 0; i < n && err == cudaSuccess; ++i) {
-    cudaEvent_t* e = &p->prof_events[5 * i];
-    const bool split = i < (int)p->prof_split.size() && p->prof_split[i] != 0;
-    err = cudaEventSynchronize(e[split ? 4 : 3]);
-    // the single-kernel path records only events 0, 1, 3 (no extra records between its two kernels)
-    const int pairs[4][2] = {{0, 1}, {1, 2}, {split ? 2 : 1, 3}, {3, 4}};
-    for (int k = 0; k < 4 && err == cudaSuccess; ++k) {
-      if (!split && (k == 1 || k == 3)) continue;
-      float v = 0.f;
-      err = cudaEventElapsedTime(&v, e[pairs[k][0]], e[pairs[k][1]]);
-      acc[k] += v;
-    }
-  }
   int ns = 0;
-  for (int v : p->prof_split) ns += v;
-  for (cudaEvent_t e : p->prof_events) cudaEventDestroy(e);
-  p->prof_events.clear();
-  p->prof_split.clear();
+  for (auto& c : p->prof_calls) {
+    if (err == cudaSuccess && !c.ev.empty()) err = cudaEventSynchronize(c.ev.back());
+    for (size_t k = 0; k + 1 < c.ev.size() && err == cudaSuccess; ++k) {
+      float v = 0.f;
+      err = cudaEventElapsedTime(&v, c.ev[k], c.ev[k + 1]);
+      acc[c.slot[k]] += v;
+    }
+    ns += c.split ? 1 : 0;
+    for (cudaEvent_t e : c.ev) cudaEventDestroy(e);
+  }
+  p->prof_calls.clear();
   if (err != cudaSuccess) return fail(WWF_ERR_CUDA, "wwf_profile_read: %s", cudaGetErrorString(err));
   for (int k = 0; k < 4; ++k) ms[k] = n ? acc[k] / n : 0.0;
   *n_calls = n;
@@ -388,7 +382,8 @@ static int ensure_conv_constants(wwf_plan* p) {
   build_conv_tables(tw, fl, ftw);
   int rc;
   if ((rc = upload(&p->d_conv_tw, tw)) || (rc = upload(&p->d_fused_l, fl)) || (rc = upload(&p->d_fused_tw, ftw))) return rc;
-  WWF_CUDA(cudaFuncSetAttribute((const void*)conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemBytes));
+  WWF_CUDA(cudaFuncSetAttribute((const void*)conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemBytes));
+  WWF_CUDA(cudaFuncSetAttribute((const void*)conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemBytes));
   WWF_CUDA(cudaFuncSetAttribute((const void*)rir_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemBytes));
   return WWF_OK;
 }
@@ -694,35 +689,40 @@ extern "C" size_t wwf_workspace_bytes(const wwf_plan* p, int B, int N) {
 
 static bool wants_reverb(const wwf_plan* p, const wwf_aug* aug) { return aug && aug->rir_idx && p->n_rir > 0; }
 
-// Overlap-save reverb of the clips whose rir_idx addresses the bank into the workspace.
-static int launch_conv(wwf_plan* p, const float* wav, int B, int N, int64_t wav_stride, const wwf_aug* aug,
-                       void* workspace, size_t workspace_bytes, cudaStream_t st, float** rev, int64_t* rev_stride,
-                       const float** es_part, int* es_nb) {
-  *rev = nullptr;
-  *rev_stride = 0;
-  *es_part = nullptr;
-  *es_nb = 0;
+// Overlap-save reverb of the clips whose rir_idx addresses the bank into the workspace: geometry and pointers ...
+static int conv_setup(wwf_plan* p, const float* wav, int B, int N, int64_t wav_stride, const wwf_aug* aug,
+                      void* workspace, size_t workspace_bytes, ConvParams* cp, bool* active) {
+  *active = false;
+  *cp = ConvParams{};
   if (!wants_reverb(p, aug)) return WWF_OK;
   const size_t need = conv_ws_bytes(p, B, N);
   if (!workspace || workspace_bytes < need) return fail(WWF_ERR_WORKSPACE, "workspace too small: %zu < %zu bytes", workspace_bytes, need);
   if (reinterpret_cast<uintptr_t>(workspace) & 15) return fail(WWF_ERR_WORKSPACE, "workspace must be 16-byte aligned");
-  ConvParams cp{};
-  cp.wav = wav; cp.wav_stride = wav_stride;
-  cp.rev = (float*)workspace; cp.rev_stride = round_up4(N);
-  cp.rir_idx = aug->rir_idx; cp.B = B; cp.N = N; cp.n_rir = p->n_rir;
+  cp->wav = wav; cp->wav_stride = wav_stride;
+  cp->rev = (float*)workspace; cp->rev_stride = round_up4(N);
+  cp->rir_idx = aug->rir_idx; cp->B = B; cp->N = N; cp->n_rir = p->n_rir;
   int nb = 1;
-  conv_geometry(p, N, &cp.hist, &cp.valid, &nb);
-  cp.es_part = cp.rev + (size_t)B * cp.rev_stride;
-  cp.es_nb = nb;
-  cp.spec = p->d_spec; cp.tw = p->d_conv_tw; cp.fused_l = p->d_fused_l; cp.fused_tw = p->d_fused_tw;
-  int grid = nb * B < p->sm_count ? nb * B : p->sm_count;
-  conv_kernel<<<grid, kConvThreads, kConvSmemBytes, st>>>(cp);
+  conv_geometry(p, N, &cp->hist, &cp->valid, &nb);
+  cp->es_part = cp->rev + (size_t)B * cp->rev_stride;
+  cp->es_nb = nb;
+  cp->spec = p->d_spec; cp->tw = p->d_conv_tw; cp->fused_l = p->d_fused_l; cp->fused_tw = p->d_fused_tw;
+  *active = true;
+  return WWF_OK;
+}
+
+// ... and the launch (pdl: chained behind one of our own kernels with programmatic dependent launch)
+static int conv_launch(wwf_plan* p, const ConvParams& cp, cudaStream_t st, bool pdl) {
+  const int items = cp.es_nb * cp.B;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(items < p->sm_count ? items : p->sm_count); cfg.blockDim = dim3(kConvThreads);
+  cfg.dynamicSmemBytes = kConvSmemBytes; cfg.stream = st;
+  cudaLaunchAttribute at{};
+  at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &at; cfg.numAttrs = pdl ? 1 : 0;
+  if (cp.mix_g != nullptr) WWF_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel<true>, cp));
+  else WWF_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel<false>, cp));
   g_launches++;
-  WWF_CUDA(cudaGetLastError());
-  *rev = cp.rev;
-  *rev_stride = cp.rev_stride;
-  *es_part = cp.es_part;
-  *es_nb = nb;
   return WWF_OK;
 }
 
@@ -782,51 +782,70 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
     WWF_CUDA(cudaMemsetAsync(fp.clip_max, 0x80, (size_t)round_up4(B) * sizeof(int), st));
   }
 
-  cudaEvent_t pe[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  if (p->prof) {
-    for (auto& e : pe) WWF_CUDA(cudaEventCreate(&e));
-    WWF_CUDA(cudaEventRecord(pe[0], st));
-  }
-  float* rev = nullptr;
-  int64_t rev_stride = 0;
-  const float* es_part = nullptr;
-  int es_nb = 0;
-  if ((rc = launch_conv(p, wav, B, N, wav_stride, aug, workspace, workspace_bytes, st, &rev, &rev_stride, &es_part, &es_nb))) return rc;
-  if (p->prof) WWF_CUDA(cudaEventRecord(pe[1], st));
-  fp.rev = rev; fp.rev_stride = rev_stride;
-  if (!rev) { fp.rir_idx = nullptr; fp.n_rir = 0; }
-  fp.es_part = es_part; fp.es_nb = es_nb;
+  // optional per-kernel timing: an event before the first kernel and after every kernel of the call
+  wwf_plan::ProfCall pc;
+  pc.split = flat;
+  auto mark = [&](int slot) -> cudaError_t {                   // slot < 0: the opening event
+    if (!p->prof) return cudaSuccess;
+    cudaEvent_t e;
+    cudaError_t err = cudaEventCreate(&e);
+    if (err == cudaSuccess) err = cudaEventRecord(e, st);
+    if (err == cudaSuccess) { pc.ev.push_back(e); if (slot >= 0) pc.slot.push_back(slot); }
+    return err;
+  };
+  WWF_CUDA(mark(-1));
+  ConvParams cp;
+  bool conv_on = false;
+  if ((rc = conv_setup(p, wav, B, N, wav_stride, aug, workspace, workspace_bytes, &cp, &conv_on))) return rc;
+  fp.rev = conv_on ? cp.rev : nullptr; fp.rev_stride = conv_on ? cp.rev_stride : 0;
+  if (!conv_on) { fp.rir_idx = nullptr; fp.n_rir = 0; }
+  fp.es_part = conv_on ? cp.es_part : nullptr; fp.es_nb = conv_on ? cp.es_nb : 0;
   const bool pdl = p->opt_pdl && !p->prof;   // (only behind one of OUR kernels: what runs before the first of them may still be producing the inputs)
 
   if (flat) {
-    // noise: the per-clip mix records (one CTA per clip; its noise side runs before the programmatic-launch wait)
-    const bool need_prep = fp.mix_g != nullptr;
-    if (need_prep) WWF_CUDA(launch_feat((FeatKernel)feat_prep_kernel<0>, fp, (unsigned)B, 256, 0, st, pdl && rev != nullptr));
-    if (p->prof) WWF_CUDA(cudaEventRecord(pe[2], st));
-    WWF_CUDA(launch_feat(p->frames, fp, l->frames_grid, (unsigned)(l->frames_warps * 32), l->frames_smem, st, pdl && (need_prep || rev != nullptr)));
-    if (p->prof) WWF_CUDA(cudaEventRecord(pe[3], st));
-    WWF_CUDA(launch_feat(l->ep_kernel, fp, l->ep_grid, (unsigned)l->ep_threads, l->ep_smem, st, pdl));
-    g_launches += need_prep ? 3 : 2;
-    WWF_CUDA(cudaGetLastError());
-    if (p->prof) {
-      WWF_CUDA(cudaEventRecord(pe[4], st));
-      p->prof_events.insert(p->prof_events.end(), pe, pe + 5);
-      p->prof_split.push_back(1);
+    // Noise: one mix record per clip.  conv_kernel makes them itself (single-block clips, a bounded number of clips
+    // per CTA); otherwise feat_prep_kernel does, after the reverb (one CTA per clip; its noise side runs before the
+    // programmatic-launch wait).
+    const bool need_mix = fp.mix_g != nullptr;
+    const int conv_grid = conv_on ? std::min(cp.es_nb * B, p->sm_count) : 1;
+    const bool mix_in_conv = need_mix && conv_on && cp.es_nb == 1 && (B + conv_grid - 1) / conv_grid <= kConvMaxOwn;
+    bool chained = false;                                      // is there a kernel of this call in front of the next launch?
+    if (conv_on) {
+      if (mix_in_conv) {
+        cp.mix_g = fp.mix_g; cp.noise = fp.noise; cp.noise_idx = fp.noise_idx; cp.noise_off = fp.noise_off; cp.snr_db = fp.snr_db;
+      }
+      if ((rc = conv_launch(p, cp, st, false))) return rc;
+      WWF_CUDA(mark(0));
+      chained = true;
     }
+    if (need_mix && !mix_in_conv) {
+      WWF_CUDA(launch_feat((FeatKernel)feat_prep_kernel<0>, fp, (unsigned)B, 256, 0, st, pdl && chained));
+      g_launches++;
+      WWF_CUDA(mark(1));
+      chained = true;
+    }
+    WWF_CUDA(launch_feat(p->frames, fp, l->frames_grid, (unsigned)(l->frames_warps * 32), l->frames_smem, st, pdl && chained));
+    WWF_CUDA(mark(2));
+    WWF_CUDA(launch_feat(l->ep_kernel, fp, l->ep_grid, (unsigned)l->ep_threads, l->ep_smem, st, pdl));
+    g_launches += 2;
+    WWF_CUDA(cudaGetLastError());
+    WWF_CUDA(mark(3));
+    if (p->prof) p->prof_calls.push_back(std::move(pc));
     return WWF_OK;
   }
   if (!l->fused_ok)
     return fail(WWF_ERR_UNSUPPORTED, "clip too long for the in-shared-memory tile of the single-kernel path: %zu bytes of tiles/tables "
                 "(N=%d, T=%d, n_mels=%d)%s", l->fused_fixed, N, T, M,
                 p->cfg.cmvn ? "; CMVN plans have no other path" : "; pass a workspace of wwf_workspace_bytes() to use the flat path");
-  WWF_CUDA(launch_feat(p->kernel, fp, (unsigned)l->fused_grid, (unsigned)(l->fused_warps * 32), l->fused_smem, st, pdl && rev != nullptr));   // behind conv_kernel only
+  if (conv_on) {
+    if ((rc = conv_launch(p, cp, st, false))) return rc;
+    WWF_CUDA(mark(0));
+  }
+  WWF_CUDA(launch_feat(p->kernel, fp, (unsigned)l->fused_grid, (unsigned)(l->fused_warps * 32), l->fused_smem, st, pdl && conv_on));   // behind conv_kernel only
   g_launches++;
   WWF_CUDA(cudaGetLastError());
-  if (p->prof) {
-    WWF_CUDA(cudaEventRecord(pe[3], st));
-    p->prof_events.insert(p->prof_events.end(), pe, pe + 5);
-    p->prof_split.push_back(0);
-  }
+  WWF_CUDA(mark(2));
+  if (p->prof) p->prof_calls.push_back(std::move(pc));
   return WWF_OK;
 }
 
@@ -838,12 +857,15 @@ extern "C" int wwf_augment(wwf_plan* p, const float* wav, int B, int N, int64_t 
   if (!guard.ok) return fail(WWF_ERR_CUDA, "cudaSetDevice(%d) failed", p->device);
   cudaStream_t st = (cudaStream_t)stream;
   if (wants_reverb(p, aug) && out_wav == wav) return fail(WWF_ERR_INVALID, "wwf_augment: in-place is not allowed with reverb");
-  float* rev = nullptr;
-  int64_t rev_stride = 0;
-  const float* es_part = nullptr;
-  int es_nb = 0;
-  int rc = launch_conv(p, wav, B, N, wav_stride, aug, workspace, workspace_bytes, st, &rev, &rev_stride, &es_part, &es_nb);
+  ConvParams cp;
+  bool conv_on = false;
+  int rc = conv_setup(p, wav, B, N, wav_stride, aug, workspace, workspace_bytes, &cp, &conv_on);
   if (rc) return rc;
+  if (conv_on && (rc = conv_launch(p, cp, st, false))) return rc;
+  float* rev = conv_on ? cp.rev : nullptr;
+  const int64_t rev_stride = conv_on ? cp.rev_stride : 0;
+  const float* es_part = conv_on ? cp.es_part : nullptr;
+  const int es_nb = conv_on ? cp.es_nb : 0;
   MixParams mp{};
   mp.wav = wav; mp.wav_stride = wav_stride; mp.rev = rev; mp.rev_stride = rev_stride;
   if (aug) {
