@@ -152,8 +152,10 @@ WWF_HD int run_of(int l) { return ConvRad::pos(l) >> 4; }   // run holding frequ
 // l = 512 pairs the run with itself (k = 512 + 1024 r <-> 512 + 1024 (15 - r)): u and v are then two copies of the same
 // run, every pair is simply computed from both ends, and both copies are written back to the same place - the same
 // straight-line code as every other task, so the warp that owns it does not diverge.
-template <class SpecLoad>
-WWF_HD void fused_pair_task(float2* z, int l, float2 wl, SpecLoad spec) {
+// after(r) runs right after pair r (the kernel re-fills its rotating spectrum registers there).
+struct NoAfter { WWF_HD void operator()(int) const {} };
+template <class SpecLoad, class After = NoAfter>
+WWF_HD void fused_pair_task(float2* z, int l, float2 wl, SpecLoad spec, After after = After()) {
   const int a = run_of(l), ap = run_of(kRuns - l);
   float2* zu = z + 17 * a;    // pad(16 a + q) = 17 a + q
   float2* zv = z + 17 * ap;
@@ -166,6 +168,7 @@ WWF_HD void fused_pair_task(float2* z, int l, float2 wl, SpecLoad spec) {
     constexpr int r = decltype(Rr)::value;
     const float2 w = cmul_cs<false>(wl, TwC<r, 32>::c, TwC<r, 32>::s);   // w_P^{l + 1024 r} = w_P^l w_32^r
     pair_convolve(u[r], v[15 - r], r == 0 ? wl : w, spec(r));
+    after(r);
   });
   dft<16, true>(u);           // first inverse pass
   dft<16, true>(v);
@@ -261,11 +264,25 @@ __device__ __forceinline__ void conv_load_block(float2* z, const float* __restri
 // fused middle of one block: thread t owns run pair l(t) (t = 511: the self-paired run l = 512); thread 511 then
 // also does the run l = 0 - the only divergent stretch, half a task long (it used to do BOTH self-paired runs on a
 // separate path while its warp waited: that warp spent two task times in this phase and everyone else at the barrier)
-__device__ __forceinline__ void conv_fused_middle(float2* zc, const float4* __restrict__ spec,
+// The RIR spectrum comes from L2 (131 KB per RIR, one float4 per pair): its latency was the largest stall of the kernel
+// (13 % of the samples on the multiplications that consume it).  The first kSpecPf of a thread's 16 entries are therefore
+// requested BEFORE the barrier in front of this phase (conv_fused_prefetch), and each register is re-filled with entry
+// r + kSpecPf as soon as pair r has used it: every load has a barrier or kSpecPf pairs of arithmetic to land.
+#ifndef WWF_SPEC_PF
+#define WWF_SPEC_PF 8
+#endif
+constexpr int kSpecPf = WWF_SPEC_PF;         // spectrum entries in flight per thread (a power of two <= 16)
+__device__ __forceinline__ void conv_fused_prefetch(float4 (&h)[kSpecPf], const float4* __restrict__ spec) {
+  const float4* sp = spec + threadIdx.x;
+#pragma unroll
+  for (int r = 0; r < kSpecPf; ++r) h[r] = __ldg(sp + r * 512);
+}
+__device__ __forceinline__ void conv_fused_middle(float2* zc, const float4* __restrict__ spec, float4 (&h)[kSpecPf],
                                                   const uint16_t* __restrict__ fused_l, const float2* __restrict__ fused_tw) {
   const int t = threadIdx.x;
   const float4* sp = spec + t;
-  fused_pair_task(zc, (int)__ldg(fused_l + t), __ldg(fused_tw + t), [&](int r) { return __ldg(sp + r * 512); });
+  fused_pair_task(zc, (int)__ldg(fused_l + t), __ldg(fused_tw + t), [&](int r) { return h[r & (kSpecPf - 1)]; },
+                  [&](int r) { if (r + kSpecPf < 16) h[r & (kSpecPf - 1)] = __ldg(sp + (r + kSpecPf) * 512); });
   if (t == kFusedTasks - 1) {
     const float4* sd = spec + kSpecSpecial;
     fused_dc_task(zc, [&](int i) { return __ldg(sd + i); });
@@ -403,8 +420,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams 
     }
     __syncthreads();
     conv_pass1<false>(zc, t1);
-    __syncthreads();
-    conv_fused_middle(zc, p.spec + (size_t)r * kSpecPerRir, p.fused_l, p.fused_tw);
+    {
+      float4 h[kSpecPf];
+      conv_fused_prefetch(h, p.spec + (size_t)r * kSpecPerRir);
+      __syncthreads();
+      conv_fused_middle(zc, p.spec + (size_t)r * kSpecPerRir, h, p.fused_l, p.fused_tw);
+    }
     __syncthreads();
     {  // pull the next work item's samples into L2 while this block's inverse passes run (no registers held)
       const int nitem = item + gridDim.x;
