@@ -20,6 +20,7 @@ using namespace wwf;
 template <int NFFT>
 static void stft_pair(const float* fa, const float* fb, float* pa, float* pb) {
   using Rad = typename StftPlan<NFFT>::Rad;
+  constexpr bool kNatural = stft_natural_out<NFFT>();       // the kernel's choice: last pass stores in natural order
   std::vector<float2> tw;
   build_stft_twiddles<Rad>(tw);
   std::vector<float2> z(NFFT);
@@ -28,10 +29,16 @@ static void stft_pair(const float* fa, const float* fb, float* pa, float* pb) {
     constexpr int i = decltype(I)::value;
     constexpr int R = Rad::R(i), L = Rad::L(i);
     const float2* t = tw.data() + Rad::tw_off(i);
-    for (int u = 0; u < NFFT / R; ++u) pass_task<R, false>(z.data(), L, u, [&](int q) { return t[q]; });
+    if constexpr (kNatural && i == Rad::npass - 1) {
+      const std::vector<float2> snap = z;                    // on the GPU: all lanes load, __syncwarp, all lanes store
+      for (int u = 0; u < NFFT / R; ++u) pass_task_natural<R, Rad::R(0)>(snap.data(), z.data(), u, [] {});
+    } else {
+      for (int u = 0; u < NFFT / R; ++u) pass_task<R, false>(z.data(), L, u, [&](int q) { return t[q]; });
+    }
   });
   for (int k = 0; k <= NFFT / 2; ++k) {
-    const int pk = Rad::pos(k), pm = Rad::pos(k == 0 ? 0 : NFFT - k);
+    const int kn = k == 0 ? 0 : NFFT - k;
+    const int pk = kNatural ? k : Rad::pos(k), pm = kNatural ? kn : Rad::pos(kn);
     const float2 pw = pair_split_power(z[pk], z[pm]);
     pa[k] = pw.x;
     pb[k] = pw.y;
@@ -250,10 +257,9 @@ int emul_mel_schedule(int n_fft, int n_freqs, int n_mels, const float* fb, const
   }
   ofs[n_mels] = (int)w.size();
   if (w.empty()) w.push_back(0.f);
-  std::function<int(int)> zmap;
-  if (n_fft == 400) zmap = [](int i) { return IdentityMap()(i); };
-  else zmap = [](int i) { return PadMap2()(i); };
-  const MelSchedule s = build_mel_schedule(lo, ofs, w, zmap);
+  (void)n_fft;
+  auto zmap = [](int i) { return i; };                         // the power spectra are stored in plain bin order
+  const MelSchedule s = build_mel_schedule(lo, ofs, w);
   std::vector<int> owners(n_mels, 0);
   int worst = 1, nsplit = 0;
   for (int r = 0; r < s.rounds; ++r) {

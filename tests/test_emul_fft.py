@@ -119,6 +119,7 @@ def test_mel_lane_schedule_equals_dense_filterbank(emul, n_fft, n_mels):
     rounds, iters, worst, nsplit = list(stats)
     naive = sum(-(-max((int(np.count_nonzero(fb[:, m])) and (np.nonzero(fb[:, m])[0][-1] - np.nonzero(fb[:, m])[0][0] + 1))
                        for m in range(r, min(r + 32, n_mels))) // 2) for r in range(0, n_mels, 32))
-    assert iters <= naive, (iters, naive)
+    assert iters <= naive + 1, (iters, naive)     # (a round may grow by one iteration to free a bank residue)
+    assert worst <= 2, worst          # conflict-free by construction, except first bins too small to be shifted
     print(f"n_fft {n_fft} n_mels {n_mels}: rounds {rounds}, two-tap iterations {iters} (filter-per-lane order: {naive}), "
           f"worst half-warp residue multiplicity {worst}, split filters {nsplit}")

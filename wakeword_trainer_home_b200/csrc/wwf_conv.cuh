@@ -394,10 +394,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams 
   float2* zp0 = zc + u + (u >> 4);                               // pad(u): pass-0 elements at zp0[544 q]
   const int nblk = p.es_nb;
   pdl_wait();                                                    // the clips may come from a kernel of ours (gather / stretch)
-  __syncthreads();                                               // twiddle tables visible
-  // (after the barrier: the warps that chase the noise-side pointers arrive late at the first barrier of the item loop
-  // while the others already run their first pass; the records are first read at the end of the first item)
   if constexpr (MIX) conv_mix_prologue(p, s_mix);
+  __syncthreads();                                               // twiddle tables and mix records visible (a dry first
+                                                                 // item reads its record straight away)
   for (int item = blockIdx.x; item < p.B * nblk; item += gridDim.x) {
     const int b = item / nblk, blk = item - b * nblk;
     const int r = __ldg(p.rir_idx + b);

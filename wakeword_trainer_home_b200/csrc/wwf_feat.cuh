@@ -43,6 +43,12 @@ template <> struct StftPlan<2048> { using Rad = Radices<16, 16, 8>; using Map = 
 template <int NFFT> constexpr int stft_zlen() {
   return (typename StftPlan<NFFT>::Map()(NFFT - 1) + 2) & ~1;
 }
+// Two-pass plans whose last pass fits one warp round for all G transforms (400 = 16 x 25: 2 x 16 tasks; 256 = 16 x 16)
+// leave the spectrum in natural order (pass_task_natural); the others in digit-reversed order (Radices::pos).
+template <int NFFT> constexpr bool stft_natural_out() {
+  using P = StftPlan<NFFT>;
+  return P::Rad::npass == 2 && P::G * (NFFT / P::Rad::R(1)) <= 32;
+}
 
 struct FeatParams {
   // inputs
@@ -181,7 +187,6 @@ __device__ __forceinline__ float frame_group_to_db(const float* __restrict__ x, 
   constexpr int K = NFFT / 2 + 1;
   constexpr int NC = (NFFT + 31) / 32;                       // 32-sample columns per frame
   constexpr int ZL = stft_zlen<NFFT>();                      // scratch elements per FFT (with padding)
-  constexpr int NI = (G * K + 31) / 32;                      // split items per lane
   static_assert(Rad::n == NFFT, "radix plan");
   const Map zmap;
   const int lane = threadIdx.x & 31;
@@ -260,49 +265,61 @@ __device__ __forceinline__ float frame_group_to_db(const float* __restrict__ x, 
     }
   }
   __syncwarp();
-  // 2. forward FFT passes (in place, digit-reversed result)
+  // 2. forward FFT passes (in place; digit-reversed result, or natural order when the last pass is one warp round)
+  constexpr bool kNatural = stft_natural_out<NFFT>();
   static_for<0, Rad::npass>([&](auto I) {
     constexpr int i = decltype(I)::value;
     constexpr int R = Rad::R(i), L = Rad::L(i), tasks = NFFT / R;
     const float2* tw = tb.tw + Rad::tw_off(i);
-    // tasks of the G FFTs share the rounds of 32 lanes, unless one FFT per round costs no extra round (n_fft 400:
-    // 25 radix-16 tasks per FFT, 2 rounds either way) - then no half-warp straddles two FFTs (no bank conflicts
-    // between their columns or twiddles) and the task index needs no division
-    constexpr bool kPerFft = tasks < 32 && G * ((tasks + 31) / 32) == (G * tasks + 31) / 32;
-    if constexpr (kPerFft) {
-#pragma unroll 1   // one copy of each radix butterfly: the hot loop has to stay inside the instruction cache
-      for (int g = 0; g < G; ++g)
-        if (lane < tasks) pass_task<R, false, Map>(z + g * ZL, L, lane, [&](int q) { return tw[q]; });
+    if constexpr (kNatural && i == Rad::npass - 1) {
+      // all G * tasks <= 32 tasks of the group in ONE round: every lane loads its inputs, the warp syncs, every lane
+      // stores frequency k = u + R0 r at position k
+      const int g = lane / tasks, uu = lane - g * tasks;
+      if (lane < G * tasks) pass_task_natural<R, Rad::R(0), Map>(z + g * ZL, z + g * ZL, uu, [] { __syncwarp(); });
+      else __syncwarp();
     } else {
+      // tasks of the G FFTs share the rounds of 32 lanes, unless one FFT per round costs no extra round (n_fft 400:
+      // 25 radix-16 tasks per FFT, 2 rounds either way) - then no half-warp straddles two FFTs (no bank conflicts
+      // between their columns or twiddles) and the task index needs no division
+      constexpr bool kPerFft = tasks < 32 && G * ((tasks + 31) / 32) == (G * tasks + 31) / 32;
+      if constexpr (kPerFft) {
+#pragma unroll 1   // one copy of each radix butterfly: the hot loop has to stay inside the instruction cache
+        for (int g = 0; g < G; ++g)
+          if (lane < tasks) pass_task<R, false, Map>(z + g * ZL, L, lane, [&](int q) { return tw[q]; });
+      } else {
 #pragma unroll 1
-      for (int u = lane; u < G * tasks; u += 32) {
-        const int g = u / tasks, uu = u - g * tasks;
-        pass_task<R, false, Map>(z + g * ZL, L, uu, [&](int q) { return tw[q]; });
+        for (int u = lane; u < G * tasks; u += 32) {
+          const int g = u / tasks, uu = u - g * tasks;
+          pass_task<R, false, Map>(z + g * ZL, L, uu, [&](int q) { return tw[q]; });
+        }
       }
     }
     __syncwarp();
   });
   // 3. split the packed pair into two power spectra (|A[k]|^2, |B[k]|^2): read every (Z[k], Z[n-k])
-  //    first, then store the powers in plain bin order
+  //    first, then store the powers in plain bin order.  Half-warps take 16 consecutive bins of ONE transform
+  //    (slot = 16-bin block; K rounded up to K16 blocks per transform), so a half-warp's two gathers never straddle
+  //    two transforms.
   {
-    float2 pw[NI];
+    constexpr int K16 = (K + 15) / 16;                       // 16-bin blocks per transform
+    constexpr int NS = (G * K16 + 1) / 2;                    // split items per lane
+    const int hw = lane >> 4, l16 = lane & 15;
+    float2 pw[NS];
 #pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      const int idx = lane + 32 * i;
-      if (idx < G * K) {
-        const int g = idx / K, k = idx - g * K;
+    for (int i = 0; i < NS; ++i) {
+      const int slot = 2 * i + hw, g = slot / K16, k = 16 * (slot - g * K16) + l16;
+      if (g < G && k < K) {
         const float2* zz = z + g * ZL;
-        pw[i] = pair_split_power(zz[zmap(Rad::pos(k))], zz[zmap(Rad::pos(k == 0 ? 0 : NFFT - k))]);
+        const int kn = k == 0 ? 0 : NFFT - k;
+        pw[i] = kNatural ? pair_split_power(zz[zmap(k)], zz[zmap(kn)])
+                         : pair_split_power(zz[zmap(Rad::pos(k))], zz[zmap(Rad::pos(kn))]);
       }
     }
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < NI; ++i) {
-      const int idx = lane + 32 * i;
-      if (idx < G * K) {
-        const int g = idx / K, k = idx - g * K;
-        z[g * ZL + zmap(k)] = pw[i];
-      }
+    for (int i = 0; i < NS; ++i) {
+      const int slot = 2 * i + hw, g = slot / K16, k = 16 * (slot - g * K16) + l16;
+      if (g < G && k < K) z[g * ZL + k] = pw[i];           // plain bin order: what the mel lane schedule is built for
     }
   }
   __syncwarp();
@@ -321,7 +338,7 @@ __device__ __forceinline__ float frame_group_to_db(const float* __restrict__ x, 
     int i = 0;
     for (; i + 1 < n; i += 2) {
       const float w0 = wr[32 * i], w1 = wr[32 * i + 32];
-      const int p0 = zmap(k0 + i), p1 = zmap(k0 + i + 1);
+      const int p0 = k0 + i, p1 = k0 + i + 1;
 #pragma unroll
       for (int g = 0; g < G; ++g) {
         acc[g] = cfma_s(z[g * ZL + p0], w0, acc[g]);
@@ -330,7 +347,7 @@ __device__ __forceinline__ float frame_group_to_db(const float* __restrict__ x, 
     }
     if (i < n) {
       const float w0 = wr[32 * i];
-      const int p0 = zmap(k0 + i);
+      const int p0 = k0 + i;
 #pragma unroll
       for (int g = 0; g < G; ++g) acc[g] = cfma_s(z[g * ZL + p0], w0, acc[g]);
     }

@@ -326,6 +326,23 @@ WWF_HD void pass_task(float2* z, int L, int u, TwLoad twload, Map map = Map()) {
   for (int q = 0; q < R; ++q) z[map(base + q * s)] = v[q];
 }
 
+// Last pass of a TWO-pass plan (R0, R) with the results stored in NATURAL frequency order: task u = d0 transforms the
+// R contiguous elements u R .. u R + R - 1 (s = 1: no twiddles) and output r is frequency k = u + R0 r, written to
+// zout[map(k)] instead of back in place.  Every task overwrites other tasks' inputs, so this is only valid when ALL
+// tasks of the transform run in one converged warp instruction stream (loads of all lanes, sync(), stores of all
+// lanes); the host emulation passes a snapshot as zin.  The spectrum split can then read Z[k] and Z[n - k] from
+// consecutive addresses (no digit-reversal arithmetic, no bank conflicts).
+template <int R, int R0, class Map = IdentityMap, class Sync>
+WWF_HD void pass_task_natural(const float2* zin, float2* zout, int u, Sync sync, Map map = Map()) {
+  float2 v[R];
+#pragma unroll
+  for (int q = 0; q < R; ++q) v[q] = zin[map(u * R + q)];
+  dft<R, false>(v);
+  sync();
+#pragma unroll
+  for (int r = 0; r < R; ++r) zout[map(u + R0 * r)] = v[r];
+}
+
 // ----------------------------------------------------------------------------------------
 // Static description of an FFT as a list of radices (up to 4 passes).
 // ----------------------------------------------------------------------------------------

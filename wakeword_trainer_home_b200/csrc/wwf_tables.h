@@ -84,11 +84,16 @@ inline std::vector<float> mel_fbanks32(int n_freqs, float f_min, float f_max, in
 // The filterbank has at most two non-zeros per FFT bin, so each filter is a short run of consecutive bins
 // (2 .. ~30 taps).  One lane per filter in filter order leaves the warp waiting for its widest filter (21 two-tap
 // iterations for 40 mels at n_fft 400, 25 of 32 lanes active on average) and reads bins lo[m] + i whose bank
-// residues collide (1.9 wavefronts per load, ncu round 1).  The schedule built here instead
+// residues collide (1.7 - 2.4 wavefronts per load on every configuration, ncu + tools/mel_sched_sim.cu).  The schedule
+// built here instead
 //   * cuts filters wider than a threshold W into two halves on ADJACENT lanes (one __shfl_xor joins them),
 //   * sorts the resulting tasks by length and fills rounds of 32 lanes, so the lanes of a round finish together,
-//   * places tasks inside a round so that the 16 lanes of a half-warp start at bins with distinct bank residues,
-//   * stores the weights interleaved per round (w[(base + i) * 32 + lane]): conflict-free by construction.
+//   * makes every half-warp CONFLICT-FREE by construction: the power spectra are stored in plain bin order (8-byte
+//     elements: 16 banks per half-warp) and all lanes advance one bin per tap, so two lanes collide on every tap or
+//     on none, depending only on (first bin mod 16).  A task whose residue is taken starts d bins EARLIER with d
+//     leading zero weights (first bin k0 - d, n + d taps): tasks are placed longest first, each taking the half-warp
+//     and the smallest d that keep the round short,
+//   * stores the weights interleaved per round (w[(base + i) * 32 + lane]): conflict-free as well.
 // W is chosen by minimising the modelled issue cost (two-tap iterations of each round's longest task + a fixed
 // per-round overhead).  A task is an int2: x = first bin | ntaps << 16,  y = weight base (in rows of 32 floats)
 // | filter << 16 | flags << 24.
@@ -98,70 +103,90 @@ struct MelSchedule {
   std::vector<int2> tasks;        // [rounds * 32]
   std::vector<float> w;           // interleaved weights, rows of 32
   int iterations = 0;             // two-tap iterations summed over the rounds (for reports)
+  int conflicts = 0;              // half-warp tap rows that still hit a bank twice (0 unless a residue could not be freed)
 };
 
-// lo[m] / ofs[m] / w: CSR rows of the filterbank (first bin, offsets into w); zmap: scratch index map of the kernel
-inline MelSchedule build_mel_schedule(const std::vector<int>& lo, const std::vector<int>& ofs, const std::vector<float>& w,
-                                      const std::function<int(int)>& zmap) {
+// lo[m] / ofs[m] / w: CSR rows of the filterbank (first bin, offsets into w)
+inline MelSchedule build_mel_schedule(const std::vector<int>& lo, const std::vector<int>& ofs, const std::vector<float>& w) {
   const int M = (int)lo.size();
-  struct Task { int m, k0, o, n, flags; };
-  struct Unit { Task a, b; bool pair; int len() const { return pair ? std::max(a.n, b.n) : a.n; } };
-  struct Round { std::vector<std::pair<int, Task>> placed; int mx = 0; };
-  // all units of a threshold W, longest first, placed round by round: a unit goes to the half-warp (of the current
-  // round) that has room and the fewest tasks starting on the same bank residue; pairs fill a half from lane 0 upwards
-  // (even aligned), singles from lane 15 downwards; when neither half has room the round is closed
+  struct Task { int m, k0, o, n, flags, d; };                  // d: leading zero-weight taps
+  struct Unit { Task a, b; bool pair; int len() const { return pair ? std::max(a.n, b.n) : a.n; } int lanes() const { return pair ? 2 : 1; } };
+  struct Placed { int lane; Task t; };
+  struct Round { std::vector<Placed> placed; int mx = 0, conflicts = 0; };
   auto layout = [&](int W) {
     std::vector<Unit> u;
     for (int m = 0; m < M; ++m) {
       const int n = ofs[m + 1] - ofs[m];
       if (n > W && n >= 2) {
         const int n1 = (n + 1) / 2;
-        u.push_back({{m, lo[m], ofs[m], n1, kMelOwner | kMelPartner}, {m, lo[m] + n1, ofs[m] + n1, n - n1, 0}, true});
+        u.push_back({{m, lo[m], ofs[m], n1, kMelOwner | kMelPartner, 0}, {m, lo[m] + n1, ofs[m] + n1, n - n1, 0, 0}, true});
       } else {
-        u.push_back({{m, lo[m], ofs[m], n, kMelOwner}, {}, false});
+        u.push_back({{m, lo[m], ofs[m], n, kMelOwner, 0}, {}, false});
       }
     }
     std::stable_sort(u.begin(), u.end(), [](const Unit& x, const Unit& y) { return x.len() > y.len(); });
-    std::vector<Round> rounds(1);
-    int pair_cur[2] = {0, 0}, single_cur[2] = {15, 15};
-    int resid[2][16] = {};
+    std::vector<Round> rounds;
+    int used = 32;
+    int lanes_used[2] = {0, 0}, pair_cur[2] = {0, 0}, single_cur[2] = {15, 15};
+    bool taken[2][16];
+    // cheapest shift d <= min(k0, 15) of a task in half h: a shift beyond the round's current length costs issue slots
+    // for the whole warp (7 per tap), a residue that is already taken costs a second wavefront on each of the
+    // task's taps (3 per tap); `also` = residue of the unit's other half
+    auto shift_for = [&](int h, const Task& t, int also, int mx_now, int* cost_out) {
+      int best_d = 0, best_c = 1 << 30;
+      for (int d = 0; d <= std::min(t.k0, 15); ++d) {
+        const int r = (t.k0 - d) & 15;
+        const int c = 7 * std::max(0, t.n + d - mx_now) + ((taken[h][r] || r == also) ? 3 * t.n : 0);
+        if (c < best_c) { best_c = c; best_d = d; }
+      }
+      *cost_out = best_c;
+      return best_d;
+    };
     for (const Unit& x : u) {
-      const int need = x.pair ? 2 : 1;
-      int best_h = -1;
-      for (int attempt = 0; attempt < 2 && best_h < 0; ++attempt) {
-        int best_col = 1 << 30, best_free = -1;
-        for (int h = 0; h < 2; ++h) {
-          const int free_l = single_cur[h] - pair_cur[h] + 1;
-          if (free_l < need) continue;
-          int col = resid[h][zmap(x.a.k0) & 15];
-          if (x.pair) col += resid[h][zmap(x.b.k0) & 15];
-          if (col < best_col || (col == best_col && free_l > best_free)) { best_h = h; best_col = col; best_free = free_l; }
-        }
-        if (best_h < 0) {                                        // no room: next round
-          rounds.emplace_back();
-          pair_cur[0] = pair_cur[1] = 0; single_cur[0] = single_cur[1] = 15;
-          for (auto& rr : resid) for (int& v : rr) v = 0;
-        }
+      if (used + x.lanes() > 32 || (lanes_used[0] + x.lanes() > 16 && lanes_used[1] + x.lanes() > 16)) {
+        rounds.emplace_back();
+        used = 0;
+        lanes_used[0] = lanes_used[1] = 0; pair_cur[0] = pair_cur[1] = 0; single_cur[0] = single_cur[1] = 15;
+        for (auto& tr : taken) for (bool& v : tr) v = false;
       }
       Round& r = rounds.back();
-      r.mx = std::max(r.mx, x.len());
-      if (x.pair) {
-        const int l = 16 * best_h + pair_cur[best_h];
-        pair_cur[best_h] += 2;
-        r.placed.push_back({l, x.a});
-        r.placed.push_back({l + 1, x.b});
-        resid[best_h][zmap(x.a.k0) & 15]++;
-        resid[best_h][zmap(x.b.k0) & 15]++;
-      } else {
-        r.placed.push_back({16 * best_h + single_cur[best_h]--, x.a});
-        resid[best_h][zmap(x.a.k0) & 15]++;
+      const int mx_now = std::max(r.mx, x.len());               // (units arrive longest first)
+      // the half-warp (with room) where the unit is cheapest; ties: the emptier half
+      int best_h = -1, best_cost = 1 << 30, best_da = 0, best_db = 0;
+      for (int h = 0; h < 2; ++h) {
+        if (lanes_used[h] + x.lanes() > 16) continue;
+        int ca = 0, cb = 0, db = 0;
+        const int da = shift_for(h, x.a, -1, mx_now, &ca);
+        if (x.pair) db = shift_for(h, x.b, (x.a.k0 - da) & 15, mx_now, &cb);
+        if (ca + cb < best_cost || (ca + cb == best_cost && lanes_used[h] < lanes_used[best_h])) {
+          best_h = h; best_cost = ca + cb; best_da = da; best_db = db;
+        }
       }
+      const int h = best_h;
+      Task ta = x.a, tb = x.b;
+      ta.d = best_da; tb.d = best_db;
+      if (taken[h][(ta.k0 - ta.d) & 15]) r.conflicts += ta.n;
+      taken[h][(ta.k0 - ta.d) & 15] = true;
+      r.mx = std::max(r.mx, ta.n + ta.d);
+      if (x.pair) {
+        if (taken[h][(tb.k0 - tb.d) & 15]) r.conflicts += tb.n;
+        taken[h][(tb.k0 - tb.d) & 15] = true;
+        r.mx = std::max(r.mx, tb.n + tb.d);
+        const int l = 16 * h + pair_cur[h];
+        pair_cur[h] += 2;
+        r.placed.push_back({l, ta});
+        r.placed.push_back({l + 1, tb});
+      } else {
+        r.placed.push_back({16 * h + single_cur[h]--, ta});
+      }
+      lanes_used[h] += x.lanes();
+      used += x.lanes();
     }
     return rounds;
   };
   auto cost = [](const std::vector<Round>& r) {                  // issue slots: two-tap iterations + per-round overhead
     int c = 0;
-    for (const Round& rr : r) c += 14 * ((rr.mx + 1) / 2) + 45;
+    for (const Round& rr : r) c += 14 * ((rr.mx + 1) / 2) + 45 + 8 * rr.conflicts;
     return c;
   };
   int maxw = 1;
@@ -179,13 +204,14 @@ inline MelSchedule build_mel_schedule(const std::vector<int>& lo, const std::vec
   for (int r = 0; r < s.rounds; ++r) {
     const int mx = rounds[r].mx;
     s.w.resize((size_t)(wbase + mx) * 32, 0.f);
-    for (const auto& pl : rounds[r].placed) {
-      const Task& t = pl.second;
-      for (int i = 0; i < t.n; ++i) s.w[(size_t)(wbase + i) * 32 + pl.first] = w[t.o + i];
-      s.tasks[(size_t)r * 32 + pl.first] = make_int2(t.k0 | (t.n << 16), wbase | (t.m << 16) | (t.flags << 24));
+    for (const Placed& pl : rounds[r].placed) {
+      const Task& t = pl.t;
+      for (int i = 0; i < t.n; ++i) s.w[(size_t)(wbase + t.d + i) * 32 + pl.lane] = w[t.o + i];   // rows < d stay 0
+      s.tasks[(size_t)r * 32 + pl.lane] = make_int2((t.k0 - t.d) | ((t.n + t.d) << 16), wbase | (t.m << 16) | (t.flags << 24));
     }
     wbase += mx;
     s.iterations += (mx + 1) / 2;
+    s.conflicts += rounds[r].conflicts;
   }
   if (s.w.empty()) s.w.push_back(0.f);
   return s;

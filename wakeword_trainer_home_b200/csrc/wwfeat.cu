@@ -86,7 +86,6 @@ struct wwf_plan {
   FeatKernel frames = nullptr;          // flat path: flat frames kernel (same n_fft / hop variant)
   FeatKernel epilogue_block = nullptr;  // flat path, log-mel: feat_epilogue_block_kernel<float | __half>
   FeatKernel epilogue_mma = nullptr;    // flat path, MFCC: feat_epilogue_mma_kernel<float | __half>
-  std::function<int(int)> zmap;         // index map of the feature kernels' FFT scratch (for the mel lane schedule)
   // device constants
   float* d_window = nullptr;
   float2* d_tw = nullptr;
@@ -154,7 +153,6 @@ static void select_kernel(wwf_plan* p, std::vector<float2>& tw) {
   p->frames = (FeatKernel)feat_frames_kernel<NFFT, 0>;
   p->epilogue_block = f16 ? (FeatKernel)feat_epilogue_block_kernel<__half> : (FeatKernel)feat_epilogue_block_kernel<float>;
   p->epilogue_mma = f16 ? (FeatKernel)feat_epilogue_mma_kernel<__half> : (FeatKernel)feat_epilogue_mma_kernel<float>;
-  p->zmap = [](int i) { return typename Plan::Map()(i); };
   {
     // register-staged frame loads for hops that are a multiple of 32 and instantiated: 128, 160, 256
     if (!p->generic_load) {
@@ -261,7 +259,7 @@ extern "C" int wwf_plan_create(const wwf_config* cfg, int device, wwf_plan** out
   }
   ofs[M] = (int)w.size();
   if (w.empty()) w.push_back(0.f);
-  const MelSchedule sched = build_mel_schedule(lo, ofs, w, p->zmap);
+  const MelSchedule sched = build_mel_schedule(lo, ofs, w);
   p->n_melw = (int)sched.w.size();
   p->mel_rounds = sched.rounds;
 
