@@ -257,9 +257,8 @@ int emul_mel_schedule(int n_fft, int n_freqs, int n_mels, const float* fb, const
   }
   ofs[n_mels] = (int)w.size();
   if (w.empty()) w.push_back(0.f);
-  (void)n_fft;
   auto zmap = [](int i) { return i; };                         // the power spectra are stored in plain bin order
-  const MelSchedule s = build_mel_schedule(lo, ofs, w);
+  const MelSchedule s = build_mel_schedule(lo, ofs, w, n_fft);
   std::vector<int> owners(n_mels, 0);
   int worst = 1, nsplit = 0;
   for (int r = 0; r < s.rounds; ++r) {

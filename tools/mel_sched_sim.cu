@@ -20,7 +20,7 @@ int main(int argc, char** argv) {
   ofs[M] = (int)w.size();
   (void)pad;
   auto zmap = [](int i) { return i; };                     // the power spectra are stored in plain bin order
-  MelSchedule s = build_mel_schedule(lo, ofs, w);
+  MelSchedule s = build_mel_schedule(lo, ofs, w, n_fft);
   long ideal = 0, actual = 0;
   for (int r = 0; r < s.rounds; ++r) {
     int mx = 0;

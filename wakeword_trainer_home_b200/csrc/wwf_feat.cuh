@@ -28,17 +28,20 @@
 namespace wwf {
 
 constexpr int kMaxMasks = 8;
+constexpr int kMaxMelRounds = 16;              // rounds of the mel lane schedule (128 filters need 4 - 5)
 
 // Per-n_fft plan: radix list, G = complex FFTs (frame pairs) per warp iteration, the launch bounds
 // (max threads per CTA, min CTAs per SM) the kernel is compiled for, and the index map of the warp's
 // FFT scratch: the power-of-two sizes need one pad element per 16 (their later passes would
 // otherwise be 4- to 16-way bank conflicted); 400 = 16 x 25 has an odd stride and needs none.
 template <int NFFT> struct StftPlan;
-template <> struct StftPlan<256>  { using Rad = Radices<16, 16>;    using Map = PadMap2;     static constexpr int G = 2, kThreads = 320, kMinCtas = 2; };
-template <> struct StftPlan<400>  { using Rad = Radices<16, 25>;    using Map = IdentityMap; static constexpr int G = 2, kThreads = 320, kMinCtas = 2; };
-template <> struct StftPlan<512>  { using Rad = Radices<16, 8, 4>;  using Map = PadMap2;     static constexpr int G = 1, kThreads = 512, kMinCtas = 1; };
-template <> struct StftPlan<1024> { using Rad = Radices<16, 16, 4>; using Map = PadMap2;     static constexpr int G = 1, kThreads = 512, kMinCtas = 1; };
-template <> struct StftPlan<2048> { using Rad = Radices<16, 16, 8>; using Map = PadMap2;     static constexpr int G = 1, kThreads = 512, kMinCtas = 1; };
+// kFlatThreads: CTA width the flat frames kernel is compiled for (same 2 CTAs per SM): n_fft 400 fits 80 registers
+// there (24 resident warps instead of 20: 128.9 -> 125.5 us on the bench workload; 64 registers / 32 warps spill and lose).
+template <> struct StftPlan<256>  { using Rad = Radices<16, 16>;    using Map = PadMap2;     static constexpr int G = 2, kThreads = 320, kMinCtas = 2, kFlatThreads = 320; };
+template <> struct StftPlan<400>  { using Rad = Radices<16, 25>;    using Map = IdentityMap; static constexpr int G = 2, kThreads = 320, kMinCtas = 2, kFlatThreads = 384; };
+template <> struct StftPlan<512>  { using Rad = Radices<16, 8, 4>;  using Map = PadMap2;     static constexpr int G = 1, kThreads = 512, kMinCtas = 1, kFlatThreads = 512; };
+template <> struct StftPlan<1024> { using Rad = Radices<16, 16, 4>; using Map = PadMap2;     static constexpr int G = 1, kThreads = 512, kMinCtas = 1, kFlatThreads = 512; };
+template <> struct StftPlan<2048> { using Rad = Radices<16, 16, 8>; using Map = PadMap2;     static constexpr int G = 1, kThreads = 512, kMinCtas = 1, kFlatThreads = 512; };
 // complex elements of one FFT's scratch buffer (mapped length, rounded up to an even count)
 template <int NFFT> constexpr int stft_zlen() {
   return (typename StftPlan<NFFT>::Map()(NFFT - 1) + 2) & ~1;
@@ -65,6 +68,7 @@ struct FeatParams {
   //   | colmask u8[T] | z float2 [nwarps][G][ZL]
   int off_res, off_window, off_tw, off_melw, off_dct, off_meltasks, off_rowmask, off_colmask, off_z;
   int n_melw, mel_rounds, c8;                    // interleaved mel weight count, schedule rounds; n_mfcc rounded up to 8
+  unsigned short mel_pairs[kMaxMelRounds];        // two-tap iterations of each round (warp-uniform trip counts)
   // device constants (plan-owned)
   const float* window;                           // [NFFT]
   const float2* tw;                              // concatenated per-pass twiddle tables
@@ -174,6 +178,7 @@ struct MelTables {          // shared-memory copies
   const float* melw;        // lane-interleaved filter weights
   const int2* tasks;        // [rounds*32] mel lane schedule
   int rounds;
+  const unsigned short* pairs;   // [rounds] two-tap iterations per round (kernel parameter space: uniform loads)
 };
 
 template <int NFFT, int HOP32, class Sink>
@@ -328,28 +333,24 @@ __device__ __forceinline__ float frame_group_to_db(const float* __restrict__ x, 
   float vmax = -INFINITY;
   for (int r = 0; r < tb.rounds; ++r) {
     const int2 task = tb.tasks[r * 32 + lane];
-    const int k0 = task.x & 0xffff, n = (int)((unsigned)task.x >> 16);
+    const int k0 = task.x & 0xffff;
     const unsigned flags = (unsigned)task.y >> 24;
     const float* wr = tb.melw + (task.y & 0xffff) * 32 + lane;
-    // two independent accumulator chains per frame pair (even / odd taps) hide the LDS + FFMA2 latency
+    // two independent accumulator chains per frame pair (even / odd taps) hide the LDS + FFMA2 latency.  Every lane
+    // runs the round's full (warp-uniform) trip count: the weight rows beyond its own taps are zero, the bins it reads
+    // there are this transform's own (finite) scratch.
     float2 acc[G], acc1[G];
 #pragma unroll
     for (int g = 0; g < G; ++g) { acc[g] = make_float2(0.f, 0.f); acc1[g] = make_float2(0.f, 0.f); }
-    int i = 0;
-    for (; i + 1 < n; i += 2) {
-      const float w0 = wr[32 * i], w1 = wr[32 * i + 32];
-      const int p0 = k0 + i, p1 = k0 + i + 1;
+    const int np = tb.pairs[r];
+    const float2* zk = z + k0;
+    for (int it = 0; it < np; ++it) {
+      const float w0 = wr[64 * it], w1 = wr[64 * it + 32];
 #pragma unroll
       for (int g = 0; g < G; ++g) {
-        acc[g] = cfma_s(z[g * ZL + p0], w0, acc[g]);
-        acc1[g] = cfma_s(z[g * ZL + p1], w1, acc1[g]);
+        acc[g] = cfma_s(zk[g * ZL + 2 * it], w0, acc[g]);
+        acc1[g] = cfma_s(zk[g * ZL + 2 * it + 1], w1, acc1[g]);
       }
-    }
-    if (i < n) {
-      const float w0 = wr[32 * i];
-      const int p0 = k0 + i;
-#pragma unroll
-      for (int g = 0; g < G; ++g) acc[g] = cfma_s(z[g * ZL + p0], w0, acc[g]);
     }
 #pragma unroll
     for (int g = 0; g < G; ++g) acc[g] = cadd(acc[g], acc1[g]);
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
   unsigned char* s_rowmask = reinterpret_cast<unsigned char*>(smem + p.off_rowmask);
   unsigned char* s_colmask = reinterpret_cast<unsigned char*>(smem + p.off_colmask);
   float2* z = reinterpret_cast<float2*>(smem + p.off_z) + (size_t)warp * G * ZL;
-  const MelTables tb{s_window, s_tw, s_melw, s_tasks, p.mel_rounds};
+  const MelTables tb{s_window, s_tw, s_melw, s_tasks, p.mel_rounds, p.mel_pairs};
 
   // ---- constants -> shared memory, once per (persistent) CTA ---------------------------
   for (int i = tid; i < NFFT; i += blockDim.x) s_window[i] = __ldg(p.window + i);
@@ -593,7 +594,7 @@ __global__ void __launch_bounds__(256) feat_prep_kernel(const FeatParams p) {
 
 // ---- frames: STFT -> power -> mel -> dB into the global tile (warp-autonomous, flat over clips) ----
 template <int NFFT, int HOP32>
-__global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMinCtas) feat_frames_kernel(const FeatParams p) {
+__global__ void __launch_bounds__(StftPlan<NFFT>::kFlatThreads, StftPlan<NFFT>::kMinCtas) feat_frames_kernel(const FeatParams p) {
   using Plan = StftPlan<NFFT>;
   using Rad = typename Plan::Rad;
   constexpr int G = Plan::G;
@@ -608,7 +609,7 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kThreads, StftPlan<NFFT>::kMin
   float* s_melw = smem + p.f_off_melw;
   int2* s_tasks = reinterpret_cast<int2*>(smem + p.f_off_meltasks);
   float2* z = reinterpret_cast<float2*>(smem + p.f_off_z) + (size_t)warp * G * ZL;
-  const MelTables tb{s_window, s_tw, s_melw, s_tasks, p.mel_rounds};
+  const MelTables tb{s_window, s_tw, s_melw, s_tasks, p.mel_rounds, p.mel_pairs};
 
   // ---- constants -> shared memory, once per (persistent) CTA; the only CTA-wide barrier ----
   for (int i = tid; i < NFFT; i += blockDim.x) s_window[i] = __ldg(p.window + i);

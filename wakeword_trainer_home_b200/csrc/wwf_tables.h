@@ -102,12 +102,14 @@ struct MelSchedule {
   int rounds = 0;
   std::vector<int2> tasks;        // [rounds * 32]
   std::vector<float> w;           // interleaved weights, rows of 32
+  std::vector<int> pairs;         // [rounds] two-tap iterations of each round (every lane runs them all: the weight
+                                  // rows beyond a lane's own taps are zero)
   int iterations = 0;             // two-tap iterations summed over the rounds (for reports)
   int conflicts = 0;              // half-warp tap rows that still hit a bank twice (0 unless a residue could not be freed)
 };
 
-// lo[m] / ofs[m] / w: CSR rows of the filterbank (first bin, offsets into w)
-inline MelSchedule build_mel_schedule(const std::vector<int>& lo, const std::vector<int>& ofs, const std::vector<float>& w) {
+// lo[m] / ofs[m] / w: CSR rows of the filterbank (first bin, offsets into w); n_fft: elements of a transform's scratch
+inline MelSchedule build_mel_schedule(const std::vector<int>& lo, const std::vector<int>& ofs, const std::vector<float>& w, int n_fft) {
   const int M = (int)lo.size();
   struct Task { int m, k0, o, n, flags, d; };                  // d: leading zero-weight taps
   struct Unit { Task a, b; bool pair; int len() const { return pair ? std::max(a.n, b.n) : a.n; } int lanes() const { return pair ? 2 : 1; } };
@@ -202,15 +204,21 @@ inline MelSchedule build_mel_schedule(const std::vector<int>& lo, const std::vec
   s.tasks.assign((size_t)s.rounds * 32, make_int2(0, 0xff << 16));
   int wbase = 0;
   for (int r = 0; r < s.rounds; ++r) {
-    const int mx = rounds[r].mx;
-    s.w.resize((size_t)(wbase + mx) * 32, 0.f);
+    const int rows = 2 * ((rounds[r].mx + 1) / 2);              // every lane runs rows / 2 two-tap iterations
+    s.w.resize((size_t)(wbase + rows) * 32, 0.f);
+    for (int lane = 0; lane < 32; ++lane) s.tasks[(size_t)r * 32 + lane] = make_int2(0, wbase | (0xff << 16));   // idle: zero weights
     for (const Placed& pl : rounds[r].placed) {
       const Task& t = pl.t;
-      for (int i = 0; i < t.n; ++i) s.w[(size_t)(wbase + t.d + i) * 32 + pl.lane] = w[t.o + i];   // rows < d stay 0
-      s.tasks[(size_t)r * 32 + pl.lane] = make_int2((t.k0 - t.d) | ((t.n + t.d) << 16), wbase | (t.m << 16) | (t.flags << 24));
+      // a lane reads bins k0 .. k0 + rows - 1 whatever its own tap count: keep that inside the transform's scratch
+      // (n_fft elements) by starting earlier, with more leading zero weights
+      int k0 = t.k0 - t.d, d = t.d;
+      if (k0 + rows > n_fft) { const int sh = std::min(k0, k0 + rows - n_fft); k0 -= sh; d += sh; }
+      for (int i = 0; i < t.n; ++i) s.w[(size_t)(wbase + d + i) * 32 + pl.lane] = w[t.o + i];   // rows < d and >= d + n stay 0
+      s.tasks[(size_t)r * 32 + pl.lane] = make_int2(k0 | ((t.n + d) << 16), wbase | (t.m << 16) | (t.flags << 24));
     }
-    wbase += mx;
-    s.iterations += (mx + 1) / 2;
+    wbase += rows;
+    s.pairs.push_back(rows / 2);
+    s.iterations += rows / 2;
     s.conflicts += rounds[r].conflicts;
   }
   if (s.w.empty()) s.w.push_back(0.f);

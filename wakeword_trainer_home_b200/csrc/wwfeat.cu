@@ -81,7 +81,8 @@ static void free_launch(FeatLaunch* l);
 struct wwf_plan {
   wwf_config cfg;
   int device = 0, sm_count = 0, max_smem = 0;
-  int K = 0, n_feat = 0, G = 1, zlen = 0, tw_total = 0, n_melw = 0, mel_rounds = 0, max_warps = 16;
+  int K = 0, n_feat = 0, G = 1, zlen = 0, tw_total = 0, n_melw = 0, mel_rounds = 0, max_warps = 16, max_warps_flat = 16;
+  unsigned short mel_pairs[kMaxMelRounds] = {};
   FeatKernel kernel = nullptr;          // fused per-clip kernel
   FeatKernel frames = nullptr;          // flat path: flat frames kernel (same n_fft / hop variant)
   FeatKernel epilogue_block = nullptr;  // flat path, log-mel: feat_epilogue_block_kernel<float | __half>
@@ -147,6 +148,7 @@ static void select_kernel(wwf_plan* p, std::vector<float2>& tw) {
   p->G = Plan::G;
   p->zlen = stft_zlen<NFFT>();
   p->max_warps = Plan::kThreads / 32;
+  p->max_warps_flat = Plan::kFlatThreads / 32;
   p->tw_total = Plan::Rad::tw_total;
   const bool f16 = p->cfg.out_dtype == WWF_OUT_F16;
   p->kernel = f16 ? (FeatKernel)feat_kernel<NFFT, 0, __half> : (FeatKernel)feat_kernel<NFFT, 0, float>;
@@ -259,7 +261,9 @@ extern "C" int wwf_plan_create(const wwf_config* cfg, int device, wwf_plan** out
   }
   ofs[M] = (int)w.size();
   if (w.empty()) w.push_back(0.f);
-  const MelSchedule sched = build_mel_schedule(lo, ofs, w);
+  const MelSchedule sched = build_mel_schedule(lo, ofs, w, n);
+  if (sched.rounds > kMaxMelRounds) { delete p; return fail(WWF_ERR_UNSUPPORTED, "mel lane schedule needs %d rounds (max %d)", sched.rounds, kMaxMelRounds); }
+  for (int r = 0; r < sched.rounds; ++r) p->mel_pairs[r] = (unsigned short)sched.pairs[r];
   p->n_melw = (int)sched.w.size();
   p->mel_rounds = sched.rounds;
 
@@ -550,6 +554,7 @@ static FeatLaunch* build_launch(wwf_plan* p, int B, int N) {
   fp.c8 = mfcc ? ((F + 7) & ~7) : 0;
   fp.n_melw = p->n_melw;
   fp.mel_rounds = p->mel_rounds;
+  memcpy(fp.mel_pairs, p->mel_pairs, sizeof(fp.mel_pairs));
   // ---- single-kernel path: shared-memory layout (64-bit: very long clips must not wrap) ----
   long long o = al4((long long)M * pitch);
   const long long off_res = o;      o += (mfcc && p->cfg.cmvn) ? al4((long long)F * pitch) : 0;
@@ -612,7 +617,7 @@ static FeatLaunch* build_launch(wwf_plan* p, int B, int N) {
     const size_t f_fixed = (size_t)fo * sizeof(float);
     int fc = 1, fbest = -1;
     for (int c : cands) {
-      if (c > p->max_warps) continue;
+      if (c > p->max_warps_flat) continue;
       const size_t sm = f_fixed + (size_t)c * per_warp;
       if (sm > budget) continue;
       int nb = 0;
