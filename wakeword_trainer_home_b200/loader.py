@@ -106,10 +106,27 @@ class GpuBatchLoader:
         # the collate function of the reference's evaluator (src/evaluation/evaluator.py:257-268, :313)
         self.metadata = metadata
         self.epoch = 0
-        self.step = 0
+        self.step = 0                   # batches produced in the whole run: keys the augmentation draws
+        self._skip = 0                  # batches of the current epoch to skip after load_state_dict (mid-epoch resume)
+        self._batches_done = 0          # batches produced so far in the current epoch
 
     def set_epoch(self, epoch: int):
         self.epoch = epoch
+
+    # ---- resume: sits beside the reference's checkpoint dict (src/training/trainer.py:486-525) ----
+    def state_dict(self) -> dict:
+        """Everything a resumed run needs to see the same batches with the same augmentation draws: the run seed,
+        the epoch (it fixes the permutation) and the number of batches already produced (it keys the per-step draws)."""
+        return {"kind": "GpuBatchLoader", "seed": self.seed, "epoch": self.epoch, "step": self.step,
+                "batches_done": self._batches_done, "rank": self.rank, "world_size": self.world}
+
+    def load_state_dict(self, state: dict):
+        if state.get("kind") != "GpuBatchLoader":
+            raise ValueError(f"not a GpuBatchLoader state: {state.get('kind')!r}")
+        if (state["rank"], state["world_size"]) != (self.rank, self.world):
+            raise ValueError("loader state was saved for another rank / world size")
+        self.seed, self.epoch, self.step = int(state["seed"]), int(state["epoch"]), int(state["step"])
+        self._skip = int(state.get("batches_done", 0))
 
     def _indices(self) -> torch.Tensor:
         n = self.clips.shape[0]
@@ -130,7 +147,11 @@ class GpuBatchLoader:
         idx = self._indices()
         dev = self.plan.device
         on_dev = self.clips.is_cuda
-        for i in range(len(self)):
+        first, self._skip = self._skip, 0
+        if first >= len(self):                                            # the saved epoch was complete
+            first = 0
+        self._batches_done = first
+        for i in range(first, len(self)):
             sel = idx[i * self.batch_size:(i + 1) * self.batch_size]
             B = sel.numel()
             wav = self.clips.index_select(0, sel.to(self.clips.device))
@@ -147,6 +168,7 @@ class GpuBatchLoader:
                 aug = aug or AugParams()
                 aug.fmask_start, aug.fmask_len, aug.tmask_start, aug.tmask_len = m.fmask_start, m.fmask_len, m.tmask_start, m.tmask_len
             self.step += 1
+            self._batches_done = i + 1
             feats = self.plan.featurize(wav, aug)
             targets = self.labels.index_select(0, sel.to(self.labels.device)).to(dev, non_blocking=True)
             if self.metadata is not None:
@@ -174,9 +196,27 @@ class DeviceBatchLoader:
         self.rank, self.world, self.drop_last = rank, world_size, drop_last
         self.epoch = 0
         self.samples_drawn = 0          # checkpoint this (with seed) to resume with identical augmentations
+        self._skip = 0                  # batches of the current epoch to skip after load_state_dict (mid-epoch resume)
+        self._batches_done = 0          # batches produced so far in the current epoch
 
     def set_epoch(self, epoch: int):
         self.epoch = epoch
+
+    # ---- resume: sits beside the reference's checkpoint dict (src/training/trainer.py:486-525) ----
+    def state_dict(self) -> dict:
+        """seed + epoch fix the permutation, ``samples_drawn`` is the Philox counter of the next augmentation draw and
+        ``batches_done`` the position inside the epoch: a loader restored from this continues with bit-identical batches."""
+        return {"kind": "DeviceBatchLoader", "seed": self.seed, "epoch": self.epoch, "samples_drawn": self.samples_drawn,
+                "batches_done": self._batches_done, "rank": self.rank, "world_size": self.world}
+
+    def load_state_dict(self, state: dict):
+        if state.get("kind") != "DeviceBatchLoader":
+            raise ValueError(f"not a DeviceBatchLoader state: {state.get('kind')!r}")
+        if (state["rank"], state["world_size"]) != (self.rank, self.world):
+            raise ValueError("loader state was saved for another rank / world size")
+        self.seed, self.epoch = int(state["seed"]), int(state["epoch"])
+        self.samples_drawn = int(state["samples_drawn"])
+        self._skip = int(state.get("batches_done", 0))
 
     def __len__(self) -> int:
         a, b = shard_range(self.bank.shape[0], self.rank, self.world)
@@ -194,7 +234,11 @@ class DeviceBatchLoader:
         idx = perm[a:b].to(self.bank.device)                              # one small upload per epoch
         # ranks draw from disjoint counter ranges: sample numbers are offset by rank * 2^40
         base = (self.rank << 40) + self.samples_drawn
-        for i in range(len(self)):
+        first, self._skip = self._skip, 0
+        if first >= len(self):                                            # the saved epoch was complete
+            first = 0
+        self._batches_done = first
+        for i in range(first, len(self)):
             sel = idx[i * self.batch_size:(i + 1) * self.batch_size]
             wav = gather_clips(self.bank, sel)
             aug = None
@@ -202,4 +246,5 @@ class DeviceBatchLoader:
                 aug = self.plan.draw_aug(self.draw, base, sel.numel(), wav.shape[1])
             base += sel.numel()
             self.samples_drawn += sel.numel()
+            self._batches_done = i + 1
             yield self.plan.featurize(wav, aug), self.labels.index_select(0, sel)

@@ -350,6 +350,10 @@ class FeaturePlan:
         """(B, N) -> (B, N): clip b played rates[b] times faster without changing its pitch (torchaudio's
         STFT -> phase_vocoder -> iSTFT), cropped / zero-padded to N; rates[b] == 1.0 copies the clip.
         ``rate_lo`` is a lower bound of the rates (sizes the workspace); it is read from ``rates`` when omitted."""
+        with self._range("wwf.time_stretch"):
+            return self._time_stretch(wav, rates, rate_lo, out)
+
+    def _time_stretch(self, wav, rates, rate_lo, out):
         wav = self._check_wav(wav)
         B, n = wav.shape
         rates = torch.as_tensor(rates)
@@ -372,6 +376,10 @@ class FeaturePlan:
                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """(B, N) -> (B, N): torchaudio F.pitch_shift by n_steps[b] semitones per clip (0 copies the clip).
         ``step_range`` = (lo, hi) bounds of n_steps; read from the tensor when omitted."""
+        with self._range("wwf.pitch_shift"):
+            return self._pitch_shift(wav, n_steps, step_range, out)
+
+    def _pitch_shift(self, wav, n_steps, step_range, out):
         wav = self._check_wav(wav)
         B, n = wav.shape
         n_steps = torch.as_tensor(n_steps)
@@ -428,9 +436,24 @@ class FeaturePlan:
             wav = wav.contiguous()
         return wav
 
+    def nvtx(self, enable: bool = True):
+        """Bracket every ``featurize`` / ``augment`` / ``time_stretch`` / ``pitch_shift`` call with an NVTX range
+        (``wwf.featurize`` ...) so the path shows up by stage on an Nsight timeline (profiling)."""
+        self._nvtx = bool(enable)
+
+    def _range(self, name: str):
+        if getattr(self, "_nvtx", False):
+            return torch.cuda.nvtx.range(name)
+        import contextlib
+        return contextlib.nullcontext()
+
     def featurize(self, wav: torch.Tensor, aug: Optional[AugParams] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """(B, N) float32 clips -> (B, 1, n_feat, T) features, one fused GPU pass
         (reverb -> noise -> STFT -> mel -> dB -> [DCT] -> [CMVN] -> [masks])."""
+        with self._range("wwf.featurize"):
+            return self._featurize(wav, aug, out)
+
+    def _featurize(self, wav, aug, out):
         wav = self._check_wav(wav)
         B, n = wav.shape
         T = self.num_frames(n)
@@ -459,6 +482,15 @@ class FeaturePlan:
         N.check(self.lib.wwf_augment(self._handle, _ptr(wav), B, n, wav.stride(0), None if st is None else C.byref(st),
                                      _ptr(out), out.stride(0), _ptr(ws), ws_bytes, C.c_void_p(stream.cuda_stream)))
         return out
+
+
+def as_sequence(features: torch.Tensor) -> torch.Tensor:
+    """(B, 1, F, T) features -> the (B, T, F) view the reference's LSTM / GRU classifiers take
+    (src/models/architectures.py:177 "Input tensor (batch, time_steps, features)").  A view: no copy; call
+    ``.contiguous()`` where a kernel needs it (cuDNN RNNs accept the strided view)."""
+    if features.dim() != 4 or features.shape[1] != 1:
+        raise ValueError(f"expected (B, 1, F, T) features, got {tuple(features.shape)}")
+    return features.squeeze(1).transpose(1, 2)
 
 
 def gather_clips(bank: torch.Tensor, idx: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
