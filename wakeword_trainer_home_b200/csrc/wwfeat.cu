@@ -648,7 +648,13 @@ static FeatLaunch* build_launch(wwf_plan* p, int B, int N) {
     int eocc = 0;
     if (l->ep_smem <= (size_t)p->max_smem - kEpStaticSmem &&
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&eocc, (const void*)l->ep_kernel, l->ep_threads, l->ep_smem) == cudaSuccess && eocc >= 1)
-      l->ep_grid = (unsigned)std::min<long long>(eitems, (long long)p->sm_count * eocc);
+    {
+      // persistent CTAs with equal shares: 1208 row blocks over 592 CTA slots would be two full rounds plus a third one
+      // for 24 CTAs (3 item times for 2.04 items' worth of work); ceil(items / rounds) CTAs do exactly `rounds` each
+      const long long slots = (long long)p->sm_count * eocc;
+      const long long rounds = (eitems + slots - 1) / slots;
+      l->ep_grid = (unsigned)((eitems + rounds - 1) / rounds);
+    }
     l->flat_ok = l->frames_warps > 0 && l->frames_grid > 0 && l->ep_grid > 0 && (long long)B * fp.ngroups < (1ll << 31) - (1 << 20);
   }
   cudaGetLastError();   // a failed occupancy query must not poison the next launch check
