@@ -134,7 +134,11 @@ static int upload(T** dst, const std::vector<T>& src) {
   *dst = nullptr;
   if (src.empty()) return WWF_OK;
   WWF_CUDA(cudaMalloc((void**)dst, src.size() * sizeof(T)));
+  // pageable host memory: cudaMemcpy may return once the data is staged, before the DMA has landed, and the streams
+  // PyTorch hands in are non-blocking (they do not synchronise with the legacy default stream the copy runs on) - so
+  // wait for the copy itself; kernels launched afterwards on any stream then see the table
   WWF_CUDA(cudaMemcpy(*dst, src.data(), src.size() * sizeof(T), cudaMemcpyHostToDevice));
+  WWF_CUDA(cudaStreamSynchronize(0));
   return WWF_OK;
 }
 
@@ -1003,8 +1007,11 @@ extern "C" int wwf_set_stretch_window(wwf_plan* p, const float* window) {
   std::lock_guard<std::mutex> lk(p->lazy_mu);
   int rc = ensure_pv_constants_locked(p);
   if (rc) return rc;
-  // plain synchronous copy: ordered after every kernel already launched on the device
+  // stretch kernels of this plan may still be reading the old window on some (non-blocking) stream: wait for the
+  // device, replace the table, wait for the copy to land (a pageable-memory cudaMemcpy may return before it has)
+  WWF_CUDA(cudaDeviceSynchronize());
   WWF_CUDA(cudaMemcpy(p->d_pv_window, window, kPvN * sizeof(float), cudaMemcpyHostToDevice));
+  WWF_CUDA(cudaStreamSynchronize(0));
   return WWF_OK;
 }
 
