@@ -1055,7 +1055,8 @@ def test_bench_shape_matches_oracle_on_sampled_clips(ww, cfg):
     plan.profile(True)
     got = plan.featurize(x.cuda(), p)
     _, n_calls, n_flat = plan.profile_read_kernels()
-    assert n_calls == 1 and n_flat == 1, "the bench shape must take the flat path"
+    if os.environ.get("WWF_FEAT_PATH") != "fused":           # (the suite is also run with one path forced)
+        assert n_calls == 1 and n_flat == 1, "the bench shape must take the flat path"
     sel = torch.arange(0, B, B // 64)[:64]
     ref = tao.pipeline(x[sel], rirs=rirs, rir_idx=p.rir_idx[sel], noise_bank=noise, noise_idx=p.noise_idx[sel],
                        noise_off=p.noise_off[sel], snr_db=p.snr_db[sel], sample_rate=16000, feature_type=ft, n_mels=M,
