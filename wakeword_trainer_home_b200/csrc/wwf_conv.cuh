@@ -66,6 +66,8 @@ struct ConvParams {
   const float2* tw;                          // pass tables (kConvTwTotal)
   const uint16_t* fused_l;                   // [512] l of fused task t (bank-conflict-free order)
   const float2* fused_tw;                    // [512] w_P^{l(t)}
+  int* clip_max; int n_clip_max;             // flat feature path: running clip maxima to reset (or nullptr): saves the
+                                             // memset in front of this kernel, so that it can be chained (PDL) too
   // noise-mix records of the flat feature path made HERE (single-block clips, at most kConvMaxOwn items per CTA), or
   // mix_g == nullptr: feat_prep_kernel makes them
   ClipMix* mix_g;                            // [B]
@@ -393,7 +395,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams 
   const float2* t1 = s_tw + kConvTw1;
   float2* zp0 = zc + u + (u >> 4);                               // pad(u): pass-0 elements at zp0[544 q]
   const int nblk = p.es_nb;
-  pdl_wait();                                                    // the clips may come from a kernel of ours (gather / stretch)
+  pdl_wait();                                                    // the clips may come from a kernel of ours (gather / stretch);
+                                                                 // the previous call's epilogue has read its clip maxima
+  if (p.clip_max != nullptr)                                     // identity of the running maxima (wwf_feat.cuh: kMaxKeyMemset)
+    for (int i = blockIdx.x * kConvThreads + threadIdx.x; i < p.n_clip_max; i += gridDim.x * kConvThreads)
+      p.clip_max[i] = (int)0x80808080;
   if constexpr (MIX) conv_mix_prologue(p, s_mix);
   __syncthreads();                                               // twiddle tables and mix records visible (a dry first
                                                                  // item reads its record straight away)

@@ -790,9 +790,6 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
     fp.tile_g = (float*)fw;
     fp.clip_max = (int*)(fw + l->off_clipmax);
     fp.mix_g = fp.noise_idx ? (ClipMix*)(fw + l->off_mix) : nullptr;
-    // identity of the clip maxima: a byte-wise memset, BEFORE the reverb launch so that the kernels of the step
-    // stay chained (programmatic dependent launch)
-    WWF_CUDA(cudaMemsetAsync(fp.clip_max, 0x80, (size_t)round_up4(B) * sizeof(int), st));
   }
 
   // optional per-kernel timing: an event before the first kernel and after every kernel of the call
@@ -813,7 +810,14 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
   fp.rev = conv_on ? cp.rev : nullptr; fp.rev_stride = conv_on ? cp.rev_stride : 0;
   if (!conv_on) { fp.rir_idx = nullptr; fp.n_rir = 0; }
   fp.es_part = conv_on ? cp.es_part : nullptr; fp.es_nb = conv_on ? cp.es_nb : 0;
-  const bool pdl = p->opt_pdl && !p->prof;   // (only behind one of OUR kernels: what runs before the first of them may still be producing the inputs)
+  // Programmatic dependent launch: every kernel of the call stages its plan constants first and touches inputs /
+  // predecessors' results only after cudaGridDependencySynchronize(), so it is safe behind anything on the stream.
+  const bool pdl = p->opt_pdl && !p->prof;
+  if (flat) {
+    // identity of the clip maxima: conv_kernel resets them in its prologue; without reverb a byte-wise memset
+    if (conv_on) { cp.clip_max = fp.clip_max; cp.n_clip_max = (int)round_up4(B); }
+    else WWF_CUDA(cudaMemsetAsync(fp.clip_max, 0x80, (size_t)round_up4(B) * sizeof(int), st));
+  }
 
   if (flat) {
     // Noise: one mix record per clip.  conv_kernel makes them itself (single-block clips, a bounded number of clips
@@ -822,22 +826,19 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
     const bool need_mix = fp.mix_g != nullptr;
     const int conv_grid = conv_on ? std::min(cp.es_nb * B, p->sm_count) : 1;
     const bool mix_in_conv = need_mix && conv_on && cp.es_nb == 1 && (B + conv_grid - 1) / conv_grid <= kConvMaxOwn;
-    bool chained = false;                                      // is there a kernel of this call in front of the next launch?
     if (conv_on) {
       if (mix_in_conv) {
         cp.mix_g = fp.mix_g; cp.noise = fp.noise; cp.noise_idx = fp.noise_idx; cp.noise_off = fp.noise_off; cp.snr_db = fp.snr_db;
       }
-      if ((rc = conv_launch(p, cp, st, false))) return rc;
+      if ((rc = conv_launch(p, cp, st, pdl))) return rc;
       WWF_CUDA(mark(0));
-      chained = true;
     }
     if (need_mix && !mix_in_conv) {
-      WWF_CUDA(launch_feat((FeatKernel)feat_prep_kernel<0>, fp, (unsigned)B, 256, 0, st, pdl && chained));
+      WWF_CUDA(launch_feat((FeatKernel)feat_prep_kernel<0>, fp, (unsigned)B, 256, 0, st, pdl));
       g_launches++;
       WWF_CUDA(mark(1));
-      chained = true;
     }
-    WWF_CUDA(launch_feat(p->frames, fp, l->frames_grid, (unsigned)(l->frames_warps * 32), l->frames_smem, st, pdl && chained));
+    WWF_CUDA(launch_feat(p->frames, fp, l->frames_grid, (unsigned)(l->frames_warps * 32), l->frames_smem, st, pdl));
     WWF_CUDA(mark(2));
     WWF_CUDA(launch_feat(l->ep_kernel, fp, l->ep_grid, (unsigned)l->ep_threads, l->ep_smem, st, pdl));
     g_launches += 2;
@@ -854,7 +855,7 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
     if ((rc = conv_launch(p, cp, st, false))) return rc;
     WWF_CUDA(mark(0));
   }
-  WWF_CUDA(launch_feat(p->kernel, fp, (unsigned)l->fused_grid, (unsigned)(l->fused_warps * 32), l->fused_smem, st, pdl && conv_on));   // behind conv_kernel only
+  WWF_CUDA(launch_feat(p->kernel, fp, (unsigned)l->fused_grid, (unsigned)(l->fused_warps * 32), l->fused_smem, st, pdl));
   g_launches++;
   WWF_CUDA(cudaGetLastError());
   WWF_CUDA(mark(2));
