@@ -98,15 +98,32 @@ __device__ __forceinline__ ClipNoise resolve_noise(const NoiseBankDev& bank, con
 static __device__ __noinline__ double warp_seg_energy(const ClipNoise& c, int a, int b) {
   const int lane = threadIdx.x & 31;
   const int lo = (a + kNoiseBlk - 1) / kNoiseBlk, hi = b / kNoiseBlk;
-  float e = 0.f;
+  // Every edge sample a lane needs (at most 4 at either end, or 8 when the segment lies inside two blocks) is
+  // requested before the first one is used: as rolled load-then-accumulate loops the edges were up to eight
+  // SERIAL memory latencies - most of the 6.7 us this pointer chase cost the kernel that runs it.  Same values, same
+  // order of accumulation (missing samples contribute fmaf(0, 0, e) = e).
+  float v[8];
   double mid = 0.0;
   if (lo <= hi) {
-    mid = c.P[hi] - c.P[lo];
-    for (int q = a + lane; q < lo * kNoiseBlk; q += 32) { const float v = __ldg(c.nz + q); e = fmaf(v, v, e); }
-    for (int q = hi * kNoiseBlk + lane; q < b; q += 32) { const float v = __ldg(c.nz + q); e = fmaf(v, v, e); }
+    const double p_hi = c.P[hi], p_lo = c.P[lo];
+    const int e0 = lo * kNoiseBlk, t0 = hi * kNoiseBlk;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int q = a + lane + 32 * i, r = t0 + lane + 32 * i;
+      v[i] = q < e0 ? __ldg(c.nz + q) : 0.f;
+      v[4 + i] = r < b ? __ldg(c.nz + r) : 0.f;
+    }
+    mid = p_hi - p_lo;
   } else {
-    for (int q = a + lane; q < b; q += 32) { const float v = __ldg(c.nz + q); e = fmaf(v, v, e); }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int q = a + lane + 32 * i;
+      v[i] = q < b ? __ldg(c.nz + q) : 0.f;
+    }
   }
+  float e = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) e = fmaf(v[i], v[i], e);
   return mid + (double)warp_sum(e);
 }
 
