@@ -93,51 +93,57 @@ __device__ __forceinline__ ClipNoise resolve_noise(const NoiseBankDev& bank, con
   return c;
 }
 
-// sum of nz[q]^2 over [a, b), 0 <= a <= b <= len: prefix table for whole 128-blocks, direct sum
-// of the (< 128-sample) edges.  Executed by a full warp; every lane returns the result.
-static __device__ __noinline__ double warp_seg_energy(const ClipNoise& c, int a, int b) {
+// Loads of one segment [a, b) of a noise clip, 0 <= a <= b <= len: the prefix-table entries of its whole 128-blocks
+// and the (< 128-sample) edges - every edge sample a lane needs (at most 4 at either end, or 8 when the segment lies
+// inside two blocks) is requested before the first one is used: as rolled load-then-accumulate loops the edges were
+// up to eight SERIAL memory latencies.
+struct SegLoads { float v[8]; double p_hi, p_lo; };
+__device__ __forceinline__ SegLoads seg_issue(const ClipNoise& c, int a, int b) {
   const int lane = threadIdx.x & 31;
   const int lo = (a + kNoiseBlk - 1) / kNoiseBlk, hi = b / kNoiseBlk;
-  // Every edge sample a lane needs (at most 4 at either end, or 8 when the segment lies inside two blocks) is
-  // requested before the first one is used: as rolled load-then-accumulate loops the edges were up to eight
-  // SERIAL memory latencies - most of the 6.7 us this pointer chase cost the kernel that runs it.  Same values, same
-  // order of accumulation (missing samples contribute fmaf(0, 0, e) = e).
-  float v[8];
-  double mid = 0.0;
+  SegLoads s;
+  s.p_hi = 0.0; s.p_lo = 0.0;
   if (lo <= hi) {
-    const double p_hi = c.P[hi], p_lo = c.P[lo];
+    s.p_hi = c.P[hi]; s.p_lo = c.P[lo];
     const int e0 = lo * kNoiseBlk, t0 = hi * kNoiseBlk;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int q = a + lane + 32 * i, r = t0 + lane + 32 * i;
-      v[i] = q < e0 ? __ldg(c.nz + q) : 0.f;
-      v[4 + i] = r < b ? __ldg(c.nz + r) : 0.f;
+      s.v[i] = q < e0 ? __ldg(c.nz + q) : 0.f;
+      s.v[4 + i] = r < b ? __ldg(c.nz + r) : 0.f;
     }
-    mid = p_hi - p_lo;
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int q = a + lane + 32 * i;
-      v[i] = q < b ? __ldg(c.nz + q) : 0.f;
+      s.v[i] = q < b ? __ldg(c.nz + q) : 0.f;
     }
   }
+  return s;
+}
+// sum of nz[q]^2 over the segment: whole blocks from the table + the edges in a fixed order (missing samples
+// contribute fmaf(0, 0, e) = e).  Executed by a full warp; every lane returns the result.
+__device__ __forceinline__ double seg_energy(const SegLoads& s) {
   float e = 0.f;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) e = fmaf(v[i], v[i], e);
-  return mid + (double)warp_sum(e);
+  for (int i = 0; i < 8; ++i) e = fmaf(s.v[i], s.v[i], e);
+  return (s.p_hi - s.p_lo) + (double)warp_sum(e);
 }
 
-// Energy of the N-sample noise segment nz[(off + i) mod len], i < N.
-__device__ __forceinline__ float warp_noise_energy(const ClipNoise& c, int N) {
+// Energy of the N-sample noise segment nz[(off + i) mod len], i < N: the stretch up to the end of the clip, whole
+// passes over the clip, and the remainder from its start - the loads of BOTH partial stretches are in flight together
+// (a segment that wraps - every one when the noise clip is as long as the speech clip - was two dependent rounds).
+static __device__ __noinline__ float warp_noise_energy(const ClipNoise& c, int N) {
   const int first = min(N, c.len - c.off);
-  double e = warp_seg_energy(c, c.off, c.off + first);
   int rem = N - first;
-  if (rem > 0) {
-    const int loops = rem / c.len;
-    rem -= loops * c.len;
-    if (loops > 0) e += (double)loops * c.P[(c.len + kNoiseBlk - 1) / kNoiseBlk];
-    if (rem > 0) e += warp_seg_energy(c, 0, rem);
-  }
+  const int loops = rem > 0 ? rem / c.len : 0;
+  rem -= loops * c.len;
+  const SegLoads sa = seg_issue(c, c.off, c.off + first);
+  const SegLoads sb = seg_issue(c, 0, rem);                    // (rem = 0: no loads, contributes 0)
+  const double whole = loops > 0 ? c.P[(c.len + kNoiseBlk - 1) / kNoiseBlk] : 0.0;
+  double e = seg_energy(sa);
+  if (loops > 0) e += (double)loops * whole;
+  if (rem > 0) e += seg_energy(sb);
   return (float)e;
 }
 
