@@ -1113,3 +1113,36 @@ def test_wide_mfcc_accuracy_against_float64(ww, path):
         small = ref.abs() < 50.0
         assert float(err[small].max()) <= 5e-4 + 2.0 * float(own[small].max()), (path, n_fft, C, float(err[small].max()), float(own[small].max()))
         assert bool((err <= ABS_DB + 1e-4 * ref.abs()).all()), (path, n_fft, C, float(err.max()))
+
+
+def test_mix_records_from_every_producer_agree(ww):
+    """The flat path's per-clip noise-mix records have three producers: conv_kernel itself (single-block reverb, at
+    most 16 clips per CTA), feat_prep_kernel behind the reverb (more clips per CTA than that, or multi-block clips) and
+    feat_prep_kernel alone (no reverb in the call).  Same clips, same draws: log-mel features must equal the fused
+    kernel's bit for bit whichever producer ran (reverberated clips; dry clips may differ in the last ulp of the scale,
+    their energy is summed by CTAs of different width)."""
+    noise, rirs = synth_banks(21, 5, 9000, 3, 2000)
+    gen = torch.Generator().manual_seed(21)
+    N = 6000
+    for B in (40, 2500):                                       # 2500 clips over 148 CTAs = 17 per CTA: feat_prep_kernel
+        x = (0.1 * torch.randn(B, N, generator=gen)).cuda()
+        plan = ww.FeaturePlan(16000, "mel", 40, 40, 400, 160, "cuda")
+        plan.register_noise(noise); plan.register_rirs(rirs)
+        base = dict(noise_idx=torch.randint(-1, 5, (B,), generator=gen, dtype=torch.int32),
+                    noise_off=torch.randint(0, 9000, (B,), generator=gen), snr_db=5.0 + 15.0 * torch.rand(B, generator=gen))
+        for rir in (torch.randint(0, 3, (B,), generator=gen, dtype=torch.int32),          # every clip reverberated
+                    torch.randint(-1, 3, (B,), generator=gen, dtype=torch.int32)):         # a third of them dry
+            p = ww.AugParams(rir_idx=rir, **base)
+            plan.set_path("fused"); a = plan.featurize(x, p).clone()
+            plan.set_path("flat"); b = plan.featurize(x, p).clone()
+            rev = (rir >= 0).cuda()
+            assert torch.equal(a[rev], b[rev]), (B, "reverberated clips")
+            assert float((a[~rev].float() - b[~rev].float()).abs().max() if (~rev).any() else 0.0) <= 2e-4, (B, "dry clips")
+        plan.set_path("auto")
+    # oracle spot check of the prep-kernel route (B = 2500, all producers exercised above)
+    from oracle import ta_oracle as tao
+    sel = torch.arange(0, B, B // 16)[:16]
+    ref = tao.pipeline(x[sel].cpu(), rirs=rirs, rir_idx=p.rir_idx[sel], noise_bank=noise, noise_idx=p.noise_idx[sel],
+                       noise_off=p.noise_off[sel], snr_db=p.snr_db[sel], sample_rate=16000, feature_type="mel", n_mels=40,
+                       n_mfcc=40, n_fft=400, hop_length=160)
+    assert_features_close(plan.featurize(x, p)[sel.cuda()].cpu().numpy(), ref.numpy(), "prep-kernel route vs oracle")
