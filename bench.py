@@ -698,7 +698,9 @@ def run_cfg3(args, rank: int, local_rank: int, world: int):
                                                n_samples=N, seed=0, noise=noise, rirs=rirs)
     T, F = plan.num_frames(N), plan.n_feat
     timed = dt.TimedLoader(train)
-    trainer = dt.build_ddp_trainer(cfg, timed, [], dev, local_rank=local_rank)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):      # the reference prints a CUDA banner: keep stdout to the one JSON line
+        trainer = dt.build_ddp_trainer(cfg, timed, [], dev, local_rank=local_rank)
     gbytes = dt.grad_bytes(trainer.model)
 
     class Steps:
