@@ -281,11 +281,32 @@ __device__ __forceinline__ float frame_group_to_db(const float* __restrict__ x, 
     constexpr int R = Rad::R(i), L = Rad::L(i), tasks = NFFT / R;
     const float2* tw = tb.tw + Rad::tw_off(i);
     if constexpr (kNatural && i == Rad::npass - 1) {
-      // all G * tasks <= 32 tasks of the group in ONE round: every lane loads its inputs, the warp syncs, every lane
-      // stores frequency k = u + R0 r at position k
-      const int g = lane / tasks, uu = lane - g * tasks;
-      if (lane < G * tasks) pass_task_natural<R, Rad::R(0), Map>(z + g * ZL, z + g * ZL, uu, [] { __syncwarp(); });
-      else __syncwarp();
+      // Last pass of a two-pass plan (R0 = 16 tasks per transform, G = 2: lane = 16 g + u) fused with the spectrum
+      // split: task u leaves frequencies k = u + 16 r, r < R, in its REGISTERS; the partner Z[n - k] of the split is
+      // frequency (16 - u) + 16 (R - 1 - r): lane 16 - u of the same half-warp, register R - 1 - r - a compile-time
+      // register index, so one shuffle pair per bin fetches it (u = 0 pairs with itself: 16 (R - r)).  The spectrum
+      // never goes back to shared memory: 26 shuffles replace 25 stores + 26 loads of 8 bytes per lane (-13 % of the
+      // kernel's shared-memory wavefronts), and the powers land in plain bin order for the mel stage.
+      static_assert(!kNatural || (tasks == 16 && G == 2 && Rad::R(0) == 16), "natural-order split: 2 x 16 tasks");
+      const int g = lane >> 4, u = lane & 15;
+      float2* zz = z + g * ZL;
+      float2 v[R];
+#pragma unroll
+      for (int q = 0; q < R; ++q) v[q] = zz[zmap(u * R + q)];
+      dft<R, false>(v);
+      __syncwarp();                                            // every lane has read its inputs: zz may be overwritten
+      const int src = (lane & 16) | ((16 - u) & 15);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (16 * r <= NFFT / 2) {                              // (compile-time) some lane of the half-warp has k <= n/2
+          float2 pz;
+          pz.x = __shfl_sync(0xffffffffu, v[R - 1 - r].x, src);
+          pz.y = __shfl_sync(0xffffffffu, v[R - 1 - r].y, src);
+          if (u == 0) pz = v[r == 0 ? 0 : R - r];
+          const int k = u + 16 * r;
+          if (k <= NFFT / 2) zz[k] = pair_split_power(v[r], pz);     // plain bin order: what the mel lane schedule is built for
+        }
+      }
     } else {
       // tasks of the G FFTs share the rounds of 32 lanes, unless one FFT per round costs no extra round (n_fft 400:
       // 25 radix-16 tasks per FFT, 2 rounds either way) - then no half-warp straddles two FFTs (no bank conflicts
@@ -308,8 +329,8 @@ __device__ __forceinline__ float frame_group_to_db(const float* __restrict__ x, 
   // 3. split the packed pair into two power spectra (|A[k]|^2, |B[k]|^2): read every (Z[k], Z[n-k])
   //    first, then store the powers in plain bin order.  Half-warps take 16 consecutive bins of ONE transform
   //    (slot = 16-bin block; K rounded up to K16 blocks per transform), so a half-warp's two gathers never straddle
-  //    two transforms.
-  {
+  //    two transforms.  (The natural-order plans have done this inside their last pass.)
+  if constexpr (!kNatural) {
     constexpr int K16 = (K + 15) / 16;                       // 16-bin blocks per transform
     constexpr int NS = (G * K16 + 1) / 2;                    // split items per lane
     const int hw = lane >> 4, l16 = lane & 15;
@@ -320,8 +341,7 @@ __device__ __forceinline__ float frame_group_to_db(const float* __restrict__ x, 
       if (g < G && k < K) {
         const float2* zz = z + g * ZL;
         const int kn = k == 0 ? 0 : NFFT - k;
-        pw[i] = kNatural ? pair_split_power(zz[zmap(k)], zz[zmap(kn)])
-                         : pair_split_power(zz[zmap(Rad::pos(k))], zz[zmap(Rad::pos(kn))]);
+        pw[i] = pair_split_power(zz[zmap(Rad::pos(k))], zz[zmap(Rad::pos(kn))]);
       }
     }
     __syncwarp();
