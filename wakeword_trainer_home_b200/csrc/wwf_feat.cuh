@@ -276,7 +276,10 @@ __device__ __forceinline__ float frame_group_to_db(const float* __restrict__ x, 
   __syncwarp();
   // 2. forward FFT passes (in place; digit-reversed result, or natural order when the last pass is one warp round)
   constexpr bool kNatural = stft_natural_out<NFFT>();
-  static_for<0, Rad::npass>([&](auto I) {
+  // three-pass plans that end with radix 4 (512 = 16.8.4, 1024 = 16.16.4; one transform per warp): the last pass is
+  // fused with the spectrum split below (pair units), so the generic loop stops one pass early
+  constexpr bool kPairSplit = !kNatural && G == 1 && Rad::npass == 3 && Rad::R(2) == 4 && (NFFT / 8) % 32 == 0;
+  static_for<0, Rad::npass - (kPairSplit ? 1 : 0)>([&](auto I) {
     constexpr int i = decltype(I)::value;
     constexpr int R = Rad::R(i), L = Rad::L(i), tasks = NFFT / R;
     const float2* tw = tb.tw + Rad::tw_off(i);
@@ -330,7 +333,53 @@ __device__ __forceinline__ float frame_group_to_db(const float* __restrict__ x, 
   //    first, then store the powers in plain bin order.  Half-warps take 16 consecutive bins of ONE transform
   //    (slot = 16-bin block; K rounded up to K16 blocks per transform), so a half-warp's two gathers never straddle
   //    two transforms.  (The natural-order plans have done this inside their last pass.)
-  if constexpr (!kNatural) {
+  if constexpr (kPairSplit) {
+    // Last pass (radix 4 on 4 contiguous elements, no twiddles) + split in registers.  Last-pass task t (= k mod Q,
+    // Q = n / 4) produces the bins t + Q r; their split partners n - k = (Q - t) + Q (3 - r) come from task Q - t.  One
+    // lane therefore takes the PAIR of tasks (t, Q - t), t = 1 .. Q/2 - 1, and has everything four bins need in its own
+    // registers - no digit-reversed gather, no pos() arithmetic per bin, the spectrum is not stored again: 8 loads +
+    // 4 stores per unit instead of 8 + 8 (pass) + 8 + 4 (split).  Unit 0 takes the two self-paired tasks 0 and Q/2
+    // (bins 0, Q, 2Q = n/2 and Q/2, 3Q/2).  Every unit's results wait in registers until all units of the warp have
+    // read their inputs (the bins overwrite the transform in place).
+    constexpr int Q = NFFT / 4, NU = Q / 2, ROUNDS = NU / 32;
+    float2 pw[ROUNDS][4];
+    float2 pw0_extra = make_float2(0.f, 0.f);                  // unit 0 has a fifth bin
+#pragma unroll
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+      const int w = lane + 32 * rd;
+      const int ta = w, tb_ = w == 0 ? Q / 2 : Q - w;
+      const float2* pa = z + zmap(Rad::pos(ta));               // positions pos(t) + q, q < 4: one group of 16, no pad inside
+      const float2* pb = z + zmap(Rad::pos(tb_));
+      float2 va[4], vb[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { va[q] = pa[q]; vb[q] = pb[q]; }
+      dft<4, false>(va);
+      dft<4, false>(vb);
+      if (w != 0) {
+        pw[rd][0] = pair_split_power(va[0], vb[3]);            // k = t
+        pw[rd][1] = pair_split_power(va[1], vb[2]);            // k = t + Q
+        pw[rd][2] = pair_split_power(vb[0], va[3]);            // k = Q - t
+        pw[rd][3] = pair_split_power(vb[1], va[2]);            // k = 2Q - t
+      } else {
+        pw[rd][0] = pair_split_power(va[0], va[0]);            // k = 0 (DC)
+        pw[rd][1] = pair_split_power(va[1], va[3]);            // k = Q
+        pw0_extra = pair_split_power(va[2], va[2]);            // k = 2Q = n / 2 (Nyquist)
+        pw[rd][2] = pair_split_power(vb[0], vb[3]);            // k = Q / 2
+        pw[rd][3] = pair_split_power(vb[1], vb[2]);            // k = 3Q / 2
+      }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+      const int w = lane + 32 * rd;
+      const int ka = w, kb = w == 0 ? Q / 2 : Q - w;
+      z[ka] = pw[rd][0];
+      z[ka + Q] = pw[rd][1];
+      z[kb] = pw[rd][2];
+      z[kb + Q] = pw[rd][3];
+      if (w == 0) z[2 * Q] = pw0_extra;
+    }
+  } else if constexpr (!kNatural) {
     constexpr int K16 = (K + 15) / 16;                       // 16-bin blocks per transform
     constexpr int NS = (G * K16 + 1) / 2;                    // split items per lane
     const int hw = lane >> 4, l16 = lane & 15;
