@@ -203,6 +203,9 @@ __device__ __forceinline__ float frame_group_to_db(const float* __restrict__ x, 
   const float* s_window = tb.window;
 
   // 1. load + window: z[g][j] = w[j] * (frame(f0+2g)[j] + i frame(f0+2g+1)[j])
+  // (kRegFirst: register-staged groups of the 512 / 1024 plans also run the first radix-16 pass here, in registers)
+  constexpr bool kRegFirst = HOP32 > 0 && G == 1 && Rad::R(0) == 16 && Rad::S(0) % 32 == 0 && NC <= 32 && NFFT % 32 == 0;
+  bool first_done = false;
   bool staged = false;
   if constexpr (HOP32 > 0) {
     constexpr int NR = (2 * G - 1) * HOP32 + NC;             // registers holding the group's sample span
@@ -238,6 +241,30 @@ __device__ __forceinline__ float frame_group_to_db(const float* __restrict__ x, 
             }
           }
         }
+        if constexpr (kRegFirst) {
+          // First pass in registers: its radix-16 tasks combine elements j + S0 q, and S0 is a whole number of
+          // 32-sample columns (512: one, 1024: two), so all 16 inputs of task j = 32 c0 + lane are THIS lane's staged
+          // columns c0 + CPT q - the windowed samples go through the butterfly and the twiddles before they are stored
+          // for the first time: the pass costs no shared-memory loads and the window store is its output store.
+          constexpr int S0 = Rad::S(0), CPT = S0 / 32;
+          const float2* tw0 = tb.tw + Rad::tw_off(0);
+#pragma unroll
+          for (int c0 = 0; c0 < CPT; ++c0) {
+            const int jt = 32 * c0 + lane;
+            float2 v[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+              const int c = c0 + CPT * q;
+              const float w = s_window[32 * c + lane];
+              v[q] = make_float2(w * sreg[c], w * sreg[HOP32 + c]);
+            }
+            dft<16, false>(v);
+            twiddle16(v, S0, jt, [&](int q) { return tw0[q]; });
+#pragma unroll
+            for (int r = 0; r < 16; ++r) z[zmap(jt + S0 * r)] = v[r];
+          }
+          first_done = true;
+        } else {
 #pragma unroll
         for (int c = 0; c < CH; ++c) {
           const int j = 32 * (r0 + c) + lane;
@@ -247,6 +274,7 @@ __device__ __forceinline__ float frame_group_to_db(const float* __restrict__ x, 
             for (int g = 0; g < G; ++g)
               z[g * ZL + zmap(j)] = make_float2(w * sreg[2 * g * HOP32 + c], w * sreg[(2 * g + 1) * HOP32 + c]);
           }
+        }
         }
       }
     }
@@ -283,6 +311,9 @@ __device__ __forceinline__ float frame_group_to_db(const float* __restrict__ x, 
     constexpr int i = decltype(I)::value;
     constexpr int R = Rad::R(i), L = Rad::L(i), tasks = NFFT / R;
     const float2* tw = tb.tw + Rad::tw_off(i);
+    if constexpr (kRegFirst && i == 0) {
+      if (first_done) return;                                  // (warp-uniform) done in registers while loading
+    }
     if constexpr (kNatural && i == Rad::npass - 1) {
       // Last pass of a two-pass plan (R0 = 16 tasks per transform, G = 2: lane = 16 g + u) fused with the spectrum
       // split: task u leaves frequencies k = u + 16 r, r < R, in its REGISTERS; the partner Z[n - k] of the split is

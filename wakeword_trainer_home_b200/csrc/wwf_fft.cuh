@@ -300,6 +300,24 @@ struct PadMap2 {
   WWF_HD constexpr int operator()(int i) const { return i + (i >> 4) + (i >> 8); }
 };
 
+// Output twiddles of a forward radix-16 task (v[r] *= w_L^{j r}): six loaded powers (w, w^2, w^3 and w^4, w^8, w^12)
+// and nine products w^{4a+b} = w^{4a} w^b instead of fifteen loads: the STFT kernels are bound by the shared-memory
+// pipe before the FMA pipe.  Every derived twiddle is the product of two correctly rounded table entries (1.5 ulp; a
+// chain w^8 w^4 w^2 w would reach 3.5 ulp and pushed the CMVN test, which divides by a row's standard deviation, past
+// its bound).  tw[(r-1) s + j] = w_L^{j r}.
+template <class TwLoad>
+WWF_HD void twiddle16(float2 (&v)[16], int s, int j, TwLoad twload) {
+  float2 w[16];
+  w[1] = twload(j); w[2] = twload(s + j); w[3] = twload(2 * s + j);
+  w[4] = twload(3 * s + j); w[8] = twload(7 * s + j); w[12] = twload(11 * s + j);
+#pragma unroll
+  for (int a = 1; a < 4; ++a)
+#pragma unroll
+    for (int b = 1; b < 4; ++b) w[4 * a + b] = cmul(w[4 * a], w[b]);
+#pragma unroll
+  for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], w[r]);
+}
+
 template <int R, bool INV, class Map = IdentityMap, class TwLoad>
 WWF_HD void pass_task(float2* z, int L, int u, TwLoad twload, Map map = Map()) {
   const int s = L / R;
@@ -313,19 +331,7 @@ WWF_HD void pass_task(float2* z, int L, int u, TwLoad twload, Map map = Map()) {
     dft<R, false>(v);
     if (s > 1) {
       if constexpr (R == 16) {
-        // six loaded powers (w, w^2, w^3 and w^4, w^8, w^12) and nine products w^{4a+b} = w^{4a} w^b instead of fifteen
-        // loads: the STFT kernels are bound by the shared-memory pipe before the FMA pipe.  Every derived twiddle is
-        // the product of two correctly rounded table entries (1.5 ulp; a chain w^8 w^4 w^2 w would reach 3.5 ulp and
-        // pushed the CMVN test, which divides by a row's standard deviation, past its bound).
-        float2 w[16];
-        w[1] = twload(j); w[2] = twload(s + j); w[3] = twload(2 * s + j);
-        w[4] = twload(3 * s + j); w[8] = twload(7 * s + j); w[12] = twload(11 * s + j);
-#pragma unroll
-        for (int a = 1; a < 4; ++a)
-#pragma unroll
-          for (int b = 1; b < 4; ++b) w[4 * a + b] = cmul(w[4 * a], w[b]);
-#pragma unroll
-        for (int r = 1; r < 16; ++r) v[r] = cmul(v[r], w[r]);
+        twiddle16(v, s, j, twload);
       } else {
 #pragma unroll
         for (int r = 1; r < R; ++r) v[r] = cmul(v[r], twload((r - 1) * s + j));
