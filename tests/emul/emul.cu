@@ -113,7 +113,7 @@ int emul_cfft(int nfft, const float* in, float* out) {
   return -1;
 }
 
-// the 511 run pairs + the self-paired run l = 512 (task 511) + the run l = 0 must cover every run exactly once
+// the 511 run pairs + the self-paired run l = 512 (task kFusedSelfTask) + the run l = 0 must cover every run exactly once
 int emul_pair_task_coverage(void) {
   std::vector<float2> tw, ftw;
   std::vector<uint16_t> fl;
@@ -121,12 +121,39 @@ int emul_pair_task_coverage(void) {
   std::vector<int> seen(kRuns, 0);
   for (int t = 0; t < kFusedTasks; ++t) {
     const int l = fl[t];
-    if (l <= 0 || l > kRuns / 2 || (l == kRuns / 2) != (t == kFusedTasks - 1)) return -1;
+    if (l <= 0 || l >= kRuns || (l == kRuns / 2) != (t == kFusedSelfTask)) return -1;
     seen[run_of(l)]++;
     if (l != kRuns / 2) seen[run_of(kRuns - l)]++;
   }
   seen[run_of(0)]++;
   for (int a = 0; a < kRuns; ++a) if (seen[a] != 1) return -2 - a;
+  return 0;
+}
+
+// conv_kernel separates forward pass 1, the fused run pairs and inverse pass 1 by __syncwarp() only: every warp must
+// touch exactly its own 1024 positions (its pair of 512-element sub-transforms) in all three phases.
+// Returns 0, or -(1 + warp) for the first warp whose three position sets differ / overlap another warp's.
+int emul_conv_warp_locality(void) {
+  std::vector<float2> tw, ftw;
+  std::vector<uint16_t> fl;
+  build_conv_tables(tw, fl, ftw);
+  std::vector<int> owner(kConvM, -1);
+  for (int w = 0; w < kConvThreads / 32; ++w) {
+    std::vector<char> p1(kConvM, 0), fu(kConvM, 0);
+    for (int lane = 0; lane < 32; ++lane) {
+      const int blk = (lane & 16) ? conv_sub_b(w) : conv_sub_a(w), j = lane & 15;     // conv_pass1
+      for (int q = 0; q < 32; ++q) p1[512 * blk + j + 16 * q] = 1;
+      const int t = 32 * w + lane, l = fl[t];                                          // fused_pair_task
+      for (int q = 0; q < 16; ++q) { fu[16 * run_of(l) + q] = 1; fu[16 * run_of(kRuns - l) + q] = 1; }
+      if (t == kFusedSelfTask) for (int q = 0; q < 16; ++q) fu[16 * run_of(0) + q] = 1;  // fused_dc_task
+    }
+    int n = 0;
+    for (int i = 0; i < kConvM; ++i) {
+      if (p1[i] != fu[i]) return -(1 + w);
+      if (p1[i]) { if (owner[i] >= 0) return -(1 + w); owner[i] = w; ++n; }
+    }
+    if (n != 1024) return -(1 + w);
+  }
   return 0;
 }
 
@@ -175,13 +202,25 @@ int emul_rir_conv(const float* x, int N, const float* h, int L, int lmax, float*
   if ((int64_t)N + lmax - 1 > kConvP) { hist = (lmax - 1 + 3) & ~3; valid = kConvP - hist; nb = (N + valid - 1) / valid; }
   for (int blk = 0; blk < nb; ++blk) {
     load_block(z.data(), x, N, blk * valid - hist);
-    conv_passes<false>(z.data(), tw.data());
-    for (int t = 0; t < kFusedTasks; ++t) {
-      const float4* sp = spec.data() + t;
-      fused_pair_task(z.data(), (int)fl[t], ftw[t], [&](int r) { return sp[r * 512]; });
+    const float2* t0 = tw.data() + kConvTw0;
+    const float2* t1 = tw.data() + kConvTw1;
+    for (int u = 0; u < kConvM / 32; ++u) pass32_derived<false, PadMap>(z.data(), ConvRad::L(0), u, [&](int q) { return t0[q]; });
+    // the warp-local middle, one warp COMPLETELY after the other (on the GPU only __syncwarp() separates its phases):
+    // a warp that needed another warp's pass-1 results would read stale data here
+    for (int w = 0; w < kConvThreads / 32; ++w) {
+      auto sub_task = [&](int lane) { return 16 * ((lane & 16) ? conv_sub_b(w) : conv_sub_a(w)) + (lane & 15); };
+      for (int lane = 0; lane < 32; ++lane)
+        pass_task<32, false, PadMap>(z.data(), ConvRad::L(1), sub_task(lane), [&](int q) { return t1[q]; });
+      for (int lane = 0; lane < 32; ++lane) {
+        const int t = 32 * w + lane;
+        const float4* sp = spec.data() + t;
+        fused_pair_task(z.data(), (int)fl[t], ftw[t], [&](int r) { return sp[r * 512]; });
+        if (t == kFusedSelfTask) fused_dc_task(z.data(), [&](int i) { return spec[kSpecSpecial + i]; });
+      }
+      for (int lane = 0; lane < 32; ++lane)
+        pass_task<32, true, PadMap>(z.data(), ConvRad::L(1), sub_task(lane), [&](int q) { return t1[q]; });
     }
-    fused_dc_task(z.data(), [&](int i) { return spec[kSpecSpecial + i]; });
-    conv_passes<true>(z.data(), tw.data());
+    for (int u = 0; u < kConvM / 32; ++u) pass32_derived<true, PadMap>(z.data(), ConvRad::L(0), u, [&](int q) { return t0[q]; });
     for (int m = 0; m < kConvM; ++m) {
       for (int c = 0; c < 2; ++c) {
         const int i = 2 * m + c;

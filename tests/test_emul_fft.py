@@ -53,7 +53,12 @@ def test_complex_fft_and_pair_split(emul, n):
 
 def test_pair_tasks_cover_every_bin_once_without_bad_conflicts(emul):
     assert emul.emul_pair_task_coverage() == 0
-    assert emul.emul_pair_bank_conflicts() <= 2
+    assert emul.emul_pair_bank_conflicts() == 1
+
+
+def test_conv_middle_phases_are_warp_local(emul):
+    # conv_kernel separates forward pass 1, the fused run pairs and inverse pass 1 by __syncwarp() only
+    assert emul.emul_conv_warp_locality() == 0
 
 
 @pytest.mark.parametrize("N,L,lmax", [(24000, 8000, 8000), (16000, 500, 8000), (40000, 8000, 8000),

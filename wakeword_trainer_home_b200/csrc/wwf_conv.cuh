@@ -34,8 +34,28 @@ constexpr int kConvThreads = 512;
 using ConvRad = Radices<32, 32, 16>;
 constexpr int kRunLen = 16;                  // last radix: 16 contiguous positions = one run
 constexpr int kRuns = kConvM / kRunLen;      // 1024 runs, run(l) for l = k mod 1024
-constexpr int kFusedTasks = kRuns / 2;       // 511 run pairs {l, 1024-l}, 0 < l < 512, + the self-paired run l = 512 (task 511);
+constexpr int kFusedTasks = kRuns / 2;       // 511 run pairs {l, 1024-l} + the self-paired run l = 512 (kFusedSelfTask);
                                              // the other self-paired run, l = 0 (DC / Nyquist), is fused_dc_task
+constexpr int kFusedSelfTask = 0;            // the thread that owns l = 512 also does the run l = 0
+
+// WARP-LOCAL MIDDLE.  Position p = 512 d0 + 16 d1 + d2 holds frequency k = d0 + 32 d1 + 1024 d2, so the 512-element
+// sub-transform d0 (what pass 1 works on) holds the frequencies k = d0 mod 32, and the partner M - k of any of them
+// lies in sub-transform (32 - d0) mod 32.  Everything between the two radix-32 passes over the whole block - forward
+// pass 1, the fused run pairs, inverse pass 1 - therefore closes over the sub-transform PAIRS {d0, 32 - d0}
+// (d0 = 1..15) and {0, 16} (both self-paired): 16 pairs of 1024 elements = 32 radix-32 tasks and 32 run pairs each,
+// exactly one per lane of the 16 warps.  Warp w owns pair w: lanes 0-15 take sub-transform conv_sub_a(w), lanes 16-31
+// conv_sub_b(w) in pass 1; lane i owns the runs l = w + 32 i and 1024 - l in the fused phase.  Only __syncwarp()
+// separates the three phases (the CTA barriers around pass 0 remain), so the warps drift apart and one warp's
+// shared-memory traffic overlaps another's arithmetic.
+WWF_HD int conv_sub_a(int w) { return w; }
+WWF_HD int conv_sub_b(int w) { return w == 0 ? 16 : 32 - w; }
+// l of fused task t = 32 w + lane (host table fused_l; any l in [1, 1023] names the pair {l, 1024 - l})
+WWF_HD int conv_fused_l(int t) {
+  const int w = t >> 5, i = t & 31;
+  if (w > 0) return w + 32 * i;
+  if (i >= 16) return 16 + 32 * (i - 16);     // sub-transform 16 pairs with itself: d1 <-> 31 - d1
+  return i == 0 ? 512 : 32 * i;               // sub-transform 0: d1 <-> 32 - d1; d1 = 16 is l = 512, d1 = 0 the DC task
+}
 
 constexpr int kConvSmemElems = kConvM + (kConvM >> 4);
 
@@ -285,7 +305,7 @@ __device__ __forceinline__ void conv_fused_middle(float2* zc, const float4* __re
   const float4* sp = spec + t;
   fused_pair_task(zc, (int)__ldg(fused_l + t), __ldg(fused_tw + t), [&](int r) { return h[r & (kSpecPf - 1)]; },
                   [&](int r) { if (r + kSpecPf < 16) h[r & (kSpecPf - 1)] = __ldg(sp + (r + kSpecPf) * 512); });
-  if (t == kFusedTasks - 1) {
+  if (t == kFusedSelfTask) {
     const float4* sd = spec + kSpecSpecial;
     fused_dc_task(zc, [&](int i) { return __ldg(sd + i); });
   }
@@ -298,10 +318,12 @@ __device__ __forceinline__ void conv_fused_middle(float2* zc, const float4* __re
 constexpr int kConvStride0 = ConvRad::S(0) + ConvRad::S(0) / 16;   // 544: pass 0, elements u + 512 q
 constexpr int kConvStride1 = ConvRad::S(1) + ConvRad::S(1) / 16;   // 17:  pass 1, elements 512 blk + j + 16 q
 
-// second radix-32 pass (sub-transforms of length 512, full twiddle table in shared memory), in place
+// second radix-32 pass (sub-transforms of length 512, full twiddle table in shared memory), in place; the warp works
+// on its own pair of sub-transforms (see WARP-LOCAL MIDDLE above)
 template <bool INV>
 __device__ __forceinline__ void conv_pass1(float2* z, const float2* t1) {
-  const int u = threadIdx.x, blk = u >> 4, j = u & 15;
+  const int u = threadIdx.x, w = u >> 5, j = u & 15;
+  const int blk = (u & 16) ? conv_sub_b(w) : conv_sub_a(w);
   float2* zp = z + blk * (512 + 32) + j;                         // pad(512 blk + j), j < 16
   float2 v[32];
 #pragma unroll
@@ -428,10 +450,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams 
     {
       float4 h[kSpecPf];
       conv_fused_prefetch(h, p.spec + (size_t)r * kSpecPerRir);
-      __syncthreads();
+      __syncwarp();                                              // the warp's own sub-transform pair: no CTA barrier
       conv_fused_middle(zc, p.spec + (size_t)r * kSpecPerRir, h, p.fused_l, p.fused_tw);
     }
-    __syncthreads();
+    __syncwarp();
     {  // pull the next work item's samples into L2 while this block's inverse passes run (no registers held)
       const int nitem = item + gridDim.x;
       if (nitem < p.B * nblk) {

@@ -39,13 +39,13 @@ inline void build_conv_tables(std::vector<float2>& tw, std::vector<uint16_t>& fu
     for (int j = 0; j < s0; ++j) tw[kConvTw0 + b * s0 + j] = W((long long)j << b, ConvRad::L(0));
   for (int r = 1; r < 32; ++r)
     for (int j = 0; j < s1; ++j) tw[kConvTw1 + (r - 1) * s1 + j] = W((long long)j * r, ConvRad::L(1));
-  // task t owns runs l and 1024 - l, l = d0 + 32 d1 with d1 = (t+1) & 15, d0 = (t+1) >> 4: the 16 lanes of
-  // a half-warp get 16 distinct (run mod 16) = d1 for both runs -> conflict-free 8-byte accesses
+  // task t = 32 w + lane owns the runs l and 1024 - l of warp w's sub-transform pair (conv_fused_l, wwf_conv.cuh): the
+  // run index of l = d0 + 32 d1 is 32 d0 + d1, so the 16 lanes of a half-warp get 16 distinct (run mod 16) for both
+  // runs -> conflict-free 8-byte accesses
   fused_l.resize(kFusedTasks);
   fused_tw.resize(kFusedTasks);
   for (int t = 0; t < kFusedTasks; ++t) {
-    // (t = 511: tt = 512 -> the self-paired run l = 512, run residue 0 next to the residues 1..15 of its half-warp)
-    const int tt = t + 1, l = tt == kRuns / 2 ? kRuns / 2 : (tt >> 4) + 32 * (tt & 15);
+    const int l = conv_fused_l(t);
     fused_l[t] = (uint16_t)l;
     fused_tw[t] = W(l, kConvP);
   }
