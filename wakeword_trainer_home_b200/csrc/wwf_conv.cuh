@@ -372,7 +372,8 @@ __device__ __forceinline__ void conv_load_pass0(float2 (&v)[32], const float* __
 // Persistent: grid = min(#SMs, work items); work item = (clip b, overlap-save block blk).
 // Shared-memory round trips per block: pass 0 (store only: its inputs come from global memory) | pass 1 | fused middle
 // | inverse pass 1 | inverse pass 0 (load only: its results go straight to global memory) = 4 stores + 4 loads of the
-// block (was 6 + 6 with a staging copy at either end) and 5 CTA barriers (was 9).
+// block (was 6 + 6 with a staging copy at either end) and 2 CTA barriers - one on either side of the warp-local middle
+// (was 9, then 5).
 // The flat feature path's per-clip noise-mix records (ClipMix) are produced here too (MIX): in the prologue every warp
 // resolves the noise side of one of the CTA's own clips (bank lookups + segment energy: a chain of dependent loads
 // that overlaps the table staging) and parks it in SHARED memory; when a clip's block is done, thread 0 turns the
@@ -405,11 +406,32 @@ static __device__ __noinline__ void conv_mix_finish(const ConvParams& p, const C
   p.mix_g[b] = m;
 }
 
+// warp 0, behind a CTA barrier: total energy of the item parked in s_pend / s_part (if any) -> es_part, mix record
+template <bool MIX>
+__device__ __forceinline__ void conv_flush_energy(const ConvParams& p, const ClipMix* s_mix, const float (*s_part)[kConvThreads / 32],
+                                                  int* s_pend) {
+  const int b = s_pend[0];
+  if (b < 0) return;                                             // warp-uniform
+  const int blk = s_pend[1];
+  float e = threadIdx.x < kConvThreads / 32 ? s_part[s_pend[2]][threadIdx.x] : 0.f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+  if (threadIdx.x == 0) {
+    s_pend[0] = -1;
+    if (p.es_part != nullptr) p.es_part[(size_t)b * p.es_nb + blk] = e;
+    if constexpr (MIX) conv_mix_finish(p, s_mix, b, e);         // F.add_noise's scale, now that the clip's energy is known
+  }
+}
+
 template <bool MIX>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams p) {
   extern __shared__ __align__(16) float2 zc[];
   __shared__ float red[32];
+  __shared__ float s_part[2][kConvThreads / 32];                 // per-warp energy partials of the last two items
+  __shared__ int s_pend[3];                                      // {clip, block, s_part row} of the item not yet summed
   __shared__ ClipMix s_mix[MIX ? kConvMaxOwn : 1];
+  if (threadIdx.x == 0) s_pend[0] = -1;
+  int par = 0;
   float2* s_tw = zc + kConvSmemElems;
   conv_load_tables(s_tw, p.tw);
   const int u = threadIdx.x;
@@ -440,12 +462,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams 
       float2 v[32];
       conv_load_pass0(v, x, p.N, blk * p.valid - p.hist, (reinterpret_cast<uintptr_t>(x) & 7) == 0);
       pass32_core<false>(v, ConvRad::S(0), u, [&](int q) { return t0[q]; });
-      // (no barrier needed here: every completed item ends with the barrier of its energy reduction, which all
-      // threads pass only after their last shared-memory loads of that item)
+      // (no barrier needed here: these are the 32 positions this very thread loaded in the previous item's last pass)
 #pragma unroll
       for (int q = 0; q < 32; ++q) zp0[kConvStride0 * q] = v[q];
     }
     __syncthreads();
+    if (threadIdx.x < 32) conv_flush_energy<MIX>(p, s_mix, s_part, s_pend);   // the previous item's energy
     conv_pass1<false>(zc, t1);
     {
       float4 h[kSpecPf];
@@ -504,22 +526,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams 
         }
       }
     }
-    // energy of this block's output samples (fixed reduction order)
+    // energy of this block's output samples (fixed reduction order): the warps park their partial sums; warp 0 adds
+    // them up behind the NEXT barrier every thread passes anyway (conv_flush_energy), so that no barrier ends the item:
+    // a thread's last-pass loads and its first-pass stores of the next item touch the same 32 positions, and a warp
+    // that is done goes straight on to the next item's global loads while the others still finish this one
     float e = e0 + e1;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = e;
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      e = threadIdx.x < kConvThreads / 32 ? red[threadIdx.x] : 0.f;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-      if (threadIdx.x == 0) {
-        if (p.es_part != nullptr) p.es_part[(size_t)b * nblk + blk] = e;
-        if constexpr (MIX) conv_mix_finish(p, s_mix, b, e);     // F.add_noise's scale, now that the clip's energy is known
-      }
-    }
+    if ((threadIdx.x & 31) == 0) s_part[par][threadIdx.x >> 5] = e;
+    if (threadIdx.x == 0) { s_pend[1] = blk; s_pend[2] = par; s_pend[0] = b; }
+    par ^= 1;
   }
+  __syncthreads();
+  if (threadIdx.x < 32) conv_flush_energy<MIX>(p, s_mix, s_part, s_pend);
 }
 
 // Spectrum of one zero-padded RIR in the layout the fused task consumes (registration time).
