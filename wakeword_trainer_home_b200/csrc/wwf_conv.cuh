@@ -100,8 +100,10 @@ constexpr int kConvMaxOwn = 16;              // items per CTA whose records fit 
 // ------------------------------------------------------------------------------------------
 // register-level core: v[q] = element j + q s of a length-L sub-transform (s = L / 32); forward: DFT_32 then the
 // output twiddles w_L^{j r}; inverse: their conjugates, then the inverse DFT_32.
-template <bool INV, class TwLoad>
-WWF_HD void pass32_core(float2 (&v)[32], int s, int j, TwLoad tw5) {
+struct NoAfter { WWF_HD void operator()(int) const {} };
+// mid(0) runs once every input register has been consumed by the (inverse) twiddle multiplications
+template <bool INV, class TwLoad, class Mid = NoAfter>
+WWF_HD void pass32_core(float2 (&v)[32], int s, int j, TwLoad tw5, Mid mid = Mid()) {
   constexpr int R = 32;
   const float2 w1 = tw5(j), w2 = tw5(s + j), w4 = tw5(2 * s + j), w8 = tw5(3 * s + j), w16 = tw5(4 * s + j);
   const float2 w24 = cmul(w16, w8);
@@ -123,6 +125,7 @@ WWF_HD void pass32_core(float2 (&v)[32], int s, int j, TwLoad tw5) {
     v[16 + r2] = apply(v[16 + r2], r2 == 0 ? w16 : cmul(lo, w16));
     v[24 + r2] = apply(v[24 + r2], r2 == 0 ? w24 : cmul(lo, w24));
   });
+  mid(0);
   if constexpr (INV) dft<R, true>(v);
 }
 
@@ -175,7 +178,6 @@ WWF_HD int run_of(int l) { return ConvRad::pos(l) >> 4; }   // run holding frequ
 // run, every pair is simply computed from both ends, and both copies are written back to the same place - the same
 // straight-line code as every other task, so the warp that owns it does not diverge.
 // after(r) runs right after pair r (the kernel re-fills its rotating spectrum registers there).
-struct NoAfter { WWF_HD void operator()(int) const {} };
 template <class SpecLoad, class After = NoAfter>
 WWF_HD void fused_pair_task(float2* z, int l, float2 wl, SpecLoad spec, After after = After()) {
   const int a = run_of(l), ap = run_of(kRuns - l);
@@ -369,6 +371,35 @@ __device__ __forceinline__ void conv_load_pass0(float2 (&v)[32], const float* __
   }
 }
 
+// The NEXT item's inputs, staged by the thread that will use them: once a thread's last-pass loads of the current
+// item have landed, its 32 shared-memory positions are free, and they are exactly the positions its first pass of the
+// next item fills - so it has cp.async bring the next item's sample pairs (the same addresses conv_load_pass0 reads)
+// into them and goes on with the inverse butterfly, the global stores and the energy: the L2 latency of those loads
+// (about a microsecond per item that every warp of the CTA used to sit out at the same time) runs under arithmetic and
+// needs no register.  Only for the common case conv_load_pass0 takes without branches.
+__device__ __forceinline__ void conv_stage_pass0(float2* zp0, const float* __restrict__ x, int N, int start) {
+  const int n0 = start + 2 * (int)threadIdx.x;
+#pragma unroll
+  for (int q = 0; q < 32; ++q) {
+    const int n = n0 + 2 * ConvRad::S(0) * q;
+    if (n < N) {
+      const unsigned dst = (unsigned)__cvta_generic_to_shared(zp0 + kConvStride0 * q);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(x + n) : "memory");
+    }
+  }
+}
+__device__ __forceinline__ void conv_stage_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void conv_load_staged(float2 (&v)[32], const float2* zp0, int N, int start) {
+  const int n0 = start + 2 * (int)threadIdx.x;
+#pragma unroll
+  for (int q = 0; q < 32; ++q) {
+    const int n = n0 + 2 * ConvRad::S(0) * q;
+    float2 t = make_float2(0.f, 0.f);
+    if (n < N) t = zp0[kConvStride0 * q];
+    v[q] = t;
+  }
+}
+
 // Persistent: grid = min(#SMs, work items); work item = (clip b, overlap-save block blk).
 // Shared-memory round trips per block: pass 0 (store only: its inputs come from global memory) | pass 1 | fused middle
 // | inverse pass 1 | inverse pass 0 (load only: its results go straight to global memory) = 4 stores + 4 loads of the
@@ -406,17 +437,19 @@ static __device__ __noinline__ void conv_mix_finish(const ConvParams& p, const C
   p.mix_g[b] = m;
 }
 
-// warp 0, behind a CTA barrier: total energy of the item parked in s_pend / s_part (if any) -> es_part, mix record
+// The LAST warp (warp 0 already carries the extra DC task of the fused phase), behind a CTA barrier: total energy of
+// the item parked in s_pend / s_part (if any) -> es_part, mix record
+constexpr int kConvFlushThread = kConvThreads - 32;
 template <bool MIX>
 __device__ __forceinline__ void conv_flush_energy(const ConvParams& p, const ClipMix* s_mix, const float (*s_part)[kConvThreads / 32],
                                                   int* s_pend) {
   const int b = s_pend[0];
   if (b < 0) return;                                             // warp-uniform
-  const int blk = s_pend[1];
-  float e = threadIdx.x < kConvThreads / 32 ? s_part[s_pend[2]][threadIdx.x] : 0.f;
+  const int blk = s_pend[1], lane = threadIdx.x & 31;
+  float e = lane < kConvThreads / 32 ? s_part[s_pend[2]][lane] : 0.f;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
-  if (threadIdx.x == 0) {
+  if (lane == 0) {
     s_pend[0] = -1;
     if (p.es_part != nullptr) p.es_part[(size_t)b * p.es_nb + blk] = e;
     if constexpr (MIX) conv_mix_finish(p, s_mix, b, e);         // F.add_noise's scale, now that the clip's energy is known
@@ -424,14 +457,17 @@ __device__ __forceinline__ void conv_flush_energy(const ConvParams& p, const Cli
 }
 
 template <bool MIX>
-__global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams p) {
+__global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const __grid_constant__ ConvParams p) {   // (grid constant:
+  // the __noinline__ helpers take p by reference; without it the kernel keeps a 200-byte local-memory copy of the
+  // parameters and reads N, the strides, ... through LDL inside the hot loop)
   extern __shared__ __align__(16) float2 zc[];
   __shared__ float red[32];
   __shared__ float s_part[2][kConvThreads / 32];                 // per-warp energy partials of the last two items
   __shared__ int s_pend[3];                                      // {clip, block, s_part row} of the item not yet summed
   __shared__ ClipMix s_mix[MIX ? kConvMaxOwn : 1];
-  if (threadIdx.x == 0) s_pend[0] = -1;
+  if (threadIdx.x == kConvFlushThread) s_pend[0] = -1;
   int par = 0;
+  int staged = -1;                                               // item whose first-pass inputs wait in shared memory
   float2* s_tw = zc + kConvSmemElems;
   conv_load_tables(s_tw, p.tw);
   const int u = threadIdx.x;
@@ -460,14 +496,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams 
     }
     {
       float2 v[32];
-      conv_load_pass0(v, x, p.N, blk * p.valid - p.hist, (reinterpret_cast<uintptr_t>(x) & 7) == 0);
+      conv_stage_wait();                                         // (nothing pending unless the last item staged one)
+      if (staged == item) conv_load_staged(v, zp0, p.N, blk * p.valid - p.hist);
+      else conv_load_pass0(v, x, p.N, blk * p.valid - p.hist, (reinterpret_cast<uintptr_t>(x) & 7) == 0);
       pass32_core<false>(v, ConvRad::S(0), u, [&](int q) { return t0[q]; });
       // (no barrier needed here: these are the 32 positions this very thread loaded in the previous item's last pass)
 #pragma unroll
       for (int q = 0; q < 32; ++q) zp0[kConvStride0 * q] = v[q];
     }
     __syncthreads();
-    if (threadIdx.x < 32) conv_flush_energy<MIX>(p, s_mix, s_part, s_pend);   // the previous item's energy
+    if (threadIdx.x >= kConvFlushThread) conv_flush_energy<MIX>(p, s_mix, s_part, s_pend);   // the previous item's energy
     conv_pass1<false>(zc, t1);
     {
       float4 h[kSpecPf];
@@ -499,7 +537,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams 
       float2 v[32];
 #pragma unroll
       for (int q = 0; q < 32; ++q) v[q] = zp0[kConvStride0 * q];
-      pass32_core<true>(v, ConvRad::S(0), u, [&](int q) { return t0[q]; });
+      pass32_core<true>(v, ConvRad::S(0), u, [&](int q) { return t0[q]; }, [&](int) {
+        // every loaded value is in use: the positions are free for the next item's inputs (a dry next item simply
+        // leaves them unused; whatever lands is overwritten by the next first pass after its conv_stage_wait())
+        const int nitem = item + gridDim.x;
+        if (nitem < p.B * nblk) {
+          const int nb_ = nitem / nblk, nstart = (nitem - nb_ * nblk) * p.valid - p.hist;
+          const float* nx = p.wav + (size_t)nb_ * p.wav_stride;
+          if (nstart >= 0 && !(p.N & 1) && (reinterpret_cast<uintptr_t>(nx) & 7) == 0) {
+            conv_stage_pass0(zp0, nx, p.N, nstart);
+            staged = nitem;
+          }
+        }
+      });
       float* y = p.rev + (size_t)b * p.rev_stride;
       const int nbase = blk * p.valid - p.hist + 2 * u;
       if (p.hist == 0 && !(p.N & 1) && (reinterpret_cast<uintptr_t>(y) & 7) == 0) {
@@ -534,11 +584,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const ConvParams 
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
     if ((threadIdx.x & 31) == 0) s_part[par][threadIdx.x >> 5] = e;
-    if (threadIdx.x == 0) { s_pend[1] = blk; s_pend[2] = par; s_pend[0] = b; }
+    if (threadIdx.x == kConvFlushThread) { s_pend[1] = blk; s_pend[2] = par; s_pend[0] = b; }
     par ^= 1;
   }
   __syncthreads();
-  if (threadIdx.x < 32) conv_flush_energy<MIX>(p, s_mix, s_part, s_pend);
+  if (threadIdx.x >= kConvFlushThread) conv_flush_energy<MIX>(p, s_mix, s_part, s_pend);
 }
 
 // Spectrum of one zero-padded RIR in the layout the fused task consumes (registration time).
