@@ -45,7 +45,7 @@ enum { WWF_FEAT_LOGMEL = 0, WWF_FEAT_MFCC = 1 };
 enum { WWF_OUT_F32 = 0, WWF_OUT_F16 = 1 };
 enum { WWF_BANK_NOISE = 0, WWF_BANK_RIR = 1 };
 enum { WWF_BANK_F32 = 0, WWF_BANK_I16 = 1 }; /* element type of a device-resident clip bank */
-enum { WWF_OPT_FEAT_PATH = 0, WWF_OPT_PDL = 1 };              /* wwf_plan_set_option */
+enum { WWF_OPT_FEAT_PATH = 0, WWF_OPT_PDL = 1, WWF_OPT_EPILOGUE_WARP = 2 };   /* wwf_plan_set_option */
 enum { WWF_PATH_AUTO = 0, WWF_PATH_FUSED = 1, WWF_PATH_FLAT = 2 };
 
 /*
@@ -306,8 +306,10 @@ int wwf_profile_read_kernels(wwf_plan* plan, double* kernel_ms, int* n_calls, in
 /*
  * Launch options of a plan.  WWF_OPT_FEAT_PATH: WWF_PATH_AUTO (default: the library picks per batch shape),
  * WWF_PATH_FUSED (one kernel per call) or WWF_PATH_FLAT (flat frame queue + epilogue; needs the workspace);
- * WWF_OPT_PDL: 1 (default) chains the kernels of a call with programmatic dependent launch, 0 = plain launches.
- * The same two can be preset through the environment (WWF_FEAT_PATH=fused|split, WWF_NO_PDL), which is read
+ * WWF_OPT_PDL: 1 (default) chains the kernels of a call with programmatic dependent launch, 0 = plain launches;
+ * WWF_OPT_EPILOGUE_WARP: 1 (default) lets MFCC calls without SpecAugment flags of the common shapes take the
+ * warp-autonomous tensor-core epilogue (feat_epilogue_mma_warp_kernel), 0 = the block-wise one for every call.
+ * They can be preset through the environment (WWF_FEAT_PATH=fused|split, WWF_NO_PDL, WWF_NO_EP_WARP), which is read
  * once, at wwf_plan_create.  Changing an option drops the plan's cached launch shapes; call it between, not
  * concurrently with, wwf_featurize calls.  No reference counterpart: test / measurement control only.
  */
@@ -315,6 +317,14 @@ int wwf_plan_set_option(wwf_plan* plan, int option, int value);
 
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 int64_t wwf_launch_count(void);
+
+/*
+ * Test control: fills the shared memory of every SM of `device` with the bit pattern `word` (0x7fc00000 = quiet NaN)
+ * and synchronises.  Kernels must never depend on what a predecessor left in shared memory - not even through a
+ * product with a zero weight; the GPU tests poison it (and freshly allocated global memory) before parity runs.
+ * No reference counterpart.
+ */
+int wwf_debug_poison_smem(int device, uint32_t word);
 
 #ifdef __cplusplus
 }

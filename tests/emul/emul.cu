@@ -5,6 +5,7 @@
 // digit-reversed positions, pair-split, overlap-save pair pass) are driven here sequentially
 // - one "thread" after the other, one pass after the other - and compared with numpy by
 // tests/test_emul_fft.py.  Nothing in the product loads this library.
+#define WWF_EMUL_HOST 1
 #include <cstdint>
 #include <algorithm>
 #include <cstring>
@@ -297,7 +298,8 @@ int emul_mel_schedule(int n_fft, int n_freqs, int n_mels, const float* fb, const
   ofs[n_mels] = (int)w.size();
   if (w.empty()) w.push_back(0.f);
   auto zmap = [](int i) { return i; };                         // the power spectra are stored in plain bin order
-  const MelSchedule s = build_mel_schedule(lo, ofs, w, n_fft);
+  const int extent = n_fft == 400 ? n_fft : n_freqs;          // what wwf_plan_create passes (400: identity-mapped scratch)
+  const MelSchedule s = build_mel_schedule(lo, ofs, w, n_fft, extent);
   std::vector<int> owners(n_mels, 0);
   int worst = 1, nsplit = 0;
   for (int r = 0; r < s.rounds; ++r) {
@@ -312,6 +314,9 @@ int emul_mel_schedule(int n_fft, int n_freqs, int n_mels, const float* fb, const
       if (i < n) a0 = fmaf(power[k0 + i], wr[32 * i], a0);
       acc[lane] = a0 + a1;
       if (n > 0 && k0 + n > n_freqs) return -1;
+      // the kernel runs every lane for the round's full trip count (zero weights beyond the lane's taps): all of
+      // those reads must stay inside the slots this frame group has written
+      if (k0 + 2 * s.pairs[r] > extent) return -5;
     }
     for (int h = 0; h < 2; ++h) {
       int cnt[16] = {};

@@ -105,7 +105,8 @@ def test_phase_vocoder_analysis_synthesis_pair(emul):
     assert np.abs(ya - fa).max() <= 2e-6 and np.abs(yb - fb).max() <= 2e-6
 
 
-@pytest.mark.parametrize("n_fft,n_mels", [(400, 40), (400, 128), (256, 40), (512, 64), (1024, 128), (1024, 80), (2048, 128), (400, 13), (2048, 32)])
+@pytest.mark.parametrize("n_fft,n_mels", [(400, 40), (400, 128), (256, 40), (512, 64), (1024, 128), (1024, 80), (2048, 128), (400, 13), (2048, 32),
+                                          (2048, 80), (2048, 20), (2048, 40), (1024, 40), (512, 20), (512, 128), (256, 64), (256, 20), (400, 64), (400, 80), (400, 20)])
 def test_mel_lane_schedule_equals_dense_filterbank(emul, n_fft, n_mels):
     """The lane schedule of the sparse mel projection (wwf_tables.h: filters cut in halves, sorted into rounds of 32
     lanes, weights interleaved) visits every non-zero of torchaudio's filterbank exactly once: evaluated on the CPU in

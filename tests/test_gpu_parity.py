@@ -1148,3 +1148,78 @@ def test_mix_records_from_every_producer_agree(ww):
                        noise_off=p.noise_off[sel], snr_db=p.snr_db[sel], sample_rate=16000, feature_type="mel", n_mels=40,
                        n_mfcc=40, n_fft=400, hop_length=160)
     assert_features_close(plan.featurize(x, p)[sel.cuda()].cpu().numpy(), ref.numpy(), "prep-kernel route vs oracle")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,N", [(1, 16000), (3, 24000), (37, 12345), (130, 24000)])
+def test_warp_epilogue_equals_blockwise_epilogue_and_oracle(ww, B, N):
+    """MFCC 40 x 40 without SpecAugment flags: the flat path ends in the warp-autonomous tensor-core epilogue
+    (16-row slabs, cp.async double buffer, floor + centring on the fragments).  Same arithmetic as the block-wise
+    kernel it replaces for these calls -> bit-identical features, for row counts that are / are not multiples of 16,
+    slabs that straddle clips, float32 and float16 outputs; a NaN sample raises the plan's non-finite flag on both."""
+    from oracle import ta_oracle as tao
+    gen = torch.Generator().manual_seed(B * 1000 + N)
+    x = 0.1 * torch.randn(B, N, generator=gen)
+    x[0, N // 2:] = 0.0                                          # digital silence: the top_db floor is active
+    for dtype in (torch.float32, torch.float16):
+        plan = ww.FeaturePlan(16000, "mfcc", 40, 40, 400, 160, "cuda", out_dtype=dtype)
+        plan.set_path("flat")
+        got_w = plan.featurize(x.cuda()).cpu()
+        plan.set_epilogue_warp(False)
+        got_b = plan.featurize(x.cuda()).cpu()
+        assert torch.equal(got_w, got_b)
+        if dtype == torch.float32:
+            ref = tao.featurize(x.double(), sample_rate=16000, feature_type="mfcc", n_mels=40, n_mfcc=40, n_fft=400,
+                                hop_length=160, dtype=torch.float64).numpy()
+            assert_features_close(got_w.numpy(), ref, f"warp epilogue B={B} N={N}")
+    plan = ww.FeaturePlan(16000, "mfcc", 40, 40, 400, 160, "cuda")
+    plan.set_path("flat")
+    xn = x.clone()
+    xn[B - 1, 777] = float("nan")
+    out = plan.featurize(xn.cuda())
+    assert not plan.check_finite()
+    assert torch.isnan(out[B - 1]).any() and (B == 1 or torch.isfinite(out[:B - 1]).all())
+
+
+@pytest.mark.parametrize("n_fft,hop,M,C,ftype", [(2048, 160, 80, 8, "mfcc"), (2048, 200, 80, 33, "mel"), (400, 160, 40, 40, "mfcc"),
+                                                 (1024, 160, 128, 40, "mfcc"), (512, 160, 64, 32, "mel"), (256, 128, 20, 13, "mfcc")])
+def test_results_do_not_depend_on_stale_memory(ww, n_fft, hop, M, C, ftype):
+    """Shared memory of every SM and the memory the allocator hands out next are filled with NaN before the call
+    (wwf_debug_poison_smem + freed NaN tensors): a kernel that reads a slot nobody of this call wrote - even to multiply
+    it by a zero weight, as the mel lane schedule's padding taps once did beyond the n_fft / 2 + 1 stored power values -
+    turns features into NaN.  Both launch shapes, with and without augmentation / masks."""
+    from wakeword_trainer_home_b200 import _native
+    lib = _native.load()
+    gen = torch.Generator().manual_seed(n_fft + M)
+    B, N = 4, 16783
+    T = N // hop + 1
+    F = C if ftype == "mfcc" else M
+    x = (0.1 * torch.randn(B, N, generator=gen)).cuda()
+    noise, rirs = synth_banks(5, 3, 9000, 3, 3000)
+    for use_aug in (False, True):
+        plan = ww.FeaturePlan(16000, ftype, M, C, n_fft, hop, "cuda", n_freq_masks=2 if use_aug else 0,
+                              n_time_masks=1 if use_aug else 0, mask_value=-3.0)
+        ap = ww.AugParams()
+        if use_aug:
+            plan.register_noise(noise); plan.register_rirs(rirs)
+            ap.rir_idx = torch.tensor([0, 2, -1, -1], dtype=torch.int32)
+            ap.noise_idx = torch.tensor([2, 0, -1, 0], dtype=torch.int32)
+            ap.noise_off = torch.tensor([5, 400, 0, 8999], dtype=torch.int64)
+            ap.snr_db = torch.tensor([3.0, 10.0, 0.0, 20.0])
+            ap.fmask_start, ap.fmask_len = ww.draw_mask_params(gen, B, F, min(15, F), 2)
+            ap.tmask_start, ap.tmask_len = ww.draw_mask_params(gen, B, T, min(35, T), 1)
+        for path in ("fused", "flat"):
+            plan.set_path(path)
+            try:
+                clean = plan.featurize(x, ap).cpu()
+            except ww.WwfError as e:                             # the fused kernel refuses tiles beyond shared memory
+                assert path == "fused" and e.code == -2
+                continue
+            assert torch.isfinite(clean).all()
+            for word in (0x7fc00000, 0xff800000):                # quiet NaN, -inf
+                plan.release_workspaces()
+                junk = [torch.full((1 << 22,), float("nan"), device="cuda") for _ in range(16)]
+                del junk
+                _native.check(lib.wwf_debug_poison_smem(0, word))
+                got = plan.featurize(x, ap).cpu()
+                assert torch.equal(got, clean), f"n_fft={n_fft} M={M} {ftype} aug={use_aug} path={path} word={word:#x}"

@@ -18,7 +18,7 @@ FEAT_LOGMEL, FEAT_MFCC = 0, 1
 OUT_F32, OUT_F16 = 0, 1
 BANK_NOISE, BANK_RIR = 0, 1
 BANK_F32, BANK_I16 = 0, 1
-OPT_FEAT_PATH, OPT_PDL = 0, 1
+OPT_FEAT_PATH, OPT_PDL, OPT_EPILOGUE_WARP = 0, 1, 2
 PATH_AUTO, PATH_FUSED, PATH_FLAT = 0, 1, 2
 MAX_MASKS = 8
 SUPPORTED_N_FFT = (256, 400, 512, 1024, 2048)
@@ -109,6 +109,7 @@ SYMBOLS = {
     "wwf_profile_read_kernels": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "wwf_plan_set_option": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "wwf_launch_count": (C.c_int64, []),
+    "wwf_debug_poison_smem": (C.c_int, [C.c_int, C.c_uint32]),
 }
 
 _lib = None

@@ -232,6 +232,11 @@ WWF_HD void fused_dc_task(float2* z, SpecLoad spec) {
 // ------------------------------------------------------------------------------------------
 // device side
 // ------------------------------------------------------------------------------------------
+#ifdef WWF_EMUL_HOST                         // tests/emul compiles these headers for the host with nvcc's default arch
+#define WWF_GRID_CONSTANT
+#else
+#define WWF_GRID_CONSTANT __grid_constant__
+#endif
 // copy the pass tables into shared memory (once per persistent CTA)
 __device__ __forceinline__ void conv_load_tables(float2* s_tw, const float2* __restrict__ tw) {
   for (int i = threadIdx.x; i < kConvTwTotal; i += kConvThreads) s_tw[i] = __ldg(tw + i);
@@ -307,7 +312,12 @@ __device__ __forceinline__ void conv_fused_middle(float2* zc, const float4* __re
   const float4* sp = spec + t;
   fused_pair_task(zc, (int)__ldg(fused_l + t), __ldg(fused_tw + t), [&](int r) { return h[r & (kSpecPf - 1)]; },
                   [&](int r) { if (r + kSpecPf < 16) h[r & (kSpecPf - 1)] = __ldg(sp + (r + kSpecPf) * 512); });
-  if (t == kFusedSelfTask) {
+#ifndef WWF_DIAG_NO_DC
+  if (t == kFusedSelfTask)
+#else
+  if (t == 10000)
+#endif
+  {
     const float4* sd = spec + kSpecSpecial;
     fused_dc_task(zc, [&](int i) { return __ldg(sd + i); });
   }
@@ -457,7 +467,7 @@ __device__ __forceinline__ void conv_flush_energy(const ConvParams& p, const Cli
 }
 
 template <bool MIX>
-__global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const __grid_constant__ ConvParams p) {   // (grid constant:
+__global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const WWF_GRID_CONSTANT ConvParams p) {   // (grid constant:
   // the __noinline__ helpers take p by reference; without it the kernel keeps a 200-byte local-memory copy of the
   // parameters and reads N, the strides, ... through LDL inside the hot loop)
   extern __shared__ __align__(16) float2 zc[];

@@ -851,8 +851,11 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&
 #endif
 }
 
-template <typename OutT>
-__global__ void __launch_bounds__(kEmThreads) feat_epilogue_mma_kernel(const FeatParams p) {
+// KS / NTC > 0: the number of k-steps (n_mels / 8, rounded up) / of 8-coefficient tiles (<= kEmNT) is a compile-time
+// constant - the tile predicates fold and the k loop unrolls (40 mels x 40 coefficients: KS = NTC = 5); 0 = run time.
+template <typename OutT, int KS = 0, int NTC = 0>
+__global__ void __launch_bounds__(kEmThreads, 3) feat_epilogue_mma_kernel(const FeatParams p) {
+  static_assert(NTC <= kEmNT, "a specialised tile count must fit one pass");
   extern __shared__ __align__(16) float smem[];               // A [128][ap] | B fragments uint4 [k8/8][c8/8][32]
   __shared__ float s_cut[kEmRows], s_mu[kEmRows];             // per row: top_db floor and centre of its clip's value range
   __shared__ float s_colsum[128];
@@ -861,7 +864,7 @@ __global__ void __launch_bounds__(kEmThreads) feat_epilogue_mma_kernel(const Fea
   __shared__ unsigned char s_colmask[kEmRows];
   __shared__ uint32_t s_rowbits[kEmMaxSlots][4];              // per clip slot: bit c set = feature row c is masked
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int T = p.T, M = p.n_mels, C = p.n_feat, mp = p.mp, k8 = p.em_k8, ap = p.em_ap, c8 = p.c8;
+  const int T = p.T, M = p.n_mels, C = p.n_feat, mp = p.mp, k8 = KS ? KS * 8 : p.em_k8, ap = p.em_ap, c8 = NTC ? NTC * 8 : p.c8;
   const int ntiles = c8 / 8, nfrag = (k8 / 8) * ntiles * 32;
   float* sA = smem;
   uint4* sB = reinterpret_cast<uint4*>(smem + kEmRows * ap);
@@ -959,11 +962,12 @@ __global__ void __launch_bounds__(kEmThreads) feat_epilogue_mma_kernel(const Fea
     // warp-uniform: every row of the slab exists, nothing of it is masked, no padded coefficient -> plain stores
     const bool plain = !has_fmask && C == c8 && __all_sync(0xffffffffu, okA && okB && !cmA && !cmB);
     for (int n0 = 0; n0 < ntiles; n0 += kEmNT) {
-      const int nt = min(kEmNT, ntiles - n0);                  // tiles of this pass (warp-uniform)
+      const int nt = NTC ? NTC : min(kEmNT, ntiles - n0);      // tiles of this pass (warp-uniform)
       float acc[kEmNT][4];
 #pragma unroll
       for (int j = 0; j < kEmNT; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
       const uint4* bf = sB + (size_t)n0 * 32 + lane;
+#pragma unroll(KS > 0 && KS <= 8 ? KS : 1)
       for (int k0 = 0; k0 < k8; k0 += 8, bf += ntiles * 32) {
         const float av[4] = {arow0[k0], arow1[k0], arow0[k0 + 4], arow1[k0 + 4]};
         uint32_t ah[4], al[4];
@@ -1006,6 +1010,138 @@ __global__ void __launch_bounds__(kEmThreads) feat_epilogue_mma_kernel(const Fea
         }
       }
     }
+  }
+  if (__any_sync(0xffffffffu, chk != 0.f) && lane == 0 && p.nonfinite_flag != nullptr) atomicOr(p.nonfinite_flag, 1);
+}
+
+// ---- the same epilogue for the unmasked common shapes, warp-autonomous and software-pipelined -------------------
+// feat_epilogue_mma_kernel is a sequence of CTA-wide phases per 128-row block (issue the loads | barrier | clamp into
+// shared memory | barrier | MMA | stores) and ncu shows it latency-bound, not issue- or bandwidth-bound (a third of the
+// issue slots used, 9 M warp-instructions for 49 MB).  Without SpecAugment flags, with n_mels and n_mfcc multiples of 8
+// known at compile time and every row complete in the tile matrix (mp == n_mels), a WARP can own a 16-row slab from
+// the load to the store: cp.async brings the NEXT slab's 16 x n_mels raw dB values (one contiguous span of the flat
+// matrix) into the warp's second buffer while it works on the current one, the clip maxima of the next slab's rows
+// are requested one iteration ahead too, the top_db floor and the centring happen on the A fragments as they are
+// loaded (every element is loaded by exactly one lane), and nothing but __syncwarp() synchronises.
+// Same arithmetic as feat_epilogue_mma_kernel (split TF32, rows centred, un-centred in float32).
+template <int KS> struct EmWarp {
+  static constexpr int kAp = KS * 8 + 4;                     // pitch = 4 (mod 8) floats: conflict-free fragment loads
+  static constexpr int kBufFloats = 16 * kAp;
+  static constexpr int kWarps = kEmThreads / 32;
+  static constexpr size_t smem_bytes(int ntc) {
+    return (size_t)kWarps * 2 * kBufFloats * sizeof(float) + (size_t)KS * ntc * 32 * sizeof(uint4);
+  }
+};
+
+template <typename OutT, int KS, int NTC>
+__global__ void __launch_bounds__(kEmThreads, 3) feat_epilogue_mma_warp_kernel(const FeatParams p) {
+  static_assert(NTC >= 1 && NTC <= kEmNT, "one pass over A");
+  using W = EmWarp<KS>;
+  constexpr int M = KS * 8, kAp = W::kAp, kChunks = 16 * M / 4;      // 16-byte chunks per slab
+  extern __shared__ __align__(16) float smem[];               // per warp: 2 x A [16][kAp] | B fragments uint4 [KS][NTC][32]
+  __shared__ float s_colsum[NTC * 8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float* bufs = smem + (size_t)warp * 2 * W::kBufFloats;
+  uint4* sB = reinterpret_cast<uint4*>(smem + (size_t)W::kWarps * 2 * W::kBufFloats);
+  for (int i = tid; i < KS * NTC * 32; i += kEmThreads) sB[i] = __ldg(p.dct_frag + i);
+  for (int i = tid; i < NTC * 8; i += kEmThreads) s_colsum[i] = __ldg(p.dct_colsum + i);
+  __syncthreads();                                            // the only CTA barrier
+  pdl_wait();                                                 // the tiles and maxima of feat_frames_kernel
+  const int T = p.T;
+  const long long rows = (long long)p.B * T;
+  const long long nslabs = (rows + 15) / 16;
+  const long long stride = (long long)gridDim.x * W::kWarps;
+  const int g = lane >> 2, t4 = lane & 3;
+  const bool has_floor = p.top_db >= 0.f;
+  const float half_range = has_floor ? 0.5f * p.top_db : 40.0f;
+  float chk = 0.f;
+  // stage slab sl into buffer bi: chunk i = row i / (M/4), columns 4 (i mod M/4) ..; rows beyond the matrix are not read
+  auto issue = [&](long long sl, int bi) {
+    const float* src = p.tile_g + (size_t)sl * 16 * M;
+    const long long left = (rows - sl * 16) * (M / 4);        // chunks that exist
+    float* dstb = bufs + bi * W::kBufFloats;
+#pragma unroll
+    for (int u = 0; u < (kChunks + 31) / 32; ++u) {
+      const int i = u * 32 + lane;
+      if (i < kChunks && i < left) {
+        const int row = i / (M / 4), c4 = i - row * (M / 4);
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(dstb + row * kAp + 4 * c4);
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src + 4 * i) : "memory");
+      }
+    }
+  };
+  // clip and frame of a row, and its clip's running-maximum key (rows beyond the matrix: clip -1)
+  auto row_info = [&](long long r, int& b, int& t, int& key) {
+    b = -1; t = 0; key = kMaxKeyMemset;
+    if (r < rows) {
+      b = (int)(r / T);
+      t = (int)(r - (long long)b * T);
+      key = __ldcg(p.clip_max + b);
+    }
+  };
+  long long sl = (long long)blockIdx.x * W::kWarps + warp;
+  int bA, tA, keyA, bB, tB, keyB;
+  if (sl < nslabs) {
+    issue(sl, 0);
+    row_info(sl * 16 + g, bA, tA, keyA);
+    row_info(sl * 16 + g + 8, bB, tB, keyB);
+  }
+  for (int cur = 0; sl < nslabs; sl += stride, cur ^= 1) {
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();                                             // every lane's chunks have landed; the other buffer is free
+    const long long nsl = sl + stride;
+    int nbA = -1, ntA = 0, nkeyA = kMaxKeyMemset, nbB = -1, ntB = 0, nkeyB = kMaxKeyMemset;
+    if (nsl < nslabs) {
+      issue(nsl, cur ^ 1);
+      row_info(nsl * 16 + g, nbA, ntA, nkeyA);
+      row_info(nsl * 16 + g + 8, nbB, ntB, nkeyB);
+    }
+    const float mxA = clip_max_value(keyA), mxB = clip_max_value(keyB);
+    const float cutA = has_floor ? mxA - p.top_db : -INFINITY, cutB = has_floor ? mxB - p.top_db : -INFINITY;
+    const float muA = bA >= 0 ? mxA - half_range : 0.f, muB = bB >= 0 ? mxB - half_range : 0.f;
+    const float* arow0 = bufs + cur * W::kBufFloats + g * kAp + t4;
+    const float* arow1 = arow0 + 8 * kAp;
+    float acc[NTC][4];
+#pragma unroll
+    for (int j = 0; j < NTC; ++j) { acc[j][0] = 0.f; acc[j][1] = 0.f; acc[j][2] = 0.f; acc[j][3] = 0.f; }
+    const uint4* bf = sB + lane;
+#pragma unroll(KS <= 8 ? KS : 2)
+    for (int ks = 0; ks < KS; ++ks) {
+      // rows beyond the matrix hold stale buffer contents: they become zeros here (their results are not stored)
+      const float av[4] = {bA >= 0 ? fmax_nan(arow0[8 * ks], cutA) - muA : 0.f, bB >= 0 ? fmax_nan(arow1[8 * ks], cutB) - muB : 0.f,
+                           bA >= 0 ? fmax_nan(arow0[8 * ks + 4], cutA) - muA : 0.f, bB >= 0 ? fmax_nan(arow1[8 * ks + 4], cutB) - muB : 0.f};
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { ah[i] = tf32_rna(av[i]); al[i] = tf32_rna(av[i] - __uint_as_float(ah[i])); }
+      uint4 b[NTC];
+#pragma unroll
+      for (int j = 0; j < NTC; ++j) b[j] = bf[(ks * NTC + j) * 32];
+#pragma unroll
+      for (int j = 0; j < NTC; ++j) mma_tf32_16x8x8(acc[j], al, b[j].x, b[j].y);
+#pragma unroll
+      for (int j = 0; j < NTC; ++j) mma_tf32_16x8x8(acc[j], ah, b[j].z, b[j].w);
+#pragma unroll
+      for (int j = 0; j < NTC; ++j) mma_tf32_16x8x8(acc[j], ah, b[j].x, b[j].y);
+    }
+    OutT* outA = reinterpret_cast<OutT*>(p.out) + (size_t)max(bA, 0) * p.out_stride + tA;
+    OutT* outB = reinterpret_cast<OutT*>(p.out) + (size_t)max(bB, 0) * p.out_stride + tB;
+#pragma unroll
+    for (int j = 0; j < NTC; ++j) {
+      const int c = j * 8 + 2 * t4;
+      const float2 cs = *reinterpret_cast<const float2*>(s_colsum + c);
+      acc[j][0] = fmaf(muA, cs.x, acc[j][0]); acc[j][1] = fmaf(muA, cs.y, acc[j][1]);
+      acc[j][2] = fmaf(muB, cs.x, acc[j][2]); acc[j][3] = fmaf(muB, cs.y, acc[j][3]);
+      const int o0 = c * T, o1 = o0 + T;
+      if (bA >= 0) {
+        chk = fmaf(acc[j][0], 0.f, fmaf(acc[j][1], 0.f, chk));
+        outA[o0] = to_out<OutT>(acc[j][0]); outA[o1] = to_out<OutT>(acc[j][1]);
+      }
+      if (bB >= 0) {
+        chk = fmaf(acc[j][2], 0.f, fmaf(acc[j][3], 0.f, chk));
+        outB[o0] = to_out<OutT>(acc[j][2]); outB[o1] = to_out<OutT>(acc[j][3]);
+      }
+    }
+    bA = nbA; tA = ntA; keyA = nkeyA; bB = nbB; tB = ntB; keyB = nkeyB;
   }
   if (__any_sync(0xffffffffu, chk != 0.f) && lane == 0 && p.nonfinite_flag != nullptr) atomicOr(p.nonfinite_flag, 1);
 }

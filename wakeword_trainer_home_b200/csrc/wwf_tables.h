@@ -109,7 +109,13 @@ struct MelSchedule {
 };
 
 // lo[m] / ofs[m] / w: CSR rows of the filterbank (first bin, offsets into w); n_fft: elements of a transform's scratch
-inline MelSchedule build_mel_schedule(const std::vector<int>& lo, const std::vector<int>& ofs, const std::vector<float>& w, int n_fft) {
+// read_extent: the scratch slots [0, read_extent) are safe for a lane to read and multiply by a zero weight: the
+// n_fft / 2 + 1 power values in general; all n_fft slots for the identity-mapped plan (n_fft 400), where this very
+// frame group's first FFT pass has written every slot (finite whenever the pair's samples are - and if they are not,
+// both frames of the pair are non-finite anyway).
+inline MelSchedule build_mel_schedule(const std::vector<int>& lo, const std::vector<int>& ofs, const std::vector<float>& w, int n_fft,
+                                      int read_extent = 0) {
+  if (read_extent <= 0) read_extent = n_fft / 2 + 1;
   const int M = (int)lo.size();
   struct Task { int m, k0, o, n, flags, d; };                  // d: leading zero-weight taps
   struct Unit { Task a, b; bool pair; int len() const { return pair ? std::max(a.n, b.n) : a.n; } int lanes() const { return pair ? 2 : 1; } };
@@ -209,10 +215,12 @@ inline MelSchedule build_mel_schedule(const std::vector<int>& lo, const std::vec
     for (int lane = 0; lane < 32; ++lane) s.tasks[(size_t)r * 32 + lane] = make_int2(0, wbase | (0xff << 16));   // idle: zero weights
     for (const Placed& pl : rounds[r].placed) {
       const Task& t = pl.t;
-      // a lane reads bins k0 .. k0 + rows - 1 whatever its own tap count: keep that inside the transform's scratch
-      // (n_fft elements) by starting earlier, with more leading zero weights
+      // a lane reads bins k0 .. k0 + rows - 1 whatever its own tap count: keep that inside read_extent by starting
+      // earlier with more leading zero weights.  (Anything beyond is NOT safe to multiply by a zero weight: the padded
+      // index maps of the power-of-two transforms leave slots of the scratch that no pass ever writes, and whatever
+      // an earlier kernel left there - a NaN, say - would turn 0 * x into NaN.  tests: poisoned shared memory.)
       int k0 = t.k0 - t.d, d = t.d;
-      if (k0 + rows > n_fft) { const int sh = std::min(k0, k0 + rows - n_fft); k0 -= sh; d += sh; }
+      if (k0 + rows > read_extent) { const int sh = std::min(k0, k0 + rows - read_extent); k0 -= sh; d += sh; }
       for (int i = 0; i < t.n; ++i) s.w[(size_t)(wbase + d + i) * 32 + pl.lane] = w[t.o + i];   // rows < d and >= d + n stay 0
       s.tasks[(size_t)r * 32 + pl.lane] = make_int2(k0 | ((t.n + d) << 16), wbase | (t.m << 16) | (t.flags << 24));
     }

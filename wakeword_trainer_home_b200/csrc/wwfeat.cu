@@ -87,6 +87,8 @@ struct wwf_plan {
   FeatKernel frames = nullptr;          // flat path: flat frames kernel (same n_fft / hop variant)
   FeatKernel epilogue_block = nullptr;  // flat path, log-mel: feat_epilogue_block_kernel<float | __half>
   FeatKernel epilogue_mma = nullptr;    // flat path, MFCC: feat_epilogue_mma_kernel<float | __half>
+  FeatKernel epilogue_warp = nullptr;   // flat path, MFCC, calls without SpecAugment flags, common shapes: feat_epilogue_mma_warp_kernel
+  size_t epilogue_warp_smem = 0;
   // device constants
   float* d_window = nullptr;
   float2* d_tw = nullptr;
@@ -97,7 +99,7 @@ struct wwf_plan {
   uint4* d_dct_frag = nullptr;
   float* d_dct_colsum = nullptr;
   // options (environment at plan creation, wwf_plan_set_option afterwards) and the per-(B, N) launch cache
-  int opt_path = WWF_PATH_AUTO, opt_pdl = 1;
+  int opt_path = WWF_PATH_AUTO, opt_pdl = 1, opt_ep_warp = 1;
   std::mutex cache_mu;
   std::vector<struct FeatLaunch*> launches;
   // noise bank (borrowed data, owned offsets)
@@ -160,6 +162,20 @@ static void select_kernel(wwf_plan* p, std::vector<float2>& tw) {
   p->epilogue_block = f16 ? (FeatKernel)feat_epilogue_block_kernel<__half> : (FeatKernel)feat_epilogue_block_kernel<float>;
   p->epilogue_mma = f16 ? (FeatKernel)feat_epilogue_mma_kernel<__half> : (FeatKernel)feat_epilogue_mma_kernel<float>;
   {
+    // shapes with compile-time k-step / tile counts: 40 mels x 40 coefficients (BASELINE configs[1]) and the
+    // reference's DataConfig defaults, 128 mels x 40 coefficients
+    const int ks = (p->cfg.n_mels + 7) / 8, ntc = (p->cfg.n_mfcc + 7) / 8;
+    if (ks == 5 && ntc == 5) {
+      p->epilogue_mma = f16 ? (FeatKernel)feat_epilogue_mma_kernel<__half, 5, 5> : (FeatKernel)feat_epilogue_mma_kernel<float, 5, 5>;
+      if (p->cfg.n_mels == 40 && p->cfg.n_mfcc == 40) {        // no padded column or coefficient: the warp-autonomous form
+        p->epilogue_warp = f16 ? (FeatKernel)feat_epilogue_mma_warp_kernel<__half, 5, 5> : (FeatKernel)feat_epilogue_mma_warp_kernel<float, 5, 5>;
+        p->epilogue_warp_smem = EmWarp<5>::smem_bytes(5);
+      }
+    }
+    else if (ks == 16 && ntc == 5)
+      p->epilogue_mma = f16 ? (FeatKernel)feat_epilogue_mma_kernel<__half, 16, 5> : (FeatKernel)feat_epilogue_mma_kernel<float, 16, 5>;
+  }
+  {
     // register-staged frame loads for hops that are a multiple of 32 and instantiated: 128, 160, 256
     if (!p->generic_load) {
       switch (p->cfg.hop_length) {
@@ -180,6 +196,28 @@ static void select_kernel(wwf_plan* p, std::vector<float2>& tw) {
 extern "C" int wwf_version(void) { return WWF_VERSION; }
 extern "C" const char* wwf_last_error(void) { return g_err; }
 extern "C" int64_t wwf_launch_count(void) { return g_launches.load(); }
+
+namespace {
+__global__ void poison_smem_kernel(uint32_t word, int n_words) {
+  extern __shared__ uint32_t poison_buf[];
+  for (int i = threadIdx.x; i < n_words; i += blockDim.x) poison_buf[i] = word;
+  __syncthreads();
+  if (poison_buf[(threadIdx.x * 97) % n_words] != word) __trap();   // (keeps the stores alive)
+}
+}  // namespace
+
+extern "C" int wwf_debug_poison_smem(int device, uint32_t word) {
+  DeviceGuard guard(device);
+  cudaDeviceProp prop;
+  WWF_CUDA(cudaGetDeviceProperties(&prop, device));
+  const int bytes = (int)prop.sharedMemPerBlockOptin - 1024;
+  WWF_CUDA(cudaFuncSetAttribute((const void*)poison_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  // one CTA per SM at a time (it takes nearly all of the SM's shared memory); a few rounds so that every SM gets one
+  poison_smem_kernel<<<8 * prop.multiProcessorCount, 1024, bytes>>>(word, bytes / 4);
+  WWF_CUDA(cudaGetLastError());
+  WWF_CUDA(cudaDeviceSynchronize());
+  return WWF_OK;
+}
 
 extern "C" void wwf_plan_destroy(wwf_plan* p) {
   if (!p) return;
@@ -234,6 +272,7 @@ extern "C" int wwf_plan_create(const wwf_config* cfg, int device, wwf_plan** out
   if (const char* e = getenv("WWF_FEAT_WARPS")) p->feat_warps_override = atoi(e);
   if (const char* e = getenv("WWF_FEAT_PATH")) p->opt_path = !strcmp(e, "fused") ? WWF_PATH_FUSED : !strcmp(e, "split") ? WWF_PATH_FLAT : WWF_PATH_AUTO;
   p->opt_pdl = getenv("WWF_NO_PDL") ? 0 : 1;
+  p->opt_ep_warp = getenv("WWF_NO_EP_WARP") ? 0 : 1;          // A/B: the block-wise tensor-core epilogue for every call
   p->generic_load = getenv("WWF_FEAT_GENERIC_LOAD") != nullptr;
 
   std::vector<float2> tw;
@@ -265,7 +304,7 @@ extern "C" int wwf_plan_create(const wwf_config* cfg, int device, wwf_plan** out
   }
   ofs[M] = (int)w.size();
   if (w.empty()) w.push_back(0.f);
-  const MelSchedule sched = build_mel_schedule(lo, ofs, w, n);
+  const MelSchedule sched = build_mel_schedule(lo, ofs, w, n, n == 400 ? n : n / 2 + 1);   // (400: the identity-mapped plan)
   if (sched.rounds > kMaxMelRounds) { delete p; return fail(WWF_ERR_UNSUPPORTED, "mel lane schedule needs %d rounds (max %d)", sched.rounds, kMaxMelRounds); }
   for (int r = 0; r < sched.rounds; ++r) p->mel_pairs[r] = (unsigned short)sched.pairs[r];
   p->n_melw = (int)sched.w.size();
@@ -301,6 +340,8 @@ extern "C" int wwf_plan_create(const wwf_config* cfg, int device, wwf_plan** out
   if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)p->frames, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem - 1024);
   if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)p->epilogue_block, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem - 2048);
   if (e == cudaSuccess) e = cudaFuncSetAttribute((const void*)p->epilogue_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem - kEpStaticSmem);
+  if (e == cudaSuccess && p->epilogue_warp)
+    e = cudaFuncSetAttribute((const void*)p->epilogue_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->epilogue_warp_smem);
   if (e != cudaSuccess) {
     wwf_plan_destroy(p);
     return fail(WWF_ERR_CUDA, "cudaFuncSetAttribute(feat_kernel): %s (is libwwfeat.so built for this GPU?)", cudaGetErrorString(e));
@@ -518,6 +559,7 @@ struct FeatLaunch {
   size_t frames_smem = 0, ep_smem = 0;
   int ep_threads = 0;
   FeatKernel ep_kernel = nullptr;   // feat_epilogue_mma_kernel (MFCC) or feat_epilogue_block_kernel (log-mel)
+  unsigned epw_grid = 0;            // feat_epilogue_mma_warp_kernel (0: not available for this plan / shape)
 };
 static void free_launch(FeatLaunch* l) { delete l; }
 
@@ -659,6 +701,13 @@ static FeatLaunch* build_launch(wwf_plan* p, int B, int N) {
       const long long rounds = (eitems + slots - 1) / slots;
       l->ep_grid = (unsigned)((eitems + rounds - 1) / rounds);
     }
+    if (mfcc && p->epilogue_warp && fp.mp == M && p->epilogue_warp_smem <= (size_t)p->max_smem - 1024) {
+      int wocc = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&wocc, (const void*)p->epilogue_warp, kEmThreads, p->epilogue_warp_smem) == cudaSuccess && wocc >= 1) {
+        const long long slabs = ((long long)B * T + 15) / 16, per_cta = kEmThreads / 32;
+        l->epw_grid = (unsigned)std::min<long long>((long long)p->sm_count * wocc, (slabs + per_cta - 1) / per_cta);
+      }
+    }
     l->flat_ok = l->frames_warps > 0 && l->frames_grid > 0 && l->ep_grid > 0 && (long long)B * fp.ngroups < (1ll << 31) - (1 << 20);
   }
   cudaGetLastError();   // a failed occupancy query must not poison the next launch check
@@ -685,6 +734,8 @@ extern "C" int wwf_plan_set_option(wwf_plan* p, int option, int value) {
     p->opt_path = value;
   } else if (option == WWF_OPT_PDL) {
     p->opt_pdl = value != 0;
+  } else if (option == WWF_OPT_EPILOGUE_WARP) {
+    p->opt_ep_warp = value != 0;
   } else {
     return fail(WWF_ERR_INVALID, "wwf_plan_set_option: unknown option %d", option);
   }
@@ -840,7 +891,11 @@ extern "C" int wwf_featurize(wwf_plan* p, const float* wav, int B, int N, int64_
     }
     WWF_CUDA(launch_feat(p->frames, fp, l->frames_grid, (unsigned)(l->frames_warps * 32), l->frames_smem, st, pdl));
     WWF_CUDA(mark(2));
-    WWF_CUDA(launch_feat(l->ep_kernel, fp, l->ep_grid, (unsigned)l->ep_threads, l->ep_smem, st, pdl));
+    const bool masked = (fp.fs != nullptr && fp.nF > 0) || (fp.ts != nullptr && fp.nT > 0);
+    if (l->epw_grid > 0 && !masked && p->opt_ep_warp)
+      WWF_CUDA(launch_feat(p->epilogue_warp, fp, l->epw_grid, (unsigned)kEmThreads, p->epilogue_warp_smem, st, pdl));
+    else
+      WWF_CUDA(launch_feat(l->ep_kernel, fp, l->ep_grid, (unsigned)l->ep_threads, l->ep_smem, st, pdl));
     g_launches += 2;
     WWF_CUDA(cudaGetLastError());
     WWF_CUDA(mark(3));

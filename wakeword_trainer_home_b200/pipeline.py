@@ -344,6 +344,11 @@ class FeaturePlan:
         """Chain the kernels of a call with programmatic dependent launch (default on)."""
         N.check(self.lib.wwf_plan_set_option(self._handle, N.OPT_PDL, int(bool(enable))))
 
+    def set_epilogue_warp(self, enable: bool = True):
+        """MFCC calls without SpecAugment flags of the common shapes take the warp-autonomous tensor-core epilogue
+        (default on); off = the block-wise one for every call.  Test / measurement control."""
+        N.check(self.lib.wwf_plan_set_option(self._handle, N.OPT_EPILOGUE_WARP, int(bool(enable))))
+
     # ------------------------------------------------------------------ waveform-shape augmentations
     def time_stretch(self, wav: torch.Tensor, rates: torch.Tensor, rate_lo: Optional[float] = None,
                      out: Optional[torch.Tensor] = None) -> torch.Tensor:
