@@ -1223,3 +1223,27 @@ def test_results_do_not_depend_on_stale_memory(ww, n_fft, hop, M, C, ftype):
                 _native.check(lib.wwf_debug_poison_smem(0, word))
                 got = plan.featurize(x, ap).cpu()
                 assert torch.equal(got, clean), f"n_fft={n_fft} M={M} {ftype} aug={use_aug} path={path} word={word:#x}"
+
+
+def test_shape_augmentations_do_not_depend_on_stale_memory(ww):
+    """Time-stretch, pitch-shift and resample with NaN-poisoned shared memory and allocator memory (see above): their
+    spectra / vocoder / synthesis workspaces and warp scratch must be written before they are read."""
+    from wakeword_trainer_home_b200 import _native
+    lib = _native.load()
+    gen = torch.Generator().manual_seed(4242)
+    B, N = 5, 19999
+    x = (0.1 * torch.randn(B, N, generator=gen)).cuda()
+    rates = torch.tensor([0.8137, 1.0, 1.1931, 0.9377, 1.0713], dtype=torch.float64)
+    steps = torch.tensor([2, 0, -2, 1, -1], dtype=torch.int32)
+    plan = ww.FeaturePlan(16000, "mel", 40, 40, 400, 160, "cuda")
+    ops = {"stretch": lambda: plan.time_stretch(x, rates), "pitch": lambda: plan.pitch_shift(x, steps),
+           "resample": lambda: plan.resample(x, 44100, 16000)}
+    for name, op in ops.items():
+        clean = op().cpu()
+        assert torch.isfinite(clean).all(), name
+        for word in (0x7fc00000, 0xff800000):
+            plan.release_workspaces()
+            junk = [torch.full((1 << 22,), float("nan"), device="cuda") for _ in range(16)]
+            del junk
+            _native.check(lib.wwf_debug_poison_smem(0, word))
+            assert torch.equal(op().cpu(), clean), f"{name} word={word:#x}"
