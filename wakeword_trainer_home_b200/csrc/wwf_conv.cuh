@@ -306,21 +306,66 @@ __device__ __forceinline__ void conv_fused_prefetch(float4 (&h)[kSpecPf], const 
 #pragma unroll
   for (int r = 0; r < kSpecPf; ++r) h[r] = __ldg(sp + r * 512);
 }
+// The run l = 0 (DC / Nyquist), lane-parallel: fused_dc_task on ONE lane was a divergent 384-instruction stretch that
+// made warp 0 the last one at the barrier behind the middle.  Here the 16 elements sit on 16 lanes (both half-warps
+// compute the same thing; only the first stores): a radix-2 DIF FFT by butterfly shuffles leaves frequency
+// bitrev4(q) on lane q, the partner 16 - r comes by one more shuffle, every lane does its own pair (r and 16 - r
+// both evaluate the pair (min, max) and keep their half of the result), and the mirrored DIT passes bring the run back
+// in natural order - about 90 warp-wide instructions, no divergence.  w16[k] = w_16^k and w32[r] = w_32^r are rows
+// of the pass-1 table (t1[(16 - 1) 16 + j] = w_512^{16 j}).
+__device__ __forceinline__ float2 shfl_xor2(float2 v, int m) {
+  return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m, 16), __shfl_xor_sync(0xffffffffu, v.y, m, 16));
+}
+__device__ __forceinline__ void conv_fused_dc_warp(float2* zc, const float4* __restrict__ spec_special, const float2* t1) {
+  const int q = threadIdx.x & 15;
+  const float2* w32 = t1 + 15 * 16;                            // w32[r] = w_32^r, r < 16; w_16^k = w32[2 k]
+  float2 x = zc[q];                                            // run_of(0) = 0: element q of the run at pad(q) = q
+#pragma unroll
+  for (int half = 8; half >= 1; half >>= 1) {                  // forward DIF: (a, b) -> (a + b, (a - b) w^j)
+    const float2 y = shfl_xor2(x, half);
+    const bool lower = (q & half) != 0;
+    float2 s2 = lower ? csub(y, x) : cadd(x, y);
+    if (half > 1 && lower) s2 = cmul(s2, w32[2 * (q & (half - 1)) * (8 / half)]);
+    x = s2;
+  }
+  {
+    const int r = (int)(__brev((unsigned)q) >> 28);            // this lane's frequency / 1024
+    const int rp = (16 - r) & 15, qp = (int)(__brev((unsigned)rp) >> 28);
+    const float2 y = make_float2(__shfl_sync(0xffffffffu, x.x, qp, 16), __shfl_sync(0xffffffffu, x.y, qp, 16));
+    const bool first = r <= 8;                                 // r = 0 and r = 8 pair with themselves (y == x)
+    const int rr = first ? r : 16 - r;
+    float2 a = first ? x : y, b = first ? y : x;
+    pair_convolve(a, b, rr == 0 ? make_float2(1.f, 0.f) : w32[rr], __ldg(spec_special + rr));
+    x = first ? a : b;
+  }
+#pragma unroll
+  for (int half = 1; half <= 8; half <<= 1) {                  // inverse DIT: (A, B) -> (A + B w*^j, A - B w*^j)
+    const bool lower = (q & half) != 0;
+    if (half > 1 && lower) x = cmulc(x, w32[2 * (q & (half - 1)) * (8 / half)]);
+    const float2 y = shfl_xor2(x, half);
+    x = lower ? csub(y, x) : cadd(x, y);
+  }
+  if ((threadIdx.x & 16) == 0) zc[q] = x;
+}
+
 __device__ __forceinline__ void conv_fused_middle(float2* zc, const float4* __restrict__ spec, float4 (&h)[kSpecPf],
-                                                  const uint16_t* __restrict__ fused_l, const float2* __restrict__ fused_tw) {
+                                                  const uint16_t* __restrict__ fused_l, const float2* __restrict__ fused_tw,
+                                                  const float2* t1) {
   const int t = threadIdx.x;
   const float4* sp = spec + t;
   fused_pair_task(zc, (int)__ldg(fused_l + t), __ldg(fused_tw + t), [&](int r) { return h[r & (kSpecPf - 1)]; },
                   [&](int r) { if (r + kSpecPf < 16) h[r & (kSpecPf - 1)] = __ldg(sp + (r + kSpecPf) * 512); });
-#ifndef WWF_DIAG_NO_DC
-  if (t == kFusedSelfTask)
-#else
-  if (t == 10000)
-#endif
-  {
+#ifdef WWF_DC_ONE_LANE
+  if (t == kFusedSelfTask) {
     const float4* sd = spec + kSpecSpecial;
     fused_dc_task(zc, [&](int i) { return __ldg(sd + i); });
   }
+#else
+  if (t < 32) {                                                // warp 0 (warp-uniform): it owns sub-transform 0, whose first run this is
+    __syncwarp();                                              // (its lanes' regular tasks do not touch the run, but keep the order explicit)
+    conv_fused_dc_warp(zc, spec + kSpecSpecial, t1);
+  }
+#endif
 }
 
 // ---- the passes of conv_kernel in pointer form ------------------------------------------------------------------
@@ -521,7 +566,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const WWF_GRID_CO
       float4 h[kSpecPf];
       conv_fused_prefetch(h, p.spec + (size_t)r * kSpecPerRir);
       __syncwarp();                                              // the warp's own sub-transform pair: no CTA barrier
-      conv_fused_middle(zc, p.spec + (size_t)r * kSpecPerRir, h, p.fused_l, p.fused_tw);
+      conv_fused_middle(zc, p.spec + (size_t)r * kSpecPerRir, h, p.fused_l, p.fused_tw, t1);
     }
     __syncwarp();
     {  // pull the next work item's samples into L2 while this block's inverse passes run (no registers held)
