@@ -611,12 +611,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const WWF_GRID_CO
         // single-block clips of even length (CTA-uniform): predicated 8-byte stores, no branches
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
-          const int n = nbase + 2 * ConvRad::S(0) * q;
-          const bool in = n < p.N;
-          if (in) *reinterpret_cast<float2*>(y + n) = v[q];
-          const float ax = in ? v[q].x : 0.f, ay = in ? v[q].y : 0.f;
-          if (q & 1) e1 = fmaf(ax, ax, fmaf(ay, ay, e1));
-          else e0 = fmaf(ax, ax, fmaf(ay, ay, e0));
+          // store and energy under ONE predicate, the values read in place: selecting zeros into copies first cost
+          // two moves per element - each a write-after-read wait on a register the store before it still had to
+          // read (5 % of the kernel's stall samples) - and 3 M warp-instructions per launch
+          if (nbase + 2 * ConvRad::S(0) * q < p.N) {
+            *reinterpret_cast<float2*>(y + nbase + 2 * ConvRad::S(0) * q) = v[q];
+            if (q & 1) e1 = fmaf(v[q].x, v[q].x, fmaf(v[q].y, v[q].y, e1));
+            else e0 = fmaf(v[q].x, v[q].x, fmaf(v[q].y, v[q].y, e0));
+          }
         }
       } else {
 #pragma unroll
