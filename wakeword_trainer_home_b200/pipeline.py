@@ -190,6 +190,7 @@ class FeaturePlan:
         self._stretch_tables = False   # torch's float32 Hann window of the stretch stage is handed over on first use
         self._noise = None          # keeps the borrowed noise bank alive
         self._workspace: dict[int, torch.Tensor] = {}
+        self._ws_need: dict[tuple, int] = {}                    # wwf_workspace_bytes(B, n), a pure function of the plan
         self.n_noise = self.n_rir = 0
 
     # ------------------------------------------------------------------ lifetime
@@ -281,6 +282,7 @@ class FeaturePlan:
         arr = (C.c_int64 * len(offs))(*offs)
         stream = torch.cuda.current_stream(self.device)
         N.check(self.lib.wwf_bank_register(self._handle, kind, _ptr(flat), arr, len(clips), C.c_void_p(stream.cuda_stream)))
+        self._ws_need.clear()                                   # the reverb workspace depends on the registered RIR bank
         return flat
 
     def register_noise(self, clips: Sequence[torch.Tensor]):
@@ -315,7 +317,12 @@ class FeaturePlan:
         return st, a            # keep `a` alive until the call returns
 
     def _ws(self, B: int, n: int, stream_id: int):
-        return self._ws_bytes(int(self.lib.wwf_workspace_bytes(self._handle, B, n)), stream_id)
+        need = self._ws_need.get((B, n))                        # (a ctypes round trip per call otherwise: the 1-clip path is host-bound)
+        if need is None:
+            if len(self._ws_need) >= 256:
+                self._ws_need.clear()
+            need = self._ws_need[(B, n)] = int(self.lib.wwf_workspace_bytes(self._handle, B, n))
+        return self._ws_bytes(need, stream_id)
 
     def _ws_bytes(self, need: int, key):
         if need == 0:
@@ -339,15 +346,18 @@ class FeaturePlan:
         'auto' (the library picks per batch shape).  Test / measurement control (wwf_plan_set_option)."""
         code = {"auto": N.PATH_AUTO, "fused": N.PATH_FUSED, "flat": N.PATH_FLAT, "split": N.PATH_FLAT}[path]
         N.check(self.lib.wwf_plan_set_option(self._handle, N.OPT_FEAT_PATH, code))
+        self._ws_need.clear()
 
     def set_pdl(self, enable: bool = True):
         """Chain the kernels of a call with programmatic dependent launch (default on)."""
         N.check(self.lib.wwf_plan_set_option(self._handle, N.OPT_PDL, int(bool(enable))))
+        self._ws_need.clear()
 
     def set_epilogue_warp(self, enable: bool = True):
         """MFCC calls without SpecAugment flags of the common shapes take the warp-autonomous tensor-core epilogue
         (default on); off = the block-wise one for every call.  Test / measurement control."""
         N.check(self.lib.wwf_plan_set_option(self._handle, N.OPT_EPILOGUE_WARP, int(bool(enable))))
+        self._ws_need.clear()
 
     # ------------------------------------------------------------------ waveform-shape augmentations
     def time_stretch(self, wav: torch.Tensor, rates: torch.Tensor, rate_lo: Optional[float] = None,
@@ -455,6 +465,8 @@ class FeaturePlan:
     def featurize(self, wav: torch.Tensor, aug: Optional[AugParams] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """(B, N) float32 clips -> (B, 1, n_feat, T) features, one fused GPU pass
         (reverb -> noise -> STFT -> mel -> dB -> [DCT] -> [CMVN] -> [masks])."""
+        if not getattr(self, "_nvtx", False):
+            return self._featurize(wav, aug, out)
         with self._range("wwf.featurize"):
             return self._featurize(wav, aug, out)
 
