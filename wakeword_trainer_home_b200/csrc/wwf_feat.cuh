@@ -34,11 +34,14 @@ constexpr int kMaxMelRounds = 16;              // rounds of the mel lane schedul
 // (max threads per CTA, min CTAs per SM) the kernel is compiled for, and the index map of the warp's
 // FFT scratch: the power-of-two sizes need one pad element per 16 (their later passes would
 // otherwise be 4- to 16-way bank conflicted); 400 = 16 x 25 has an odd stride and needs none.
+#ifndef WWF_FLAT400
+#define WWF_FLAT400 384
+#endif
 template <int NFFT> struct StftPlan;
 // kFlatThreads: CTA width the flat frames kernel is compiled for (same 2 CTAs per SM): n_fft 400 fits 80 registers
 // there (24 resident warps instead of 20: 128.9 -> 125.5 us on the bench workload; 64 registers / 32 warps spill and lose).
 template <> struct StftPlan<256>  { using Rad = Radices<16, 16>;    using Map = PadMap2;     static constexpr int G = 2, kThreads = 320, kMinCtas = 2, kFlatThreads = 320; };
-template <> struct StftPlan<400>  { using Rad = Radices<16, 25>;    using Map = IdentityMap; static constexpr int G = 2, kThreads = 320, kMinCtas = 2, kFlatThreads = 384; };
+template <> struct StftPlan<400>  { using Rad = Radices<16, 25>;    using Map = IdentityMap; static constexpr int G = 2, kThreads = 320, kMinCtas = 2, kFlatThreads = WWF_FLAT400; };
 template <> struct StftPlan<512>  { using Rad = Radices<16, 8, 4>;  using Map = PadMap2;     static constexpr int G = 1, kThreads = 512, kMinCtas = 1, kFlatThreads = 512; };
 template <> struct StftPlan<1024> { using Rad = Radices<16, 16, 4>; using Map = PadMap2;     static constexpr int G = 1, kThreads = 512, kMinCtas = 1, kFlatThreads = 512; };
 template <> struct StftPlan<2048> { using Rad = Radices<16, 16, 8>; using Map = PadMap2;     static constexpr int G = 1, kThreads = 512, kMinCtas = 1, kFlatThreads = 512; };

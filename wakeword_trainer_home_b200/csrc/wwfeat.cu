@@ -616,7 +616,7 @@ static FeatLaunch* build_launch(wwf_plan* p, int B, int N) {
   const size_t budget = (size_t)p->max_smem - 1024;   // static smem of the kernel is 256 B
   l->fused_fixed = (size_t)o * sizeof(float);
   l->fused_ok = l->fused_fixed + per_warp <= budget;           // else: only the flat path (no per-clip tile) can run
-  const int cands[] = {16, 12, 11, 10, 8, 6, 4, 2, 1};
+  const int cands[] = {16, 14, 13, 12, 11, 10, 8, 6, 4, 2, 1};
   if (l->fused_ok) {
     fp.off_res = (int)off_res; fp.off_window = (int)off_window; fp.off_tw = (int)off_tw; fp.off_melw = (int)off_melw;
     fp.off_dct = (int)off_dct; fp.off_meltasks = (int)off_meltasks; fp.off_rowmask = (int)off_rowmask;
