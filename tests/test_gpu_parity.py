@@ -1247,3 +1247,36 @@ def test_shape_augmentations_do_not_depend_on_stale_memory(ww):
             del junk
             _native.check(lib.wwf_debug_poison_smem(0, word))
             assert torch.equal(op().cpu(), clean), f"{name} word={word:#x}"
+
+
+@pytest.mark.parametrize("B,N", [(400, 24000), (333, 24001), (210, 40000), (150, 33000)])
+def test_reverb_many_items_per_cta_with_dry_clips_in_between(ww, B, N):
+    """conv_kernel is persistent (one CTA per SM) and pipelines across its work items: the next item's inputs are staged
+    by cp.async under the current item's last pass, the block energy is summed one item later, warps run ahead of each
+    other inside an item.  More items than SMs, dry clips between reverberated ones (their record needs the block
+    energy, not the FFT), single- and multi-block clips (40000 = 2 blocks, 33000 = 2 blocks with a short second one),
+    even and odd lengths (odd: the staged path is off): time-domain result and features against the oracle, for both
+    kernel variants (plain: augment / fused path; with mix records: flat path)."""
+    from oracle import ta_oracle as tao
+    gen = torch.Generator().manual_seed(B + N)
+    x = 0.1 * torch.randn(B, N, generator=gen)
+    noise, rirs = synth_banks(B, 5, 26000, 4, 8000)
+    plan = ww.FeaturePlan(16000, "mfcc", 40, 40, 400, 160, "cuda")
+    plan.register_noise(noise); plan.register_rirs(rirs)
+    rir_idx = torch.randint(-1, 4, (B,), generator=gen, dtype=torch.int32)
+    rir_idx[torch.rand(B, generator=gen) < 0.3] = -1            # ~45 % dry, scattered
+    p = ww.AugParams(rir_idx=rir_idx, noise_idx=torch.randint(-1, 5, (B,), generator=gen, dtype=torch.int32),
+                     noise_off=torch.randint(0, 26000, (B,), generator=gen), snr_db=5 + 15 * torch.rand(B, generator=gen))
+    got = plan.augment(x.cuda(), p).cpu()
+    sel = torch.arange(0, B, 3)                                  # the oracle on every third clip
+    ps = {k: getattr(p, k)[sel] for k in ("rir_idx", "noise_idx", "noise_off", "snr_db")}
+    want = tao.augment_wave(x[sel], rirs=rirs, noise_bank=noise, **ps)
+    rms = want.pow(2).mean(dim=1).sqrt()
+    assert ((got[sel] - want).abs().amax(dim=1) <= 2e-5 * rms).all()
+    ref = tao.featurize(want.double(), sample_rate=16000, feature_type="mfcc", n_mels=40, n_mfcc=40, n_fft=400,
+                        hop_length=160, dtype=torch.float64).numpy()
+    for path in ("flat", "fused"):
+        plan.set_path(path)
+        feats = plan.featurize(x.cuda(), p).cpu()
+        assert_features_close(feats[sel].numpy(), ref, f"B={B} N={N} path={path}")
+        assert torch.equal(feats, plan.featurize(x.cuda(), p).cpu())        # and deterministic from call to call
