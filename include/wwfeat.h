@@ -45,7 +45,7 @@ enum { WWF_FEAT_LOGMEL = 0, WWF_FEAT_MFCC = 1 };
 enum { WWF_OUT_F32 = 0, WWF_OUT_F16 = 1 };
 enum { WWF_BANK_NOISE = 0, WWF_BANK_RIR = 1 };
 enum { WWF_BANK_F32 = 0, WWF_BANK_I16 = 1 }; /* element type of a device-resident clip bank */
-enum { WWF_OPT_FEAT_PATH = 0, WWF_OPT_PDL = 1, WWF_OPT_EPILOGUE_WARP = 2 };   /* wwf_plan_set_option */
+enum { WWF_OPT_FEAT_PATH = 0, WWF_OPT_PDL = 1, WWF_OPT_EPILOGUE_WARP = 2, WWF_OPT_CONV_ORDER = 3 };   /* wwf_plan_set_option */
 enum { WWF_PATH_AUTO = 0, WWF_PATH_FUSED = 1, WWF_PATH_FLAT = 2 };
 
 /*
@@ -308,8 +308,14 @@ int wwf_profile_read_kernels(wwf_plan* plan, double* kernel_ms, int* n_calls, in
  * WWF_PATH_FUSED (one kernel per call) or WWF_PATH_FLAT (flat frame queue + epilogue; needs the workspace);
  * WWF_OPT_PDL: 1 (default) chains the kernels of a call with programmatic dependent launch, 0 = plain launches;
  * WWF_OPT_EPILOGUE_WARP: 1 (default) lets MFCC calls without SpecAugment flags of the common shapes take the
- * warp-autonomous tensor-core epilogue (feat_epilogue_mma_warp_kernel), 0 = the block-wise one for every call.
- * They can be preset through the environment (WWF_FEAT_PATH=fused|split, WWF_NO_PDL, WWF_NO_EP_WARP), which is read
+ * warp-autonomous tensor-core epilogue (feat_epilogue_mma_warp_kernel), 0 = the block-wise one for every call;
+ * WWF_OPT_CONV_ORDER: 1 (default) = when a call has more reverb work items than SMs, the reverb kernel deals the
+ * reverberated clips round-robin over its persistent CTAs (it builds the order itself; a call that reverberates 30 %
+ * of 1024 clips runs 1.8x faster), 0 = batch order - what a caller that KNOWS every clip of its batches is
+ * reverberated may set to save the ~2 us the ordering costs (the Python shim does, per batch, from host-side draws).
+ * This option does not drop the cached launch shapes.
+ * They can be preset through the environment (WWF_FEAT_PATH=fused|split, WWF_NO_PDL, WWF_NO_EP_WARP,
+ * WWF_NO_CONV_ORDER), which is read
  * once, at wwf_plan_create.  Changing an option drops the plan's cached launch shapes; call it between, not
  * concurrently with, wwf_featurize calls.  No reference counterpart: test / measurement control only.
  */

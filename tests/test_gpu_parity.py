@@ -1268,6 +1268,15 @@ def test_reverb_many_items_per_cta_with_dry_clips_in_between(ww, B, N):
     p = ww.AugParams(rir_idx=rir_idx, noise_idx=torch.randint(-1, 5, (B,), generator=gen, dtype=torch.int32),
                      noise_off=torch.randint(0, 26000, (B,), generator=gen), snr_db=5 + 15 * torch.rand(B, generator=gen))
     got = plan.augment(x.cuda(), p).cpu()
+    # the order in which the persistent CTAs take the clips (reverberated ones dealt round-robin / batch order) is
+    # scheduling only: bit-identical results
+    plan.set_conv_order(False)
+    assert torch.equal(plan.augment(x.cuda(), p).cpu(), got)
+    plan.set_path("flat")
+    batch_order = plan.featurize(x.cuda(), p).cpu()
+    plan.set_conv_order(True)
+    assert torch.equal(plan.featurize(x.cuda(), p).cpu(), batch_order)
+    plan.set_conv_order(None)
     sel = torch.arange(0, B, 3)                                  # the oracle on every third clip
     ps = {k: getattr(p, k)[sel] for k in ("rir_idx", "noise_idx", "noise_off", "snr_db")}
     want = tao.augment_wave(x[sel], rirs=rirs, noise_bank=noise, **ps)

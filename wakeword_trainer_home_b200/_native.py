@@ -18,7 +18,7 @@ FEAT_LOGMEL, FEAT_MFCC = 0, 1
 OUT_F32, OUT_F16 = 0, 1
 BANK_NOISE, BANK_RIR = 0, 1
 BANK_F32, BANK_I16 = 0, 1
-OPT_FEAT_PATH, OPT_PDL, OPT_EPILOGUE_WARP = 0, 1, 2
+OPT_FEAT_PATH, OPT_PDL, OPT_EPILOGUE_WARP, OPT_CONV_ORDER = 0, 1, 2, 3
 PATH_AUTO, PATH_FUSED, PATH_FLAT = 0, 1, 2
 MAX_MASKS = 8
 SUPPORTED_N_FFT = (256, 400, 512, 1024, 2048)

@@ -86,6 +86,7 @@ struct ConvParams {
   const float2* tw;                          // pass tables (kConvTwTotal)
   const uint16_t* fused_l;                   // [512] l of fused task t (bank-conflict-free order)
   const float2* fused_tw;                    // [512] w_P^{l(t)}
+  int ordered;                               // 1: work items follow the CTA-built clip order (reverberated clips first)
   int* clip_max; int n_clip_max;             // flat feature path: running clip maxima to reset (or nullptr): saves the
                                              // memset in front of this kernel, so that it can be chained (PDL) too
   // noise-mix records of the flat feature path made HERE (single-block clips, at most kConvMaxOwn items per CTA), or
@@ -94,6 +95,15 @@ struct ConvParams {
   NoiseBankDev noise; const int32_t* noise_idx; const int64_t* noise_off; const float* snr_db;
 };
 constexpr int kConvMaxOwn = 16;              // items per CTA whose records fit the shared-memory staging area
+// ORDER OF THE WORK ITEMS.  Item i of the persistent grid goes to CTA i mod grid.  With clip order = batch order, a call
+// that reverberates only some clips (rir_prob 0.25 - 0.3 in the reference's presets) gives every CTA a random number
+// of expensive items: BASELINE configs[3] (1024 clips, 30 % reverberated, 2 blocks each) averaged 4.2 blocks per CTA
+// but the slowest had 9 - and the kernel takes as long as the slowest.  Every CTA therefore builds the same
+// permutation in shared memory first: the reverberated clips in batch order, then the dry ones (one pass over
+// rir_idx + a block-wide prefix sum, ~1 us), and items are (order[i / nblk], i mod nblk): the expensive items are
+// dealt round-robin, at most one more on one CTA than on another.  Batches of up to kConvMaxOrder clips (uint16 ids).
+constexpr int kConvMaxOrder = 8192;
+constexpr size_t conv_smem_bytes(int B, bool ordered) { return kConvSmemBytes + (ordered ? ((size_t)B * 2 + 15) / 16 * 16 : 0); }
 
 // ------------------------------------------------------------------------------------------
 // radix-32 pass with derived twiddles (pass 0).  tw5[b*s + j] = w_L^{j 2^b}, b = 0..4.
@@ -470,11 +480,47 @@ __device__ __forceinline__ void conv_load_staged(float2 (&v)[32], const float2* 
 // launch and load latency per step) sits in front of the frames kernel any more.  Measured (B = 1024): plain kernel
 // 127.2 us, with the records 135.8 us - 6.7 us of it the prologue's pointer chase (three dependent global loads per
 // clip), which is serial latency wherever it is put (as its own kernel in front of this one: 8 us) - against 16 us.
-static __device__ __noinline__ void conv_mix_prologue(const ConvParams& p, ClipMix* s_mix) {
+static __device__ __noinline__ void conv_build_order(const ConvParams& p, uint16_t* s_order, int* s_scan) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int per = (p.B + kConvThreads - 1) / kConvThreads;
+  const int i0 = min(p.B, tid * per), i1 = min(p.B, i0 + per);
+  int cnt = 0;
+  for (int i = i0; i < i1; ++i) cnt += rir_in_range(__ldg(p.rir_idx + i), p.n_rir) ? 1 : 0;
+  int incl = cnt;                                                // inclusive prefix sum over the CTA
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+  if (lane == 31) s_scan[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    int v = lane < kConvThreads / 32 ? s_scan[lane] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += t; }
+    if (lane < kConvThreads / 32) s_scan[lane] = v;             // inclusive warp totals
+  }
+  __syncthreads();
+  const int n_rev = s_scan[kConvThreads / 32 - 1];
+  int pr = incl - cnt + (warp > 0 ? s_scan[warp - 1] : 0);       // reverberated clips before i0
+  int pd = n_rev + (i0 - pr);                                    // dry clips go behind all reverberated ones
+  for (int i = i0; i < i1; ++i) {
+    if (rir_in_range(__ldg(p.rir_idx + i), p.n_rir)) s_order[pr++] = (uint16_t)i;
+    else s_order[pd++] = (uint16_t)i;
+  }
+  __syncthreads();
+}
+// clip of work item `item` (single-block clips: item = position in the order)
+template <bool ORD>
+__device__ __forceinline__ int conv_item_clip(const uint16_t* s_order, int ci) {
+  if constexpr (ORD) return (int)s_order[ci];
+  else return ci;
+}
+
+template <bool ORD>
+static __device__ __noinline__ void conv_mix_prologue(const ConvParams& p, ClipMix* s_mix, const uint16_t* s_order) {
   const int warp = threadIdx.x >> 5;
   for (int k = warp; k < kConvMaxOwn; k += kConvThreads / 32) {
-    const int b = blockIdx.x + k * gridDim.x;                    // (single-block clips: item = clip)
-    if (b >= p.B) break;
+    const int ci = blockIdx.x + k * gridDim.x;                   // (single-block clips: item = position in the order)
+    if (ci >= p.B) break;
+    const int b = conv_item_clip<ORD>(s_order, ci);
     const ClipNoise cn = resolve_noise(p.noise, p.noise_idx, p.noise_off, b);   // warp-uniform
     ClipMix m{0.f, 0, 0, 1, 0, 0.f, 0.f};
     if (cn.nz != nullptr) {
@@ -485,9 +531,9 @@ static __device__ __noinline__ void conv_mix_prologue(const ConvParams& p, ClipM
     if ((threadIdx.x & 31) == 0) s_mix[k] = m;
   }
 }
-// record of clip b (the CTA's item number (b - blockIdx.x) / gridDim.x) once its energy es is known; one thread
-static __device__ __noinline__ void conv_mix_finish(const ConvParams& p, const ClipMix* s_mix, int b, float es) {
-  ClipMix m = s_mix[(b - (int)blockIdx.x) / (int)gridDim.x];
+// record of clip b, the CTA's k-th item, once its energy es is known; one thread
+static __device__ __noinline__ void conv_mix_finish(const ConvParams& p, const ClipMix* s_mix, int b, int k, float es) {
+  ClipMix m = s_mix[k];
   if (m.has_noise) m.scale = snr_scale(es, m.en, m.snr);
   p.mix_g[b] = m;
 }
@@ -500,30 +546,32 @@ __device__ __forceinline__ void conv_flush_energy(const ConvParams& p, const Cli
                                                   int* s_pend) {
   const int b = s_pend[0];
   if (b < 0) return;                                             // warp-uniform
-  const int blk = s_pend[1], lane = threadIdx.x & 31;
+  const int blk = s_pend[1], k = s_pend[3], lane = threadIdx.x & 31;   // k: the CTA's item ordinal
   float e = lane < kConvThreads / 32 ? s_part[s_pend[2]][lane] : 0.f;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
   if (lane == 0) {
     s_pend[0] = -1;
     if (p.es_part != nullptr) p.es_part[(size_t)b * p.es_nb + blk] = e;
-    if constexpr (MIX) conv_mix_finish(p, s_mix, b, e);         // F.add_noise's scale, now that the clip's energy is known
+    if constexpr (MIX) conv_mix_finish(p, s_mix, b, k, e);      // F.add_noise's scale, now that the clip's energy is known
   }
 }
 
-template <bool MIX>
+template <bool MIX, bool ORD>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const WWF_GRID_CONSTANT ConvParams p) {   // (grid constant:
   // the __noinline__ helpers take p by reference; without it the kernel keeps a 200-byte local-memory copy of the
   // parameters and reads N, the strides, ... through LDL inside the hot loop)
   extern __shared__ __align__(16) float2 zc[];
   __shared__ float red[32];
   __shared__ float s_part[2][kConvThreads / 32];                 // per-warp energy partials of the last two items
-  __shared__ int s_pend[3];                                      // {clip, block, s_part row} of the item not yet summed
+  __shared__ int s_pend[4];                                      // {clip, block, s_part row, item ordinal} of the item not yet summed
+  __shared__ int s_scan[kConvThreads / 32];
   __shared__ ClipMix s_mix[MIX ? kConvMaxOwn : 1];
   if (threadIdx.x == kConvFlushThread) s_pend[0] = -1;
   int par = 0;
   int staged = -1;                                               // item whose first-pass inputs wait in shared memory
   float2* s_tw = zc + kConvSmemElems;
+  uint16_t* s_order = reinterpret_cast<uint16_t*>(s_tw + kConvTwTotal);   // [B] when p.ordered
   conv_load_tables(s_tw, p.tw);
   const int u = threadIdx.x;
   const float2* t0 = s_tw + kConvTw0;
@@ -535,17 +583,20 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const WWF_GRID_CO
   if (p.clip_max != nullptr)                                     // identity of the running maxima (wwf_feat.cuh: kMaxKeyMemset)
     for (int i = blockIdx.x * kConvThreads + threadIdx.x; i < p.n_clip_max; i += gridDim.x * kConvThreads)
       p.clip_max[i] = (int)0x80808080;
-  if constexpr (MIX) conv_mix_prologue(p, s_mix);
+  if constexpr (ORD) conv_build_order(p, s_order, s_scan);
+  if constexpr (MIX) conv_mix_prologue<ORD>(p, s_mix, s_order);
   __syncthreads();                                               // twiddle tables and mix records visible (a dry first
                                                                  // item reads its record straight away)
   for (int item = blockIdx.x; item < p.B * nblk; item += gridDim.x) {
-    const int b = item / nblk, blk = item - b * nblk;
+    const int ci = item / nblk, blk = item - ci * nblk;
+    const int b = conv_item_clip<ORD>(s_order, ci);
     const int r = __ldg(p.rir_idx + b);
     const float* x = p.wav + (size_t)b * p.wav_stride;
     if (!rir_in_range(r, p.n_rir)) {                             // dry clip (CTA-uniform): only its mix record
       if constexpr (MIX) {
-        const float es = s_mix[(b - (int)blockIdx.x) / (int)gridDim.x].has_noise ? block_energy(x, p.N, red) : 0.f;
-        if (threadIdx.x == 0) conv_mix_finish(p, s_mix, b, es);
+        const int k = (item - (int)blockIdx.x) / (int)gridDim.x;
+        const float es = s_mix[k].has_noise ? block_energy(x, p.N, red) : 0.f;
+        if (threadIdx.x == 0) conv_mix_finish(p, s_mix, b, k, es);
       }
       continue;
     }
@@ -572,7 +623,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const WWF_GRID_CO
     {  // pull the next work item's samples into L2 while this block's inverse passes run (no registers held)
       const int nitem = item + gridDim.x;
       if (nitem < p.B * nblk) {
-        const int nb_ = nitem / nblk, nblk_ = nitem - nb_ * nblk;
+        const int nci = nitem / nblk, nblk_ = nitem - nci * nblk, nb_ = conv_item_clip<ORD>(s_order, nci);
         const float* nx = p.wav + (size_t)nb_ * p.wav_stride;
         const int nstart = nblk_ * p.valid - p.hist;
         for (int q = threadIdx.x * 32; q < kConvP; q += kConvThreads * 32) {   // one 128-byte line per request
@@ -595,10 +646,11 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const WWF_GRID_CO
       pass32_core<true>(v, ConvRad::S(0), u, [&](int q) { return t0[q]; }, [&](int) {
         // every loaded value is in use: the positions are free for the next item's inputs (a dry next item simply
         // leaves them unused; whatever lands is overwritten by the next first pass after its conv_stage_wait())
+        // (computed here rather than parked in shared memory by the prefetch block above: that variant spilled)
         const int nitem = item + gridDim.x;
         if (nitem < p.B * nblk) {
-          const int nb_ = nitem / nblk, nstart = (nitem - nb_ * nblk) * p.valid - p.hist;
-          const float* nx = p.wav + (size_t)nb_ * p.wav_stride;
+          const int nci = nitem / nblk, nstart = (nitem - nci * nblk) * p.valid - p.hist;
+          const float* nx = p.wav + (size_t)conv_item_clip<ORD>(s_order, nci) * p.wav_stride;
           if (nstart >= 0 && !(p.N & 1) && (reinterpret_cast<uintptr_t>(nx) & 7) == 0) {
             conv_stage_pass0(zp0, nx, p.N, nstart);
             staged = nitem;
@@ -641,7 +693,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_kernel(const WWF_GRID_CO
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
     if ((threadIdx.x & 31) == 0) s_part[par][threadIdx.x >> 5] = e;
-    if (threadIdx.x == kConvFlushThread) { s_pend[1] = blk; s_pend[2] = par; s_pend[0] = b; }
+    if (threadIdx.x == kConvFlushThread) { s_pend[1] = blk; s_pend[2] = par; s_pend[3] = (item - (int)blockIdx.x) / (int)gridDim.x; s_pend[0] = b; }
     par ^= 1;
   }
   __syncthreads();

@@ -99,7 +99,7 @@ struct wwf_plan {
   uint4* d_dct_frag = nullptr;
   float* d_dct_colsum = nullptr;
   // options (environment at plan creation, wwf_plan_set_option afterwards) and the per-(B, N) launch cache
-  int opt_path = WWF_PATH_AUTO, opt_pdl = 1, opt_ep_warp = 1;
+  int opt_path = WWF_PATH_AUTO, opt_pdl = 1, opt_ep_warp = 1, opt_conv_order = 1;
   std::mutex cache_mu;
   std::vector<struct FeatLaunch*> launches;
   // noise bank (borrowed data, owned offsets)
@@ -272,6 +272,7 @@ extern "C" int wwf_plan_create(const wwf_config* cfg, int device, wwf_plan** out
   if (const char* e = getenv("WWF_FEAT_WARPS")) p->feat_warps_override = atoi(e);
   if (const char* e = getenv("WWF_FEAT_PATH")) p->opt_path = !strcmp(e, "fused") ? WWF_PATH_FUSED : !strcmp(e, "split") ? WWF_PATH_FLAT : WWF_PATH_AUTO;
   p->opt_pdl = getenv("WWF_NO_PDL") ? 0 : 1;
+  p->opt_conv_order = getenv("WWF_NO_CONV_ORDER") ? 0 : 1;    // A/B: reverb work items in batch order
   p->opt_ep_warp = getenv("WWF_NO_EP_WARP") ? 0 : 1;          // A/B: the block-wise tensor-core epilogue for every call
   p->generic_load = getenv("WWF_FEAT_GENERIC_LOAD") != nullptr;
 
@@ -429,8 +430,10 @@ static int ensure_conv_constants(wwf_plan* p) {
   build_conv_tables(tw, fl, ftw);
   int rc;
   if ((rc = upload(&p->d_conv_tw, tw)) || (rc = upload(&p->d_fused_l, fl)) || (rc = upload(&p->d_fused_tw, ftw))) return rc;
-  WWF_CUDA(cudaFuncSetAttribute((const void*)conv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemBytes));
-  WWF_CUDA(cudaFuncSetAttribute((const void*)conv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemBytes));
+  WWF_CUDA(cudaFuncSetAttribute((const void*)conv_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemBytes));
+  WWF_CUDA(cudaFuncSetAttribute((const void*)conv_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemBytes));
+  WWF_CUDA(cudaFuncSetAttribute((const void*)conv_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes(kConvMaxOrder, true)));
+  WWF_CUDA(cudaFuncSetAttribute((const void*)conv_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem_bytes(kConvMaxOrder, true)));
   WWF_CUDA(cudaFuncSetAttribute((const void*)rir_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kConvSmemBytes));
   return WWF_OK;
 }
@@ -729,6 +732,10 @@ static FeatLaunch* get_launch(wwf_plan* p, int B, int N) {
 extern "C" int wwf_plan_set_option(wwf_plan* p, int option, int value) {
   if (!p) return fail(WWF_ERR_INVALID, "wwf_plan_set_option: null plan");
   std::lock_guard<std::mutex> lk(p->cache_mu);
+  if (option == WWF_OPT_CONV_ORDER) {                          // (not part of the cached launch shapes)
+    p->opt_conv_order = value != 0;
+    return WWF_OK;
+  }
   if (option == WWF_OPT_FEAT_PATH) {
     if (value != WWF_PATH_AUTO && value != WWF_PATH_FUSED && value != WWF_PATH_FLAT) return fail(WWF_ERR_INVALID, "wwf_plan_set_option: path %d", value);
     p->opt_path = value;
@@ -775,17 +782,24 @@ static int conv_setup(wwf_plan* p, const float* wav, int B, int N, int64_t wav_s
 }
 
 // ... and the launch (pdl: chained behind one of our own kernels with programmatic dependent launch)
-static int conv_launch(wwf_plan* p, const ConvParams& cp, cudaStream_t st, bool pdl) {
+static int conv_launch(wwf_plan* p, ConvParams& cp, cudaStream_t st, bool pdl) {
   const int items = cp.es_nb * cp.B;
+  // more items than CTAs: deal the reverberated clips round-robin (the CTAs build the order themselves, wwf_conv.cuh)
+  cp.ordered = items > p->sm_count && cp.B <= kConvMaxOrder && p->opt_conv_order ? 1 : 0;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(items < p->sm_count ? items : p->sm_count); cfg.blockDim = dim3(kConvThreads);
-  cfg.dynamicSmemBytes = kConvSmemBytes; cfg.stream = st;
+  cfg.dynamicSmemBytes = conv_smem_bytes(cp.B, cp.ordered != 0); cfg.stream = st;
   cudaLaunchAttribute at{};
   at.id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at.val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = &at; cfg.numAttrs = pdl ? 1 : 0;
-  if (cp.mix_g != nullptr) WWF_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel<true>, cp));
-  else WWF_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel<false>, cp));
+  if (cp.mix_g != nullptr) {
+    if (cp.ordered) WWF_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel<true, true>, cp));
+    else WWF_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel<true, false>, cp));
+  } else {
+    if (cp.ordered) WWF_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel<false, true>, cp));
+    else WWF_CUDA(cudaLaunchKernelEx(&cfg, conv_kernel<false, false>, cp));
+  }
   g_launches++;
   return WWF_OK;
 }

@@ -10,6 +10,8 @@ and SpecAugment masks passed in explicitly"), so the same draws can be handed to
 """
 from __future__ import annotations
 
+import os
+
 import ctypes as C
 from dataclasses import dataclass, fields
 from typing import Optional, Sequence
@@ -45,6 +47,10 @@ class AugParams:
     pitch_steps int32 [B]      pitch shift in semitones, 0 = untouched
     stretch_lo / pitch_range   host-side bounds of the two arrays above (they size the workspace);
                                filled in automatically from host tensors or by the on-GPU draw
+    all_reverb                 host-side fact about rir_idx, filled in the same way: True = every clip of the batch is
+                               reverberated.  A scheduling hint only (FeaturePlan._conv_order): with dry clips in a
+                               large batch the reverb kernel deals the reverberated ones round-robin over its CTAs,
+                               which costs ~2 us that an all-reverb batch need not pay.  None = unknown (order on).
     Order of application: time-stretch -> pitch-shift -> reverb -> noise -> features -> masks.
     """
     rir_idx: Optional[torch.Tensor] = None
@@ -59,6 +65,7 @@ class AugParams:
     pitch_steps: Optional[torch.Tensor] = None
     stretch_lo: Optional[float] = None
     pitch_range: Optional[tuple] = None
+    all_reverb: Optional[bool] = None
     resident_on: Optional[torch.device] = None   # set by .to(): every tensor already has the ABI's dtype on that device
 
     _DTYPES = dict(rir_idx=torch.int32, noise_idx=torch.int32, noise_off=torch.int64, snr_db=torch.float32,
@@ -69,7 +76,7 @@ class AugParams:
         return [f.name for f in fields(self) if f.name in self._DTYPES]
 
     def to(self, device, non_blocking: bool = False) -> "AugParams":
-        kw = dict(stretch_lo=self.stretch_lo, pitch_range=self.pitch_range)
+        kw = dict(stretch_lo=self.stretch_lo, pitch_range=self.pitch_range, all_reverb=self.all_reverb)
         for name in self.tensor_fields():
             v = getattr(self, name)
             if v is not None:
@@ -79,6 +86,8 @@ class AugParams:
                     kw["stretch_lo"] = float(v.min())
                 if name == "pitch_steps" and kw["pitch_range"] is None and not v.is_cuda and v.numel():
                     kw["pitch_range"] = (int(v.min()), int(v.max()))
+                if name == "rir_idx" and kw["all_reverb"] is None and not v.is_cuda and v.numel():
+                    kw["all_reverb"] = bool((v >= 0).all())
                 v = v.to(device=device, dtype=self._DTYPES[name], non_blocking=non_blocking).contiguous()
             kw[name] = v
         moved = [kw[n] for n in self.tensor_fields() if kw.get(n) is not None]
@@ -190,6 +199,8 @@ class FeaturePlan:
         self._stretch_tables = False   # torch's float32 Hann window of the stretch stage is handed over on first use
         self._noise = None          # keeps the borrowed noise bank alive
         self._workspace: dict[int, torch.Tensor] = {}
+        self._conv_order_pinned = bool(os.environ.get("WWF_NO_CONV_ORDER"))      # (the library read it at plan creation)
+        self._conv_order_now = 0 if self._conv_order_pinned else 1
         self._ws_need: dict[tuple, int] = {}                    # wwf_workspace_bytes(B, n), a pure function of the plan
         self.n_noise = self.n_rir = 0
 
@@ -223,7 +234,8 @@ class FeaturePlan:
         a = AugParams(rir_idx=torch.empty(B, dtype=torch.int32, device=dev),
                       noise_idx=torch.empty(B, dtype=torch.int32, device=dev),
                       noise_off=torch.empty(B, dtype=torch.int64, device=dev),
-                      snr_db=torch.empty(B, dtype=torch.float32, device=dev), resident_on=dev)
+                      snr_db=torch.empty(B, dtype=torch.float32, device=dev), resident_on=dev,
+                      all_reverb=bool(cfg.rir_prob >= 1.0))
         if self.n_freq_masks:
             a.fmask_start = torch.empty(B, self.n_freq_masks, dtype=torch.int32, device=dev)
             a.fmask_len = torch.empty(B, self.n_freq_masks, dtype=torch.int32, device=dev)
@@ -353,6 +365,21 @@ class FeaturePlan:
         N.check(self.lib.wwf_plan_set_option(self._handle, N.OPT_PDL, int(bool(enable))))
         self._ws_need.clear()
 
+    def _conv_order(self, aug: Optional[AugParams]):
+        """Per batch: WWF_OPT_CONV_ORDER off iff the draws are known to reverberate every clip (AugParams.all_reverb)."""
+        want = 0 if (aug is not None and aug.all_reverb) else 1
+        if want != self._conv_order_now and not self._conv_order_pinned:
+            N.check(self.lib.wwf_plan_set_option(self._handle, N.OPT_CONV_ORDER, want))
+            self._conv_order_now = want
+
+    def set_conv_order(self, enable: Optional[bool] = None):
+        """Reverb work items dealt round-robin over the CTAs (True), in batch order (False), or chosen per batch from
+        ``AugParams.all_reverb`` (None, the default).  Test / measurement control."""
+        self._conv_order_pinned = enable is not None
+        if enable is not None:
+            N.check(self.lib.wwf_plan_set_option(self._handle, N.OPT_CONV_ORDER, int(bool(enable))))
+            self._conv_order_now = int(bool(enable))
+
     def set_epilogue_warp(self, enable: bool = True):
         """MFCC calls without SpecAugment flags of the common shapes take the warp-autonomous tensor-core epilogue
         (default on); off = the block-wise one for every call.  Test / measurement control."""
@@ -479,6 +506,7 @@ class FeaturePlan:
         elif out.shape != (B, 1, self.n_feat, T) or out.dtype != self.out_dtype or out.device != self.device or not out.is_contiguous():
             raise ValueError("out must be a contiguous (B, 1, n_feat, T) tensor of the plan's dtype on the plan's device")
         st, keep = self._aug_struct(aug, B)
+        self._conv_order(keep)
         wav = self._shape_augs(wav, keep)
         stream = torch.cuda.current_stream(self.device)
         ws, ws_bytes = self._ws(B, n, stream.cuda_stream)
@@ -493,6 +521,7 @@ class FeaturePlan:
         if out is None:
             out = torch.empty(B, n, dtype=torch.float32, device=self.device)
         st, keep = self._aug_struct(aug, B)
+        self._conv_order(keep)
         wav = self._shape_augs(wav, keep)
         stream = torch.cuda.current_stream(self.device)
         ws, ws_bytes = self._ws(B, n, stream.cuda_stream)
