@@ -11,8 +11,10 @@
 // of frequency k = l + 1024 d2 is M - k = (1024 - l) + 1024 (15 - d2), i.e. run(l) pairs with
 // run(1024 - l) element d2 <-> 15 - d2, so one thread owns both runs (32 complex values), and
 // the inverse consumes the digit-reversed order - no reordering or separate pair pass exists.
-// Shared-memory traffic per block: load + 2 radix-32 passes + fused + 2 radix-32 passes + store
-// = 6 round trips (was 10 with radices 4,16,16,16 and a separate pair pass).
+// Shared-memory traffic per block: 4 stores + 4 loads of the block (the first forward pass reads global memory,
+// the last inverse pass writes it; was 10 round trips with radices 4,16,16,16 and a separate pair pass); two CTA
+// barriers per block, one on either side of a middle in which every warp works on its own pair of 512-element
+// sub-transforms (WARP-LOCAL MIDDLE below); the next item's inputs arrive by cp.async under the last pass.
 //
 // A clip with N + Lmax - 1 <= P is a single block (plain zero-padded linear convolution);
 // longer clips use overlap-save blocks with H0 = roundup4(Lmax-1) samples of history.
@@ -477,8 +479,8 @@ __device__ __forceinline__ void conv_load_staged(float2 (&v)[32], const float2* 
 // loop - it sits at the 128-register limit and its code generation is touchy: variants that kept anything live across
 // it, or merely shared one instantiation with the plain kernel, cost 6-12 us per 1024 clips - so the record code lives
 // in two __noinline__ helpers and the kernel is a template.  No kernel of its own (feat_prep_kernel: 16 us of mostly
-// launch and load latency per step) sits in front of the frames kernel any more.  Measured (B = 1024): plain kernel
-// 127.2 us, with the records 135.8 us - 6.7 us of it the prologue's pointer chase (three dependent global loads per
+// launch and load latency per step) sits in front of the frames kernel any more.  Measured (B = 1024, final build):
+// plain kernel 106.4 us, with the records 110.6 us - the prologue's pointer chase (three dependent global loads per
 // clip), which is serial latency wherever it is put (as its own kernel in front of this one: 8 us) - against 16 us.
 static __device__ __noinline__ void conv_build_order(const ConvParams& p, uint16_t* s_order, int* s_scan) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
