@@ -742,9 +742,12 @@ __global__ void __launch_bounds__(StftPlan<NFFT>::kFlatThreads, StftPlan<NFFT>::
     int noff = 0, nlen = 1;
     float scale = 0.f;
     if (p.mix_g != nullptr) {
+      // both halves of the 32-byte record in one go: fetching the noise offset only once has_noise had arrived put the
+      // noise loads of the group one L2 round trip behind its sample loads
       const int4 m0 = __ldg(reinterpret_cast<const int4*>(p.mix_g + b));
+      const int4 m1 = __ldg(reinterpret_cast<const int4*>(p.mix_g + b) + 1);
       if (m0.y != 0) {
-        nz = p.noise.data + __ldg(reinterpret_cast<const long long*>(p.mix_g + b) + 2);
+        nz = p.noise.data + (((long long)m1.y << 32) | (unsigned)m1.x);
         scale = __int_as_float(m0.x); noff = m0.z; nlen = m0.w;
       }
     }
