@@ -279,3 +279,16 @@ def test_split_manifest_and_npy_shapes(tmp_path):
     assert formats.npy_kind(np.zeros((3, 1, 40, 11))) == "features"
     with pytest.raises(ValueError):
         formats.npy_kind(np.zeros(5))
+
+
+def test_aug_params_all_reverb_hint_is_taken_from_host_draws():
+    """AugParams.all_reverb (a scheduling hint for the reverb kernel, never a correctness input): filled in by .to() while
+    rir_idx is still a host tensor, kept when given, unknown (None) without rir_idx."""
+    import torch
+    from wakeword_trainer_home_b200 import AugParams
+    assert AugParams(rir_idx=torch.tensor([0, 3, 1], dtype=torch.int32)).to("cpu").all_reverb is True
+    assert AugParams(rir_idx=torch.tensor([0, -1, 1], dtype=torch.int32)).to("cpu").all_reverb is False
+    assert AugParams(noise_idx=torch.tensor([0, 1], dtype=torch.int32)).to("cpu").all_reverb is None
+    assert AugParams(rir_idx=torch.tensor([0, -1], dtype=torch.int32), all_reverb=True).to("cpu").all_reverb is True
+    a = AugParams(rir_idx=torch.tensor([2, 2], dtype=torch.int64)).to("cpu")
+    assert a.rir_idx.dtype == torch.int32 and a.all_reverb is True and a.to("cpu").all_reverb is True
