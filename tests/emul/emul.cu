@@ -319,10 +319,15 @@ int emul_mel_schedule(int n_fft, int n_freqs, int n_mels, const float* fb, const
       if (k0 + 2 * s.pairs[r] > extent) return -5;
     }
     for (int h = 0; h < 2; ++h) {
-      int cnt[16] = {};
+      // distinct ADDRESSES per bank residue: idle lanes (n = 0) read as well, but the same address as another lane is a
+      // broadcast, not a conflict
+      std::vector<int> seen[16];
       for (int l = 0; l < 16; ++l) {
         const int2 t = s.tasks[(size_t)r * 32 + 16 * h + l];
-        if (((unsigned)t.x >> 16) > 0) worst = std::max(worst, ++cnt[zmap(t.x & 0xffff) & 15]);
+        const int k0 = zmap(t.x & 0xffff);
+        std::vector<int>& v = seen[k0 & 15];
+        if (std::find(v.begin(), v.end(), k0) == v.end()) v.push_back(k0);
+        worst = std::max(worst, (int)v.size());
       }
     }
     for (int lane = 0; lane < 32; ++lane) {

@@ -224,6 +224,21 @@ inline MelSchedule build_mel_schedule(const std::vector<int>& lo, const std::vec
       for (int i = 0; i < t.n; ++i) s.w[(size_t)(wbase + d + i) * 32 + pl.lane] = w[t.o + i];   // rows < d and >= d + n stay 0
       s.tasks[(size_t)r * 32 + pl.lane] = make_int2(k0 | ((t.n + d) << 16), wbase | (t.m << 16) | (t.flags << 24));
     }
+    // idle lanes run the round's taps too (zero weights): they read wherever an ACTIVE lane of their half-warp reads
+    // (same addresses = a broadcast), not bin 0 - which shares a bank with every active lane whose first bin is a
+    // multiple of 16 and cost that half-warp a second wavefront per tap (11 % of the mel reads of n_fft 400 / 40 mels)
+    for (int h = 0; h < 2; ++h) {
+      int k0_active = -1;
+      for (int l = 0; l < 16 && k0_active < 0; ++l) {
+        const int2 t = s.tasks[(size_t)r * 32 + 16 * h + l];
+        if (((unsigned)t.x >> 16) > 0) k0_active = t.x & 0xffff;
+      }
+      if (k0_active < 0) continue;
+      for (int l = 0; l < 16; ++l) {
+        int2& t = s.tasks[(size_t)r * 32 + 16 * h + l];
+        if (((unsigned)t.x >> 16) == 0) t.x = k0_active;         // n stays 0
+      }
+    }
     wbase += rows;
     s.pairs.push_back(rows / 2);
     s.iterations += rows / 2;
